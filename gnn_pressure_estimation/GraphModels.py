@@ -1,0 +1,3 @@
+"""``gnn_pressure_estimation.GraphModels`` -> B200 implementation (see gnn_pressure_estimation_b200/GraphModels.py)."""
+from gnn_pressure_estimation_b200.GraphModels import *  # noqa: F401,F403
+from gnn_pressure_estimation_b200.GraphModels import GATResMeanConv, GResBlockMeanConv  # noqa: F401

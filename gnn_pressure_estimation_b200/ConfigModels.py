@@ -1,0 +1,64 @@
+"""Model registry for the GATRes configurations (drop-in for the GATRes rows of
+/root/reference/gnn_pressure_estimation/ConfigModels.py:22-42, :123-178).
+
+``select_model(args, name, reset_model_path)`` keeps the reference's contract:
+it fills ``args.criterion / norm_type / use_data_edge_attrs / model_path`` and
+returns ``(args, model)``.  Only the GATRes family lives on the B200 hot path;
+asking for one of the reference's baseline models raises.
+"""
+from __future__ import annotations
+
+import argparse
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+
+from .GraphModels import GATResMeanConv
+
+# (default variant name, num_blocks, nc, the authors' default checkpoint path)
+_GATRES_VARIANTS: Dict[str, Tuple[str, int, int, str]] = {
+    "gatres_small": ("GATResMeanConv_small_znorm_15b_32c", 15, 32,
+                     r"experiments_logs\simple_test\gatres_znorm\best_GATResMeanConv_znorm_20235922.pth"),
+    "gatres_large": ("GATRes_Large_znorm_25b_128c", 25, 128,
+                     r"experiments_logs\simple_test\GATResMeanConvLarge_znorm_25b_128c_20235401_20230601_1754"
+                     r"\best_GATResMeanConvLarge_znorm_25b_128c_20235401.pth"),
+    "gatres_small_tough": ("GATResMeanConv_small_tough_znorm_15b_32c", 15, 32,
+                           r"experiments_logs\simple_test\GATRes_small_tough_znorm_15b_32c"
+                           r"\best_GATRes_small_tough_znorm_15b_32c_20233629.pth"),
+}
+_NOT_ON_HOT_PATH = ("gin", "graphconvwat", "chebnet", "mgcn", "gcn2", "gat")
+
+
+def _configure(variant: str) -> Callable[[argparse.Namespace, Optional[str]], Tuple[argparse.Namespace, torch.nn.Module]]:
+    default_name, num_blocks, nc, ckpt = _GATRES_VARIANTS[variant]
+
+    def config(args: argparse.Namespace, test_model_variant_name: Optional[str] = None):
+        args.model_path = ckpt
+        args.criterion = "mse"
+        args.use_data_edge_attrs = None
+        args.norm_type = "znorm"
+        return args, GATResMeanConv(name=test_model_variant_name or default_name, num_blocks=num_blocks, nc=nc)
+
+    config.__name__ = f"config_{variant}"
+    return config
+
+
+config_gatres_small = _configure("gatres_small")
+config_gatres_large = _configure("gatres_large")
+config_gatres_small_tough = _configure("gatres_small_tough")
+
+
+def select_model(args: argparse.Namespace, test_model_variant_name: Optional[str] = None,
+                 reset_model_path: bool = False) -> Tuple[argparse.Namespace, torch.nn.Module]:
+    """``args.model`` (default ``gatres_small``) -> (args with the model's defaults, model)."""
+    which = getattr(args, "model", "gatres_small")
+    previous_path = getattr(args, "model_path", None)
+    if which in _NOT_ON_HOT_PATH:
+        raise NotImplementedError(f"model {which!r} is a baseline of the reference and is not part of the "
+                                  "B200 GATRes hot path; use gatres_small / gatres_large")
+    if which not in ("gatres_small", "gatres_large"):
+        raise NotImplementedError(f"Unknown model! Got {which}!")
+    args, model = (config_gatres_small if which == "gatres_small" else config_gatres_large)(args, test_model_variant_name)
+    if reset_model_path:
+        args.model_path = previous_path
+    return args, model

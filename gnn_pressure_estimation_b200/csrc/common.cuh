@@ -1,0 +1,110 @@
+// Shared device/host helpers for libgatres_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/gatres_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define GATRES_HOST_PASS 1
+#endif
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgatres_b200 is written for sm_100a (B200); compile with -gencode arch=compute_100a,code=sm_100a"
+#endif
+
+namespace gatres {
+
+constexpr float kNegSlope = 0.2f;      // GATConv negative_slope default
+constexpr float kSoftmaxEps = 1e-16f;  // torch_geometric.utils.softmax denominator epsilon
+constexpr int kThreads = 256;          // CTA size of the row kernels
+constexpr int kWarps = kThreads / 32;
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+int sm_count();
+
+#define GATRES_REQUIRE(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      gatres::set_error(__VA_ARGS__);        \
+      return GATRES_ERR_ARG;                 \
+    }                                        \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------ device
+__device__ __forceinline__ float lrelu(float z) { return z > 0.f ? z : kNegSlope * z; }
+__device__ __forceinline__ float lrelu_slope(float z) { return z > 0.f ? 1.f : kNegSlope; }
+
+// read-only 128-bit load (L1-allocating: neighbour rows are re-read by adjacent rows)
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming 128-bit load: data touched once by this kernel, keep it out of L1
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ void fma4(float4& acc, float s, float4 v) {
+  acc.x = fmaf(s, v.x, acc.x);
+  acc.y = fmaf(s, v.y, acc.y);
+  acc.z = fmaf(s, v.z, acc.z);
+  acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ void add4(float4& acc, float4 v) {
+  acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+}
+
+// butterfly sum over aligned groups of `width` lanes (width power of two <= 32);
+// `mask` must name every lane of the groups that execute this call together.
+template <int width>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int off = width / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+  return v;
+}
+
+// ---- row <-> lane mapping of the aggregation kernels -----------------------
+// A feature row of F = H*C floats is F/4 float4 "chunks".  LPR lanes share one
+// row (one chunk each, or V chunks each when F/4 > 32), so a warp works on
+// RPW = 32/LPR rows at a time.  Chunk q covers floats [4q, 4q+4) and belongs to
+// head 4q / C.
+template <int H, int C>
+struct RowMap {
+  static constexpr int F = H * C;
+  static constexpr int CHUNKS = F / 4;
+  static constexpr int LPR = CHUNKS < 32 ? CHUNKS : 32;   // lanes per row
+  static constexpr int V = CHUNKS / LPR;                  // chunks per lane
+  static constexpr int RPW = 32 / LPR;                    // rows per warp
+  static constexpr int LPH = (C / 4) < 32 ? (C / 4) : 32; // lanes holding one head of one row
+  static_assert(F % 4 == 0 && CHUNKS % LPR == 0 && (LPR & (LPR - 1)) == 0, "unsupported row width");
+  static_assert(V == 1 || V == H, "with several chunks per lane each chunk must be its own head");
+  __device__ static __forceinline__ int chunk(int lig, int v) { return lig + v * LPR; }
+  __device__ static __forceinline__ int head(int lig, int v) { return (4 * (lig + v * LPR)) / C; }
+};
+
+// Sum per-lane float4 accumulators over all lanes of a CTA that hold the same
+// chunk (same lane-in-row, any row slot, any warp) and write them to
+// dst[4*chunk ..].  red: shared scratch of kWarps*32*4 floats.  All threads call.
+template <int LPR>
+__device__ __forceinline__ void cta_chunk_sum_store(float4 acc, float* red, float* dst, int chunk_of_lig0_stride_v) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  st4(red + (warp * 32 + lane) * 4, acc);
+  __syncthreads();
+  if (threadIdx.x < LPR) {
+    float4 s = f4zero();
+    for (int w = 0; w < kWarps; ++w)
+#pragma unroll
+      for (int sub = 0; sub < 32 / LPR; ++sub) add4(s, *reinterpret_cast<float4*>(red + (w * 32 + sub * LPR + threadIdx.x) * 4));
+    st4(dst + 4 * (threadIdx.x + chunk_of_lig0_stride_v), s);
+  }
+}
+
+}  // namespace gatres

@@ -1,0 +1,565 @@
+// Node-wise dense contractions of the GATRes path (sm_100a): the GATConv
+// projection with the attention-score epilogue, its data/weight gradients, and
+// the Linear(1,nc) encoder / Linear(nc,1) decoder
+// (/root/reference/gnn_pressure_estimation/GraphModels.py:458-459, :477, :484;
+// SURVEY.md §A.2 step 1, §A.4 last two lines).
+//
+// fp32 FFMA on purpose: the parity contract is 1e-4 relative through 30 chained
+// projections, and these GEMMs are skinny (K <= 256, ~10 flop/B) and
+// HBM-bound, so the kernels are organised around the memory system instead:
+// persistent CTAs keep the whole weight matrix resident in shared memory and
+// stream row tiles through a cp.async double buffer.
+#include "common.cuh"
+
+namespace gatres {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float f4get(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+// ---------------------------------------------------------------------------
+// C[M,NN] = A[M,KK] * Bm[KK,NN]  over persistent CTAs.
+//   MODE 0 (projection fwd): Bm[k][n] = W[n][k] (W is [NN,KK]); epilogue also
+//          emits s_src/s_dst[m,h] = <C[m,h,:], att[h,:]>.
+//   MODE 1 (data gradient) : Bm = W as stored ([KK,NN]); epilogue adds `e0`
+//          (residual gradient) and masks by `e1 > 0` (ReLU of the layer input).
+// Thread (tx,ty) owns rows {ty + i*TY} and, per 4-wide column group jv, columns
+// jv*(NN/NV) + 4*tx .. +3, so every shared/global access of a warp is contiguous.
+// ---------------------------------------------------------------------------
+template <int KK, int NN, int BM, int TM, int TN, int STAGES, int MODE, int H>
+__global__ void __launch_bounds__(256)
+gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                 const float* __restrict__ e0, const float* __restrict__ e1,
+                 float* __restrict__ Cout, float* __restrict__ s0, float* __restrict__ s1, unsigned M) {
+  constexpr int TX = NN / TN, TY = BM / TM, NV = TN / 4, LDA = KK + 4, LDB = NN + 4, CG = NN / NV;
+  static_assert(TX * TY == 256 && TN % 4 == 0 && TX <= 32 && (32 % TX) == 0, "bad tiling");
+  static_assert(MODE == 1 || (H == 1 || NV == 1 || NV == 2), "score epilogue layout");
+  extern __shared__ __align__(16) float smem[];
+  float* Bs = smem;                       // [KK][LDB]
+  float* As = smem + KK * LDB;            // [STAGES][BM][LDA]
+  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  const unsigned ntiles = (M + BM - 1) / BM;
+
+  auto load_tile = [&](unsigned tile, int stage) {
+    float* dst = As + stage * BM * LDA;
+    for (int idx = tid; idx < BM * (KK / 4); idx += 256) {
+      const int m = idx / (KK / 4), kv = idx % (KK / 4);
+      const unsigned row = tile * BM + m;
+      const bool ok = row < M;
+      cp_async16(dst + m * LDA + 4 * kv, A + (size_t)(ok ? row : 0) * KK + 4 * kv, ok ? 16 : 0);
+    }
+  };
+
+  unsigned tile = blockIdx.x;
+  if (tile < ntiles) load_tile(tile, 0);
+  cp_async_commit();
+
+  if (MODE == 0) {
+    for (int idx = tid; idx < NN * (KK / 4); idx += 256) {
+      const int n = idx / (KK / 4), kv = idx % (KK / 4);
+      const float4 w = ldg4(W + (size_t)n * KK + 4 * kv);
+      Bs[(4 * kv + 0) * LDB + n] = w.x;
+      Bs[(4 * kv + 1) * LDB + n] = w.y;
+      Bs[(4 * kv + 2) * LDB + n] = w.z;
+      Bs[(4 * kv + 3) * LDB + n] = w.w;
+    }
+  } else {
+    for (int idx = tid; idx < KK * (NN / 4); idx += 256) {
+      const int k = idx / (NN / 4), nv = idx % (NN / 4);
+      st4(Bs + k * LDB + 4 * nv, ldg4(W + (size_t)k * NN + 4 * nv));
+    }
+  }
+  float att_s[TN], att_d[TN];
+  if (MODE == 0) {
+#pragma unroll
+    for (int jv = 0; jv < NV; ++jv) {
+      const float4 a = ldg4(e0 + jv * CG + 4 * tx), d = ldg4(e1 + jv * CG + 4 * tx);
+      att_s[jv * 4 + 0] = a.x; att_s[jv * 4 + 1] = a.y; att_s[jv * 4 + 2] = a.z; att_s[jv * 4 + 3] = a.w;
+      att_d[jv * 4 + 0] = d.x; att_d[jv * 4 + 1] = d.y; att_d[jv * 4 + 2] = d.z; att_d[jv * 4 + 3] = d.w;
+    }
+  }
+
+  int stage = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const unsigned next = tile + gridDim.x;
+    if (STAGES == 2) {
+      if (next < ntiles) load_tile(next, stage ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    const float* as = As + stage * BM * LDA;
+#pragma unroll 2
+    for (int k4 = 0; k4 < KK / 4; ++k4) {
+      float4 a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(as + (ty + i * TY) * LDA + 4 * k4);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float b[TN];
+#pragma unroll
+        for (int jv = 0; jv < NV; ++jv) {
+          const float4 t = *reinterpret_cast<const float4*>(Bs + (4 * k4 + kk) * LDB + jv * CG + 4 * tx);
+          b[jv * 4 + 0] = t.x; b[jv * 4 + 1] = t.y; b[jv * 4 + 2] = t.z; b[jv * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          const float ai = f4get(a[i], kk);
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ai, b[j], acc[i][j]);
+        }
+      }
+    }
+
+    // ---- epilogue (registers -> global) ----
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const unsigned row = tile * BM + ty + i * TY;
+      const bool ok = row < M;
+      if (MODE == 0) {
+        float ps[NV], pd[NV];
+#pragma unroll
+        for (int jv = 0; jv < NV; ++jv) {
+          ps[jv] = pd[jv] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            ps[jv] = fmaf(acc[i][jv * 4 + c], att_s[jv * 4 + c], ps[jv]);
+            pd[jv] = fmaf(acc[i][jv * 4 + c], att_d[jv * 4 + c], pd[jv]);
+          }
+        }
+        if (H == 1) {
+          float a = ps[0], d = pd[0];
+#pragma unroll
+          for (int jv = 1; jv < NV; ++jv) { a += ps[jv]; d += pd[jv]; }
+          a = group_sum<TX>(a, 0xffffffffu);
+          d = group_sum<TX>(d, 0xffffffffu);
+          if (ok && tx == 0) { s0[row] = a; s1[row] = d; }
+        } else if (NV == 2) {          // column group jv == head jv
+#pragma unroll
+          for (int jv = 0; jv < NV; ++jv) {
+            const float a = group_sum<TX>(ps[jv], 0xffffffffu), d = group_sum<TX>(pd[jv], 0xffffffffu);
+            if (ok && tx == 0) { s0[(size_t)row * 2 + jv] = a; s1[(size_t)row * 2 + jv] = d; }
+          }
+        } else {                       // NV == 1: heads split the tx range in halves
+          const float a = group_sum<TX / 2>(ps[0], 0xffffffffu), d = group_sum<TX / 2>(pd[0], 0xffffffffu);
+          if (ok && (tx % (TX / 2)) == 0) {
+            s0[(size_t)row * 2 + tx / (TX / 2)] = a;
+            s1[(size_t)row * 2 + tx / (TX / 2)] = d;
+          }
+        }
+      }
+      if (ok) {
+#pragma unroll
+        for (int jv = 0; jv < NV; ++jv) {
+          const size_t o = (size_t)row * NN + jv * CG + 4 * tx;
+          float4 v = make_float4(acc[i][jv * 4 + 0], acc[i][jv * 4 + 1], acc[i][jv * 4 + 2], acc[i][jv * 4 + 3]);
+          if (MODE == 1) {
+            if (e0 != nullptr) add4(v, ldg4_stream(e0 + o));
+            if (e1 != nullptr) {
+              const float4 r = ldg4_stream(e1 + o);
+              v.x = r.x > 0.f ? v.x : 0.f; v.y = r.y > 0.f ? v.y : 0.f;
+              v.z = r.z > 0.f ? v.z : 0.f; v.w = r.w > 0.f ? v.w : 0.f;
+            }
+          }
+          st4(Cout + o, v);
+        }
+      }
+    }
+    __syncthreads();                    // everyone is done with As[stage]
+    if (STAGES == 1) {
+      if (next < ntiles) load_tile(next, 0);
+      cp_async_commit();
+    } else {
+      stage ^= 1;
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------
+// Weight gradient dW[NO,KI] = dh^T x, reduced over this CTA's row tiles and
+// written once to its row of `partial` (deterministic two-stage reduction).
+// Thread (tk,tn) owns TNn x TKk outputs.
+// ---------------------------------------------------------------------------
+template <int NO, int KI, int BM, int TNn, int TKk>
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* __restrict__ partial,
+             long long P, long long off_W, unsigned M) {
+  constexpr int TKT = KI / TKk, TNT = NO / TNn, LDH = NO + 4, LDX = KI + 4;
+  constexpr int NVn = TNn / 4, CGn = NO / NVn;
+  constexpr int KW = TKk >= 4 ? 4 : TKk;            // contiguous k run per group
+  constexpr int NVk = TKk / KW, CGk = KI / NVk;
+  static_assert(TKT * TNT == 256 && TNn % 4 == 0 && (TKk == 2 || TKk % 4 == 0), "bad wgrad tiling");
+  extern __shared__ __align__(16) float smem[];
+  float* Hs = smem;                         // [2][BM][LDH]
+  float* Xs = smem + 2 * BM * LDH;          // [2][BM][LDX]
+  const int tid = threadIdx.x, tk = tid % TKT, tn = tid / TKT;
+  const unsigned ntiles = (M + BM - 1) / BM;
+
+  auto load_tile = [&](unsigned tile, int stage) {
+    float* hd = Hs + stage * BM * LDH;
+    float* xd = Xs + stage * BM * LDX;
+    for (int idx = tid; idx < BM * (NO / 4); idx += 256) {
+      const int m = idx / (NO / 4), v = idx % (NO / 4);
+      const unsigned row = tile * BM + m;
+      const bool ok = row < M;
+      cp_async16(hd + m * LDH + 4 * v, dh + (size_t)(ok ? row : 0) * NO + 4 * v, ok ? 16 : 0);
+    }
+    for (int idx = tid; idx < BM * (KI / 4); idx += 256) {
+      const int m = idx / (KI / 4), v = idx % (KI / 4);
+      const unsigned row = tile * BM + m;
+      const bool ok = row < M;
+      cp_async16(xd + m * LDX + 4 * v, x + (size_t)(ok ? row : 0) * KI + 4 * v, ok ? 16 : 0);
+    }
+  };
+
+  float acc[TNn][TKk];
+#pragma unroll
+  for (int i = 0; i < TNn; ++i)
+#pragma unroll
+    for (int j = 0; j < TKk; ++j) acc[i][j] = 0.f;
+
+  unsigned tile = blockIdx.x;
+  if (tile < ntiles) load_tile(tile, 0);
+  cp_async_commit();
+  int stage = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const unsigned next = tile + gridDim.x;
+    if (next < ntiles) load_tile(next, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* hs = Hs + stage * BM * LDH;
+    const float* xs = Xs + stage * BM * LDX;
+#pragma unroll 4
+    for (int m = 0; m < BM; ++m) {
+      float a[TNn], b[TKk];
+#pragma unroll
+      for (int jv = 0; jv < NVn; ++jv) {
+        const float4 t = *reinterpret_cast<const float4*>(hs + m * LDH + jv * CGn + 4 * tn);
+        a[jv * 4 + 0] = t.x; a[jv * 4 + 1] = t.y; a[jv * 4 + 2] = t.z; a[jv * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int jv = 0; jv < NVk; ++jv) {
+        if constexpr (KW == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(xs + m * LDX + jv * CGk + 4 * tk);
+          b[jv * 4 + 0] = t.x; b[jv * 4 + 1] = t.y; b[jv * 4 + 2] = t.z; b[jv * 4 + 3] = t.w;
+        } else {
+          const float2 t = *reinterpret_cast<const float2*>(xs + m * LDX + 2 * tk);
+          b[0] = t.x; b[1] = t.y;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TNn; ++i)
+#pragma unroll
+        for (int j = 0; j < TKk; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+  cp_async_wait<0>();
+
+  float* dst = partial + (size_t)blockIdx.x * P + off_W;
+#pragma unroll
+  for (int i = 0; i < TNn; ++i) {
+    const int n = (i / 4) * CGn + 4 * tn + (i % 4);
+#pragma unroll
+    for (int jv = 0; jv < NVk; ++jv) {
+      if constexpr (KW == 4) {
+        st4(dst + (size_t)n * KI + jv * CGk + 4 * tk,
+            make_float4(acc[i][jv * 4 + 0], acc[i][jv * 4 + 1], acc[i][jv * 4 + 2], acc[i][jv * 4 + 3]));
+      } else {
+        *reinterpret_cast<float2*>(dst + (size_t)n * KI + 2 * tk) = make_float2(acc[i][0], acc[i][1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ host launchers
+template <int KK, int NN, int BM, int TM, int TN, int STAGES, int MODE, int H>
+static int launch_gemm(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
+                       float* s1, unsigned M, cudaStream_t st, const char* what) {
+  constexpr size_t smem = (size_t)(KK * (NN + 4) + STAGES * BM * (KK + 4)) * sizeof(float);
+  auto kern = gemm_rows_kernel<KK, NN, BM, TM, TN, STAGES, MODE, H>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch(what);
+    configured = true;
+  }
+  const unsigned ntiles = (M + BM - 1) / BM;
+  unsigned per_sm = (unsigned)((200 * 1024) / smem);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  unsigned grid = (unsigned)sm_count() * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<grid, 256, smem, st>>>(A, W, e0, e1, Cout, s0, s1, M);
+  return check_launch(what);
+}
+
+template <int NO, int KI, int TNn, int TKk>
+static int launch_wgrad(const float* dh, const float* x, float* partial, long long P, int slots, long long off_W,
+                        unsigned M, cudaStream_t st) {
+  constexpr int BM = 32;
+  constexpr size_t smem = (size_t)(2 * BM * (NO + 4) + 2 * BM * (KI + 4)) * sizeof(float);
+  auto kern = wgrad_kernel<NO, KI, BM, TNn, TKk>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch("wgrad");
+    configured = true;
+  }
+  kern<<<slots, 256, smem, st>>>(dh, x, partial, P, off_W, M);
+  return check_launch("wgrad");
+}
+
+// (K, H*C) -> tiling; the same six shapes serve forward (KK=K, NN=H*C) and the
+// data gradient (KK=H*C, NN=K).
+template <int MODE, int H>
+static int dispatch_gemm(int KK, int NN, const float* A, const float* W, const float* e0, const float* e1,
+                         float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st, const char* what) {
+#define G(KKv, NNv, BM, TM, TN, ST) \
+  if (KK == KKv && NN == NNv) return launch_gemm<KKv, NNv, BM, TM, TN, ST, MODE, H>(A, W, e0, e1, Cout, s0, s1, M, st, what)
+  G(32, 64, 64, 4, 4, 2);
+  G(64, 32, 128, 4, 4, 2);
+  G(64, 128, 64, 4, 8, 2);
+  G(128, 64, 64, 4, 4, 2);
+  G(128, 256, 64, 8, 8, 2);
+  G(256, 128, 64, 4, 8, 1);
+#undef G
+  set_error("%s: unsupported contraction [M,%d] x [%d,%d]", what, KK, KK, NN);
+  return GATRES_ERR_ARG;
+}
+
+// ------------------------------------------------- encoder / decoder kernels
+__global__ void __launch_bounds__(256)
+encoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                   float* __restrict__ out, size_t total4, int nc4) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total4; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = idx / nc4;
+    const int c = (int)(idx - m * nc4);
+    const float xv = __ldg(x + m);
+    const float4 wv = ldg4(w + 4 * c), bv = ldg4(b + 4 * c);
+    st4(out + idx * 4, make_float4(fmaf(xv, wv.x, bv.x), fmaf(xv, wv.y, bv.y), fmaf(xv, wv.z, bv.z), fmaf(xv, wv.w, bv.w)));
+  }
+}
+
+// column sums over rows of g (db) and of g * x[m] (dw); thread owns chunk tid % nc4
+__global__ void __launch_bounds__(256)
+encoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ partial,
+                   long long P, long long off_w, long long off_b, unsigned M, int nc4) {
+  __shared__ float red[2 * 256 * 4];
+  const int c = threadIdx.x % nc4, rl = threadIdx.x / nc4, rows_per_pass = 256 / nc4;
+  float4 aw = f4zero(), ab = f4zero();
+  for (size_t m = (size_t)blockIdx.x * rows_per_pass + rl; m < M; m += (size_t)gridDim.x * rows_per_pass) {
+    const float4 gv = ldg4_stream(g + m * (size_t)(nc4 * 4) + 4 * c);
+    fma4(aw, __ldg(x + m), gv);
+    add4(ab, gv);
+  }
+  st4(red + threadIdx.x * 4, aw);
+  st4(red + (256 + threadIdx.x) * 4, ab);
+  __syncthreads();
+  if (threadIdx.x < nc4) {
+    float4 sw = f4zero(), sb = f4zero();
+    for (int k = 0; k < rows_per_pass; ++k) {
+      add4(sw, *reinterpret_cast<float4*>(red + (k * nc4 + threadIdx.x) * 4));
+      add4(sb, *reinterpret_cast<float4*>(red + (256 + k * nc4 + threadIdx.x) * 4));
+    }
+    float* row = partial + (size_t)blockIdx.x * P;
+    st4(row + off_w + 4 * threadIdx.x, sw);
+    st4(row + off_b + 4 * threadIdx.x, sb);
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                   float* __restrict__ out, const int* __restrict__ poison, unsigned M) {
+  constexpr int LPR = NC / 4, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, lig = lane % LPR;
+  const float4 wv = ldg4(w + 4 * lig);
+  const float bias = __ldg(b);
+  const bool bad = poison != nullptr && __ldg(poison) != 0;
+  constexpr unsigned rows_per_cta = kWarps * RPW;
+  for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
+    const unsigned r = r0 + warp * RPW + sub;
+    float p = 0.f;
+    if (r < M) p = dot4(ldg4_stream(x + (size_t)r * NC + 4 * lig), wv);
+    p = group_sum<LPR>(p, 0xffffffffu);
+    if (r < M && lig == 0) out[r] = bad ? __int_as_float(0x7fc00000) : p + bias;
+  }
+}
+
+// dx[m,c] = g[m] w[c] (masked by x>0 when mask_relu), dw[c] = sum_m g[m] x[m,c], db = sum_m g[m]
+template <int NC>
+__global__ void __launch_bounds__(256)
+decoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
+                   float* __restrict__ dx, float* __restrict__ partial, long long P, long long off_w,
+                   long long off_b, unsigned M, int mask_relu) {
+  constexpr int LPR = NC / 4, RPW = 32 / LPR;
+  __shared__ float red[kWarps * 32 * 4];
+  __shared__ float redb[kWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, lig = lane % LPR;
+  const float4 wv = ldg4(w + 4 * lig);
+  float4 aw = f4zero();
+  float ab = 0.f;
+  constexpr unsigned rows_per_cta = kWarps * RPW;
+  for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
+    const unsigned r = r0 + warp * RPW + sub;
+    if (r >= M) continue;
+    const float gv = __ldg(g + r);
+    const float4 xv = ldg4_stream(x + (size_t)r * NC + 4 * lig);
+    float4 d = make_float4(gv * wv.x, gv * wv.y, gv * wv.z, gv * wv.w);
+    if (mask_relu) {
+      d.x = xv.x > 0.f ? d.x : 0.f; d.y = xv.y > 0.f ? d.y : 0.f;
+      d.z = xv.z > 0.f ? d.z : 0.f; d.w = xv.w > 0.f ? d.w : 0.f;
+    }
+    st4(dx + (size_t)r * NC + 4 * lig, d);
+    fma4(aw, gv, xv);
+    if (lig == 0) ab += gv;
+  }
+  float* row = partial + (size_t)blockIdx.x * P;
+  cta_chunk_sum_store<LPR>(aw, red, row + off_w, 0);
+  ab = group_sum<32>(ab, 0xffffffffu);
+  if (lane == 0) redb[warp] = ab;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < kWarps; ++k) s += redb[k];
+    row[off_b] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, long long P, int slots, long long p_begin,
+                       long long p_end, float* __restrict__ grads) {
+  for (long long p = p_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; p < p_end;
+       p += (long long)gridDim.x * blockDim.x) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int s = 0;
+    for (; s + 4 <= slots; s += 4) {
+      s0 += __ldg(partial + (size_t)(s + 0) * P + p);
+      s1 += __ldg(partial + (size_t)(s + 1) * P + p);
+      s2 += __ldg(partial + (size_t)(s + 2) * P + p);
+      s3 += __ldg(partial + (size_t)(s + 3) * P + p);
+    }
+    for (; s < slots; ++s) s0 += __ldg(partial + (size_t)s * P + p);
+    grads[p] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+}  // namespace gatres
+
+using namespace gatres;
+
+extern "C" int gatres_linear_att_fwd(const float* x, const float* W, const float* att_src, const float* att_dst,
+                                     float* h, float* s_src, float* s_dst, int64_t M, int32_t K, int32_t H,
+                                     int32_t C, void* stream) {
+  GATRES_REQUIRE(M >= 0 && M < (1ll << 31), "linear_att_fwd: bad M=%lld", (long long)M);
+  if (M == 0) return GATRES_OK;
+  if (H == 1) return dispatch_gemm<0, 1>(K, H * C, x, W, att_src, att_dst, h, s_src, s_dst, (unsigned)M, as_stream(stream), "linear_att_fwd");
+  if (H == 2) return dispatch_gemm<0, 2>(K, H * C, x, W, att_src, att_dst, h, s_src, s_dst, (unsigned)M, as_stream(stream), "linear_att_fwd");
+  set_error("linear_att_fwd: heads must be 1 or 2, got %d", H);
+  return GATRES_ERR_ARG;
+}
+
+extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W, const float* add,
+                                 const float* relu_ref, float* dx, float* partial, int64_t P, int32_t slots,
+                                 int64_t off_W, int64_t M, int32_t K, int32_t H, int32_t C, void* stream) {
+  GATRES_REQUIRE(M > 0 && M < (1ll << 31), "linear_bwd: bad M=%lld", (long long)M);
+  GATRES_REQUIRE(slots > 0 && P % 4 == 0 && off_W % 4 == 0, "linear_bwd: bad slots/P/off_W");
+  cudaStream_t st = as_stream(stream);
+  const int NO = H * C;
+  if (dx != nullptr) {
+    int rc = dispatch_gemm<1, 1>(NO, K, dh, W, add, relu_ref, dx, nullptr, nullptr, (unsigned)M, st, "linear_bwd_dx");
+    if (rc) return rc;
+  }
+#define WG(NOv, KIv, TNn, TKk) \
+  if (NO == NOv && K == KIv) return launch_wgrad<NOv, KIv, TNn, TKk>(dh, x, partial, P, slots, off_W, (unsigned)M, st)
+  WG(64, 32, 4, 2);
+  WG(32, 64, 4, 2);
+  WG(128, 64, 8, 4);
+  WG(64, 128, 4, 8);
+  WG(256, 128, 16, 8);
+  WG(128, 256, 8, 16);
+#undef WG
+  set_error("linear_bwd: unsupported weight shape [%d,%d]", NO, K);
+  return GATRES_ERR_ARG;
+}
+
+static unsigned flat_grid(size_t work_items) {
+  size_t g = (work_items + 255) / 256;
+  const size_t cap = (size_t)sm_count() * 16;
+  return (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+extern "C" int gatres_encoder_fwd(const float* x, const float* w, const float* b, float* out, int64_t M,
+                                  int32_t nc, void* stream) {
+  GATRES_REQUIRE(M >= 0 && nc > 0 && nc % 4 == 0, "encoder_fwd: bad M=%lld nc=%d", (long long)M, nc);
+  if (M == 0) return GATRES_OK;
+  const size_t total4 = (size_t)M * (nc / 4);
+  encoder_fwd_kernel<<<flat_grid(total4), 256, 0, as_stream(stream)>>>(x, w, b, out, total4, nc / 4);
+  return check_launch("encoder_fwd");
+}
+
+extern "C" int gatres_encoder_bwd(const float* g, const float* x, float* partial, int64_t P, int32_t slots,
+                                  int64_t off_w, int64_t off_b, int64_t M, int32_t nc, void* stream) {
+  GATRES_REQUIRE(M > 0 && M < (1ll << 31) && slots > 0, "encoder_bwd: bad M/slots");
+  GATRES_REQUIRE(nc % 4 == 0 && 256 % (nc / 4) == 0 && nc / 4 <= 256, "encoder_bwd: unsupported nc=%d", nc);
+  GATRES_REQUIRE(P % 4 == 0 && off_w % 4 == 0 && off_b % 4 == 0, "encoder_bwd: misaligned offsets");
+  encoder_bwd_kernel<<<slots, 256, 0, as_stream(stream)>>>(g, x, partial, P, off_w, off_b, (unsigned)M, nc / 4);
+  return check_launch("encoder_bwd");
+}
+
+extern "C" int gatres_decoder_fwd(const float* x, const float* w, const float* b, float* out,
+                                  const int32_t* poison, int64_t M, int32_t nc, void* stream) {
+  GATRES_REQUIRE(M >= 0 && M < (1ll << 31), "decoder_fwd: bad M=%lld", (long long)M);
+  if (M == 0) return GATRES_OK;
+  cudaStream_t st = as_stream(stream);
+  const unsigned Mu = (unsigned)M;
+  switch (nc) {
+    case 32: decoder_fwd_kernel<32><<<flat_grid((size_t)M * 8), 256, 0, st>>>(x, w, b, out, poison, Mu); break;
+    case 64: decoder_fwd_kernel<64><<<flat_grid((size_t)M * 16), 256, 0, st>>>(x, w, b, out, poison, Mu); break;
+    case 128: decoder_fwd_kernel<128><<<flat_grid((size_t)M * 32), 256, 0, st>>>(x, w, b, out, poison, Mu); break;
+    default: set_error("decoder_fwd: unsupported nc=%d", nc); return GATRES_ERR_ARG;
+  }
+  return check_launch("decoder_fwd");
+}
+
+extern "C" int gatres_decoder_bwd(const float* g_out, const float* x, const float* w, float* dx, float* partial,
+                                  int64_t P, int32_t slots, int64_t off_w, int64_t off_b, int64_t M, int32_t nc,
+                                  int32_t mask_relu, void* stream) {
+  GATRES_REQUIRE(M > 0 && M < (1ll << 31) && slots > 0, "decoder_bwd: bad M/slots");
+  GATRES_REQUIRE(P % 4 == 0 && off_w % 4 == 0, "decoder_bwd: misaligned offsets");
+  cudaStream_t st = as_stream(stream);
+  const unsigned Mu = (unsigned)M;
+  switch (nc) {
+    case 32: decoder_bwd_kernel<32><<<slots, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu); break;
+    case 64: decoder_bwd_kernel<64><<<slots, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu); break;
+    case 128: decoder_bwd_kernel<128><<<slots, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu); break;
+    default: set_error("decoder_bwd: unsupported nc=%d", nc); return GATRES_ERR_ARG;
+  }
+  return check_launch("decoder_bwd");
+}
+
+extern "C" int gatres_reduce_partials(const float* partial, int64_t P, int32_t slots, int64_t p_begin,
+                                      int64_t p_end, float* grads, void* stream) {
+  GATRES_REQUIRE(slots > 0 && p_begin >= 0 && p_end >= p_begin && p_end <= P, "reduce_partials: bad range");
+  if (p_end == p_begin) return GATRES_OK;
+  reduce_partials_kernel<<<flat_grid((size_t)(p_end - p_begin)), 256, 0, as_stream(stream)>>>(
+      partial, P, slots, p_begin, p_end, grads);
+  return check_launch("reduce_partials");
+}

@@ -1,0 +1,185 @@
+// Whole-model orchestration: GATResMeanConv.forward and its backward as one C
+// call each (/root/reference/gnn_pressure_estimation/GraphModels.py:486-494 for
+// the model, :462-468 for a block; backward = what autograd does at
+// train.py:185).  One call enqueues every kernel of the stack on the caller's
+// stream, so the Python host pays two FFI crossings per training step and the
+// whole step can be captured into a CUDA graph.
+#include "common.cuh"
+
+namespace gatres {
+
+static inline int64_t a4(int64_t n) { return (n + 3) & ~(int64_t)3; }
+
+struct ParamLayout {
+  int64_t nc, nb;
+  explicit ParamLayout(int32_t num_blocks, int32_t nc_) : nc(nc_), nb(num_blocks) {}
+  int64_t lin0_w() const { return 0; }
+  int64_t lin0_b() const { return nc; }
+  int64_t block_size() const { return 4 * nc * nc + 9 * nc; }
+  int64_t block(int64_t k) const { return 2 * nc + k * block_size(); }
+  int64_t c1_W(int64_t k) const { return block(k); }
+  int64_t c1_as(int64_t k) const { return block(k) + 2 * nc * nc; }
+  int64_t c1_ad(int64_t k) const { return c1_as(k) + 2 * nc; }
+  int64_t c1_b(int64_t k) const { return c1_ad(k) + 2 * nc; }
+  int64_t c2_W(int64_t k) const { return c1_b(k) + 2 * nc; }
+  int64_t c2_as(int64_t k) const { return c2_W(k) + 2 * nc * nc; }
+  int64_t c2_ad(int64_t k) const { return c2_as(k) + nc; }
+  int64_t c2_b(int64_t k) const { return c2_ad(k) + nc; }
+  int64_t lin1_w() const { return block(nb); }
+  int64_t lin1_b() const { return lin1_w() + nc; }
+  int64_t count() const { return lin1_b() + 1; }
+};
+
+// activations forward(training) keeps for backward
+struct SavedLayout {
+  int64_t M, nc;
+  SavedLayout(int64_t M_, int64_t nc_) : M(M_), nc(nc_) {}
+  int64_t x_enc() const { return 0; }
+  int64_t block_size() const { return 6 * M * nc + 4 * a4(2 * M) + 4 * a4(M); }
+  int64_t block(int64_t k) const { return M * nc + k * block_size(); }
+  int64_t h1(int64_t k) const { return block(k); }
+  int64_t ss1(int64_t k) const { return h1(k) + 2 * M * nc; }
+  int64_t sd1(int64_t k) const { return ss1(k) + a4(2 * M); }
+  int64_t m1(int64_t k) const { return sd1(k) + a4(2 * M); }
+  int64_t l1(int64_t k) const { return m1(k) + a4(2 * M); }
+  int64_t y1(int64_t k) const { return l1(k) + a4(2 * M); }
+  int64_t h2(int64_t k) const { return y1(k) + 2 * M * nc; }
+  int64_t ss2(int64_t k) const { return h2(k) + M * nc; }
+  int64_t sd2(int64_t k) const { return ss2(k) + a4(M); }
+  int64_t m2(int64_t k) const { return sd2(k) + a4(M); }
+  int64_t l2(int64_t k) const { return m2(k) + a4(M); }
+  int64_t xout(int64_t k) const { return l2(k) + a4(M); }
+  int64_t total(int64_t nb) const { return block(nb); }
+};
+
+static int validate(const gatres_model_desc* d, const char* who) {
+  GATRES_REQUIRE(d != nullptr, "%s: null model descriptor", who);
+  GATRES_REQUIRE(d->num_blocks >= 0 && (d->nc == 32 || d->nc == 64 || d->nc == 128),
+                 "%s: unsupported model (num_blocks=%d, nc=%d; nc in {32,64,128})", who, d->num_blocks, d->nc);
+  GATRES_REQUIRE(d->N > 0 && d->B > 0 && d->B * (int64_t)d->N < (1ll << 31), "%s: bad B=%lld N=%d", who,
+                 (long long)d->B, d->N);
+  GATRES_REQUIRE(d->rowptr && d->col && d->rowptr_t && d->col_t, "%s: CSR pointers missing", who);
+  return GATRES_OK;
+}
+
+}  // namespace gatres
+
+using namespace gatres;
+
+#define TRY(call)            \
+  do {                       \
+    const int rc_ = (call);  \
+    if (rc_) return rc_;     \
+  } while (0)
+
+extern "C" int64_t gatres_param_count(int32_t num_blocks, int32_t nc) { return ParamLayout(num_blocks, nc).count(); }
+
+extern "C" int64_t gatres_saved_floats(const gatres_model_desc* d) {
+  if (validate(d, "saved_floats")) return -1;
+  return SavedLayout(d->B * (int64_t)d->N, d->nc).total(d->num_blocks);
+}
+
+extern "C" int64_t gatres_scratch_floats(const gatres_model_desc* d, int32_t training) {
+  if (validate(d, "scratch_floats")) return -1;
+  const int64_t M = d->B * (int64_t)d->N, nc = d->nc;
+  const int64_t fwd_infer = 8 * M * nc + 2 * a4(2 * M);                 // xa xb h1 y1 h2 z + ss sd
+  const int64_t fwd_train = M * nc;                                     // z
+  const int64_t bwd = 8 * M * nc + 8 * M + a4(2 * M);                   // gA gB dz dh2 dy1 dh1 rec dsd
+  return training ? (fwd_train > bwd ? fwd_train : bwd) : fwd_infer;
+}
+
+extern "C" int gatres_forward(const gatres_model_desc* d, const float* params, const float* x, float* out,
+                              float* saved, float* scratch, void* stream) {
+  TRY(validate(d, "forward"));
+  GATRES_REQUIRE(params && x && out && scratch, "forward: null buffer");
+  const int64_t M = d->B * (int64_t)d->N, nc = d->nc;
+  const int32_t N = d->N, C = d->nc;
+  const ParamLayout pl(d->num_blocks, d->nc);
+  const SavedLayout sl(M, nc);
+  const bool train = saved != nullptr;
+
+  // inference: rolling buffers carved from scratch
+  float* xa = scratch;
+  float* xb = xa + M * nc;
+  float* h1_i = xb + M * nc;
+  float* y1_i = h1_i + 2 * M * nc;
+  float* h2_i = y1_i + 2 * M * nc;
+  float* z_i = h2_i + M * nc;
+  float* ss_i = z_i + M * nc;
+  float* sd_i = ss_i + a4(2 * M);
+
+  float* x0 = train ? saved + sl.x_enc() : xa;
+  TRY(gatres_encoder_fwd(x, params + pl.lin0_w(), params + pl.lin0_b(), x0, M, C, stream));
+  for (int k = 0; k < d->num_blocks; ++k) {
+    float* h1 = train ? saved + sl.h1(k) : h1_i;
+    float* ss1 = train ? saved + sl.ss1(k) : ss_i;
+    float* sd1 = train ? saved + sl.sd1(k) : sd_i;
+    float* m1 = train ? saved + sl.m1(k) : nullptr;
+    float* l1 = train ? saved + sl.l1(k) : nullptr;
+    float* y1 = train ? saved + sl.y1(k) : y1_i;
+    float* h2 = train ? saved + sl.h2(k) : h2_i;
+    float* ss2 = train ? saved + sl.ss2(k) : ss_i;
+    float* sd2 = train ? saved + sl.sd2(k) : sd_i;
+    float* m2 = train ? saved + sl.m2(k) : nullptr;
+    float* l2 = train ? saved + sl.l2(k) : nullptr;
+    float* z = train ? scratch : z_i;
+    float* xo = train ? saved + sl.xout(k) : (x0 == xa ? xb : xa);
+    TRY(gatres_linear_att_fwd(x0, params + pl.c1_W(k), params + pl.c1_as(k), params + pl.c1_ad(k), h1, ss1, sd1, M,
+                              C, 2, C, stream));
+    TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h1, ss1, sd1, params + pl.c1_b(k), y1, m1, l1, d->B, N, 2, C, 1, stream));
+    TRY(gatres_linear_att_fwd(y1, params + pl.c2_W(k), params + pl.c2_as(k), params + pl.c2_ad(k), h2, ss2, sd2, M,
+                              2 * C, 1, C, stream));
+    TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h2, ss2, sd2, params + pl.c2_b(k), z, m2, l2, d->B, N, 1, C, 0, stream));
+    TRY(gatres_mean_res_fwd(d->rowptr, d->col, z, x0, xo, d->B, N, C, stream));
+    x0 = xo;
+  }
+  return gatres_decoder_fwd(x0, params + pl.lin1_w(), params + pl.lin1_b(), out, d->poison, M, C, stream);
+}
+
+extern "C" int gatres_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
+                               const float* d_out, float* partial, float* grads, float* scratch, void* stream) {
+  TRY(validate(d, "backward"));
+  GATRES_REQUIRE(params && x && saved && d_out && partial && grads && scratch, "backward: null buffer");
+  GATRES_REQUIRE(d->slots > 0, "backward: slots must be > 0");
+  const int64_t M = d->B * (int64_t)d->N, nc = d->nc;
+  const int32_t N = d->N, C = d->nc, S = d->slots, nb = d->num_blocks;
+  const ParamLayout pl(nb, d->nc);
+  const SavedLayout sl(M, nc);
+  const int64_t P = a4(pl.count());                      // row stride of `partial`
+
+  float* gA = scratch;
+  float* gB = gA + M * nc;
+  float* dz = gB + M * nc;
+  float* dh2 = dz + M * nc;
+  float* dy1 = dh2 + M * nc;
+  float* dh1 = dy1 + 2 * M * nc;
+  float* rec = dh1 + 2 * M * nc;
+  float* dsd = rec + 8 * M;
+
+  const float* x_last = nb > 0 ? saved + sl.xout(nb - 1) : saved + sl.x_enc();
+  TRY(gatres_decoder_bwd(d_out, x_last, params + pl.lin1_w(), gA, partial, P, S, pl.lin1_w(), pl.lin1_b(), M, C,
+                         nb > 0 ? 1 : 0, stream));
+  for (int k = nb - 1; k >= 0; --k) {
+    const float* x0 = k > 0 ? saved + sl.xout(k - 1) : saved + sl.x_enc();
+    // SimpleConv(mean) + residual: gA already carries the ReLU mask of this block's output
+    TRY(gatres_mean_res_bwd(d->rowptr, d->rowptr_t, d->col_t, gA, nullptr, dz, nullptr, d->B, N, C, stream));
+    // conv2 (heads=1, mean over one head)
+    TRY(gatres_gat_agg_bwd(d->rowptr, d->col, d->rowptr_t, d->col_t, dz, saved + sl.h2(k), saved + sl.ss2(k),
+                           saved + sl.sd2(k), saved + sl.m2(k), saved + sl.l2(k), params + pl.c2_as(k),
+                           params + pl.c2_ad(k), rec, dsd, dh2, partial, P, S, pl.c2_as(k), pl.c2_ad(k), pl.c2_b(k),
+                           d->B, N, 1, C, stream));
+    TRY(gatres_linear_bwd(dh2, saved + sl.y1(k), params + pl.c2_W(k), nullptr, saved + sl.y1(k), dy1, partial, P, S,
+                          pl.c2_W(k), M, 2 * C, 1, C, stream));
+    // conv1 (heads=2, concat) — dy1 already carries the ReLU mask of y1
+    TRY(gatres_gat_agg_bwd(d->rowptr, d->col, d->rowptr_t, d->col_t, dy1, saved + sl.h1(k), saved + sl.ss1(k),
+                           saved + sl.sd1(k), saved + sl.m1(k), saved + sl.l1(k), params + pl.c1_as(k),
+                           params + pl.c1_ad(k), rec, dsd, dh1, partial, P, S, pl.c1_as(k), pl.c1_ad(k), pl.c1_b(k),
+                           d->B, N, 2, C, stream));
+    // dx0 = dh1 W1 + (residual branch gA), masked by the previous block's ReLU (none before block 0)
+    TRY(gatres_linear_bwd(dh1, x0, params + pl.c1_W(k), gA, k > 0 ? x0 : nullptr, gB, partial, P, S, pl.c1_W(k), M, C,
+                          2, C, stream));
+    float* t = gA; gA = gB; gB = t;
+  }
+  TRY(gatres_encoder_bwd(gA, x, partial, P, S, pl.lin0_w(), pl.lin0_b(), M, C, stream));
+  return gatres_reduce_partials(partial, P, S, 0, pl.count(), grads, stream);
+}

@@ -1,0 +1,120 @@
+"""One training step of the reference loop as a fixed kernel sequence.
+
+Mirrors the per-batch body of ``train_one_epoch``
+(/root/reference/gnn_pressure_estimation/train.py:159-190): zero the masked
+inputs, forward, MSE over the masked nodes, backward, Adam(lr 5e-4, L2 6e-6,
+train.py:348,550-551) — everything on the device, on one stream, with static
+buffers so the whole step is captured once into a CUDA graph and replayed.
+The data-parallel variant inserts one gradient all-reduce (NCCL) between
+backward and Adam.
+
+Per step the host does: three H2D copies into the static input buffers (x, y,
+mask), one graph launch, and (optionally) one 4-byte D2H read of the loss.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib, ops as _gops
+from ._lib import ModelDesc, call, ptr, stream
+from .GraphModels import GATResMeanConv
+from .graph import Topology
+
+
+class TrainStep:
+    def __init__(self, model: GATResMeanConv, topo: Topology, batch: int, mask_count_per_snapshot: int,
+                 lr: float = 5e-4, weight_decay: float = 6e-6, betas=(0.9, 0.999), eps: float = 1e-8,
+                 process_group=None, use_graph: bool = True):
+        self.model, self.topo, self.B = model, topo, int(batch)
+        self.N, self.nc, self.nb = topo.N, model.nc, model.num_blocks
+        self.M = self.B * self.N
+        self.count = self.B * int(mask_count_per_snapshot)        # masked nodes per local batch
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.use_graph = use_graph
+        dev = topo.rowptr.device
+        self.device = dev
+        self.flat = model.flat_parameters()
+        P = self.flat.numel()
+        self.P = P
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.x = torch.zeros(self.M, **f32)            # static inputs (H2D targets)
+        self.y = torch.zeros(self.M, **f32)
+        self.mask = torch.zeros(self.M, dtype=torch.uint8, device=dev)
+        self.xm = torch.empty(self.M, **f32)
+        self.out = torch.empty(self.M, **f32)
+        self.d_out = torch.empty(self.M, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self._loss_part = torch.empty(1024, **f32)
+        self.grads = torch.zeros(P, **f32)
+        self.exp_avg = torch.zeros(P, **f32)
+        self.exp_avg_sq = torch.zeros(P, **f32)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.desc = ModelDesc(self.nb, self.nc, self.N, _gops.grad_slots(self.M), self.B, ptr(topo.rowptr),
+                              ptr(topo.col), ptr(topo.rowptr_t), ptr(topo.col_t), None)
+        lib = _lib.load()
+        self.saved = torch.empty(int(lib.gatres_saved_floats(C.byref(self.desc))), **f32)
+        self.scratch = torch.empty(int(lib.gatres_scratch_floats(C.byref(self.desc), 1)), **f32)
+        self.partial = torch.empty(self.desc.slots * _gops.a4(P), **f32)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.kernels_per_step = 1 + (2 + 5 * self.nb) + 2 + (3 + 9 * self.nb) + 2   # our launches per step
+
+    # ------------------------------------------------------------------ pieces
+    def _enqueue(self) -> None:
+        s = stream()
+        d = C.byref(self.desc)
+        call("gatres_apply_mask", ptr(self.x), ptr(self.mask), ptr(self.xm), self.M, s)
+        call("gatres_forward", d, ptr(self.flat), ptr(self.xm), ptr(self.out), ptr(self.saved), ptr(self.scratch), s)
+        call("gatres_masked_mse", ptr(self.out), ptr(self.y), ptr(self.mask), self.M, self.count, ptr(self.d_out),
+             ptr(self.loss), ptr(self._loss_part), s)
+        call("gatres_backward", d, ptr(self.flat), ptr(self.xm), ptr(self.saved), ptr(self.d_out), ptr(self.partial),
+             ptr(self.grads), ptr(self.scratch), s)
+        if self.pg is not None and self.world > 1:
+            # equal shard sizes and equal masked counts per snapshot -> mean of local means == global mean
+            torch.distributed.all_reduce(self.grads, group=self.pg)
+        call("gatres_adam_step", ptr(self.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+             ptr(self.step_count), self.P, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+             1.0 / self.world, s)
+
+    def capture(self, warmup: int = 2) -> None:
+        """Run the step eagerly a few times on a side stream, then capture it.
+        (The warm-up steps are real optimizer steps.)"""
+        if not self.use_graph:
+            return
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._enqueue()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        self.graph = g
+
+    # ------------------------------------------------------------------- steps
+    def load_inputs(self, x: Tensor, y: Tensor, mask: Tensor) -> None:
+        """H2D (or D2D) copy of one batch into the static buffers; x/y are the
+        UNMASKED z-normed pressures ([B*N] or [B*N,1]), mask is bool/uint8 [B*N]."""
+        self.x.copy_(x.reshape(-1), non_blocking=True)
+        self.y.copy_(y.reshape(-1), non_blocking=True)
+        m = mask.reshape(-1)
+        self.mask.copy_(m.view(torch.uint8) if m.dtype == torch.bool else m, non_blocking=True)
+
+    def run(self) -> Tensor:
+        """Enqueue one optimizer step on the resident inputs; returns the device loss scalar."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        return self.loss
+
+    def step(self, x: Tensor, y: Tensor, mask: Tensor) -> Tensor:
+        self.load_inputs(x, y, mask)
+        return self.run()

@@ -1,0 +1,238 @@
+/*
+ * gatres_b200.h — C ABI of libgatres_b200.so: the GATRes message-passing hot
+ * path (stacked GATConv-with-residual blocks, forward + backward) as hand
+ * written CUDA for sm_100a.
+ *
+ * The reference has no FFI of its own: its operator boundary is the set of
+ * PyTorch-Geometric modules it instantiates (all paths relative to
+ * /root/reference/gnn_pressure_estimation/):
+ *
+ *   GATConv(in, hc, 2, concat=True) / GATConv(2hc, out, 1, concat=False)
+ *                                     GraphModels.py:458-459, called :464-465
+ *   SimpleConv(aggr="mean") + x_0, relu     GraphModels.py:460, :466-467
+ *   Linear(1, nc) / Linear(nc, 1)           GraphModels.py:477/:487, :484/:492
+ *   GATResMeanConv.forward                  GraphModels.py:486-494
+ *   autograd backward of all of the above   train.py:185
+ *   PyG collation (replicated edge_index)   train.py:302, utils/DataLoader.py:28-37
+ *   mask + MSE over masked nodes, Adam      train.py:171-188, :348
+ *
+ * Each entry point below names the interface it replaces.  INTEGRATION.md
+ * shows the ctypes binding (the Python host side in
+ * gnn_pressure_estimation_b200/_lib.py is exactly that binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - all buffers are caller-allocated (torch owns the memory); the library
+ *     never allocates, frees or synchronises, keeps no global state except a
+ *     thread-local error string, and enqueues all work on `stream`
+ *     (a cudaStream_t passed as void*), so every call is CUDA-graph capturable;
+ *   - return value 0 = ok, negative = error (gatres_last_error() has the text);
+ *   - features are fp32, row-major [B*N, F] (snapshot-major: row = b*N + node),
+ *     heads concatenated along F ([B, N, H, C] contiguous);
+ *   - graph structure is int32 CSR, shared by all B snapshots of a batch.
+ *
+ * Flat parameter layout (P = gatres_param_count(num_blocks, nc) floats; grads
+ * use the same layout).  Matches the state_dict order of SURVEY.md §A.1:
+ *     lin0.weight[nc] lin0.bias[nc]
+ *     per block k: conv1.W[2nc,nc] conv1.att_src[2nc] conv1.att_dst[2nc] conv1.bias[2nc]
+ *                  conv2.W[nc,2nc] conv2.att_src[nc]  conv2.att_dst[nc]  conv2.bias[nc]
+ *     lin1.weight[nc] lin1.bias[1]
+ */
+#ifndef GATRES_B200_H_
+#define GATRES_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GATRES_OK 0
+#define GATRES_ERR_ARG (-1)       /* bad argument / unsupported shape */
+#define GATRES_ERR_CUDA (-2)      /* a CUDA runtime call failed        */
+
+#define GATRES_ABI_VERSION 1
+
+int gatres_abi_version(void);
+const char* gatres_last_error(void);
+/* Number of SMs of the current device (grid sizing); <0 on error. */
+int gatres_sm_count(void);
+
+/* ------------------------------------------------------------------ graph */
+
+/* Bytes of device scratch gatres_csr_build needs. */
+size_t gatres_csr_scratch_bytes(int64_t E, int32_t N);
+
+/*
+ * Build the two CSR structures all kernels share from a template edge_index
+ * (int64 [2,E], row 0 = source j, row 1 = target i; the layout PyG's
+ * from_networkx emits, utils/DataLoader.py:28-37).  Replaces the per-call
+ * remove_self_loops/add_self_loops + scatter indexing inside GATConv.forward.
+ * Existing self loops are dropped, one loop per node is appended LAST, and the
+ * list is stably sorted by target (rowptr/col = in-edges: sources of each
+ * target, in edge-list order, self-loop last) and by source
+ * (rowptr_t/col_t = out-edges: targets of each source, self-loop last).
+ * rowptr* have N+1 entries, col* have capacity E+N; E' = rowptr[N].
+ * info (device int32[4]): [0] dropped self loops, [1] E', [2] columns with an
+ * out-of-range node id (ignored), [3] reserved.  scratch: gatres_csr_scratch_bytes.
+ */
+int gatres_csr_build(const int64_t* edge_index, int64_t E, int32_t N,
+                     int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t,
+                     int32_t* info, void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * Check that a collated edge_index (int64 [2, B*E]) is B shifted copies of the
+ * template (PyG Batch collation, train.py:302): column b*E+e == template[:,e] + b*N.
+ * *mismatch (device int32) is incremented once per violating column.
+ */
+int gatres_check_replicated(const int64_t* edge_index_batch, const int64_t* edge_index_tmpl,
+                            int64_t B, int64_t E, int32_t N, int32_t* mismatch, void* stream);
+
+/* --------------------------------------------------------------- operators */
+
+/*
+ * GATConv projection + attention scores (GATConv.forward step 1; call sites
+ * GraphModels.py:464-465):  h = x W^T  ([M,K] x [H*C,K]^T -> [M,H*C]),
+ * s_src[m,h] = <h[m,h,:], att_src[h,:]>, s_dst likewise.
+ * Supported (K, H, C): C in {32,64,128}, H in {1,2}, K in {C, 2C} as the model uses.
+ */
+int gatres_linear_att_fwd(const float* x, const float* W, const float* att_src, const float* att_dst,
+                          float* h, float* s_src, float* s_dst,
+                          int64_t M, int32_t K, int32_t H, int32_t C, void* stream);
+
+/*
+ * Fused GAT aggregation (GATConv.forward steps 2-6): per target row, LeakyReLU(0.2)
+ * logits over in-edges, segment softmax, alpha-weighted sum of neighbour rows,
+ * + bias, optional ReLU (the `.relu()` at GraphModels.py:464).
+ * m/l ([M,H], may be NULL) receive the softmax row max and exp-sum for the
+ * recompute-based backward.  concat=0 requires H=1 (mean over one head).
+ */
+int gatres_gat_agg_fwd(const int32_t* rowptr, const int32_t* col,
+                       const float* h, const float* s_src, const float* s_dst, const float* bias,
+                       float* out, float* m, float* l,
+                       int64_t B, int32_t N, int32_t H, int32_t C, int32_t relu, void* stream);
+
+/*
+ * Backward of gatres_gat_agg_fwd w.r.t. h, s (folded into dh), att_src, att_dst,
+ * bias — two gather passes, no atomics, softmax recomputed from (m,l)
+ * (SURVEY.md §A.4).  g = dL/d(out) AFTER any ReLU mask has been applied.
+ *   pass 1 (per target, in-edge CSR):  rec = {s_dst, m, 1/l, D}, ds_dst
+ *   pass 2 (per source, out-edge CSR): dh [M,H*C]
+ *   rec [M,H,4] and ds_dst [M,H] are caller-allocated scratch.
+ * Parameter-gradient partial sums go to `partial` rows [slots][P] (P = row
+ * stride in floats, a multiple of 4, >= the parameter count) at offsets
+ * off_att_src / off_att_dst / off_bias (floats, multiples of 4); every one of
+ * the `slots` CTAs writes its row, gatres_reduce_partials sums them.
+ */
+int gatres_gat_agg_bwd(const int32_t* rowptr, const int32_t* col,
+                       const int32_t* rowptr_t, const int32_t* col_t,
+                       const float* g, const float* h, const float* s_src, const float* s_dst,
+                       const float* m, const float* l, const float* att_src, const float* att_dst,
+                       float* rec, float* ds_dst, float* dh,
+                       float* partial, int64_t P, int32_t slots,
+                       int64_t off_att_src, int64_t off_att_dst, int64_t off_bias,
+                       int64_t B, int32_t N, int32_t H, int32_t C, void* stream);
+
+/*
+ * SimpleConv(aggr="mean")(z) + x0, ReLU  (GraphModels.py:466-467).  Uses the
+ * in-edge CSR minus each row's trailing self-loop; isolated nodes get 0 + x0.
+ */
+int gatres_mean_res_fwd(const int32_t* rowptr, const int32_t* col,
+                        const float* z, const float* x0, float* out,
+                        int64_t B, int32_t N, int32_t C, void* stream);
+
+/*
+ * Backward of gatres_mean_res_fwd: with gm = g_out * (out > 0),
+ *   dz[j] = sum_{i : j->i} gm[i] / max(indeg(i),1)   (out-edge CSR minus self-loop)
+ *   dres  = gm                                         (gradient of the +x0 branch)
+ * `out` may be NULL when the caller already applied the ReLU mask to g_out
+ * (then gm = g_out and dres is not written).
+ */
+int gatres_mean_res_bwd(const int32_t* rowptr, const int32_t* rowptr_t, const int32_t* col_t,
+                        const float* g_out, const float* out, float* dz, float* dres,
+                        int64_t B, int32_t N, int32_t C, void* stream);
+
+/*
+ * Backward of the projection: dx = dh W (+ add, if non-NULL) (* (relu_ref > 0), if non-NULL),
+ * and dW partial sums (dh^T x) into `partial` at off_W.
+ */
+int gatres_linear_bwd(const float* dh, const float* x, const float* W,
+                      const float* add, const float* relu_ref, float* dx,
+                      float* partial, int64_t P, int32_t slots, int64_t off_W,
+                      int64_t M, int32_t K, int32_t H, int32_t C, void* stream);
+
+/* lin0 = Linear(1,nc) (GraphModels.py:487): out[m,c] = x[m]*w[c] + b[c]. */
+int gatres_encoder_fwd(const float* x, const float* w, const float* b, float* out,
+                       int64_t M, int32_t nc, void* stream);
+int gatres_encoder_bwd(const float* g, const float* x, float* partial, int64_t P, int32_t slots,
+                       int64_t off_w, int64_t off_b, int64_t M, int32_t nc, void* stream);
+/* lin1 = Linear(nc,1) (GraphModels.py:492): out[m] = <x[m,:], w> + b. `poison`
+ * (device int32, may be NULL): if nonzero the output is NaN (a failed topology check). */
+int gatres_decoder_fwd(const float* x, const float* w, const float* b, float* out,
+                       const int32_t* poison, int64_t M, int32_t nc, void* stream);
+/* dx[m,c] = g_out[m] w[c], times (x[m,c] > 0) when mask_relu (x is a ReLU output). */
+int gatres_decoder_bwd(const float* g_out, const float* x, const float* w, float* dx,
+                       float* partial, int64_t P, int32_t slots, int64_t off_w, int64_t off_b,
+                       int64_t M, int32_t nc, int32_t mask_relu, void* stream);
+
+/* grads[p] = sum_s partial[s][p] for p in [p_begin, p_end). Deterministic. */
+int gatres_reduce_partials(const float* partial, int64_t P, int32_t slots,
+                           int64_t p_begin, int64_t p_end, float* grads, void* stream);
+
+/* ------------------------------------------------------------ whole model */
+
+typedef struct gatres_model_desc {
+  int32_t num_blocks;            /* GATResMeanConv(num_blocks, nc), GraphModels.py:472 */
+  int32_t nc;
+  int32_t N;                     /* template nodes */
+  int32_t slots;                 /* CTAs used by gradient-producing kernels (= rows of `partial`) */
+  int64_t B;                     /* snapshots in this batch */
+  const int32_t* rowptr;         /* in-edge CSR incl. self loops (gatres_csr_build) */
+  const int32_t* col;
+  const int32_t* rowptr_t;       /* out-edge CSR incl. self loops */
+  const int32_t* col_t;
+  const int32_t* poison;         /* optional device flag: nonzero -> NaN output */
+} gatres_model_desc;
+
+int64_t gatres_param_count(int32_t num_blocks, int32_t nc);
+/* floats of activation storage forward(training) hands to backward */
+int64_t gatres_saved_floats(const gatres_model_desc* d);
+/* floats of scratch for forward (training=0) or forward+backward (training=1) */
+int64_t gatres_scratch_floats(const gatres_model_desc* d, int32_t training);
+
+/* GATResMeanConv.forward (GraphModels.py:486-494). x [M] -> out [M]; saved may be NULL (inference). */
+int gatres_forward(const gatres_model_desc* d, const float* params, const float* x,
+                   float* out, float* saved, float* scratch, void* stream);
+/* Backward of gatres_forward for d_out [M]: grads [param_count] (overwritten, all params).
+ * partial: [slots][align4(param_count)] floats of scratch for the two-stage reductions. */
+int gatres_backward(const gatres_model_desc* d, const float* params, const float* x,
+                    const float* saved, const float* d_out, float* partial, float* grads,
+                    float* scratch, void* stream);
+
+/* ------------------------------------------------------- caller-side fusions */
+
+/*
+ * Masked-MSE (train.py:177-183): loss = mean_{mask}( (out-y)^2 ), d_out = 2 (out-y) mask / count.
+ * mask: uint8 [M]; count = number of masked nodes (host-known: B*int(N*rate)).
+ * loss_out: device float[1] (overwritten); partial_loss: device float[blocks_used] scratch (>= 1024 floats).
+ */
+int gatres_masked_mse(const float* out, const float* y, const uint8_t* mask, int64_t M, int64_t count,
+                      float* d_out, float* loss_out, float* partial_loss, void* stream);
+/* x_masked[m] = mask[m] ? 0 : x[m]  (train.py:174) */
+int gatres_apply_mask(const float* x, const uint8_t* mask, float* x_masked, int64_t M, void* stream);
+
+/*
+ * torch.optim.Adam step (train.py:348: lr 5e-4, weight_decay 6e-6 as L2 added to the
+ * gradient) on the flat buffers.  step_count: device int32[1], incremented on device
+ * so the call can be replayed from a CUDA graph.  grad_scale multiplies grads first
+ * (1/world_size after an all-reduce sum).
+ */
+int gatres_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                     int32_t* step_count, int64_t P, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GATRES_B200_H_ */

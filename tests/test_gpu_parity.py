@@ -1,0 +1,297 @@
+"""GPU parity tests: the CUDA path (through torch.ops.gatres -> C ABI) against the
+CPU oracle on identical inputs and weights, and against the committed goldens.
+
+Tolerances (BASELINE.json north_star): indexing/CSR bit-exact; forward <= 1e-4
+relative; gradients <= 1e-3 relative, fp32.  rel = max|a-b| / max|b| per tensor.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gnn_pressure_estimation_b200 import topology as T
+from helpers import assert_close, load_case, random_directed_graph, rel_err
+from oracle import gatres_oracle as O
+from oracle import topology_oracle as TO
+
+pytestmark = pytest.mark.gpu
+FWD_TOL, GRAD_TOL = 1e-4, 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gnn_pressure_estimation_b200.GraphModels as G_
+    return G_
+
+
+def _topology(ei_cpu, n, dev):
+    from gnn_pressure_estimation_b200.graph import Topology
+    return Topology.build(ei_cpu.to(dev), n)
+
+
+# ------------------------------------------------------------------ indexing
+@pytest.mark.parametrize("case", ["tiny", "ctown", "scaled", "directed"])
+def test_csr_bit_exact(case, dev):
+    if case == "tiny":
+        ei, names = T.reference_edge_index(T.tiny_network()); n = len(names)
+    elif case == "ctown":
+        ei, names = T.reference_edge_index(T.ctown_shaped()); n = len(names)
+    elif case == "scaled":
+        ei, names = T.reference_edge_index(T.scaled_wdn(20_000, 23_000, seed=1)); n = len(names)
+    else:
+        n = 301
+        ei = random_directed_graph(n, 2000, seed=11).numpy()
+    topo = _topology(torch.from_numpy(ei), n, dev)
+    rp, col = TO.csr_by_target(ei, n)
+    rpt, colt = TO.csr_by_source(ei, n)
+    assert topo.E1 == ei.shape[1] + n
+    assert np.array_equal(topo.rowptr.cpu().numpy(), rp) and np.array_equal(topo.col.cpu().numpy(), col)
+    assert np.array_equal(topo.rowptr_t.cpu().numpy(), rpt) and np.array_equal(topo.col_t.cpu().numpy(), colt)
+
+
+def test_csr_matches_golden_fixture(dev, golden_dir):
+    g = np.load(f"{golden_dir}/topo_ctown_shaped.npz")
+    topo = _topology(torch.from_numpy(g["edge_index"]), int(g["n"]), dev)
+    for got, key in ((topo.rowptr, "rowptr"), (topo.col, "col"), (topo.rowptr_t, "rowptr_t"), (topo.col_t, "col_t")):
+        assert np.array_equal(got.cpu().numpy(), g[key]), key
+
+
+def test_csr_rejects_bad_ids_and_self_loops(dev):
+    from gnn_pressure_estimation_b200._lib import GatresError
+    with pytest.raises(GatresError):
+        _topology(torch.tensor([[0, 5], [1, 0]]), 3, dev)
+    with pytest.raises(NotImplementedError):
+        _topology(torch.tensor([[0, 1, 1], [1, 0, 1]]), 3, dev)
+
+
+def test_replication_check_and_poison(dev, G):
+    ei, names = T.reference_edge_index(T.ctown_shaped()); n = len(names)
+    ei = torch.from_numpy(ei)
+    model = G.GATResMeanConv(num_blocks=1, nc=32).to(dev)
+    x = torch.randn(4 * n, 1, device=dev)
+    good = O.collate_edge_index(ei, n, 4).to(dev)
+    with torch.no_grad():
+        assert torch.isfinite(model(x, good)).all()
+        bad = good.clone()
+        bad[0, 2000] = (bad[0, 2000] + 1) % n + 2 * n          # same shape, different wiring
+        assert torch.isnan(model(x, bad)).all()                # loud, without a per-step sync
+
+
+# ----------------------------------------------------------------- operators
+def _layer_inputs(M, fin, H, C, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(M, fin, generator=g)
+    W = torch.randn(H * C, fin, generator=g) * (1.0 / fin ** 0.5)
+    a_s = torch.randn(1, H, C, generator=g) * 0.3
+    a_d = torch.randn(1, H, C, generator=g) * 0.3
+    return x, W, a_s, a_d
+
+
+GRAPHS = {
+    "tiny": lambda: T.reference_edge_index(T.tiny_network()),
+    "ctown": lambda: T.reference_edge_index(T.ctown_shaped()),
+}
+
+
+@pytest.mark.parametrize("graph,B", [("tiny", 1), ("tiny", 5), ("ctown", 3), ("directed", 2)])
+@pytest.mark.parametrize("H,C,fin,concat,relu", [(2, 32, 32, True, True), (1, 32, 64, False, False),
+                                                 (2, 64, 64, True, True), (1, 64, 128, False, False),
+                                                 (2, 128, 128, True, False), (1, 128, 256, False, True)])
+def test_gat_conv_forward_backward(graph, B, H, C, fin, concat, relu, dev):
+    from gnn_pressure_estimation_b200 import ops as gops
+    if graph == "directed":
+        n = 97
+        ei = random_directed_graph(n, 400, seed=5)
+    else:
+        ei_np, names = GRAPHS[graph](); n = len(names); ei = torch.from_numpy(ei_np)
+    M = B * n
+    x, W, a_s, a_d = _layer_inputs(M, fin, H, C, seed=H * 1000 + C + B)
+    bias = torch.randn(H * C if concat else C, generator=torch.Generator().manual_seed(3)) * 0.1
+    eib = O.collate_edge_index(ei, n, B)
+    leaves = [t.clone().requires_grad_() for t in (x, W, a_s, a_d, bias)]
+    ref = O.gat_conv(leaves[0], eib, leaves[1], leaves[2], leaves[3], leaves[4], H, concat)
+    if relu:
+        ref = ref.relu()
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(9))
+    ref.backward(go)
+
+    topo = _topology(ei, n, dev)
+    cl = [t.detach().clone().to(dev).requires_grad_() for t in (x, W, a_s, a_d, bias)]
+    out = gops.gat_conv(cl[0], cl[1], cl[2], cl[3], cl[4], topo, B, H, concat, relu=relu)
+    out.backward(go.to(dev))
+    assert_close(out, ref, FWD_TOL, "gat_conv forward")
+    for name, a, b in zip(("dx", "dW", "datt_src", "datt_dst", "dbias"), cl, leaves):
+        assert_close(a.grad, b.grad, GRAD_TOL, name)
+
+
+@pytest.mark.parametrize("graph,B", [("tiny", 4), ("ctown", 2), ("directed", 3)])
+@pytest.mark.parametrize("C", [32, 64, 128])
+def test_mean_res_forward_backward(graph, B, C, dev):
+    from gnn_pressure_estimation_b200 import ops as gops
+    if graph == "directed":
+        n = 97
+        ei = random_directed_graph(n, 400, seed=6)
+    else:
+        ei_np, names = GRAPHS[graph](); n = len(names); ei = torch.from_numpy(ei_np)
+    g = torch.Generator().manual_seed(C + B)
+    z = torch.randn(B * n, C, generator=g)
+    x0 = torch.randn(B * n, C, generator=g)
+    eib = O.collate_edge_index(ei, n, B)
+    zr, xr = z.clone().requires_grad_(), x0.clone().requires_grad_()
+    ref = (O.simple_conv_mean(zr, eib) + xr).relu()
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+    topo = _topology(ei, n, dev)
+    zc, xc = z.to(dev).requires_grad_(), x0.to(dev).requires_grad_()
+    out = gops.mean_res(zc, xc, topo, B)
+    out.backward(go.to(dev))
+    assert_close(out, ref, 1e-6, "mean_res forward")
+    assert_close(zc.grad, zr.grad, 1e-6, "dz")
+    assert_close(xc.grad, xr.grad, 1e-6, "dres")
+    if graph == "tiny":                                   # isolated node J7: mean part is 0
+        assert torch.equal(out.view(B, n, C)[:, 6].cpu(), x0.view(B, n, C)[:, 6].relu())
+
+
+def test_block_module_matches_oracle(dev, G):
+    ei_np, names = T.reference_edge_index(T.ctown_shaped()); n = len(names); ei = torch.from_numpy(ei_np)
+    B = 2
+    ref = O.make_oracle(1, 32, seed=4).blocks[0]
+    blk = G.GResBlockMeanConv(32, 32, 32)
+    blk.load_state_dict(ref.state_dict())
+    blk = blk.to(dev)
+    x = torch.randn(B * n, 32, generator=torch.Generator().manual_seed(1))
+    eib = O.collate_edge_index(ei, n, B)
+    xr = x.clone().requires_grad_()
+    o_ref = ref(xr, eib)
+    o_ref.square().sum().backward()
+    xc = x.to(dev).requires_grad_()
+    o = blk(xc, eib.to(dev))
+    o.square().sum().backward()
+    assert_close(o, o_ref, FWD_TOL, "block forward")
+    assert_close(xc.grad, xr.grad, GRAD_TOL, "block dx")
+    for (k, p), q in zip(blk.named_parameters(), ref.parameters()):
+        assert_close(p.grad, q.grad, GRAD_TOL, k)
+
+
+# --------------------------------------------------------------- whole model
+def _cuda_model_from_case(c, G, dev):
+    ref = O.make_oracle(c["num_blocks"], c["nc"], seed=c["seed"])
+    m = G.GATResMeanConv(num_blocks=c["num_blocks"], nc=c["nc"])
+    m.load_state_dict(ref.state_dict())
+    return m.to(dev), ref
+
+
+@pytest.mark.parametrize("name", ["tiny_2b_32c_B3", "ctown_small_15b_32c_B8", "ctown_mid_3b_64c_B2",
+                                  "ctown_large_25b_128c_B2"])
+def test_model_matches_golden(name, dev, G):
+    """reference caller semantics (train.py:174-185): mask applied by the caller, MSE on masked nodes."""
+    c = load_case(name)
+    model, _ = _cuda_model_from_case(c, G, dev)
+    eib = O.collate_edge_index(c["edge_index"], c["N"], c["B"]).to(dev)
+    mask = c["mask"].to(dev)
+    out = model(c["x"].to(dev), eib, None, None)
+    loss = torch.nn.functional.mse_loss(out[mask], c["y"].to(dev)[mask])
+    loss.backward()
+    assert out.shape == c["out"].shape
+    assert_close(out, c["out"], FWD_TOL, "forward")
+    assert abs(float(loss) - float(c["loss"])) <= FWD_TOL * abs(float(c["loss"]))
+    for k, p in model.named_parameters():
+        gn = c["grad_norms"][k]
+        assert abs(float(p.grad.norm()) - gn) <= GRAD_TOL * gn + 1e-12, f"{k}: |grad| {float(p.grad.norm())} vs {gn}"
+        head = p.grad.reshape(-1)[:8].cpu()
+        assert float((head - c["grad_heads"][k]).abs().max()) <= GRAD_TOL * max(float(c["grad_heads"][k].abs().max()), gn / p.numel() ** 0.5), k
+        if "grads" in c:
+            assert_close(p.grad, c["grads"][k], GRAD_TOL, k)
+
+
+def test_model_inference_equals_training_forward_and_batch_hint(dev, G):
+    c = load_case("ctown_small_15b_32c_B8")
+    model, _ = _cuda_model_from_case(c, G, dev)
+    eib = O.collate_edge_index(c["edge_index"], c["N"], c["B"]).to(dev)
+    x = c["x"].to(dev)
+    out_train = model(x, eib)
+    batch = torch.arange(c["B"], device=dev).repeat_interleave(c["N"])
+    with torch.no_grad():
+        out_inf = model(x, eib, batch, None)
+    assert torch.equal(out_train.detach(), out_inf)        # same kernels, rolling buffers instead of saved ones
+    assert_close(out_inf, c["out"], FWD_TOL, "inference forward")
+
+
+def test_large_batch_properties(dev, G):
+    """BASELINE size (B=1024 snapshots): size-independent properties instead of the oracle."""
+    c = load_case("ctown_small_15b_32c_B8")
+    model, _ = _cuda_model_from_case(c, G, dev)
+    N, B = c["N"], 1024
+    ei = c["edge_index"]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B * N, 1, generator=g).to(dev)
+    with torch.no_grad():
+        full = model(x, O.collate_edge_index(ei, N, B).to(dev))
+        half = O.collate_edge_index(ei, N, B // 2).to(dev)
+        lo, hi = model(x[: B // 2 * N], half), model(x[B // 2 * N:], half)
+        assert torch.equal(full, torch.cat([lo, hi]))      # snapshots are independent, kernels deterministic
+        perm = torch.randperm(B, generator=g).to(dev)
+        xp = x.view(B, N)[perm].reshape(-1, 1)
+        assert torch.equal(model(xp, O.collate_edge_index(ei, N, B).to(dev)).view(B, N), full.view(B, N)[perm])
+        # the first 8 snapshots against the oracle-pinned golden inputs
+        x8 = c["x"].to(dev)
+        assert_close(model(torch.cat([x8, x[8 * N:]]), O.collate_edge_index(ei, N, B).to(dev))[: 8 * N], c["out"],
+                     FWD_TOL, "B=1024 prefix")
+
+
+def test_gradient_is_mean_over_shards(dev, G):
+    """DP contract: grads of the full batch == average of the shard grads."""
+    c = load_case("ctown_small_15b_32c_B8")
+    N = c["N"]
+    grads = []
+    for lo, hi in ((0, 8), (0, 4), (4, 8)):
+        model, _ = _cuda_model_from_case(c, G, dev)
+        sl = slice(lo * N, hi * N)
+        eib = O.collate_edge_index(c["edge_index"], N, hi - lo).to(dev)
+        mask = c["mask"][sl].to(dev)
+        out = model(c["x"][sl].to(dev), eib)
+        torch.nn.functional.mse_loss(out[mask], c["y"][sl].to(dev)[mask]).backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for p in model.ordered_parameters()]))
+    assert_close(0.5 * (grads[1] + grads[2]), grads[0], 1e-4, "shard-mean gradient")
+
+
+# --------------------------------------------------------------- train step
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_matches_oracle_adam(use_graph, dev, G):
+    from gnn_pressure_estimation_b200.train_step import TrainStep
+    c = load_case("ctown_small_15b_32c_B8")
+    model, ref = _cuda_model_from_case(c, G, dev)
+    N, B = c["N"], c["B"]
+    topo = model.set_topology(c["edge_index"].to(dev), N)
+    ts = TrainStep(model, topo, B, mask_count_per_snapshot=int(N * 0.95), use_graph=use_graph)
+    opt = torch.optim.Adam(ref.parameters(), lr=5e-4, weight_decay=6e-6)
+    eib = O.collate_edge_index(c["edge_index"], N, B)
+    steps = 3
+    if use_graph:
+        ts.capture(warmup=0)
+    for s in range(steps):
+        x, y, mask = O.synthetic_snapshots(N, B, seed=100 + s)
+        opt.zero_grad()
+        out = ref(x, eib)                         # oracle: x already has masked nodes zeroed
+        loss_ref = torch.nn.functional.mse_loss(out[mask], y[mask])
+        loss_ref.backward()
+        opt.step()
+        loss = ts.step(y.to(dev), y.to(dev), mask.to(dev))      # product masks on device (x = y unmasked)
+        assert abs(float(loss) - float(loss_ref)) <= 2e-4 * abs(float(loss_ref)), f"step {s}"
+    flat_ref = torch.cat([p.detach().reshape(-1) for p in
+                          [ref.lin0.weight, ref.lin0.bias] +
+                          [t for b in ref.blocks for t in (b.conv1.lin_src.weight, b.conv1.att_src, b.conv1.att_dst,
+                                                           b.conv1.bias, b.conv2.lin_src.weight, b.conv2.att_src,
+                                                           b.conv2.att_dst, b.conv2.bias)] +
+                          [ref.lin1.weight, ref.lin1.bias]])
+    # Adam's first steps move every weight by ~lr * sign(g): a gradient entry at rounding-noise level may
+    # flip sign between two fp32 implementations, so bound the bulk tightly and the worst case by 2*lr*steps.
+    diff = (ts.flat.cpu() - flat_ref).abs()
+    lr = 5e-4
+    assert float(diff.max()) <= 2.0 * lr * steps + 1e-7
+    assert float((diff > 0.05 * lr * steps).float().mean()) < 2e-3, "parameters after Adam steps"
+    assert int(ts.step_count.item()) == steps

@@ -1,0 +1,77 @@
+"""CPU checks of the host-side mirror of the reference interface."""
+import argparse
+
+import pytest
+import torch
+
+import gnn_pressure_estimation_b200.GraphModels as G
+from gnn_pressure_estimation_b200 import ConfigModels as CM
+from gnn_pressure_estimation_b200 import ops as gops
+from oracle import gatres_oracle as O
+
+
+def test_select_model_contract():
+    args = argparse.Namespace(model="gatres_small", model_path="keep/me.pth")
+    args, model = CM.select_model(args, None, reset_model_path=True)
+    assert isinstance(model, G.GATResMeanConv) and model.num_blocks == 15 and model.nc == 32
+    assert (args.criterion, args.norm_type, args.use_data_edge_attrs, args.model_path) == ("mse", "znorm", None, "keep/me.pth")
+    assert model.name == "GATResMeanConv_small_znorm_15b_32c"
+    args, large = CM.select_model(argparse.Namespace(model="gatres_large"), "variant")
+    assert large.num_blocks == 25 and large.nc == 128 and large.name == "variant"
+    assert args.model_path.endswith("20235401.pth")
+    with pytest.raises(NotImplementedError):
+        CM.select_model(argparse.Namespace(model="gin"))
+
+
+def test_reference_import_paths():
+    from gnn_pressure_estimation.GraphModels import GATResMeanConv, GResBlockMeanConv  # noqa: F401
+    from gnn_pressure_estimation.ConfigModels import select_model  # noqa: F401
+    assert GATResMeanConv is G.GATResMeanConv
+
+
+def test_state_dict_is_pyg_compatible_both_schemes():
+    ref = O.make_oracle(2, 32)
+    m = G.GATResMeanConv(num_blocks=2, nc=32)
+    assert list(m.state_dict()) == list(ref.state_dict())
+    assert [tuple(v.shape) for v in m.state_dict().values()] == [tuple(v.shape) for v in ref.state_dict().values()]
+    m.load_state_dict(ref.state_dict())
+    new_scheme = {k.replace("lin_src.weight", "lin.weight"): v for k, v in ref.state_dict().items() if "lin_dst" not in k}
+    m2 = G.GATResMeanConv(num_blocks=2, nc=32)
+    m2.load_state_dict(new_scheme)
+    for (k, a), b in zip(m.state_dict().items(), m2.state_dict().values()):
+        assert torch.equal(a, b), k
+    names = [n for n, _ in m.named_parameters()]
+    assert len(names) == 2 + 2 * 8 + 2 and all(("block" in n) == n.startswith("blocks.") for n in names)
+
+
+def test_flat_parameter_layout_matches_c_abi():
+    m = G.GATResMeanConv(num_blocks=3, nc=32)
+    flat = m.flat_parameters()
+    assert flat.numel() == gops.param_count(3, 32) == sum(p.numel() for p in m.parameters())
+    off = 0
+    for p in m.ordered_parameters():
+        assert p.data_ptr() == flat.data_ptr() + 4 * off        # parameters alias the flat buffer
+        assert torch.equal(p.detach().reshape(-1), flat[off:off + p.numel()])
+        off += p.numel()
+    # in-place updates (optimizers, load_state_dict) keep the aliasing; re-packing is idempotent
+    ref = O.make_oracle(3, 32)
+    m.load_state_dict(ref.state_dict())
+    assert m.flat_parameters().data_ptr() == flat.data_ptr()
+    assert torch.equal(flat[:32], ref.lin0.weight.detach().reshape(-1))
+    # a dtype/device move breaks aliasing and is repaired on the next call
+    m.double()
+    with pytest.raises(RuntimeError, match="fp32"):
+        m.flat_parameters()
+    m.float()
+    f2 = m.flat_parameters()
+    assert f2.data_ptr() != flat.data_ptr() and torch.equal(f2, flat)
+
+
+def test_default_init_statistics():
+    torch.manual_seed(0)
+    m = G.GATResMeanConv(num_blocks=1, nc=32)
+    b = m.blocks[0]
+    assert float(b.conv1.bias.abs().max()) == 0 and float(b.conv2.bias.abs().max()) == 0
+    assert float(b.conv1.lin_src.weight.abs().max()) <= (6 / (64 + 32)) ** 0.5
+    assert float(b.conv1.att_src.abs().max()) <= (6 / (2 + 32)) ** 0.5
+    assert float(m.lin0.weight.abs().max()) <= 1.0 and float(m.lin1.weight.abs().max()) <= 32 ** -0.5

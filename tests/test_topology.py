@@ -1,0 +1,90 @@
+"""Edge-ordering contract: product ingestion vs the real networkx pipeline (oracle)."""
+import random
+
+import numpy as np
+import pytest
+
+from gnn_pressure_estimation_b200 import topology as T
+from oracle import topology_oracle as TO
+
+
+def test_random_multigraphs_match_networkx_pipeline():
+    rnd = random.Random(7)
+    for _ in range(200):
+        nj, nt = rnd.randint(2, 12), rnd.randint(0, 3)
+        j = [f"J{k}" for k in range(nj)]
+        tk = [f"T{k}" for k in range(nt)]
+        pool = j + tk
+        links = [(f"L{k}", rnd.choice(pool), rnd.choice(pool)) for k in range(rnd.randint(1, 30))]
+        links = [l for l in links if l[1] != l[2]]
+        wn = T.WaterNetwork(j, [], tk, links)
+        for removal in ("keep_junction", "keep_all"):
+            a, na = T.reference_edge_index(wn, removal)
+            b, nb = TO.reference_pipeline_edge_index(wn.node_names, j, links, removal)
+            assert na == nb and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,maker", [("topo_tiny", T.tiny_network), ("topo_ctown_shaped", T.ctown_shaped)])
+def test_golden_edge_order_and_csr(golden_dir, name, maker):
+    g = np.load(f"{golden_dir}/{name}.npz")
+    ei, names = T.reference_edge_index(maker())
+    assert len(names) == int(g["n"]) and np.array_equal(ei, g["edge_index"])
+    rp, col = TO.csr_by_target(ei, len(names))
+    rpt, colt = TO.csr_by_source(ei, len(names))
+    for got, key in ((rp, "rowptr"), (col, "col"), (rpt, "rowptr_t"), (colt, "col_t")):
+        assert np.array_equal(got, g[key]), key
+
+
+def test_ctown_shape_and_parser_roundtrip():
+    wn = T.ctown_shaped()
+    ei, names = T.reference_edge_index(wn)
+    assert len(names) == 388 and ei.shape == (2, 858)
+    assert names == wn.junctions                       # tanks / reservoir dropped by keep_junction
+    assert set(map(tuple, ei.T)) == {(b, a) for a, b in ei.T}   # symmetric
+    wn2 = T.parse_inp_text(T.write_inp(wn))
+    assert (wn2.junctions, wn2.reservoirs, wn2.tanks, wn2.links) == (wn.junctions, wn.reservoirs, wn.tanks, wn.links)
+    ei2, _ = T.reference_edge_index(wn2)
+    assert np.array_equal(ei, ei2)
+    ei_all, names_all = T.reference_edge_index(wn, "keep_all")
+    assert len(names_all) == 388 + 8 and ei_all.shape[1] == 858 + 16
+
+
+def test_parser_details():
+    text = """[TITLE]
+ x ; comment
+[junctions]
+ A 1 2 ;c
+ B 1
+;whole-line comment
+[PUMPS]
+ PU1 B A HEAD 1
+[PIPES]
+ P1 A B 10 ; trailing
+[TANKS]
+ T 0
+[valves]
+ V1 T A 12 PRV
+[END]"""
+    wn = T.parse_inp_text(text)
+    assert wn.junctions == ["A", "B"] and wn.tanks == ["T"]
+    assert [l[0] for l in wn.links] == ["P1", "PU1", "V1"]      # registry order: pipes, pumps, valves
+    with pytest.raises(ValueError):
+        T.parse_inp_text("version https://git-lfs.github.com/spec/v1\noid sha256:00\nsize 1\n")
+
+
+def test_csr_rows_are_edge_order_with_self_loop_last():
+    ei, names = T.reference_edge_index(T.ctown_shaped())
+    n = len(names)
+    rp, col = TO.csr_by_target(ei, n)
+    for i in range(n):
+        row = col[rp[i]:rp[i + 1]]
+        assert row[-1] == i and list(row[:-1]) == sorted(row[:-1])     # ascending sources (source-sorted list)
+        assert list(row[:-1]) == [int(s) for s, d in ei.T if d == i]
+
+
+def test_scaled_wdn_shape():
+    wn = T.scaled_wdn(n_nodes=10_000, n_edges=11_500, seed=0)
+    ei, names = T.reference_edge_index(wn)
+    assert len(names) == 10_000 and ei.shape == (2, 23_000)
+    deg = np.bincount(ei[1], minlength=10_000)
+    assert deg.min() >= 1 and deg.max() <= 4
