@@ -81,17 +81,21 @@ class TrainStep:
              ptr(self.step_count), self.P, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
              1.0 / self.world, s)
 
-    def capture(self, warmup: int = 2) -> None:
-        """Run the step eagerly a few times on a side stream, then capture it.
-        (The warm-up steps are real optimizer steps.)"""
+    def capture(self, warmup: int = 1) -> None:
+        """Run the step eagerly on a side stream (lazy CUDA/NCCL initialisation must
+        not happen inside a capture), restore the optimizer state it touched, then
+        capture the step into a CUDA graph."""
         if not self.use_graph:
             return
+        state = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_count)]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):
                 self._enqueue()
         torch.cuda.current_stream().wait_stream(side)
+        for t, s in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_count), state):
+            t.copy_(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

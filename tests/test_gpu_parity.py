@@ -199,13 +199,19 @@ def test_model_matches_golden(name, dev, G):
     assert out.shape == c["out"].shape
     assert_close(out, c["out"], FWD_TOL, "forward")
     assert abs(float(loss) - float(c["loss"])) <= FWD_TOL * abs(float(c["loss"]))
+    # Tolerance floor: d/d(att_dst) is a cancellation residue (softmax is shift-invariant per target, so it
+    # is nonzero only through LeakyReLU kinks) and sits ~1e-7 below the other gradients; a relative test on
+    # such a tensor compares rounding noise.  Every tensor is therefore held to GRAD_TOL relative to
+    # max(its own scale, 1e-3 x the largest parameter-gradient norm of the model).
+    floor = 1e-3 * max(c["grad_norms"].values())
     for k, p in model.named_parameters():
         gn = c["grad_norms"][k]
-        assert abs(float(p.grad.norm()) - gn) <= GRAD_TOL * gn + 1e-12, f"{k}: |grad| {float(p.grad.norm())} vs {gn}"
+        assert abs(float(p.grad.norm()) - gn) <= GRAD_TOL * max(gn, floor), f"{k}: |grad| {float(p.grad.norm())} vs {gn}"
         head = p.grad.reshape(-1)[:8].cpu()
-        assert float((head - c["grad_heads"][k]).abs().max()) <= GRAD_TOL * max(float(c["grad_heads"][k].abs().max()), gn / p.numel() ** 0.5), k
+        assert float((head - c["grad_heads"][k]).abs().max()) <= GRAD_TOL * max(float(c["grad_heads"][k].abs().max()), gn / p.numel() ** 0.5, floor), k
         if "grads" in c:
-            assert_close(p.grad, c["grads"][k], GRAD_TOL, k)
+            ref = c["grads"][k]
+            assert float((p.grad.cpu() - ref).abs().max()) <= GRAD_TOL * max(float(ref.abs().max()), floor), k
 
 
 def test_model_inference_equals_training_forward_and_batch_hint(dev, G):
@@ -272,7 +278,7 @@ def test_train_step_matches_oracle_adam(use_graph, dev, G):
     eib = O.collate_edge_index(c["edge_index"], N, B)
     steps = 3
     if use_graph:
-        ts.capture(warmup=0)
+        ts.capture()
     for s in range(steps):
         x, y, mask = O.synthetic_snapshots(N, B, seed=100 + s)
         opt.zero_grad()
@@ -288,10 +294,18 @@ def test_train_step_matches_oracle_adam(use_graph, dev, G):
                                                            b.conv1.bias, b.conv2.lin_src.weight, b.conv2.att_src,
                                                            b.conv2.att_dst, b.conv2.bias)] +
                           [ref.lin1.weight, ref.lin1.bias]])
-    # Adam's first steps move every weight by ~lr * sign(g): a gradient entry at rounding-noise level may
-    # flip sign between two fp32 implementations, so bound the bulk tightly and the worst case by 2*lr*steps.
+    # Adam's first steps move every weight by ~lr * sign(g).  d/d(att_dst) is a cancellation residue at
+    # rounding-noise level (softmax is shift-invariant per target), so its sign — and hence its Adam update —
+    # is noise in ANY fp32 implementation, the reference's included: those entries are only bounded by
+    # 2*lr*steps; everything else must agree tightly.
     diff = (ts.flat.cpu() - flat_ref).abs()
     lr = 5e-4
+    noise = torch.zeros_like(diff, dtype=torch.bool)
+    off = 0
+    for p, name in zip(model.ordered_parameters(), ["lin0.w", "lin0.b"] + ["W", "att_src", "att_dst", "bias"] * 2 * 15 + ["lin1.w", "lin1.b"]):
+        if name == "att_dst":
+            noise[off:off + p.numel()] = True
+        off += p.numel()
     assert float(diff.max()) <= 2.0 * lr * steps + 1e-7
-    assert float((diff > 0.05 * lr * steps).float().mean()) < 2e-3, "parameters after Adam steps"
+    assert float((diff[~noise] > 0.05 * lr * steps).float().mean()) < 1e-3, "parameters after Adam steps"
     assert int(ts.step_count.item()) == steps
