@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-kernel-leg", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true",
+                    help="only launch each hot kernel at the HBM-regime batch (for ncu); prints nothing")
     ap.add_argument("--hbm-batch", type=int, default=2048, help="batch of the HBM-regime kernel measurement")
     ap.add_argument("--kernels-json", default=None, help="write the per-kernel table here")
     return ap.parse_args()
@@ -186,6 +188,8 @@ def time_launches(fn, reps, n_sets):
     for k in range(n_sets):
         fn(k)
     torch.cuda.synchronize()
+    if os.environ.get("GATRES_PROFILE_EAGER"):        # under ncu: plain launches, nothing to time
+        return 1.0
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for r in range(reps):
@@ -225,9 +229,9 @@ def kernel_table(B, N, topo, nc, hbm_regime, dev):
         rec, dsd = torch.empty(M, H, 4, **f), torch.empty(M, H, **f)
         dh = torch.empty(M, F, **f)
         dx = torch.empty(M, K, **f)
-        S = gops.grad_slots(M)
+        S = 0                                   # atomic gradient accumulation, as in the training step
         P = gops.a4(F * K + 3 * F)
-        partial = torch.empty(S, P, **f)
+        partial = torch.zeros(P, **f)
 
         def proj(k):
             call("gatres_linear_att_fwd", ptr(x[k]), ptr(W), ptr(a_s), ptr(a_d), ptr(h[k]), ptr(ss[k]), ptr(sd[k]), M, K,
@@ -380,6 +384,12 @@ def main():
             ms = float(t.item())
         return ms, cs.summary()
 
+    if args.profile_kernels:
+        os.environ["GATRES_PROFILE_EAGER"] = "1"
+        kernel_table(args.hbm_batch if nc == 32 else max(64, args.hbm_batch // 8), N, topo, nc, True, dev)
+        torch.cuda.synchronize()
+        return
+
     ms_res, clocks = timed(step_resident, False)
     ms_e2e, clocks_e2e = timed(step_e2e, True)
     value = world * B * K / (ms_res * 1e-3)
@@ -391,8 +401,8 @@ def main():
             "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"dp{world}",
                        "cuda_graph": not args.no_graph,
                        "l2": f"no flush: inputs rotate over {pool} resident batches and one step streams "
-                             f"~{(ts.saved.numel() + ts.scratch.numel() + ts.partial.numel()) * 4 / 1e6:.0f} MB of "
-                             "activations/partials (L2 is 126 MB)" if args.mode == "train" else
+                             f"~{(ts.saved.numel() + ts.scratch.numel()) * 4 / 1e6:.0f} MB of "
+                             "saved activations + scratch (L2 is 126 MB)" if args.mode == "train" else
                              f"no flush: inputs rotate over {pool} resident batches"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -160,6 +160,9 @@ class GATResMeanConv(nn.Module):
         self.lin1 = Linear(nc, 1)
         self._flat: Optional[Tensor] = None
         self._topologies = TopologyCache()
+        # True: parameter gradients are reduced in a fixed order (bitwise reproducible, slower backward);
+        # False: atomic accumulation, like the reference's scatter-add backward on GPU.
+        self.deterministic = False
 
     # -- flat parameter storage (layout documented in include/gatres_b200.h) ------------
     def ordered_parameters(self) -> List[nn.Parameter]:
@@ -208,5 +211,5 @@ class GATResMeanConv(nn.Module):
         topo, B = self._topologies.resolve(x.size(0), edge_index, batch)
         flat = self.flat_parameters()
         out = _gops.gatres_model(x.reshape(-1), flat, self.ordered_parameters(), topo, B, self.num_blocks, self.nc,
-                                 poison=self._topologies.mismatch)
+                                 poison=self._topologies.mismatch, deterministic=self.deterministic)
         return out.view(-1, 1)

@@ -92,8 +92,21 @@ struct RowMap {
 // Sum per-lane float4 accumulators over all lanes of a CTA that hold the same
 // chunk (same lane-in-row, any row slot, any warp) and write them to
 // dst[4*chunk ..].  red: shared scratch of kWarps*32*4 floats.  All threads call.
+// Parameter-gradient emission: either a plain store into this CTA's row of the
+// `partial` buffer (deterministic two-stage reduction) or an atomic add into the
+// final gradient buffer (any grid size; summation order not fixed).
+__device__ __forceinline__ void emit4(float* dst, float4 v, bool atomic) {
+  if (atomic) atomicAdd(reinterpret_cast<float4*>(dst), v);      // sm_90+: 128-bit red.global.add
+  else st4(dst, v);
+}
+__device__ __forceinline__ void emit1(float* dst, float v, bool atomic) {
+  if (atomic) atomicAdd(dst, v);
+  else *dst = v;
+}
+
 template <int LPR>
-__device__ __forceinline__ void cta_chunk_sum_store(float4 acc, float* red, float* dst, int chunk_of_lig0_stride_v) {
+__device__ __forceinline__ void cta_chunk_sum_store(float4 acc, float* red, float* dst, int chunk_of_lig0_stride_v,
+                                                    bool atomic) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
   st4(red + (warp * 32 + lane) * 4, acc);
@@ -103,8 +116,15 @@ __device__ __forceinline__ void cta_chunk_sum_store(float4 acc, float* red, floa
     for (int w = 0; w < kWarps; ++w)
 #pragma unroll
       for (int sub = 0; sub < 32 / LPR; ++sub) add4(s, *reinterpret_cast<float4*>(red + (w * 32 + sub * LPR + threadIdx.x) * 4));
-    st4(dst + 4 * (threadIdx.x + chunk_of_lig0_stride_v), s);
+    emit4(dst + 4 * (threadIdx.x + chunk_of_lig0_stride_v), s, atomic);
   }
+}
+
+// grid of a row-parallel kernel: enough CTAs to cover the rows, capped at a few waves
+static inline unsigned row_kernel_grid(unsigned M, unsigned rows_per_cta, unsigned ctas_per_sm) {
+  unsigned grid = (M + rows_per_cta - 1) / rows_per_cta;
+  const unsigned cap = (unsigned)sm_count() * ctas_per_sm;
+  return grid > cap ? cap : (grid < 1 ? 1 : grid);
 }
 
 }  // namespace gatres

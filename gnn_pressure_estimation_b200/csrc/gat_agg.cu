@@ -97,7 +97,7 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
                       const float* __restrict__ m, const float* __restrict__ l,
                       float* __restrict__ rec, float* __restrict__ ds_dst,
                       float* __restrict__ partial, long long P, long long off_bias,
-                      unsigned M, unsigned N) {
+                      unsigned M, unsigned N, int atomic) {
   using RM = RowMap<H, C>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
   __shared__ float red[kWarps * 32 * 4];
@@ -153,9 +153,9 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
       }
     }
   }
-  float* dst = partial + (size_t)blockIdx.x * P + off_bias;
+  float* dst = partial + (atomic ? 0 : (size_t)blockIdx.x * P) + off_bias;
 #pragma unroll
-  for (int v = 0; v < V; ++v) cta_chunk_sum_store<LPR>(bacc[v], red, dst, v * LPR);
+  for (int v = 0; v < V; ++v) cta_chunk_sum_store<LPR>(bacc[v], red, dst, v * LPR, atomic);
 }
 
 // --------------------------------------------------------- backward, pass 2
@@ -171,7 +171,7 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
                       const float* __restrict__ att_src, const float* __restrict__ att_dst,
                       float* __restrict__ dh,
                       float* __restrict__ partial, long long P, long long off_att_src, long long off_att_dst,
-                      unsigned M, unsigned N) {
+                      unsigned M, unsigned N, int atomic) {
   using RM = RowMap<H, C>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
   __shared__ float red[kWarps * 32 * 4];
@@ -230,11 +230,11 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
       }
     }
   }
-  float* row = partial + (size_t)blockIdx.x * P;
+  float* row = partial + (atomic ? 0 : (size_t)blockIdx.x * P);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    cta_chunk_sum_store<LPR>(accs[v], red, row + off_att_src, v * LPR);
-    cta_chunk_sum_store<LPR>(accd[v], red, row + off_att_dst, v * LPR);
+    cta_chunk_sum_store<LPR>(accs[v], red, row + off_att_src, v * LPR, atomic);
+    cta_chunk_sum_store<LPR>(accd[v], red, row + off_att_dst, v * LPR, atomic);
   }
 }
 
@@ -257,12 +257,14 @@ static int launch_bwd(const int* rowptr, const int* col, const int* rowptr_t, co
                       const float* att_src, const float* att_dst, float* rec, float* ds_dst, float* dh,
                       float* partial, long long P, int slots, long long off_as, long long off_ad, long long off_b,
                       unsigned M, unsigned N, cudaStream_t st) {
-  gat_agg_bwd_p1_kernel<H, C><<<slots, kThreads, 0, st>>>(rowptr, col, g, h, s_src, s_dst, m, l, rec, ds_dst,
-                                                          partial, P, off_b, M, N);
+  const int atomic = slots <= 0;
+  const unsigned grid = atomic ? row_kernel_grid(M, kWarps * RowMap<H, C>::RPW, 16) : (unsigned)slots;
+  gat_agg_bwd_p1_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr, col, g, h, s_src, s_dst, m, l, rec, ds_dst,
+                                                         partial, P, off_b, M, N, atomic);
   int rc = check_launch("gat_agg_bwd_p1");
   if (rc) return rc;
-  gat_agg_bwd_p2_kernel<H, C><<<slots, kThreads, 0, st>>>(rowptr_t, col_t, g, h, s_src, rec, ds_dst, att_src,
-                                                          att_dst, dh, partial, P, off_as, off_ad, M, N);
+  gat_agg_bwd_p2_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr_t, col_t, g, h, s_src, rec, ds_dst, att_src,
+                                                         att_dst, dh, partial, P, off_as, off_ad, M, N, atomic);
   return check_launch("gat_agg_bwd_p2");
 }
 
@@ -301,7 +303,7 @@ extern "C" int gatres_gat_agg_bwd(const int32_t* rowptr, const int32_t* col, con
                                   const float* att_dst, float* rec, float* ds_dst, float* dh, float* partial,
                                   int64_t P, int32_t slots, int64_t off_att_src, int64_t off_att_dst,
                                   int64_t off_bias, int64_t B, int32_t N, int32_t H, int32_t C, void* stream) {
-  GATRES_REQUIRE(B > 0 && N > 0 && slots > 0, "gat_agg_bwd: bad B=%lld N=%d slots=%d", (long long)B, N, slots);
+  GATRES_REQUIRE(B > 0 && N > 0, "gat_agg_bwd: bad B=%lld N=%d", (long long)B, N);
   GATRES_REQUIRE(B * (int64_t)N < (1ll << 31), "gat_agg_bwd: B*N must be < 2^31 rows");
   GATRES_REQUIRE(off_att_src % 4 == 0 && off_att_dst % 4 == 0 && off_bias % 4 == 0 && P % 4 == 0,
                  "gat_agg_bwd: partial row stride and parameter offsets must be multiples of 4 floats");

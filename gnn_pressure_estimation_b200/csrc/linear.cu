@@ -198,7 +198,7 @@ gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ W,
 template <int NO, int KI, int BM, int TNn, int TKk>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* __restrict__ partial,
-             long long P, long long off_W, unsigned M) {
+             long long P, long long off_W, unsigned M, int atomic) {
   constexpr int TKT = KI / TKk, TNT = NO / TNn, LDH = NO + 4, LDX = KI + 4;
   constexpr int NVn = TNn / 4, CGn = NO / NVn;
   constexpr int KW = TKk >= 4 ? 4 : TKk;            // contiguous k run per group
@@ -273,17 +273,18 @@ wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* _
   }
   cp_async_wait<0>();
 
-  float* dst = partial + (size_t)blockIdx.x * P + off_W;
+  float* dst = partial + (atomic ? 0 : (size_t)blockIdx.x * P) + off_W;
 #pragma unroll
   for (int i = 0; i < TNn; ++i) {
     const int n = (i / 4) * CGn + 4 * tn + (i % 4);
 #pragma unroll
     for (int jv = 0; jv < NVk; ++jv) {
       if constexpr (KW == 4) {
-        st4(dst + (size_t)n * KI + jv * CGk + 4 * tk,
-            make_float4(acc[i][jv * 4 + 0], acc[i][jv * 4 + 1], acc[i][jv * 4 + 2], acc[i][jv * 4 + 3]));
+        emit4(dst + (size_t)n * KI + jv * CGk + 4 * tk,
+              make_float4(acc[i][jv * 4 + 0], acc[i][jv * 4 + 1], acc[i][jv * 4 + 2], acc[i][jv * 4 + 3]), atomic);
       } else {
-        *reinterpret_cast<float2*>(dst + (size_t)n * KI + 2 * tk) = make_float2(acc[i][0], acc[i][1]);
+        emit1(dst + (size_t)n * KI + 2 * tk, acc[i][0], atomic);
+        emit1(dst + (size_t)n * KI + 2 * tk + 1, acc[i][1], atomic);
       }
     }
   }
@@ -322,7 +323,14 @@ static int launch_wgrad(const float* dh, const float* x, float* partial, long lo
       return check_launch("wgrad");
     configured = true;
   }
-  kern<<<slots, 256, smem, st>>>(dh, x, partial, P, off_W, M);
+  const int atomic = slots <= 0;
+  const unsigned ntiles = (M + BM - 1) / BM;
+  unsigned grid = (unsigned)slots;
+  if (atomic) {
+    grid = (unsigned)sm_count() * 2u;
+    if (grid > ntiles) grid = ntiles;
+  }
+  kern<<<grid, 256, smem, st>>>(dh, x, partial, P, off_W, M, atomic);
   return check_launch("wgrad");
 }
 
@@ -360,7 +368,7 @@ encoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 // column sums over rows of g (db) and of g * x[m] (dw); thread owns chunk tid % nc4
 __global__ void __launch_bounds__(256)
 encoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ partial,
-                   long long P, long long off_w, long long off_b, unsigned M, int nc4) {
+                   long long P, long long off_w, long long off_b, unsigned M, int nc4, int atomic) {
   __shared__ float red[2 * 256 * 4];
   const int c = threadIdx.x % nc4, rl = threadIdx.x / nc4, rows_per_pass = 256 / nc4;
   float4 aw = f4zero(), ab = f4zero();
@@ -378,9 +386,9 @@ encoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, flo
       add4(sw, *reinterpret_cast<float4*>(red + (k * nc4 + threadIdx.x) * 4));
       add4(sb, *reinterpret_cast<float4*>(red + (256 + k * nc4 + threadIdx.x) * 4));
     }
-    float* row = partial + (size_t)blockIdx.x * P;
-    st4(row + off_w + 4 * threadIdx.x, sw);
-    st4(row + off_b + 4 * threadIdx.x, sb);
+    float* row = partial + (atomic ? 0 : (size_t)blockIdx.x * P);
+    emit4(row + off_w + 4 * threadIdx.x, sw, atomic);
+    emit4(row + off_b + 4 * threadIdx.x, sb, atomic);
   }
 }
 
@@ -408,7 +416,7 @@ template <int NC>
 __global__ void __launch_bounds__(256)
 decoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
                    float* __restrict__ dx, float* __restrict__ partial, long long P, long long off_w,
-                   long long off_b, unsigned M, int mask_relu) {
+                   long long off_b, unsigned M, int mask_relu, int atomic) {
   constexpr int LPR = NC / 4, RPW = 32 / LPR;
   __shared__ float red[kWarps * 32 * 4];
   __shared__ float redb[kWarps];
@@ -431,15 +439,15 @@ decoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, con
     fma4(aw, gv, xv);
     if (lig == 0) ab += gv;
   }
-  float* row = partial + (size_t)blockIdx.x * P;
-  cta_chunk_sum_store<LPR>(aw, red, row + off_w, 0);
+  float* row = partial + (atomic ? 0 : (size_t)blockIdx.x * P);
+  cta_chunk_sum_store<LPR>(aw, red, row + off_w, 0, atomic);
   ab = group_sum<32>(ab, 0xffffffffu);
   if (lane == 0) redb[warp] = ab;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int k = 0; k < kWarps; ++k) s += redb[k];
-    row[off_b] = s;
+    emit1(row + off_b, s, atomic);
   }
 }
 
@@ -480,7 +488,7 @@ extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W
                                  const float* relu_ref, float* dx, float* partial, int64_t P, int32_t slots,
                                  int64_t off_W, int64_t M, int32_t K, int32_t H, int32_t C, void* stream) {
   GATRES_REQUIRE(M > 0 && M < (1ll << 31), "linear_bwd: bad M=%lld", (long long)M);
-  GATRES_REQUIRE(slots > 0 && P % 4 == 0 && off_W % 4 == 0, "linear_bwd: bad slots/P/off_W");
+  GATRES_REQUIRE(P % 4 == 0 && off_W % 4 == 0, "linear_bwd: bad P/off_W");
   cudaStream_t st = as_stream(stream);
   const int NO = H * C;
   if (dx != nullptr) {
@@ -517,10 +525,12 @@ extern "C" int gatres_encoder_fwd(const float* x, const float* w, const float* b
 
 extern "C" int gatres_encoder_bwd(const float* g, const float* x, float* partial, int64_t P, int32_t slots,
                                   int64_t off_w, int64_t off_b, int64_t M, int32_t nc, void* stream) {
-  GATRES_REQUIRE(M > 0 && M < (1ll << 31) && slots > 0, "encoder_bwd: bad M/slots");
+  GATRES_REQUIRE(M > 0 && M < (1ll << 31), "encoder_bwd: bad M");
   GATRES_REQUIRE(nc % 4 == 0 && 256 % (nc / 4) == 0 && nc / 4 <= 256, "encoder_bwd: unsupported nc=%d", nc);
   GATRES_REQUIRE(P % 4 == 0 && off_w % 4 == 0 && off_b % 4 == 0, "encoder_bwd: misaligned offsets");
-  encoder_bwd_kernel<<<slots, 256, 0, as_stream(stream)>>>(g, x, partial, P, off_w, off_b, (unsigned)M, nc / 4);
+  const int atomic = slots <= 0;
+  const unsigned grid = atomic ? row_kernel_grid((unsigned)M, 256 / (nc / 4), 4) : (unsigned)slots;
+  encoder_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, x, partial, P, off_w, off_b, (unsigned)M, nc / 4, atomic);
   return check_launch("encoder_bwd");
 }
 
@@ -542,14 +552,16 @@ extern "C" int gatres_decoder_fwd(const float* x, const float* w, const float* b
 extern "C" int gatres_decoder_bwd(const float* g_out, const float* x, const float* w, float* dx, float* partial,
                                   int64_t P, int32_t slots, int64_t off_w, int64_t off_b, int64_t M, int32_t nc,
                                   int32_t mask_relu, void* stream) {
-  GATRES_REQUIRE(M > 0 && M < (1ll << 31) && slots > 0, "decoder_bwd: bad M/slots");
+  GATRES_REQUIRE(M > 0 && M < (1ll << 31), "decoder_bwd: bad M");
   GATRES_REQUIRE(P % 4 == 0 && off_w % 4 == 0, "decoder_bwd: misaligned offsets");
   cudaStream_t st = as_stream(stream);
   const unsigned Mu = (unsigned)M;
+  const int atomic = slots <= 0;
+  const unsigned grid = atomic ? row_kernel_grid(Mu, kWarps * (32 / (nc / 4)), 8) : (unsigned)slots;
   switch (nc) {
-    case 32: decoder_bwd_kernel<32><<<slots, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu); break;
-    case 64: decoder_bwd_kernel<64><<<slots, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu); break;
-    case 128: decoder_bwd_kernel<128><<<slots, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu); break;
+    case 32: decoder_bwd_kernel<32><<<grid, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
+    case 64: decoder_bwd_kernel<64><<<grid, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
+    case 128: decoder_bwd_kernel<128><<<grid, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
     default: set_error("decoder_bwd: unsupported nc=%d", nc); return GATRES_ERR_ARG;
   }
   return check_launch("decoder_bwd");

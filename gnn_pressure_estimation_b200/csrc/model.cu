@@ -139,13 +139,19 @@ extern "C" int gatres_forward(const gatres_model_desc* d, const float* params, c
 extern "C" int gatres_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
                                const float* d_out, float* partial, float* grads, float* scratch, void* stream) {
   TRY(validate(d, "backward"));
-  GATRES_REQUIRE(params && x && saved && d_out && partial && grads && scratch, "backward: null buffer");
-  GATRES_REQUIRE(d->slots > 0, "backward: slots must be > 0");
+  GATRES_REQUIRE(params && x && saved && d_out && grads && scratch, "backward: null buffer");
+  GATRES_REQUIRE(d->slots <= 0 || partial != nullptr, "backward: deterministic mode (slots > 0) needs `partial`");
   const int64_t M = d->B * (int64_t)d->N, nc = d->nc;
   const int32_t N = d->N, C = d->nc, S = d->slots, nb = d->num_blocks;
   const ParamLayout pl(nb, d->nc);
   const SavedLayout sl(M, nc);
   const int64_t P = a4(pl.count());                      // row stride of `partial`
+  if (S <= 0) {
+    // atomic mode: every kernel adds its contribution straight into `grads`
+    if (cudaMemsetAsync(grads, 0, (size_t)pl.count() * sizeof(float), as_stream(stream)) != cudaSuccess)
+      return check_launch("backward: zero grads");
+    partial = grads;
+  }
 
   float* gA = scratch;
   float* gB = gA + M * nc;
@@ -181,5 +187,6 @@ extern "C" int gatres_backward(const gatres_model_desc* d, const float* params, 
     float* t = gA; gA = gB; gB = t;
   }
   TRY(gatres_encoder_bwd(gA, x, partial, P, S, pl.lin0_w(), pl.lin0_b(), M, C, stream));
+  if (S <= 0) return GATRES_OK;
   return gatres_reduce_partials(partial, P, S, 0, pl.count(), grads, stream);
 }

@@ -198,9 +198,11 @@ _def("mean_res_bwd(Tensor rowptr, Tensor rowptr_t, Tensor col_t, Tensor g_out, T
 # whole model
 # ----------------------------------------------------------------------------
 def _desc(num_blocks: int, nc: int, N: int, B: int, rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor,
-          poison: Optional[Tensor]) -> ModelDesc:
-    return ModelDesc(num_blocks, nc, N, grad_slots(B * N), B, ptr(rowptr), ptr(col), ptr(rowptr_t), ptr(col_t),
-                     ptr(poison))
+          poison: Optional[Tensor], deterministic: bool = False) -> ModelDesc:
+    """slots > 0: parameter gradients via per-CTA partial rows + a fixed-order reduction (bitwise
+    reproducible, small grids); slots = 0: atomic accumulation into the gradient buffer (full grids)."""
+    return ModelDesc(num_blocks, nc, N, grad_slots(B * N) if deterministic else 0, B, ptr(rowptr), ptr(col),
+                     ptr(rowptr_t), ptr(col_t), ptr(poison))
 
 
 def param_count(num_blocks: int, nc: int) -> int:
@@ -232,14 +234,15 @@ _def("model_forward(Tensor params, Tensor x, Tensor rowptr, Tensor col, Tensor r
 
 
 def _model_backward(params: Tensor, x: Tensor, saved: Tensor, d_out: Tensor, rowptr: Tensor, col: Tensor,
-                    rowptr_t: Tensor, col_t: Tensor, num_blocks: int, nc: int, N: int, B: int) -> Tensor:
+                    rowptr_t: Tensor, col_t: Tensor, num_blocks: int, nc: int, N: int, B: int,
+                    deterministic: bool) -> Tensor:
     params, x, d_out = _f32(params, "model_backward"), _f32(x, "model_backward"), _f32(d_out, "model_backward")
     lib = _lib.load()
-    d = _desc(num_blocks, nc, N, B, rowptr, col, rowptr_t, col_t, None)
+    d = _desc(num_blocks, nc, N, B, rowptr, col, rowptr_t, col_t, None, deterministic)
     dev = x.device
     P = params.numel()
     grads = torch.empty(P, dtype=torch.float32, device=dev)
-    partial = torch.empty(d.slots * a4(P), dtype=torch.float32, device=dev)
+    partial = torch.empty(d.slots * a4(P), dtype=torch.float32, device=dev) if deterministic else None
     scratch = torch.empty(int(lib.gatres_scratch_floats(C.byref(d), 1)), dtype=torch.float32, device=dev)
     call("gatres_backward", C.byref(d), ptr(params), ptr(x), ptr(saved), ptr(d_out), ptr(partial), ptr(grads),
          ptr(scratch), stream())
@@ -247,7 +250,8 @@ def _model_backward(params: Tensor, x: Tensor, saved: Tensor, d_out: Tensor, row
 
 
 _def("model_backward(Tensor params, Tensor x, Tensor saved, Tensor d_out, Tensor rowptr, Tensor col, "
-     "Tensor rowptr_t, Tensor col_t, int num_blocks, int nc, int N, int B) -> Tensor", _model_backward)
+     "Tensor rowptr_t, Tensor col_t, int num_blocks, int nc, int N, int B, bool deterministic) -> Tensor",
+     _model_backward)
 
 
 # ----------------------------------------------------------------------------
@@ -356,22 +360,22 @@ class _ModelFn(torch.autograd.Function):
     gradient as a view into one flat buffer (same layout as the parameters)."""
 
     @staticmethod
-    def forward(ctx, x, flat, topo, B, num_blocks, nc, poison, shapes, *params):
-        training = any(ctx.needs_input_grad[8:]) or ctx.needs_input_grad[1]
+    def forward(ctx, x, flat, topo, B, num_blocks, nc, poison, shapes, deterministic, *params):
+        training = any(ctx.needs_input_grad[9:]) or ctx.needs_input_grad[1]
         out, saved = _ops.model_forward(flat, x, topo.rowptr, topo.col, topo.rowptr_t, topo.col_t, poison, num_blocks,
                                         nc, topo.N, B, training)
         if training:
             ctx.save_for_backward(x, flat, saved)
-            ctx.cfg = (topo, B, num_blocks, nc, shapes)
+            ctx.cfg = (topo, B, num_blocks, nc, shapes, deterministic)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         x, flat, saved = ctx.saved_tensors
-        topo, B, num_blocks, nc, shapes = ctx.cfg
+        topo, B, num_blocks, nc, shapes, deterministic = ctx.cfg
         grads = _ops.model_backward(flat, x, saved, g.contiguous(), topo.rowptr, topo.col, topo.rowptr_t, topo.col_t,
-                                    num_blocks, nc, topo.N, B)
+                                    num_blocks, nc, topo.N, B, deterministic)
         outs, off = [], 0
         for shp in shapes:
             n = 1
@@ -379,10 +383,10 @@ class _ModelFn(torch.autograd.Function):
                 n *= s
             outs.append(grads[off:off + n].view(shp))
             off += n
-        return (None, None, None, None, None, None, None, None, *outs)
+        return (None, None, None, None, None, None, None, None, None, *outs)
 
 
 def gatres_model(x: Tensor, flat: Tensor, params: List[Tensor], topo, B: int, num_blocks: int, nc: int,
-                 poison: Optional[Tensor] = None) -> Tensor:
+                 poison: Optional[Tensor] = None, deterministic: bool = False) -> Tensor:
     shapes = tuple(tuple(p.shape) for p in params)
-    return _ModelFn.apply(x, flat.detach(), topo, B, num_blocks, nc, poison, shapes, *params)
+    return _ModelFn.apply(x, flat.detach(), topo, B, num_blocks, nc, poison, shapes, deterministic, *params)

@@ -28,7 +28,7 @@ from .graph import Topology
 class TrainStep:
     def __init__(self, model: GATResMeanConv, topo: Topology, batch: int, mask_count_per_snapshot: int,
                  lr: float = 5e-4, weight_decay: float = 6e-6, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None, use_graph: bool = True):
+                 process_group=None, use_graph: bool = True, deterministic: bool = False):
         self.model, self.topo, self.B = model, topo, int(batch)
         self.N, self.nc, self.nb = topo.N, model.nc, model.num_blocks
         self.M = self.B * self.N
@@ -55,14 +55,16 @@ class TrainStep:
         self.exp_avg = torch.zeros(P, **f32)
         self.exp_avg_sq = torch.zeros(P, **f32)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.desc = ModelDesc(self.nb, self.nc, self.N, _gops.grad_slots(self.M), self.B, ptr(topo.rowptr),
-                              ptr(topo.col), ptr(topo.rowptr_t), ptr(topo.col_t), None)
+        self.deterministic = deterministic
+        self.desc = ModelDesc(self.nb, self.nc, self.N, _gops.grad_slots(self.M) if deterministic else 0, self.B,
+                              ptr(topo.rowptr), ptr(topo.col), ptr(topo.rowptr_t), ptr(topo.col_t), None)
         lib = _lib.load()
         self.saved = torch.empty(int(lib.gatres_saved_floats(C.byref(self.desc))), **f32)
         self.scratch = torch.empty(int(lib.gatres_scratch_floats(C.byref(self.desc), 1)), **f32)
-        self.partial = torch.empty(self.desc.slots * _gops.a4(P), **f32)
+        self.partial = torch.empty(self.desc.slots * _gops.a4(P), **f32) if deterministic else None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.kernels_per_step = 1 + (2 + 5 * self.nb) + 2 + (3 + 9 * self.nb) + 2   # our launches per step
+        # our kernel launches per step: mask, forward, loss, backward (+ final reduction if deterministic), Adam
+        self.kernels_per_step = 1 + (2 + 5 * self.nb) + 2 + (2 + 9 * self.nb + int(deterministic)) + 2
 
     # ------------------------------------------------------------------ pieces
     def _enqueue(self) -> None:

@@ -185,12 +185,14 @@ def _cuda_model_from_case(c, G, dev):
     return m.to(dev), ref
 
 
+@pytest.mark.parametrize("deterministic", [False, True])
 @pytest.mark.parametrize("name", ["tiny_2b_32c_B3", "ctown_small_15b_32c_B8", "ctown_mid_3b_64c_B2",
                                   "ctown_large_25b_128c_B2"])
-def test_model_matches_golden(name, dev, G):
+def test_model_matches_golden(name, deterministic, dev, G):
     """reference caller semantics (train.py:174-185): mask applied by the caller, MSE on masked nodes."""
     c = load_case(name)
     model, _ = _cuda_model_from_case(c, G, dev)
+    model.deterministic = deterministic
     eib = O.collate_edge_index(c["edge_index"], c["N"], c["B"]).to(dev)
     mask = c["mask"].to(dev)
     out = model(c["x"].to(dev), eib, None, None)
@@ -273,7 +275,8 @@ def test_train_step_matches_oracle_adam(use_graph, dev, G):
     model, ref = _cuda_model_from_case(c, G, dev)
     N, B = c["N"], c["B"]
     topo = model.set_topology(c["edge_index"].to(dev), N)
-    ts = TrainStep(model, topo, B, mask_count_per_snapshot=int(N * 0.95), use_graph=use_graph)
+    ts = TrainStep(model, topo, B, mask_count_per_snapshot=int(N * 0.95), use_graph=use_graph,
+                   deterministic=not use_graph)
     opt = torch.optim.Adam(ref.parameters(), lr=5e-4, weight_decay=6e-6)
     eib = O.collate_edge_index(c["edge_index"], N, B)
     steps = 3
