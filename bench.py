@@ -324,6 +324,12 @@ def main():
         host.append((hy, hm))
         devp.append((hy.to(dev), hm.to(dev)))
 
+    if args.profile_kernels:
+        os.environ["GATRES_PROFILE_EAGER"] = "1"
+        kernel_table(args.hbm_batch if nc == 32 else max(64, args.hbm_batch // 8), N, topo, nc, True, dev)
+        torch.cuda.synchronize()
+        return
+
     if args.mode == "train":
         ts = TrainStep(model, topo, B, mask_count, process_group=pg, use_graph=not args.no_graph)
         ts.capture(warmup=2)
@@ -383,12 +389,6 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             ms = float(t.item())
         return ms, cs.summary()
-
-    if args.profile_kernels:
-        os.environ["GATRES_PROFILE_EAGER"] = "1"
-        kernel_table(args.hbm_batch if nc == 32 else max(64, args.hbm_batch // 8), N, topo, nc, True, dev)
-        torch.cuda.synchronize()
-        return
 
     ms_res, clocks = timed(step_resident, False)
     ms_e2e, clocks_e2e = timed(step_e2e, True)

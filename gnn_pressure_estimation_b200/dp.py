@@ -1,0 +1,74 @@
+"""Data-parallel plumbing: one process per GPU, snapshots sharded across ranks,
+one gradient all-reduce per step.
+
+The reference is single-process (/root/reference/gnn_pressure_estimation/train.py:306-324);
+this layer is additive and its contract is "N-rank step == 1-rank step on the
+concatenated batch".  Snapshots are independent (block-diagonal batch graph), so
+inference needs no communication at all and training needs exactly one
+collective: the SUM of the flat gradient buffer, divided by the world size
+inside the Adam kernel (every snapshot masks the same number of nodes, so the
+mean of the shard-mean losses is the global mean loss).
+
+Only host logic lives here (works with gloo on CPU for tests and NCCL on GPUs).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous snapshot range [lo, hi) of `rank`; shards must be equal-sized so
+    that averaging shard gradients equals the full-batch gradient."""
+    if global_batch % world != 0:
+        raise ValueError(f"global batch {global_batch} must be divisible by the world size {world} "
+                         "(equal shards keep mean-of-means == global mean)")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """torchrun-style rendezvous (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).  -> (rank, world, local_rank)"""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kwargs["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kwargs)
+    return rank, world, local
+
+
+def broadcast_parameters_(flat: Tensor, group=None, src: int = 0) -> None:
+    """Make every rank start from rank `src`'s weights (flat buffer, in place)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(flat, src=src, group=group)
+
+
+def allreduce_gradients_(flat_grads: Tensor, group=None, average: bool = True) -> Tensor:
+    """SUM the flat gradient buffer over ranks (optionally divide by world size)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat_grads.div_(dist.get_world_size(group))
+    return flat_grads
+
+
+def replicas_in_sync(flat: Tensor, group=None, tol: float = 0.0) -> bool:
+    """Failure detection: True iff all ranks hold the same parameters (max-min <= tol)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return True
+    hi, lo = flat.clone(), flat.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    return bool((hi - lo).abs().max() <= tol)

@@ -19,7 +19,7 @@ from typing import Optional
 import torch
 from torch import Tensor
 
-from . import _lib, ops as _gops
+from . import _lib, dp as _dp, ops as _gops
 from ._lib import ModelDesc, call, ptr, stream
 from .GraphModels import GATResMeanConv
 from .graph import Topology
@@ -40,6 +40,7 @@ class TrainStep:
         dev = topo.rowptr.device
         self.device = dev
         self.flat = model.flat_parameters()
+        _dp.broadcast_parameters_(self.flat, self.pg)           # all replicas start from rank 0's weights
         P = self.flat.numel()
         self.P = P
         f32 = dict(dtype=torch.float32, device=dev)

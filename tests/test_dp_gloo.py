@@ -1,0 +1,85 @@
+"""world_size-2 gloo tests of the data-parallel host logic on CPU (the per-rank
+compute is the oracle here — the CUDA path has no CPU mode; the same contract is
+checked on the GPU in test_gpu_parity.py::test_gradient_is_mean_over_shards)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gnn_pressure_estimation_b200 import dp
+from helpers import load_case
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _flat(tensors):
+    return torch.cat([t.reshape(-1) for t in tensors])
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from oracle import gatres_oracle as O
+    r, w, _ = dp.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    c = load_case("ctown_small_15b_32c_B8")
+    N, B = c["N"], c["B"]
+    # rank 1 starts from different weights; broadcast must repair that
+    model = O.make_oracle(3, 32, seed=0 if rank == 0 else 7)
+    params = list(model.parameters())
+    flat = _flat([p.detach() for p in params])
+    assert dp.replicas_in_sync(flat) is False
+    dp.broadcast_parameters_(flat)
+    off = 0
+    with torch.no_grad():
+        for p in params:
+            p.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+    assert dp.replicas_in_sync(flat)
+
+    lo, hi = dp.shard_bounds(B, rank, world)
+    sl = slice(lo * N, hi * N)
+    eib = O.collate_edge_index(c["edge_index"], N, hi - lo)
+    _, loss, grads = O.train_step_loss_and_grads(model, c["x"][sl], c["y"][sl], c["mask"][sl], eib)
+    g = _flat([grads[k] for k, _ in model.named_parameters()])
+    dp.allreduce_gradients_(g)
+
+    # every rank applies the same Adam step -> replicas stay bit-identical
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    O.adam_reference_step(flat, g, m, v, step=1)
+    assert dp.replicas_in_sync(flat)
+    if rank == 0:
+        ret["grad"] = g.clone()
+        ret["loss"] = float(loss)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_single_rank_step():
+    from oracle import gatres_oracle as O
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+        g_dp = ret["grad"]
+    c = load_case("ctown_small_15b_32c_B8")
+    model = O.make_oracle(3, 32, seed=0)
+    eib = O.collate_edge_index(c["edge_index"], c["N"], c["B"])
+    _, _, grads = O.train_step_loss_and_grads(model, c["x"], c["y"], c["mask"], eib)
+    g_full = _flat([grads[k] for k, _ in model.named_parameters()])
+    assert float((g_dp - g_full).abs().max()) <= 1e-5 * float(g_full.abs().max())
+
+
+def test_shard_bounds():
+    assert [dp.shard_bounds(1024, r, 8) for r in (0, 7)] == [(0, 128), (896, 1024)]
+    assert dp.shard_bounds(16384, 3, 8) == (6144, 8192)
+    with pytest.raises(ValueError):
+        dp.shard_bounds(10, 0, 4)
