@@ -5,10 +5,33 @@
 // SURVEY.md §A.2/§A.4).  One group of LPR lanes owns one (snapshot, row); each
 // lane owns one 128-bit chunk of the row, so every neighbour-row gather is a
 // coalesced 16 B/lane load and no per-edge tensor is ever materialised.
+//
+// The per-edge scalar work (logit, LeakyReLU, exp, softmax weight) is done
+// COOPERATIVELY: within the LPH lanes that hold one head of a row, lane t
+// evaluates edge t of that row, the row max / sum are butterflies over those
+// lanes, and the accumulation loop only broadcasts (neighbour id, weight) with
+// two shuffles per edge.  (Round-1 profile: the one-lane-does-everything version
+// was issue-bound at ~330 instructions per warp pass.)  Rows with more than LPH
+// in-edges are handled in LPH-sized chunks with an online-softmax rescale.
 #include <math_constants.h>
 #include "common.cuh"
 
 namespace gatres {
+
+template <int width>
+__device__ __forceinline__ float group_max(float v, unsigned mask) {
+#pragma unroll
+  for (int off = width / 2; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, off));
+  return v;
+}
+
+// r / n for r < 2^32 with magic = floor(2^32 / n) (n >= 2) or 0xffffffff (n == 1)
+__device__ __forceinline__ void divmod(unsigned r, unsigned n, unsigned magic, unsigned& q, unsigned& rem) {
+  q = __umulhi(r, magic);
+  rem = r - q * n;
+  if (rem >= n) { ++q; rem -= n; }
+}
+static inline unsigned div_magic(unsigned n) { return n <= 1 ? 0xffffffffu : (unsigned)((1ull << 32) / n); }
 
 // ------------------------------------------------------------------ forward
 template <int H, int C>
@@ -17,11 +40,13 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                    const float* __restrict__ h, const float* __restrict__ s_src,
                    const float* __restrict__ s_dst, const float* __restrict__ bias,
                    float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ l_out,
-                   unsigned M, unsigned N, int relu) {
+                   unsigned M, unsigned N, unsigned magic, int relu) {
   using RM = RowMap<H, C>;
-  constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW;
+  constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
+  constexpr int PRE = 4;                          // gathers issued before the softmax math (mean WDN in-degree+1 = 3.2)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR;
+  const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
   constexpr unsigned rows_per_cta = kWarps * RPW;
 
   float4 bv[V];
@@ -30,43 +55,74 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
 
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
-    if (r >= M) continue;                         // no cross-lane traffic in this kernel
-    const unsigned b = r / N, i = r - b * N;
-    const size_t base = (size_t)b * N;
-    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    if (r >= M) continue;                         // uniform across the LPR lanes of a row
+    unsigned b, i;
+    divmod(r, N, magic, b, i);
+    const float* hb = h + (size_t)b * N * F + 4 * lig;            // this lane's chunk column of snapshot b
+    const float* ssb = s_src + (size_t)b * N * H;
+    const int beg = __ldg(rowptr + i), deg = __ldg(rowptr + i + 1) - beg;
 
-    float sd[V], mx[V], l[V];
+    float sd[V], mrun[V], lrun[V];
     float4 acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       sd[v] = __ldg(s_dst + (size_t)r * H + RM::head(lig, v));
-      mx[v] = -CUDART_INF_F;
-      l[v] = 0.f;
+      mrun[v] = -CUDART_INF_F;
+      lrun[v] = 0.f;
       acc[v] = f4zero();
     }
-    // pass 1: row max of the LeakyReLU logits (scores only: 4 B per edge per head)
-    for (int e = beg; e < end; ++e) {
-      const size_t j = base + __ldg(col + e);
+    for (int e0 = 0; e0 < deg; e0 += LPH) {
+      // lane `slot` of each head group evaluates edge e0 + slot
+      const bool valid = e0 + slot < deg;
+      const int j = valid ? __ldg(col + beg + e0 + slot) : 0;
+      const int cnt = min(LPH, deg - e0);
+      // issue the first PRE neighbour-row gathers now: they only depend on `col`, so they fly while the
+      // scores are fetched and the softmax is computed (the kernel is latency-bound, not issue-bound)
+      float4 x[PRE][V];
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        mx[v] = fmaxf(mx[v], lrelu(__ldg(s_src + j * H + RM::head(lig, v)) + sd[v]));
-    }
-    // pass 2: exp, running sum, weighted accumulation of neighbour rows
-#pragma unroll 4
-    for (int e = beg; e < end; ++e) {
-      const size_t j = base + __ldg(col + e);
-      const float* hj = h + j * F;
+      for (int u = 0; u < PRE; ++u) {
+        const int ju = __shfl_sync(gmask, j, u, LPH);
+#pragma unroll
+        for (int v = 0; v < V; ++v) x[u][v] = u < cnt ? ldg4(hb + (unsigned)ju * F + 4 * v * LPR) : f4zero();
+      }
+      float p[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float4 x = ldg4(hj + 4 * RM::chunk(lig, v));
-        const float p = __expf(lrelu(__ldg(s_src + j * H + RM::head(lig, v)) + sd[v]) - mx[v]);
-        l[v] += p;
-        fma4(acc[v], p, x);
+        const float a = valid ? lrelu(__ldg(ssb + (unsigned)j * H + RM::head(lig, v)) + sd[v]) : -CUDART_INF_F;
+        const float nm = fmaxf(mrun[v], group_max<LPH>(a, gmask));
+        if (e0 > 0) {                              // online-softmax rescale (never taken for WDN degrees)
+          const float sc = __expf(mrun[v] - nm);
+          lrun[v] *= sc;
+          acc[v].x *= sc; acc[v].y *= sc; acc[v].z *= sc; acc[v].w *= sc;
+        }
+        p[v] = __expf(a - nm);                     // exp(-inf) = 0 for the idle slots
+        lrun[v] += group_sum<LPH>(p[v], gmask);
+        mrun[v] = nm;
+      }
+#pragma unroll
+      for (int u = 0; u < PRE; ++u)
+#pragma unroll
+        for (int v = 0; v < V; ++v) fma4(acc[v], __shfl_sync(gmask, p[v], u, LPH), x[u][v]);   // p = 0 beyond cnt
+      for (int t = PRE; t < cnt; t += 2) {         // rows with more than PRE in-edges: two gathers in flight
+        const bool two = t + 1 < cnt;
+        const int j0 = __shfl_sync(gmask, j, t, LPH), j1 = __shfl_sync(gmask, j, t + 1, LPH);
+        float4 x0[V], x1[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          x0[v] = ldg4(hb + (unsigned)j0 * F + 4 * v * LPR);
+          x1[v] = two ? ldg4(hb + (unsigned)j1 * F + 4 * v * LPR) : f4zero();
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float p0 = __shfl_sync(gmask, p[v], t, LPH), p1 = __shfl_sync(gmask, p[v], t + 1, LPH);
+          fma4(acc[v], p0, x0[v]);
+          fma4(acc[v], two ? p1 : 0.f, x1[v]);
+        }
       }
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const float inv = 1.f / (l[v] + kSoftmaxEps);
+      const float inv = 1.f / (lrun[v] + kSoftmaxEps);
       float4 o;
       o.x = fmaf(acc[v].x, inv, bv[v].x);
       o.y = fmaf(acc[v].y, inv, bv[v].y);
@@ -76,9 +132,9 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
       }
       st4(out + (size_t)r * F + 4 * RM::chunk(lig, v), o);
-      if (m_out != nullptr && (RM::chunk(lig, v) % (C / 4)) == 0) {
-        m_out[(size_t)r * H + RM::head(lig, v)] = mx[v];
-        l_out[(size_t)r * H + RM::head(lig, v)] = l[v];
+      if (m_out != nullptr && slot == 0) {
+        m_out[(size_t)r * H + RM::head(lig, v)] = mrun[v];
+        l_out[(size_t)r * H + RM::head(lig, v)] = lrun[v];
       }
     }
   }
@@ -89,6 +145,8 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
 // dalpha_e = <g[i], h[j]>.  Emits rec[i,h] = {s_dst, m, 1/(l+eps), D} so pass 2
 // needs one 16 B load per (edge, head) for all target-side scalars.
 // Also accumulates the bias gradient (column sums of g).
+// Lane `slot` keeps (alpha, slope, dalpha) of edge `slot`; the three row sums are
+// butterflies at the end.
 template <int H, int C>
 __global__ void __launch_bounds__(kThreads)
 gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
@@ -97,12 +155,13 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
                       const float* __restrict__ m, const float* __restrict__ l,
                       float* __restrict__ rec, float* __restrict__ ds_dst,
                       float* __restrict__ partial, long long P, long long off_bias,
-                      unsigned M, unsigned N, int atomic) {
+                      unsigned M, unsigned N, unsigned magic, int atomic) {
   using RM = RowMap<H, C>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
+  constexpr int PRE = 4;                          // gathers issued ahead of the per-edge scalar math
   __shared__ float red[kWarps * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR;
+  const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
   const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
   constexpr unsigned rows_per_cta = kWarps * RPW;
 
@@ -113,9 +172,11 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
     if (r < M) {                                  // uniform across the LPR lanes of a row
-      const unsigned b = r / N, i = r - b * N;
-      const size_t base = (size_t)b * N;
-      const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+      unsigned b, i;
+      divmod(r, N, magic, b, i);
+      const float* hb = h + (size_t)b * N * F + 4 * lig;
+      const float* ssb = s_src + (size_t)b * N * H;
+      const int beg = __ldg(rowptr + i), deg = __ldg(rowptr + i + 1) - beg;
       float4 gv[V];
       float sd[V], mi[V], il[V], S1[V], S2[V], S3[V];
 #pragma unroll
@@ -128,27 +189,63 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
         il[v] = 1.f / (__ldg(l + (size_t)r * H + hd) + kSoftmaxEps);
         S1[v] = S2[v] = S3[v] = 0.f;
       }
-#pragma unroll 2
-      for (int e = beg; e < end; ++e) {
-        const size_t j = base + __ldg(col + e);
-        const float* hj = h + j * F;
+      for (int e0 = 0; e0 < deg; e0 += LPH) {
+        const bool valid = e0 + slot < deg;
+        const int j = valid ? __ldg(col + beg + e0 + slot) : 0;
+        const int cnt = min(LPH, deg - e0);
+        float4 x[PRE][V];                          // first PRE neighbour rows, in flight during the alpha math
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+          const int ju = __shfl_sync(gmask, j, u, LPH);
+#pragma unroll
+          for (int v = 0; v < V; ++v) x[u][v] = u < cnt ? ldg4(hb + (unsigned)ju * F + 4 * v * LPR) : f4zero();
+        }
+        float alpha[V], sl[V], da[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const float da = group_sum<LPH>(dot4(gv[v], ldg4(hj + 4 * RM::chunk(lig, v))), gmask);
-          const float z = __ldg(s_src + j * H + RM::head(lig, v)) + sd[v];
-          const float alpha = __expf(lrelu(z) - mi[v]) * il[v];
-          const float sl = lrelu_slope(z);
-          S1[v] = fmaf(alpha, da, S1[v]);
-          S2[v] = fmaf(alpha * sl, da, S2[v]);
-          S3[v] = fmaf(alpha, sl, S3[v]);
+          const float z = __ldg(ssb + (unsigned)j * H + RM::head(lig, v)) + sd[v];
+          alpha[v] = valid ? __expf(lrelu(z) - mi[v]) * il[v] : 0.f;
+          sl[v] = lrelu_slope(z);
+          da[v] = 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < PRE; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float d = group_sum<LPH>(dot4(gv[v], x[u][v]), gmask);
+            da[v] = slot == u ? d : da[v];
+          }
+        for (int t = PRE; t < cnt; t += 2) {
+          const bool two = t + 1 < cnt;
+          const int j0 = __shfl_sync(gmask, j, t, LPH), j1 = __shfl_sync(gmask, j, t + 1, LPH);
+          float4 x0[V], x1[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            x0[v] = ldg4(hb + (unsigned)j0 * F + 4 * v * LPR);
+            x1[v] = two ? ldg4(hb + (unsigned)j1 * F + 4 * v * LPR) : f4zero();
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float d0 = group_sum<LPH>(dot4(gv[v], x0[v]), gmask);
+            const float d1 = group_sum<LPH>(dot4(gv[v], x1[v]), gmask);
+            da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {             // idle slots have alpha = 0
+          S1[v] = fmaf(alpha[v], da[v], S1[v]);
+          S2[v] = fmaf(alpha[v] * sl[v], da[v], S2[v]);
+          S3[v] = fmaf(alpha[v], sl[v], S3[v]);
         }
       }
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        if ((RM::chunk(lig, v) % (C / 4)) == 0) {
+        const float D = group_sum<LPH>(S1[v], gmask);
+        const float T2 = group_sum<LPH>(S2[v], gmask), T3 = group_sum<LPH>(S3[v], gmask);
+        if (slot == 0) {
           const size_t o = (size_t)r * H + RM::head(lig, v);
-          st4(rec + o * 4, make_float4(sd[v], mi[v], il[v], S1[v]));
-          ds_dst[o] = S2[v] - S1[v] * S3[v];
+          st4(rec + o * 4, make_float4(sd[v], mi[v], il[v], D));
+          ds_dst[o] = T2 - D * T3;
         }
       }
     }
@@ -171,12 +268,13 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
                       const float* __restrict__ att_src, const float* __restrict__ att_dst,
                       float* __restrict__ dh,
                       float* __restrict__ partial, long long P, long long off_att_src, long long off_att_dst,
-                      unsigned M, unsigned N, int atomic) {
+                      unsigned M, unsigned N, unsigned magic, int atomic) {
   using RM = RowMap<H, C>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
+  constexpr int PRE = 4;                          // gathers issued ahead of the per-edge scalar math
   __shared__ float red[kWarps * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR;
+  const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
   const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
   constexpr unsigned rows_per_cta = kWarps * RPW;
 
@@ -192,9 +290,11 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
     if (r < M) {
-      const unsigned b = r / N, jn = r - b * N;
-      const size_t base = (size_t)b * N;
-      const int beg = __ldg(rowptr_t + jn), end = __ldg(rowptr_t + jn + 1);
+      unsigned b, jn;
+      divmod(r, N, magic, b, jn);
+      const float* gb = g + (size_t)b * N * F + 4 * lig;
+      const float* recb = rec + (size_t)b * N * H * 4;
+      const int beg = __ldg(rowptr_t + jn), deg = __ldg(rowptr_t + jn + 1) - beg;
       float4 hv[V], dacc[V];
       float ss[V], dsrc[V];
 #pragma unroll
@@ -204,28 +304,65 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
         dacc[v] = f4zero();
         dsrc[v] = 0.f;
       }
-#pragma unroll 2
-      for (int e = beg; e < end; ++e) {
-        const size_t i = base + __ldg(col_t + e);
-        const float* gi = g + i * F;
+      for (int e0 = 0; e0 < deg; e0 += LPH) {
+        const bool valid = e0 + slot < deg;
+        const int i = valid ? __ldg(col_t + beg + e0 + slot) : 0;
+        const int cnt = min(LPH, deg - e0);
+        float4 gx[PRE][V];                         // first PRE target-gradient rows, in flight during the alpha math
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+          const int iu = __shfl_sync(gmask, i, u, LPH);
+#pragma unroll
+          for (int v = 0; v < V; ++v) gx[u][v] = u < cnt ? ldg4(gb + (unsigned)iu * F + 4 * v * LPR) : f4zero();
+        }
+        float alpha[V], k2[V], Dt[V], da[V];      // k2 = alpha * lrelu'(z); Dt = D of the edge's target
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const float4 gv = ldg4(gi + 4 * RM::chunk(lig, v));
-          const float4 t = ldg4(rec + (i * H + RM::head(lig, v)) * 4);   // {s_dst, m, 1/l, D}
-          const float da = group_sum<LPH>(dot4(gv, hv[v]), gmask);
-          const float z = ss[v] + t.x;
-          const float alpha = __expf(lrelu(z) - t.y) * t.z;
-          dsrc[v] = fmaf(alpha * (da - t.w), lrelu_slope(z), dsrc[v]);
-          fma4(dacc[v], alpha, gv);
+          const float4 t4 = ldg4(recb + ((unsigned)i * H + RM::head(lig, v)) * 4);   // {s_dst, m, 1/l, D}
+          const float z = ss[v] + t4.x;
+          alpha[v] = valid ? __expf(lrelu(z) - t4.y) * t4.z : 0.f;
+          k2[v] = alpha[v] * lrelu_slope(z);
+          Dt[v] = t4.w;
+          da[v] = 0.f;
         }
+#pragma unroll
+        for (int u = 0; u < PRE; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float d = group_sum<LPH>(dot4(gx[u][v], hv[v]), gmask);
+            da[v] = slot == u ? d : da[v];
+            fma4(dacc[v], __shfl_sync(gmask, alpha[v], u, LPH), gx[u][v]);      // alpha = 0 beyond cnt
+          }
+        for (int t = PRE; t < cnt; t += 2) {
+          const bool two = t + 1 < cnt;
+          const int i0 = __shfl_sync(gmask, i, t, LPH), i1 = __shfl_sync(gmask, i, t + 1, LPH);
+          float4 g0[V], g1[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            g0[v] = ldg4(gb + (unsigned)i0 * F + 4 * v * LPR);
+            g1[v] = two ? ldg4(gb + (unsigned)i1 * F + 4 * v * LPR) : f4zero();
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float d0 = group_sum<LPH>(dot4(g0[v], hv[v]), gmask);
+            const float d1 = group_sum<LPH>(dot4(g1[v], hv[v]), gmask);
+            da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
+            const float a0 = __shfl_sync(gmask, alpha[v], t, LPH), a1 = __shfl_sync(gmask, alpha[v], t + 1, LPH);
+            fma4(dacc[v], a0, g0[v]);
+            fma4(dacc[v], two ? a1 : 0.f, g1[v]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) dsrc[v] = fmaf(k2[v], da[v] - Dt[v], dsrc[v]);
       }
 #pragma unroll
       for (int v = 0; v < V; ++v) {
+        const float ds = group_sum<LPH>(dsrc[v], gmask);
         const float dd = __ldg(ds_dst + (size_t)r * H + RM::head(lig, v));
-        fma4(dacc[v], dsrc[v], as[v]);
+        fma4(dacc[v], ds, as[v]);
         fma4(dacc[v], dd, ad[v]);
         st4(dh + (size_t)r * F + 4 * RM::chunk(lig, v), dacc[v]);
-        fma4(accs[v], dsrc[v], hv[v]);
+        fma4(accs[v], ds, hv[v]);
         fma4(accd[v], dd, hv[v]);
       }
     }
@@ -243,11 +380,9 @@ template <int H, int C>
 static int launch_fwd(const int* rowptr, const int* col, const float* h, const float* s_src, const float* s_dst,
                       const float* bias, float* out, float* m, float* l, unsigned M, unsigned N, int relu,
                       cudaStream_t st) {
-  constexpr unsigned rows_per_cta = kWarps * RowMap<H, C>::RPW;
-  unsigned grid = (M + rows_per_cta - 1) / rows_per_cta;
-  const unsigned cap = (unsigned)sm_count() * 32u;
-  if (grid > cap) grid = cap;
-  gat_agg_fwd_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr, col, h, s_src, s_dst, bias, out, m, l, M, N, relu);
+  const unsigned grid = row_kernel_grid(M, kWarps * RowMap<H, C>::RPW, 32);
+  gat_agg_fwd_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr, col, h, s_src, s_dst, bias, out, m, l, M, N,
+                                                      div_magic(N), relu);
   return check_launch("gat_agg_fwd");
 }
 
@@ -260,11 +395,12 @@ static int launch_bwd(const int* rowptr, const int* col, const int* rowptr_t, co
   const int atomic = slots <= 0;
   const unsigned grid = atomic ? row_kernel_grid(M, kWarps * RowMap<H, C>::RPW, 16) : (unsigned)slots;
   gat_agg_bwd_p1_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr, col, g, h, s_src, s_dst, m, l, rec, ds_dst,
-                                                         partial, P, off_b, M, N, atomic);
+                                                         partial, P, off_b, M, N, div_magic(N), atomic);
   int rc = check_launch("gat_agg_bwd_p1");
   if (rc) return rc;
   gat_agg_bwd_p2_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr_t, col_t, g, h, s_src, rec, ds_dst, att_src,
-                                                         att_dst, dh, partial, P, off_as, off_ad, M, N, atomic);
+                                                         att_dst, dh, partial, P, off_as, off_ad, M, N,
+                                                         div_magic(N), atomic);
   return check_launch("gat_agg_bwd_p2");
 }
 
@@ -289,6 +425,7 @@ extern "C" int gatres_gat_agg_fwd(const int32_t* rowptr, const int32_t* col, con
                                   int64_t B, int32_t N, int32_t H, int32_t C, int32_t relu, void* stream) {
   GATRES_REQUIRE(B >= 0 && N > 0, "gat_agg_fwd: bad B=%lld N=%d", (long long)B, N);
   GATRES_REQUIRE(B * (int64_t)N < (1ll << 31), "gat_agg_fwd: B*N must be < 2^31 rows");
+  GATRES_REQUIRE((int64_t)N * H * C < (1ll << 31), "gat_agg_fwd: one snapshot must be < 2^31 floats");
   GATRES_REQUIRE((m == nullptr) == (l == nullptr), "gat_agg_fwd: m and l must both be given or both NULL");
   if (B == 0) return GATRES_OK;
   const unsigned M = (unsigned)(B * N);
@@ -305,6 +442,7 @@ extern "C" int gatres_gat_agg_bwd(const int32_t* rowptr, const int32_t* col, con
                                   int64_t off_bias, int64_t B, int32_t N, int32_t H, int32_t C, void* stream) {
   GATRES_REQUIRE(B > 0 && N > 0, "gat_agg_bwd: bad B=%lld N=%d", (long long)B, N);
   GATRES_REQUIRE(B * (int64_t)N < (1ll << 31), "gat_agg_bwd: B*N must be < 2^31 rows");
+  GATRES_REQUIRE((int64_t)N * H * C < (1ll << 31), "gat_agg_bwd: one snapshot must be < 2^31 floats");
   GATRES_REQUIRE(off_att_src % 4 == 0 && off_att_dst % 4 == 0 && off_bias % 4 == 0 && P % 4 == 0,
                  "gat_agg_bwd: partial row stride and parameter offsets must be multiples of 4 floats");
   const unsigned M = (unsigned)(B * N);
