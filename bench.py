@@ -239,12 +239,12 @@ def kernel_table(B, N, topo, nc, hbm_regime, dev):
 
         def agg(k):
             call("gatres_gat_agg_fwd", ptr(topo.rowptr), ptr(topo.col), ptr(h[k]), ptr(ss[k]), ptr(sd[k]), ptr(bias),
-                 ptr(out[k]), ptr(m[k]), ptr(l[k]), B, N, H, nc, 1, stream())
+                 ptr(out[k]), ptr(m[k]), ptr(l[k]), B, N, topo.E1, H, nc, 1, stream())
 
         def aggb(k):
             call("gatres_gat_agg_bwd", ptr(topo.rowptr), ptr(topo.col), ptr(topo.rowptr_t), ptr(topo.col_t), ptr(g[k]),
                  ptr(h[k]), ptr(ss[k]), ptr(sd[k]), ptr(m[k]), ptr(l[k]), ptr(a_s), ptr(a_d), ptr(rec), ptr(dsd), ptr(dh),
-                 ptr(partial), P, S, F * K, F * K + F, F * K + 2 * F, B, N, H, nc, stream())
+                 ptr(partial), P, S, F * K, F * K + F, F * K + 2 * F, B, N, topo.E1, H, nc, stream())
 
         def linb(k):
             call("gatres_linear_bwd", ptr(g[k]), ptr(x[k]), ptr(W), None, None, ptr(dx), ptr(partial), P, S, 0, M, K, H,
@@ -443,8 +443,13 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # NCCL communicators referenced by a captured CUDA graph can stall a clean teardown: every rank is
+        # done once it passes this barrier, so leave without destroying the group.
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -25,7 +25,8 @@ _sz = C.c_size_t
 
 class ModelDesc(C.Structure):
     """struct gatres_model_desc"""
-    _fields_ = [("num_blocks", _i32), ("nc", _i32), ("N", _i32), ("slots", _i32), ("B", _i64),
+    _fields_ = [("num_blocks", _i32), ("nc", _i32), ("N", _i32), ("slots", _i32), ("E1", _i32), ("reserved", _i32),
+                ("B", _i64),
                 ("rowptr", _p), ("col", _p), ("rowptr_t", _p), ("col_t", _p), ("poison", _p)]
 
 
@@ -34,12 +35,13 @@ _PROTOTYPES = {
     "gatres_abi_version": (C.c_int, []),
     "gatres_last_error": (C.c_char_p, []),
     "gatres_sm_count": (C.c_int, []),
+    "gatres_set_tile_min_batch": (_i64, [_i64]),
     "gatres_csr_scratch_bytes": (_sz, [_i64, _i32]),
     "gatres_csr_build": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gatres_check_replicated": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p]),
     "gatres_linear_att_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
-    "gatres_gat_agg_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p]),
-    "gatres_gat_agg_bwd": (C.c_int, [_p] * 16 + [_i64, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p]),
+    "gatres_gat_agg_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
+    "gatres_gat_agg_bwd": (C.c_int, [_p] * 16 + [_i64, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p]),
     "gatres_mean_res_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "gatres_mean_res_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "gatres_linear_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i64, _i64, _i32, _i32, _i32, _p]),

@@ -14,6 +14,7 @@
 // was issue-bound at ~330 instructions per warp pass.)  Rows with more than LPH
 // in-edges are handled in LPH-sized chunks with an online-softmax rescale.
 #include <math_constants.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gatres {
@@ -46,7 +47,7 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
   constexpr int PRE = 4;                          // gathers issued before the softmax math (mean WDN in-degree+1 = 3.2)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  constexpr unsigned gmask = 0xffffffffu;          // control flow below is warp-uniform: full-mask shuffles
   constexpr unsigned rows_per_cta = kWarps * RPW;
 
   float4 bv[V];
@@ -54,13 +55,17 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
   for (int v = 0; v < V; ++v) bv[v] = ldg4(bias + 4 * RM::chunk(lig, v));
 
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
-    const unsigned r = r0 + warp * RPW + sub;
-    if (r >= M) continue;                         // uniform across the LPR lanes of a row
+    // rows past the end are clamped (their lanes redo the last row and skip the stores) so that every
+    // lane of the warp runs the same instruction stream: plain full-mask SHFLs, no convergence barriers
+    const unsigned r_raw = r0 + warp * RPW + sub;
+    const bool row_ok = r_raw < M;
+    const unsigned r = row_ok ? r_raw : M - 1;
     unsigned b, i;
     divmod(r, N, magic, b, i);
     const float* hb = h + (size_t)b * N * F + 4 * lig;            // this lane's chunk column of snapshot b
     const float* ssb = s_src + (size_t)b * N * H;
     const int beg = __ldg(rowptr + i), deg = __ldg(rowptr + i + 1) - beg;
+    const int deg_max = __reduce_max_sync(gmask, deg);
 
     float sd[V], mrun[V], lrun[V];
     float4 acc[V];
@@ -71,11 +76,12 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
       lrun[v] = 0.f;
       acc[v] = f4zero();
     }
-    for (int e0 = 0; e0 < deg; e0 += LPH) {
+    for (int e0 = 0; e0 < deg_max; e0 += LPH) {
       // lane `slot` of each head group evaluates edge e0 + slot
       const bool valid = e0 + slot < deg;
       const int j = valid ? __ldg(col + beg + e0 + slot) : 0;
       const int cnt = min(LPH, deg - e0);
+      const int cnt_max = min(LPH, deg_max - e0);
       // issue the first PRE neighbour-row gathers now: they only depend on `col`, so they fly while the
       // scores are fetched and the softmax is computed (the kernel is latency-bound, not issue-bound)
       float4 x[PRE][V];
@@ -103,23 +109,23 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
       for (int u = 0; u < PRE; ++u)
 #pragma unroll
         for (int v = 0; v < V; ++v) fma4(acc[v], __shfl_sync(gmask, p[v], u, LPH), x[u][v]);   // p = 0 beyond cnt
-      for (int t = PRE; t < cnt; t += 2) {         // rows with more than PRE in-edges: two gathers in flight
-        const bool two = t + 1 < cnt;
+      for (int t = PRE; t < cnt_max; t += 2) {     // rows with more than PRE in-edges: two gathers in flight
         const int j0 = __shfl_sync(gmask, j, t, LPH), j1 = __shfl_sync(gmask, j, t + 1, LPH);
         float4 x0[V], x1[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          x0[v] = ldg4(hb + (unsigned)j0 * F + 4 * v * LPR);
-          x1[v] = two ? ldg4(hb + (unsigned)j1 * F + 4 * v * LPR) : f4zero();
+          x0[v] = t < cnt ? ldg4(hb + (unsigned)j0 * F + 4 * v * LPR) : f4zero();
+          x1[v] = t + 1 < cnt ? ldg4(hb + (unsigned)j1 * F + 4 * v * LPR) : f4zero();
         }
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
+        for (int v = 0; v < V; ++v) {               // p is 0 in the idle slots (t >= cnt)
           const float p0 = __shfl_sync(gmask, p[v], t, LPH), p1 = __shfl_sync(gmask, p[v], t + 1, LPH);
           fma4(acc[v], p0, x0[v]);
-          fma4(acc[v], two ? p1 : 0.f, x1[v]);
+          fma4(acc[v], t + 1 < LPH ? p1 : 0.f, x1[v]);
         }
       }
     }
+    if (!row_ok) continue;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const float inv = 1.f / (lrun[v] + kSoftmaxEps);
@@ -162,7 +168,7 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
   __shared__ float red[kWarps * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  constexpr unsigned gmask = 0xffffffffu;          // warp-uniform control flow, full-mask shuffles
   constexpr unsigned rows_per_cta = kWarps * RPW;
 
   float4 bacc[V];
@@ -170,29 +176,33 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
   for (int v = 0; v < V; ++v) bacc[v] = f4zero();
 
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
-    const unsigned r = r0 + warp * RPW + sub;
-    if (r < M) {                                  // uniform across the LPR lanes of a row
+    const unsigned r_raw = r0 + warp * RPW + sub;
+    const bool row_ok = r_raw < M;                // clamped rows recompute the last row and emit nothing
+    const unsigned r = row_ok ? r_raw : M - 1;
+    {
       unsigned b, i;
       divmod(r, N, magic, b, i);
       const float* hb = h + (size_t)b * N * F + 4 * lig;
       const float* ssb = s_src + (size_t)b * N * H;
       const int beg = __ldg(rowptr + i), deg = __ldg(rowptr + i + 1) - beg;
+      const int deg_max = __reduce_max_sync(gmask, deg);
       float4 gv[V];
       float sd[V], mi[V], il[V], S1[V], S2[V], S3[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int hd = RM::head(lig, v);
         gv[v] = ldg4_stream(g + (size_t)r * F + 4 * RM::chunk(lig, v));
-        add4(bacc[v], gv[v]);
+        if (row_ok) add4(bacc[v], gv[v]);
         sd[v] = __ldg(s_dst + (size_t)r * H + hd);
         mi[v] = __ldg(m + (size_t)r * H + hd);
         il[v] = 1.f / (__ldg(l + (size_t)r * H + hd) + kSoftmaxEps);
         S1[v] = S2[v] = S3[v] = 0.f;
       }
-      for (int e0 = 0; e0 < deg; e0 += LPH) {
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
         const bool valid = e0 + slot < deg;
         const int j = valid ? __ldg(col + beg + e0 + slot) : 0;
         const int cnt = min(LPH, deg - e0);
+        const int cnt_max = min(LPH, deg_max - e0);
         float4 x[PRE][V];                          // first PRE neighbour rows, in flight during the alpha math
 #pragma unroll
         for (int u = 0; u < PRE; ++u) {
@@ -215,14 +225,13 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
             const float d = group_sum<LPH>(dot4(gv[v], x[u][v]), gmask);
             da[v] = slot == u ? d : da[v];
           }
-        for (int t = PRE; t < cnt; t += 2) {
-          const bool two = t + 1 < cnt;
+        for (int t = PRE; t < cnt_max; t += 2) {
           const int j0 = __shfl_sync(gmask, j, t, LPH), j1 = __shfl_sync(gmask, j, t + 1, LPH);
           float4 x0[V], x1[V];
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            x0[v] = ldg4(hb + (unsigned)j0 * F + 4 * v * LPR);
-            x1[v] = two ? ldg4(hb + (unsigned)j1 * F + 4 * v * LPR) : f4zero();
+            x0[v] = t < cnt ? ldg4(hb + (unsigned)j0 * F + 4 * v * LPR) : f4zero();
+            x1[v] = t + 1 < cnt ? ldg4(hb + (unsigned)j1 * F + 4 * v * LPR) : f4zero();
           }
 #pragma unroll
           for (int v = 0; v < V; ++v) {
@@ -242,7 +251,7 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
       for (int v = 0; v < V; ++v) {
         const float D = group_sum<LPH>(S1[v], gmask);
         const float T2 = group_sum<LPH>(S2[v], gmask), T3 = group_sum<LPH>(S3[v], gmask);
-        if (slot == 0) {
+        if (slot == 0 && row_ok) {
           const size_t o = (size_t)r * H + RM::head(lig, v);
           st4(rec + o * 4, make_float4(sd[v], mi[v], il[v], D));
           ds_dst[o] = T2 - D * T3;
@@ -275,7 +284,7 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
   __shared__ float red[kWarps * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  constexpr unsigned gmask = 0xffffffffu;          // warp-uniform control flow, full-mask shuffles
   constexpr unsigned rows_per_cta = kWarps * RPW;
 
   float4 as[V], ad[V], accs[V], accd[V];
@@ -288,13 +297,16 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
   }
 
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
-    const unsigned r = r0 + warp * RPW + sub;
-    if (r < M) {
+    const unsigned r_raw = r0 + warp * RPW + sub;
+    const bool row_ok = r_raw < M;
+    const unsigned r = row_ok ? r_raw : M - 1;
+    {
       unsigned b, jn;
       divmod(r, N, magic, b, jn);
       const float* gb = g + (size_t)b * N * F + 4 * lig;
       const float* recb = rec + (size_t)b * N * H * 4;
       const int beg = __ldg(rowptr_t + jn), deg = __ldg(rowptr_t + jn + 1) - beg;
+      const int deg_max = __reduce_max_sync(gmask, deg);
       float4 hv[V], dacc[V];
       float ss[V], dsrc[V];
 #pragma unroll
@@ -304,10 +316,11 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
         dacc[v] = f4zero();
         dsrc[v] = 0.f;
       }
-      for (int e0 = 0; e0 < deg; e0 += LPH) {
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
         const bool valid = e0 + slot < deg;
         const int i = valid ? __ldg(col_t + beg + e0 + slot) : 0;
         const int cnt = min(LPH, deg - e0);
+        const int cnt_max = min(LPH, deg_max - e0);
         float4 gx[PRE][V];                         // first PRE target-gradient rows, in flight during the alpha math
 #pragma unroll
         for (int u = 0; u < PRE; ++u) {
@@ -333,14 +346,13 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
             da[v] = slot == u ? d : da[v];
             fma4(dacc[v], __shfl_sync(gmask, alpha[v], u, LPH), gx[u][v]);      // alpha = 0 beyond cnt
           }
-        for (int t = PRE; t < cnt; t += 2) {
-          const bool two = t + 1 < cnt;
+        for (int t = PRE; t < cnt_max; t += 2) {
           const int i0 = __shfl_sync(gmask, i, t, LPH), i1 = __shfl_sync(gmask, i, t + 1, LPH);
           float4 g0[V], g1[V];
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            g0[v] = ldg4(gb + (unsigned)i0 * F + 4 * v * LPR);
-            g1[v] = two ? ldg4(gb + (unsigned)i1 * F + 4 * v * LPR) : f4zero();
+            g0[v] = t < cnt ? ldg4(gb + (unsigned)i0 * F + 4 * v * LPR) : f4zero();
+            g1[v] = t + 1 < cnt ? ldg4(gb + (unsigned)i1 * F + 4 * v * LPR) : f4zero();
           }
 #pragma unroll
           for (int v = 0; v < V; ++v) {
@@ -348,8 +360,8 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
             const float d1 = group_sum<LPH>(dot4(g1[v], hv[v]), gmask);
             da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
             const float a0 = __shfl_sync(gmask, alpha[v], t, LPH), a1 = __shfl_sync(gmask, alpha[v], t + 1, LPH);
-            fma4(dacc[v], a0, g0[v]);
-            fma4(dacc[v], two ? a1 : 0.f, g1[v]);
+            fma4(dacc[v], a0, g0[v]);               // alpha is 0 in the idle slots
+            fma4(dacc[v], t + 1 < LPH ? a1 : 0.f, g1[v]);
           }
         }
 #pragma unroll
@@ -361,9 +373,11 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
         const float dd = __ldg(ds_dst + (size_t)r * H + RM::head(lig, v));
         fma4(dacc[v], ds, as[v]);
         fma4(dacc[v], dd, ad[v]);
-        st4(dh + (size_t)r * F + 4 * RM::chunk(lig, v), dacc[v]);
-        fma4(accs[v], ds, hv[v]);
-        fma4(accd[v], dd, hv[v]);
+        if (row_ok) {
+          st4(dh + (size_t)r * F + 4 * RM::chunk(lig, v), dacc[v]);
+          fma4(accs[v], ds, hv[v]);
+          fma4(accd[v], dd, hv[v]);
+        }
       }
     }
   }
@@ -404,9 +418,32 @@ static int launch_bwd(const int* rowptr, const int* col, const int* rowptr_t, co
   return check_launch("gat_agg_bwd_p2");
 }
 
+// snapshot-tile (TMA-staged) variants, gat_agg_tile.cu
+bool fwd_tile_eligible(unsigned N, unsigned H, unsigned C, unsigned E1);
+int gat_agg_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
+                     const float* s_dst, const float* bias, float* out, float* m, float* l, unsigned B, unsigned N,
+                     int H, int C, int relu, cudaStream_t st);
+
+// Batches below this use the gather kernels (a snapshot-per-CTA grid would leave SMs idle).
+// GATRES_TILE_MIN_B overrides (set it huge to disable the tile kernels).
+static long long g_tile_min_batch = -1;
+static long long tile_min_batch() {
+  if (g_tile_min_batch < 0) {
+    const char* e = getenv("GATRES_TILE_MIN_B");
+    g_tile_min_batch = e ? atoll(e) : 64;
+  }
+  return g_tile_min_batch;
+}
+
 }  // namespace gatres
 
 using namespace gatres;
+
+extern "C" int64_t gatres_set_tile_min_batch(int64_t min_batch) {
+  const long long prev = tile_min_batch();
+  if (min_batch >= 0) g_tile_min_batch = min_batch;
+  return prev;
+}
 
 #define GATRES_DISPATCH_HC(H, C, CALL)                                          \
   do {                                                                          \
@@ -422,13 +459,18 @@ using namespace gatres;
 
 extern "C" int gatres_gat_agg_fwd(const int32_t* rowptr, const int32_t* col, const float* h, const float* s_src,
                                   const float* s_dst, const float* bias, float* out, float* m, float* l,
-                                  int64_t B, int32_t N, int32_t H, int32_t C, int32_t relu, void* stream) {
+                                  int64_t B, int32_t N, int32_t E1, int32_t H, int32_t C, int32_t relu,
+                                  void* stream) {
   GATRES_REQUIRE(B >= 0 && N > 0, "gat_agg_fwd: bad B=%lld N=%d", (long long)B, N);
   GATRES_REQUIRE(B * (int64_t)N < (1ll << 31), "gat_agg_fwd: B*N must be < 2^31 rows");
   GATRES_REQUIRE((int64_t)N * H * C < (1ll << 31), "gat_agg_fwd: one snapshot must be < 2^31 floats");
   GATRES_REQUIRE((m == nullptr) == (l == nullptr), "gat_agg_fwd: m and l must both be given or both NULL");
   if (B == 0) return GATRES_OK;
   const unsigned M = (unsigned)(B * N);
+  if (E1 > 0 && (H == 1 || H == 2) && (C == 32 || C == 64 || C == 128) && B >= tile_min_batch() &&
+      fwd_tile_eligible((unsigned)N, (unsigned)H, (unsigned)C, (unsigned)E1))
+    return gat_agg_fwd_tile(rowptr, col, (unsigned)E1, h, s_src, s_dst, bias, out, m, l, (unsigned)B, (unsigned)N, H, C,
+                            relu, as_stream(stream));
 #define CALL(HH, CC) launch_fwd<HH, CC>(rowptr, col, h, s_src, s_dst, bias, out, m, l, M, (unsigned)N, relu, as_stream(stream))
   GATRES_DISPATCH_HC(H, C, CALL);
 #undef CALL
@@ -439,7 +481,9 @@ extern "C" int gatres_gat_agg_bwd(const int32_t* rowptr, const int32_t* col, con
                                   const float* s_dst, const float* m, const float* l, const float* att_src,
                                   const float* att_dst, float* rec, float* ds_dst, float* dh, float* partial,
                                   int64_t P, int32_t slots, int64_t off_att_src, int64_t off_att_dst,
-                                  int64_t off_bias, int64_t B, int32_t N, int32_t H, int32_t C, void* stream) {
+                                  int64_t off_bias, int64_t B, int32_t N, int32_t E1, int32_t H, int32_t C,
+                                  void* stream) {
+  (void)E1;
   GATRES_REQUIRE(B > 0 && N > 0, "gat_agg_bwd: bad B=%lld N=%d", (long long)B, N);
   GATRES_REQUIRE(B * (int64_t)N < (1ll << 31), "gat_agg_bwd: B*N must be < 2^31 rows");
   GATRES_REQUIRE((int64_t)N * H * C < (1ll << 31), "gat_agg_bwd: one snapshot must be < 2^31 floats");

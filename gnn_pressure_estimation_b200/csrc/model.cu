@@ -126,10 +126,10 @@ extern "C" int gatres_forward(const gatres_model_desc* d, const float* params, c
     float* xo = train ? saved + sl.xout(k) : (x0 == xa ? xb : xa);
     TRY(gatres_linear_att_fwd(x0, params + pl.c1_W(k), params + pl.c1_as(k), params + pl.c1_ad(k), h1, ss1, sd1, M,
                               C, 2, C, stream));
-    TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h1, ss1, sd1, params + pl.c1_b(k), y1, m1, l1, d->B, N, 2, C, 1, stream));
+    TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h1, ss1, sd1, params + pl.c1_b(k), y1, m1, l1, d->B, N, d->E1, 2, C, 1, stream));
     TRY(gatres_linear_att_fwd(y1, params + pl.c2_W(k), params + pl.c2_as(k), params + pl.c2_ad(k), h2, ss2, sd2, M,
                               2 * C, 1, C, stream));
-    TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h2, ss2, sd2, params + pl.c2_b(k), z, m2, l2, d->B, N, 1, C, 0, stream));
+    TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h2, ss2, sd2, params + pl.c2_b(k), z, m2, l2, d->B, N, d->E1, 1, C, 0, stream));
     TRY(gatres_mean_res_fwd(d->rowptr, d->col, z, x0, xo, d->B, N, C, stream));
     x0 = xo;
   }
@@ -173,14 +173,14 @@ extern "C" int gatres_backward(const gatres_model_desc* d, const float* params, 
     TRY(gatres_gat_agg_bwd(d->rowptr, d->col, d->rowptr_t, d->col_t, dz, saved + sl.h2(k), saved + sl.ss2(k),
                            saved + sl.sd2(k), saved + sl.m2(k), saved + sl.l2(k), params + pl.c2_as(k),
                            params + pl.c2_ad(k), rec, dsd, dh2, partial, P, S, pl.c2_as(k), pl.c2_ad(k), pl.c2_b(k),
-                           d->B, N, 1, C, stream));
+                           d->B, N, d->E1, 1, C, stream));
     TRY(gatres_linear_bwd(dh2, saved + sl.y1(k), params + pl.c2_W(k), nullptr, saved + sl.y1(k), dy1, partial, P, S,
                           pl.c2_W(k), M, 2 * C, 1, C, stream));
     // conv1 (heads=2, concat) — dy1 already carries the ReLU mask of y1
     TRY(gatres_gat_agg_bwd(d->rowptr, d->col, d->rowptr_t, d->col_t, dy1, saved + sl.h1(k), saved + sl.ss1(k),
                            saved + sl.sd1(k), saved + sl.m1(k), saved + sl.l1(k), params + pl.c1_as(k),
                            params + pl.c1_ad(k), rec, dsd, dh1, partial, P, S, pl.c1_as(k), pl.c1_ad(k), pl.c1_b(k),
-                           d->B, N, 2, C, stream));
+                           d->B, N, d->E1, 2, C, stream));
     // dx0 = dh1 W1 + (residual branch gA), masked by the previous block's ReLU (none before block 0)
     TRY(gatres_linear_bwd(dh1, x0, params + pl.c1_W(k), gA, k > 0 ? x0 : nullptr, gB, partial, P, S, pl.c1_W(k), M, C,
                           2, C, stream));

@@ -115,7 +115,7 @@ def _gat_agg_fwd(rowptr: Tensor, col: Tensor, h: Tensor, s_src: Tensor, s_dst: T
     m = torch.empty(M, H, dtype=torch.float32, device=h.device) if save_stats else None
     l = torch.empty(M, H, dtype=torch.float32, device=h.device) if save_stats else None
     call("gatres_gat_agg_fwd", ptr(rowptr), ptr(col), ptr(h), ptr(s_src.contiguous()), ptr(s_dst.contiguous()),
-         ptr(_f32(bias, "bias")), ptr(out), ptr(m), ptr(l), B, N, H, C_, int(relu), stream())
+         ptr(_f32(bias, "bias")), ptr(out), ptr(m), ptr(l), B, N, col.numel(), H, C_, int(relu), stream())
     empty = out.new_empty(0)
     return [out, m if save_stats else empty, l if save_stats else empty]
 
@@ -139,7 +139,7 @@ def _gat_agg_bwd(rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor, g
     call("gatres_gat_agg_bwd", ptr(rowptr), ptr(col), ptr(rowptr_t), ptr(col_t), ptr(g), ptr(h),
          ptr(s_src.contiguous()), ptr(s_dst.contiguous()), ptr(m.contiguous()), ptr(l.contiguous()),
          ptr(_f32(att_src, "att")), ptr(_f32(att_dst, "att")), ptr(rec), ptr(ds_dst), ptr(dh), ptr(partial),
-         P, S, 0, F, 2 * F, B, N, H, C_, stream())
+         P, S, 0, F, 2 * F, B, N, col.numel(), H, C_, stream())
     grads = torch.empty(P, dtype=torch.float32, device=dev)
     call("gatres_reduce_partials", ptr(partial), P, S, 0, P, ptr(grads), stream())
     return [dh, grads[:F].view(1, H, C_), grads[F:2 * F].view(1, H, C_), grads[2 * F:]]
@@ -201,7 +201,7 @@ def _desc(num_blocks: int, nc: int, N: int, B: int, rowptr: Tensor, col: Tensor,
           poison: Optional[Tensor], deterministic: bool = False) -> ModelDesc:
     """slots > 0: parameter gradients via per-CTA partial rows + a fixed-order reduction (bitwise
     reproducible, small grids); slots = 0: atomic accumulation into the gradient buffer (full grids)."""
-    return ModelDesc(num_blocks, nc, N, grad_slots(B * N) if deterministic else 0, B, ptr(rowptr), ptr(col),
+    return ModelDesc(num_blocks, nc, N, grad_slots(B * N) if deterministic else 0, col.numel(), 0, B, ptr(rowptr), ptr(col),
                      ptr(rowptr_t), ptr(col_t), ptr(poison))
 
 

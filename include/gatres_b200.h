@@ -89,6 +89,14 @@ int gatres_csr_build(const int64_t* edge_index, int64_t E, int32_t N,
 int gatres_check_replicated(const int64_t* edge_index_batch, const int64_t* edge_index_tmpl,
                             int64_t B, int64_t E, int32_t N, int32_t* mismatch, void* stream);
 
+/*
+ * Kernel-selection knob: batches of at least `min_batch` snapshots use the TMA-staged
+ * snapshot-tile aggregation kernels when the graph fits (default 64, or the
+ * GATRES_TILE_MIN_B environment variable); smaller batches use the gather kernels.
+ * Pass a negative value to only query.  Returns the previous value.
+ */
+int64_t gatres_set_tile_min_batch(int64_t min_batch);
+
 /* --------------------------------------------------------------- operators */
 
 /*
@@ -107,11 +115,14 @@ int gatres_linear_att_fwd(const float* x, const float* W, const float* att_src, 
  * + bias, optional ReLU (the `.relu()` at GraphModels.py:464).
  * m/l ([M,H], may be NULL) receive the softmax row max and exp-sum for the
  * recompute-based backward.  concat=0 requires H=1 (mean over one head).
+ * E1 = number of CSR entries (rowptr[N], known to the host from gatres_csr_build's
+ * info[1]); when E1 > 0 and one snapshot's [N, H*C] slab fits in shared memory the
+ * TMA-staged snapshot-tile kernel is used, otherwise (or with E1 = 0) the gather kernel.
  */
 int gatres_gat_agg_fwd(const int32_t* rowptr, const int32_t* col,
                        const float* h, const float* s_src, const float* s_dst, const float* bias,
                        float* out, float* m, float* l,
-                       int64_t B, int32_t N, int32_t H, int32_t C, int32_t relu, void* stream);
+                       int64_t B, int32_t N, int32_t E1, int32_t H, int32_t C, int32_t relu, void* stream);
 
 /*
  * Backward of gatres_gat_agg_fwd w.r.t. h, s (folded into dh), att_src, att_dst,
@@ -132,7 +143,7 @@ int gatres_gat_agg_bwd(const int32_t* rowptr, const int32_t* col,
                        float* rec, float* ds_dst, float* dh,
                        float* partial, int64_t P, int32_t slots,
                        int64_t off_att_src, int64_t off_att_dst, int64_t off_bias,
-                       int64_t B, int32_t N, int32_t H, int32_t C, void* stream);
+                       int64_t B, int32_t N, int32_t E1, int32_t H, int32_t C, void* stream);
 
 /*
  * SimpleConv(aggr="mean")(z) + x0, ReLU  (GraphModels.py:466-467).  Uses the
@@ -186,7 +197,9 @@ typedef struct gatres_model_desc {
   int32_t num_blocks;            /* GATResMeanConv(num_blocks, nc), GraphModels.py:472 */
   int32_t nc;
   int32_t N;                     /* template nodes */
-  int32_t slots;                 /* CTAs used by gradient-producing kernels (= rows of `partial`) */
+  int32_t slots;                 /* > 0: deterministic gradient reduction over `slots` partial rows; 0: atomics */
+  int32_t E1;                    /* CSR entries (rowptr[N] = edges + N self loops) */
+  int32_t reserved;
   int64_t B;                     /* snapshots in this batch */
   const int32_t* rowptr;         /* in-edge CSR incl. self loops (gatres_csr_build) */
   const int32_t* col;

@@ -36,16 +36,16 @@ def test_abi_version_and_param_count():
 
 def test_argument_validation_reports_errors():
     lib = _lib.load()
-    rc = lib.gatres_gat_agg_fwd(None, None, None, None, None, None, None, None, None, 1, 4, 3, 32, 0, None)
+    rc = lib.gatres_gat_agg_fwd(None, None, None, None, None, None, None, None, None, 1, 4, 8, 3, 32, 0, None)
     assert rc == -1 and b"unsupported" in lib.gatres_last_error()
-    d = _lib.ModelDesc(15, 48, 388, 1, 8, None, None, None, None, None)
+    d = _lib.ModelDesc(15, 48, 388, 1, 1246, 0, 8, None, None, None, None, None)
     assert lib.gatres_saved_floats(ctypes.byref(d)) == -1
 
 
 def test_workspace_sizes():
     lib = _lib.load()
     one = ctypes.c_void_p(16)
-    d = _lib.ModelDesc(15, 32, 388, 97, 32, one, one, one, one, None)
+    d = _lib.ModelDesc(15, 32, 388, 97, 1246, 0, 32, one, one, one, one, None)
     M = 32 * 388
     assert lib.gatres_saved_floats(ctypes.byref(d)) == M * 32 + 15 * (6 * M * 32 + 12 * M)
     assert lib.gatres_scratch_floats(ctypes.byref(d), 0) == 8 * M * 32 + 4 * M

@@ -97,11 +97,22 @@ GRAPHS = {
 }
 
 
+@pytest.fixture(params=["gather", "tile"])
+def kernel_variant(request):
+    """run a test with the gather kernels (default for small batches) and with the
+    TMA-staged snapshot-tile kernels forced on (used for batches >= 64 by default)."""
+    from gnn_pressure_estimation_b200 import _lib
+    lib = _lib.load()
+    prev = lib.gatres_set_tile_min_batch(1 if request.param == "tile" else 1 << 40)
+    yield request.param
+    lib.gatres_set_tile_min_batch(prev)
+
+
 @pytest.mark.parametrize("graph,B", [("tiny", 1), ("tiny", 5), ("ctown", 3), ("directed", 2)])
 @pytest.mark.parametrize("H,C,fin,concat,relu", [(2, 32, 32, True, True), (1, 32, 64, False, False),
                                                  (2, 64, 64, True, True), (1, 64, 128, False, False),
                                                  (2, 128, 128, True, False), (1, 128, 256, False, True)])
-def test_gat_conv_forward_backward(graph, B, H, C, fin, concat, relu, dev):
+def test_gat_conv_forward_backward(graph, B, H, C, fin, concat, relu, dev, kernel_variant):
     from gnn_pressure_estimation_b200 import ops as gops
     if graph == "directed":
         n = 97
@@ -188,7 +199,7 @@ def _cuda_model_from_case(c, G, dev):
 @pytest.mark.parametrize("deterministic", [False, True])
 @pytest.mark.parametrize("name", ["tiny_2b_32c_B3", "ctown_small_15b_32c_B8", "ctown_mid_3b_64c_B2",
                                   "ctown_large_25b_128c_B2"])
-def test_model_matches_golden(name, deterministic, dev, G):
+def test_model_matches_golden(name, deterministic, dev, G, kernel_variant):
     """reference caller semantics (train.py:174-185): mask applied by the caller, MSE on masked nodes."""
     c = load_case(name)
     model, _ = _cuda_model_from_case(c, G, dev)
