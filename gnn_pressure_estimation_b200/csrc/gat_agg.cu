@@ -419,6 +419,12 @@ static int launch_bwd(const int* rowptr, const int* col, const int* rowptr_t, co
 }
 
 // snapshot-tile (TMA-staged) variants, gat_agg_tile.cu
+bool bwd_tile_eligible(unsigned N, unsigned H, unsigned C, unsigned E1);
+int gat_agg_bwd_tile(const int* rowptr, const int* col, const int* rowptr_t, const int* col_t, unsigned E1,
+                     const float* g, const float* h, const float* s_src, const float* s_dst, const float* m,
+                     const float* l, const float* att_src, const float* att_dst, float* dh, float* grads,
+                     long long off_as, long long off_ad, long long off_b, unsigned B, unsigned N, int H, int C,
+                     cudaStream_t st);
 bool fwd_tile_eligible(unsigned N, unsigned H, unsigned C, unsigned E1);
 int gat_agg_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
                      const float* s_dst, const float* bias, float* out, float* m, float* l, unsigned B, unsigned N,
@@ -483,13 +489,18 @@ extern "C" int gatres_gat_agg_bwd(const int32_t* rowptr, const int32_t* col, con
                                   int64_t P, int32_t slots, int64_t off_att_src, int64_t off_att_dst,
                                   int64_t off_bias, int64_t B, int32_t N, int32_t E1, int32_t H, int32_t C,
                                   void* stream) {
-  (void)E1;
   GATRES_REQUIRE(B > 0 && N > 0, "gat_agg_bwd: bad B=%lld N=%d", (long long)B, N);
   GATRES_REQUIRE(B * (int64_t)N < (1ll << 31), "gat_agg_bwd: B*N must be < 2^31 rows");
   GATRES_REQUIRE((int64_t)N * H * C < (1ll << 31), "gat_agg_bwd: one snapshot must be < 2^31 floats");
   GATRES_REQUIRE(off_att_src % 4 == 0 && off_att_dst % 4 == 0 && off_bias % 4 == 0 && P % 4 == 0,
                  "gat_agg_bwd: partial row stride and parameter offsets must be multiples of 4 floats");
   const unsigned M = (unsigned)(B * N);
+  // fused snapshot-tile backward: atomic-accumulation mode only (it adds straight into the gradient buffer)
+  if (slots <= 0 && E1 > 0 && (H == 1 || H == 2) && (C == 32 || C == 64 || C == 128) && B >= tile_min_batch() &&
+      bwd_tile_eligible((unsigned)N, (unsigned)H, (unsigned)C, (unsigned)E1))
+    return gat_agg_bwd_tile(rowptr, col, rowptr_t, col_t, (unsigned)E1, g, h, s_src, s_dst, m, l, att_src, att_dst, dh,
+                            partial, (long long)off_att_src, (long long)off_att_dst, (long long)off_bias, (unsigned)B,
+                            (unsigned)N, H, C, as_stream(stream));
 #define CALL(HH, CC)                                                                                              \
   launch_bwd<HH, CC>(rowptr, col, rowptr_t, col_t, g, h, s_src, s_dst, m, l, att_src, att_dst, rec, ds_dst, dh,   \
                      partial, (long long)P, slots, (long long)off_att_src, (long long)off_att_dst,                \

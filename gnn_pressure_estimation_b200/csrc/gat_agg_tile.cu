@@ -38,7 +38,7 @@ struct FwdTilePlan {
 };
 
 template <int H, int C, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
 gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, unsigned E1,
                         const float* __restrict__ h, const float* __restrict__ s_src,
                         const float* __restrict__ s_dst, const float* __restrict__ bias,
@@ -213,6 +213,309 @@ int gat_agg_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float
   T(1, 128);
 #undef T
   set_error("gat_agg_fwd_tile: unsupported (H=%d, C=%d)", H, C);
+  return GATRES_ERR_ARG;
+}
+
+}  // namespace gatres
+
+// =============================================================================
+// Fused backward (pass 1 + pass 2 of gat_agg.cu) for one snapshot per CTA.
+// Both feature slabs of the snapshot (h and g = dL/d(out)) and its per-node scalars
+// are staged by TMA; pass 1 leaves D and ds_dst in shared memory, so the `rec`
+// round trip through HBM and one kernel launch disappear, and h / g are read from
+// DRAM once instead of twice (12*S + 28*H algorithmic bytes per node instead of
+// 20*S + 52*H).
+// =============================================================================
+namespace gatres {
+
+struct BwdTilePlan {
+  uint32_t slab, sc, hs_off, gs_off, ss_off, sd_off, mm_off, ll_off, dd_off, dsd_off, rpi_off, ci_off, rpo_off,
+      co_off, bar_off, total, tx_bytes;
+  __host__ __device__ BwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1) {
+    slab = N * F * 4u;
+    sc = N * H * 4u;
+    hs_off = 0;
+    gs_off = slab;
+    ss_off = 2u * slab;
+    sd_off = ss_off + sc;
+    mm_off = sd_off + sc;
+    ll_off = mm_off + sc;
+    dd_off = ll_off + sc;
+    dsd_off = dd_off + sc;
+    rpi_off = dsd_off + sc;
+    const uint32_t rp = ((N + 1u) * 4u + 15u) & ~15u, cl = (E1 * 2u + 15u) & ~15u;
+    ci_off = rpi_off + rp;
+    rpo_off = ci_off + cl;
+    co_off = rpo_off + rp;
+    bar_off = co_off + cl;
+    total = bar_off + 16u;
+    tx_bytes = 2u * slab + 4u * sc;
+  }
+};
+
+template <int H, int C, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
+gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                        const int* __restrict__ rowptr_t, const int* __restrict__ col_t, unsigned E1,
+                        const float* __restrict__ g, const float* __restrict__ h,
+                        const float* __restrict__ s_src, const float* __restrict__ s_dst,
+                        const float* __restrict__ m, const float* __restrict__ l,
+                        const float* __restrict__ att_src, const float* __restrict__ att_dst,
+                        float* __restrict__ dh, float* __restrict__ grads,
+                        long long off_att_src, long long off_att_dst, long long off_bias,
+                        unsigned B, unsigned N) {
+  using RM = RowMap<H, C>;
+  constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
+  constexpr int kWarpsT = THREADS / 32;
+  constexpr unsigned gmask = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const BwdTilePlan plan(N, F, H, E1);
+  const float* HS = reinterpret_cast<const float*>(smem + plan.hs_off);
+  const float* GS = reinterpret_cast<const float*>(smem + plan.gs_off);
+  const float* SS = reinterpret_cast<const float*>(smem + plan.ss_off);
+  const float* SD = reinterpret_cast<const float*>(smem + plan.sd_off);
+  const float* MM = reinterpret_cast<const float*>(smem + plan.mm_off);
+  const float* LL = reinterpret_cast<const float*>(smem + plan.ll_off);
+  float* DD = reinterpret_cast<float*>(smem + plan.dd_off);
+  float* DSD = reinterpret_cast<float*>(smem + plan.dsd_off);
+  int* rpi = reinterpret_cast<int*>(smem + plan.rpi_off);
+  unsigned short* ci = reinterpret_cast<unsigned short*>(smem + plan.ci_off);
+  int* rpo = reinterpret_cast<int*>(smem + plan.rpo_off);
+  unsigned short* co = reinterpret_cast<unsigned short*>(smem + plan.co_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + plan.bar_off);
+  float* red = reinterpret_cast<float*>(smem);     // reused for the final CTA reduction (slabs are dead by then)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
+
+  auto issue = [&](unsigned bb) {
+    const size_t ro = (size_t)bb * N;
+    mbar_arrive_expect_tx(full, plan.tx_bytes);
+    bulk_g2s(smem + plan.hs_off, h + ro * F, plan.slab, full);
+    bulk_g2s(smem + plan.gs_off, g + ro * F, plan.slab, full);
+    bulk_g2s(smem + plan.ss_off, s_src + ro * H, plan.sc, full);
+    bulk_g2s(smem + plan.sd_off, s_dst + ro * H, plan.sc, full);
+    bulk_g2s(smem + plan.mm_off, m + ro * H, plan.sc, full);
+    bulk_g2s(smem + plan.ll_off, l + ro * H, plan.sc, full);
+  };
+
+  if (tid == 0) {
+    mbar_init(full, 1);
+    mbar_fence_init();
+  }
+  for (unsigned k = tid; k <= N; k += THREADS) { rpi[k] = __ldg(rowptr + k); rpo[k] = __ldg(rowptr_t + k); }
+  for (unsigned k = tid; k < E1; k += THREADS) {
+    ci[k] = (unsigned short)__ldg(col + k);
+    co[k] = (unsigned short)__ldg(col_t + k);
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < B) issue(blockIdx.x);
+
+  float4 as[V], ad[V], accs[V], accd[V], bacc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    as[v] = ldg4(att_src + 4 * RM::chunk(lig, v));
+    ad[v] = ldg4(att_dst + 4 * RM::chunk(lig, v));
+    accs[v] = accd[v] = bacc[v] = f4zero();
+  }
+
+  unsigned it = 0;
+  for (unsigned b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+    mbar_wait(full, it & 1);
+
+    // ---------------- pass 1: per target row, D and ds_dst into shared memory
+    for (unsigned i0 = warp * RPW; i0 < N; i0 += kWarpsT * RPW) {
+      const bool row_ok = i0 + sub < N;
+      const unsigned i = row_ok ? i0 + sub : N - 1;
+      const int beg = rpi[i], deg = rpi[i + 1] - beg;
+      const int deg_max = __reduce_max_sync(gmask, deg);
+      float4 gv[V];
+      float sd[V], mi[V], il[V], S1[V], S2[V], S3[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int hd = RM::head(lig, v);
+        gv[v] = *reinterpret_cast<const float4*>(GS + i * F + 4 * RM::chunk(lig, v));
+        if (row_ok) add4(bacc[v], gv[v]);
+        sd[v] = SD[i * H + hd];
+        mi[v] = MM[i * H + hd];
+        il[v] = 1.f / (LL[i * H + hd] + kSoftmaxEps);
+        S1[v] = S2[v] = S3[v] = 0.f;
+      }
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
+        const bool valid = e0 + slot < deg;
+        const int j = valid ? (int)ci[beg + e0 + slot] : 0;
+        float alpha[V], sl[V], da[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float z = SS[j * H + RM::head(lig, v)] + sd[v];
+          alpha[v] = valid ? __expf(lrelu(z) - mi[v]) * il[v] : 0.f;
+          sl[v] = lrelu_slope(z);
+          da[v] = 0.f;
+        }
+        const int cnt_max = min(LPH, deg_max - e0);
+        for (int t = 0; t < cnt_max; ++t) {
+          const int jt = __shfl_sync(gmask, j, t, LPH);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float4 x = *reinterpret_cast<const float4*>(HS + jt * F + 4 * RM::chunk(lig, v));
+            const float d = group_sum<LPH>(dot4(gv[v], x), gmask);
+            da[v] = slot == t ? d : da[v];
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {             // idle slots have alpha = 0
+          S1[v] = fmaf(alpha[v], da[v], S1[v]);
+          S2[v] = fmaf(alpha[v] * sl[v], da[v], S2[v]);
+          S3[v] = fmaf(alpha[v], sl[v], S3[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float D = group_sum<LPH>(S1[v], gmask);
+        const float T2 = group_sum<LPH>(S2[v], gmask), T3 = group_sum<LPH>(S3[v], gmask);
+        if (slot == 0 && row_ok) {
+          DD[i * H + RM::head(lig, v)] = D;
+          DSD[i * H + RM::head(lig, v)] = T2 - D * T3;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------- pass 2: per source row, dh and the attention-vector gradients
+    for (unsigned j0 = warp * RPW; j0 < N; j0 += kWarpsT * RPW) {
+      const bool row_ok = j0 + sub < N;
+      const unsigned jn = row_ok ? j0 + sub : N - 1;
+      const int beg = rpo[jn], deg = rpo[jn + 1] - beg;
+      const int deg_max = __reduce_max_sync(gmask, deg);
+      float4 hv[V], dacc[V];
+      float ss[V], dsrc[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        hv[v] = *reinterpret_cast<const float4*>(HS + jn * F + 4 * RM::chunk(lig, v));
+        ss[v] = SS[jn * H + RM::head(lig, v)];
+        dacc[v] = f4zero();
+        dsrc[v] = 0.f;
+      }
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
+        const bool valid = e0 + slot < deg;
+        const int i = valid ? (int)co[beg + e0 + slot] : 0;
+        float alpha[V], k2[V], Dt[V], da[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int o = i * H + RM::head(lig, v);
+          const float z = ss[v] + SD[o];
+          alpha[v] = valid ? __fdividef(__expf(lrelu(z) - MM[o]), LL[o] + kSoftmaxEps) : 0.f;
+          k2[v] = alpha[v] * lrelu_slope(z);
+          Dt[v] = DD[o];
+          da[v] = 0.f;
+        }
+        const int cnt_max = min(LPH, deg_max - e0);
+        for (int t = 0; t < cnt_max; ++t) {
+          const int itg = __shfl_sync(gmask, i, t, LPH);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float4 gx = *reinterpret_cast<const float4*>(GS + itg * F + 4 * RM::chunk(lig, v));
+            const float d = group_sum<LPH>(dot4(gx, hv[v]), gmask);
+            da[v] = slot == t ? d : da[v];
+            fma4(dacc[v], __shfl_sync(gmask, alpha[v], t, LPH), gx);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) dsrc[v] = fmaf(k2[v], da[v] - Dt[v], dsrc[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float ds = group_sum<LPH>(dsrc[v], gmask);
+        const float dd = DSD[jn * H + RM::head(lig, v)];
+        fma4(dacc[v], ds, as[v]);
+        fma4(dacc[v], dd, ad[v]);
+        if (row_ok) {
+          st4(dh + ((size_t)b * N + jn) * F + 4 * RM::chunk(lig, v), dacc[v]);
+          fma4(accs[v], ds, hv[v]);
+          fma4(accd[v], dd, hv[v]);
+        }
+      }
+    }
+    __syncthreads();                               // both slabs are free again
+    if (tid == 0) {
+      const unsigned nb = b + gridDim.x;
+      if (nb < B) {
+        fence_proxy_async();
+        issue(nb);
+      }
+    }
+  }
+
+  // ---------------- parameter gradients: CTA reduction, then one atomic add per column chunk
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    float4 accv[3] = {accs[v], accd[v], bacc[v]};
+    const long long offs[3] = {off_att_src, off_att_dst, off_bias};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      __syncthreads();
+      st4(red + tid * 4, accv[q]);
+      __syncthreads();
+      if (tid < LPR) {
+        float4 s = f4zero();
+        for (int w = 0; w < kWarpsT; ++w)
+#pragma unroll
+          for (int sb = 0; sb < 32 / LPR; ++sb) add4(s, *reinterpret_cast<float4*>(red + (w * 32 + sb * LPR + tid) * 4));
+        atomicAdd(reinterpret_cast<float4*>(grads + offs[q] + 4 * (tid + v * LPR)), s);
+      }
+    }
+  }
+}
+
+template <int H, int C>
+static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_t, const int* col_t, unsigned E1,
+                           const float* g, const float* h, const float* s_src, const float* s_dst, const float* m,
+                           const float* l, const float* att_src, const float* att_dst, float* dh, float* grads,
+                           long long off_as, long long off_ad, long long off_b, unsigned B, unsigned N,
+                           cudaStream_t st) {
+  const BwdTilePlan plan(N, H * C, H, E1);
+  unsigned per_sm = (unsigned)((227u * 1024u) / (plan.total + 1024u));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  unsigned grid = (unsigned)sm_count() * per_sm;
+  if (grid > B) grid = B;
+#define LAUNCH(THR)                                                                                               \
+  do {                                                                                                            \
+    auto kern = gat_agg_bwd_tile_kernel<H, C, THR>;                                                               \
+    static uint32_t configured = 0;                                                                               \
+    if (configured < plan.total) {                                                                                \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
+        return check_launch("gat_agg_bwd_tile: smem attribute");                                                  \
+      configured = plan.total;                                                                                    \
+    }                                                                                                             \
+    kern<<<grid, THR, plan.total, st>>>(rowptr, col, rowptr_t, col_t, E1, g, h, s_src, s_dst, m, l, att_src,      \
+                                        att_dst, dh, grads, off_as, off_ad, off_b, B, N);                         \
+  } while (0)
+  if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);
+#undef LAUNCH
+  return check_launch("gat_agg_bwd_tile");
+}
+
+bool bwd_tile_eligible(unsigned N, unsigned H, unsigned C, unsigned E1) {
+  const BwdTilePlan plan(N, H * C, H, E1);
+  return (N * H) % 4u == 0 && N < 65536u && plan.total <= 227u * 1024u && plan.slab >= 1024u * 16u && (H * C) <= 128;
+}
+
+int gat_agg_bwd_tile(const int* rowptr, const int* col, const int* rowptr_t, const int* col_t, unsigned E1,
+                     const float* g, const float* h, const float* s_src, const float* s_dst, const float* m,
+                     const float* l, const float* att_src, const float* att_dst, float* dh, float* grads,
+                     long long off_as, long long off_ad, long long off_b, unsigned B, unsigned N, int H, int C,
+                     cudaStream_t st) {
+#define T(HH, CC)                                                                                                 \
+  if (H == HH && C == CC)                                                                                         \
+  return launch_bwd_tile<HH, CC>(rowptr, col, rowptr_t, col_t, E1, g, h, s_src, s_dst, m, l, att_src, att_dst, dh, \
+                                 grads, off_as, off_ad, off_b, B, N, st)
+  T(1, 32);
+  T(2, 32);
+  T(1, 64);
+  T(2, 64);
+  T(1, 128);
+#undef T
+  set_error("gat_agg_bwd_tile: unsupported (H=%d, C=%d)", H, C);
   return GATRES_ERR_ARG;
 }
 

@@ -130,18 +130,15 @@ def _gat_agg_bwd(rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor, g
     g, h = _f32(g, "gat_agg_bwd"), _f32(h, "gat_agg_bwd")
     M, F = B * N, H * C_
     dev = h.device
-    S = grad_slots(M)
     P = 3 * F                                   # [datt_src | datt_dst | dbias], multiple of 4
-    partial = torch.empty(S, P, dtype=torch.float32, device=dev)
+    grads = torch.zeros(P, dtype=torch.float32, device=dev)      # atomic accumulation target (slots = 0)
     rec = torch.empty(M, H, 4, dtype=torch.float32, device=dev)
     ds_dst = torch.empty(M, H, dtype=torch.float32, device=dev)
     dh = torch.empty(M, F, dtype=torch.float32, device=dev)
     call("gatres_gat_agg_bwd", ptr(rowptr), ptr(col), ptr(rowptr_t), ptr(col_t), ptr(g), ptr(h),
          ptr(s_src.contiguous()), ptr(s_dst.contiguous()), ptr(m.contiguous()), ptr(l.contiguous()),
-         ptr(_f32(att_src, "att")), ptr(_f32(att_dst, "att")), ptr(rec), ptr(ds_dst), ptr(dh), ptr(partial),
-         P, S, 0, F, 2 * F, B, N, col.numel(), H, C_, stream())
-    grads = torch.empty(P, dtype=torch.float32, device=dev)
-    call("gatres_reduce_partials", ptr(partial), P, S, 0, P, ptr(grads), stream())
+         ptr(_f32(att_src, "att")), ptr(_f32(att_dst, "att")), ptr(rec), ptr(ds_dst), ptr(dh), ptr(grads),
+         P, 0, 0, F, 2 * F, B, N, col.numel(), H, C_, stream())
     return [dh, grads[:F].view(1, H, C_), grads[F:2 * F].view(1, H, C_), grads[2 * F:]]
 
 
