@@ -33,6 +33,34 @@ int sm_count();
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------
+// Every kernel of the step is launched with the programmatic-stream-serialization
+// attribute: it may start (and run its prologue: smem carve-up, weight / CSR staging,
+// barrier init) while its predecessor is still draining, and blocks in pdl_wait()
+// until the predecessor's memory is visible.  Only data that is constant within a
+// step (parameters, CSR) may be touched before pdl_wait().
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface in check_launch()
+}
+#endif
+
 // ------------------------------------------------------------------ device
 __device__ __forceinline__ float lrelu(float z) { return z > 0.f ? z : kNegSlope * z; }
 __device__ __forceinline__ float lrelu_slope(float z) { return z > 0.f ? 1.f : kNegSlope; }

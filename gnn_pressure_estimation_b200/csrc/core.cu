@@ -1,6 +1,7 @@
 // Error reporting, device queries and the caller-side fused kernels
 // (mask, masked MSE, Adam) of libgatres_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gatres {
@@ -21,6 +22,15 @@ int check_launch(const char* what) {
   return GATRES_ERR_CUDA;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GATRES_PDL");
+    v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int sm_count() {
   static int cached = 0;
   if (cached > 0) return cached;
@@ -37,6 +47,8 @@ int sm_count() {
 // x_masked = mask ? 0 : x   (train.py:174  data.x[batch_mask] = 0)
 __global__ void __launch_bounds__(256)
 apply_mask_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, float* __restrict__ out, size_t M) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x)
     out[i] = mask[i] ? 0.f : x[i];
 }
@@ -46,6 +58,8 @@ __global__ void __launch_bounds__(256)
 masked_mse_kernel(const float* __restrict__ out, const float* __restrict__ y, const uint8_t* __restrict__ mask,
                   size_t M, float inv_count, float* __restrict__ d_out, float* __restrict__ partial_loss) {
   __shared__ float red[kWarps];
+  pdl_launch_dependents();
+  pdl_wait();
   float s = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
     const float d = mask[i] ? out[i] - y[i] : 0.f;
@@ -65,6 +79,8 @@ masked_mse_kernel(const float* __restrict__ out, const float* __restrict__ y, co
 __global__ void __launch_bounds__(256)
 final_loss_kernel(const float* __restrict__ partial_loss, int n, float inv_count, float* __restrict__ loss) {
   __shared__ float red[kWarps];
+  pdl_launch_dependents();
+  pdl_wait();
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial_loss[i];
   s = group_sum<32>(s, 0xffffffffu);
@@ -77,13 +93,19 @@ final_loss_kernel(const float* __restrict__ partial_loss, int n, float inv_count
   }
 }
 
-__global__ void bump_step_kernel(int* step) { step[0] += 1; }
+__global__ void bump_step_kernel(int* step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  step[0] += 1;
+}
 
 // torch.optim.Adam, single-tensor formulation (no amsgrad, L2 weight decay)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             const int* __restrict__ step, size_t P, float lr, float b1, float b2, float eps, float wd,
             float grad_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float t = (float)__ldg(step);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
@@ -115,7 +137,7 @@ extern "C" int gatres_sm_count(void) { return sm_count(); }
 extern "C" int gatres_apply_mask(const float* x, const uint8_t* mask, float* x_masked, int64_t M, void* stream) {
   GATRES_REQUIRE(M >= 0, "apply_mask: bad M");
   if (M == 0) return GATRES_OK;
-  apply_mask_kernel<<<flat_grid((size_t)M, 8), 256, 0, as_stream(stream)>>>(x, mask, x_masked, (size_t)M);
+  launch_kernel(apply_mask_kernel, dim3(flat_grid((size_t)M, 8)), dim3(256), 0, as_stream(stream), x, mask, x_masked, (size_t)M);
   return check_launch("apply_mask");
 }
 
@@ -125,10 +147,10 @@ extern "C" int gatres_masked_mse(const float* out, const float* y, const uint8_t
   unsigned grid = flat_grid((size_t)M, 4);
   if (grid > 1024) grid = 1024;
   const float inv = 1.f / (float)count;
-  masked_mse_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, y, mask, (size_t)M, inv, d_out, partial_loss);
+  launch_kernel(masked_mse_kernel, dim3(grid), dim3(256), 0, as_stream(stream), out, y, mask, (size_t)M, inv, d_out, partial_loss);
   int rc = check_launch("masked_mse");
   if (rc) return rc;
-  final_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(partial_loss, (int)grid, inv, loss_out);
+  launch_kernel(final_loss_kernel, dim3(1), dim3(256), 0, as_stream(stream), partial_loss, (int)grid, inv, loss_out);
   return check_launch("masked_mse_final");
 }
 
@@ -136,10 +158,10 @@ extern "C" int gatres_adam_step(float* params, const float* grads, float* exp_av
                                 int32_t* step_count, int64_t P, float lr, float beta1, float beta2, float eps,
                                 float weight_decay, float grad_scale, void* stream) {
   GATRES_REQUIRE(P > 0, "adam_step: bad P");
-  bump_step_kernel<<<1, 1, 0, as_stream(stream)>>>(step_count);
+  launch_kernel(bump_step_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_count);
   int rc = check_launch("adam_bump");
   if (rc) return rc;
-  adam_kernel<<<flat_grid((size_t)P, 4), 256, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, step_count,
+  launch_kernel(adam_kernel, dim3(flat_grid((size_t)P, 4)), dim3(256), 0, as_stream(stream), params, grads, exp_avg, exp_avg_sq, step_count,
                                                                       (size_t)P, lr, beta1, beta2, eps, weight_decay,
                                                                       grad_scale);
   return check_launch("adam_step");

@@ -53,6 +53,8 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
   float4 bv[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) bv[v] = ldg4(bias + 4 * RM::chunk(lig, v));
+  pdl_launch_dependents();
+  pdl_wait();                                     // activations of the previous kernel become visible here
 
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     // rows past the end are clamped (their lanes redo the last row and skip the stores) so that every
@@ -174,6 +176,8 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
   float4 bacc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) bacc[v] = f4zero();
+  pdl_launch_dependents();
+  pdl_wait();
 
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r_raw = r0 + warp * RPW + sub;
@@ -295,6 +299,8 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
     accs[v] = f4zero();
     accd[v] = f4zero();
   }
+  pdl_launch_dependents();
+  pdl_wait();
 
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r_raw = r0 + warp * RPW + sub;
@@ -395,7 +401,7 @@ static int launch_fwd(const int* rowptr, const int* col, const float* h, const f
                       const float* bias, float* out, float* m, float* l, unsigned M, unsigned N, int relu,
                       cudaStream_t st) {
   const unsigned grid = row_kernel_grid(M, kWarps * RowMap<H, C>::RPW, 32);
-  gat_agg_fwd_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr, col, h, s_src, s_dst, bias, out, m, l, M, N,
+  launch_kernel(gat_agg_fwd_kernel<H, C>, dim3(grid), dim3(kThreads), 0, st, rowptr, col, h, s_src, s_dst, bias, out, m, l, M, N,
                                                       div_magic(N), relu);
   return check_launch("gat_agg_fwd");
 }
@@ -408,11 +414,11 @@ static int launch_bwd(const int* rowptr, const int* col, const int* rowptr_t, co
                       unsigned M, unsigned N, cudaStream_t st) {
   const int atomic = slots <= 0;
   const unsigned grid = atomic ? row_kernel_grid(M, kWarps * RowMap<H, C>::RPW, 16) : (unsigned)slots;
-  gat_agg_bwd_p1_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr, col, g, h, s_src, s_dst, m, l, rec, ds_dst,
+  launch_kernel(gat_agg_bwd_p1_kernel<H, C>, dim3(grid), dim3(kThreads), 0, st, rowptr, col, g, h, s_src, s_dst, m, l, rec, ds_dst,
                                                          partial, P, off_b, M, N, div_magic(N), atomic);
   int rc = check_launch("gat_agg_bwd_p1");
   if (rc) return rc;
-  gat_agg_bwd_p2_kernel<H, C><<<grid, kThreads, 0, st>>>(rowptr_t, col_t, g, h, s_src, rec, ds_dst, att_src,
+  launch_kernel(gat_agg_bwd_p2_kernel<H, C>, dim3(grid), dim3(kThreads), 0, st, rowptr_t, col_t, g, h, s_src, rec, ds_dst, att_src,
                                                          att_dst, dh, partial, P, off_as, off_ad, M, N,
                                                          div_magic(N), atomic);
   return check_launch("gat_agg_bwd_p2");

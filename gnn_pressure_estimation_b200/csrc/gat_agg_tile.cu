@@ -72,7 +72,9 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   }
   for (unsigned k = tid; k <= N; k += kTileThreads) rp_s[k] = __ldg(rowptr + k);
   for (unsigned k = tid; k < E1; k += kTileThreads) col_s[k] = __ldg(col + k);
+  pdl_launch_dependents();
   __syncthreads();
+  pdl_wait();                                     // CSR staging above overlapped the previous kernel's tail
   if (tid == 0) {
     if (blockIdx.x < B) issue(0, blockIdx.x);
     if (blockIdx.x + gridDim.x < B) issue(1, blockIdx.x + gridDim.x);
@@ -180,7 +182,7 @@ static int launch_fwd_tile(const int* rowptr, const int* col, unsigned E1, const
         return check_launch("gat_agg_fwd_tile: smem attribute");
       configured = plan.total;
     }
-    kern<<<grid, 512, plan.total, st>>>(rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, B, N, relu);
+    launch_kernel(kern, dim3(grid), dim3(512), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, B, N, relu);
   } else {
     auto kern = gat_agg_fwd_tile_kernel<H, C, 1024>;
     static uint32_t configured = 0;
@@ -189,7 +191,7 @@ static int launch_fwd_tile(const int* rowptr, const int* col, unsigned E1, const
         return check_launch("gat_agg_fwd_tile: smem attribute");
       configured = plan.total;
     }
-    kern<<<grid, 1024, plan.total, st>>>(rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, B, N, relu);
+    launch_kernel(kern, dim3(grid), dim3(1024), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, B, N, relu);
   }
   return check_launch("gat_agg_fwd_tile");
 }
@@ -308,9 +310,6 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     ci[k] = (unsigned short)__ldg(col + k);
     co[k] = (unsigned short)__ldg(col_t + k);
   }
-  __syncthreads();
-  if (tid == 0 && blockIdx.x < B) issue(blockIdx.x);
-
   float4 as[V], ad[V], accs[V], accd[V], bacc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
@@ -318,6 +317,10 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     ad[v] = ldg4(att_dst + 4 * RM::chunk(lig, v));
     accs[v] = accd[v] = bacc[v] = f4zero();
   }
+  pdl_launch_dependents();
+  __syncthreads();
+  pdl_wait();
+  if (tid == 0 && blockIdx.x < B) issue(blockIdx.x);
 
   unsigned it = 0;
   for (unsigned b = blockIdx.x; b < B; b += gridDim.x, ++it) {
@@ -487,7 +490,7 @@ static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_
         return check_launch("gat_agg_bwd_tile: smem attribute");                                                  \
       configured = plan.total;                                                                                    \
     }                                                                                                             \
-    kern<<<grid, THR, plan.total, st>>>(rowptr, col, rowptr_t, col_t, E1, g, h, s_src, s_dst, m, l, att_src,      \
+    launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, rowptr_t, col_t, E1, g, h, s_src, s_dst, m, l, att_src,      \
                                         att_dst, dh, grads, off_as, off_ad, off_b, B, N);                         \
   } while (0)
   if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);

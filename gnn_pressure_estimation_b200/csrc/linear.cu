@@ -56,10 +56,8 @@ gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ W,
     }
   };
 
-  unsigned tile = blockIdx.x;
-  if (tile < ntiles) load_tile(tile, 0);
-  cp_async_commit();
-
+  // weights / attention vectors are constant within a step: stage them before the dependency wait
+  pdl_launch_dependents();
   if (MODE == 0) {
     for (int idx = tid; idx < NN * (KK / 4); idx += 256) {
       const int n = idx / (KK / 4), kv = idx % (KK / 4);
@@ -84,6 +82,10 @@ gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ W,
       att_d[jv * 4 + 0] = d.x; att_d[jv * 4 + 1] = d.y; att_d[jv * 4 + 2] = d.z; att_d[jv * 4 + 3] = d.w;
     }
   }
+  pdl_wait();
+  unsigned tile = blockIdx.x;
+  if (tile < ntiles) load_tile(tile, 0);
+  cp_async_commit();
 
   int stage = 0;
   for (; tile < ntiles; tile += gridDim.x) {
@@ -233,6 +235,8 @@ wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* _
 #pragma unroll
     for (int j = 0; j < TKk; ++j) acc[i][j] = 0.f;
 
+  pdl_launch_dependents();
+  pdl_wait();
   unsigned tile = blockIdx.x;
   if (tile < ntiles) load_tile(tile, 0);
   cp_async_commit();
@@ -307,7 +311,7 @@ static int launch_gemm(const float* A, const float* W, const float* e0, const fl
   per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
   unsigned grid = (unsigned)sm_count() * per_sm;
   if (grid > ntiles) grid = ntiles;
-  kern<<<grid, 256, smem, st>>>(A, W, e0, e1, Cout, s0, s1, M);
+  launch_kernel(kern, dim3(grid), dim3(256), smem, st, A, W, e0, e1, Cout, s0, s1, M);
   return check_launch(what);
 }
 
@@ -330,7 +334,7 @@ static int launch_wgrad(const float* dh, const float* x, float* partial, long lo
     grid = (unsigned)sm_count() * 2u;
     if (grid > ntiles) grid = ntiles;
   }
-  kern<<<grid, 256, smem, st>>>(dh, x, partial, P, off_W, M, atomic);
+  launch_kernel(kern, dim3(grid), dim3(256), smem, st, dh, x, partial, P, off_W, M, atomic);
   return check_launch("wgrad");
 }
 
@@ -356,6 +360,8 @@ static int dispatch_gemm(int KK, int NN, const float* A, const float* W, const f
 __global__ void __launch_bounds__(256)
 encoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                    float* __restrict__ out, size_t total4, int nc4) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total4; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t m = idx / nc4;
     const int c = (int)(idx - m * nc4);
@@ -372,6 +378,8 @@ encoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, flo
   __shared__ float red[2 * 256 * 4];
   const int c = threadIdx.x % nc4, rl = threadIdx.x / nc4, rows_per_pass = 256 / nc4;
   float4 aw = f4zero(), ab = f4zero();
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t m = (size_t)blockIdx.x * rows_per_pass + rl; m < M; m += (size_t)gridDim.x * rows_per_pass) {
     const float4 gv = ldg4_stream(g + m * (size_t)(nc4 * 4) + 4 * c);
     fma4(aw, __ldg(x + m), gv);
@@ -400,6 +408,8 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, lig = lane % LPR;
   const float4 wv = ldg4(w + 4 * lig);
   const float bias = __ldg(b);
+  pdl_launch_dependents();
+  pdl_wait();
   const bool bad = poison != nullptr && __ldg(poison) != 0;
   constexpr unsigned rows_per_cta = kWarps * RPW;
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
@@ -424,6 +434,9 @@ decoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, con
   const float4 wv = ldg4(w + 4 * lig);
   float4 aw = f4zero();
   float ab = 0.f;
+  pdl_launch_dependents();
+  pdl_wait();
+
   constexpr unsigned rows_per_cta = kWarps * RPW;
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
@@ -454,6 +467,8 @@ decoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, con
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, long long P, int slots, long long p_begin,
                        long long p_end, float* __restrict__ grads) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long p = p_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; p < p_end;
        p += (long long)gridDim.x * blockDim.x) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -519,7 +534,7 @@ extern "C" int gatres_encoder_fwd(const float* x, const float* w, const float* b
   GATRES_REQUIRE(M >= 0 && nc > 0 && nc % 4 == 0, "encoder_fwd: bad M=%lld nc=%d", (long long)M, nc);
   if (M == 0) return GATRES_OK;
   const size_t total4 = (size_t)M * (nc / 4);
-  encoder_fwd_kernel<<<flat_grid(total4), 256, 0, as_stream(stream)>>>(x, w, b, out, total4, nc / 4);
+  launch_kernel(encoder_fwd_kernel, dim3(flat_grid(total4)), dim3(256), 0, as_stream(stream), x, w, b, out, total4, nc / 4);
   return check_launch("encoder_fwd");
 }
 
@@ -530,7 +545,7 @@ extern "C" int gatres_encoder_bwd(const float* g, const float* x, float* partial
   GATRES_REQUIRE(P % 4 == 0 && off_w % 4 == 0 && off_b % 4 == 0, "encoder_bwd: misaligned offsets");
   const int atomic = slots <= 0;
   const unsigned grid = atomic ? row_kernel_grid((unsigned)M, 256 / (nc / 4), 4) : (unsigned)slots;
-  encoder_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, x, partial, P, off_w, off_b, (unsigned)M, nc / 4, atomic);
+  launch_kernel(encoder_bwd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), g, x, partial, P, off_w, off_b, (unsigned)M, nc / 4, atomic);
   return check_launch("encoder_bwd");
 }
 
@@ -541,9 +556,9 @@ extern "C" int gatres_decoder_fwd(const float* x, const float* w, const float* b
   cudaStream_t st = as_stream(stream);
   const unsigned Mu = (unsigned)M;
   switch (nc) {
-    case 32: decoder_fwd_kernel<32><<<flat_grid((size_t)M * 8), 256, 0, st>>>(x, w, b, out, poison, Mu); break;
-    case 64: decoder_fwd_kernel<64><<<flat_grid((size_t)M * 16), 256, 0, st>>>(x, w, b, out, poison, Mu); break;
-    case 128: decoder_fwd_kernel<128><<<flat_grid((size_t)M * 32), 256, 0, st>>>(x, w, b, out, poison, Mu); break;
+    case 32: launch_kernel(decoder_fwd_kernel<32>, dim3(flat_grid((size_t)M * 8)), dim3(256), 0, st, x, w, b, out, poison, Mu); break;
+    case 64: launch_kernel(decoder_fwd_kernel<64>, dim3(flat_grid((size_t)M * 16)), dim3(256), 0, st, x, w, b, out, poison, Mu); break;
+    case 128: launch_kernel(decoder_fwd_kernel<128>, dim3(flat_grid((size_t)M * 32)), dim3(256), 0, st, x, w, b, out, poison, Mu); break;
     default: set_error("decoder_fwd: unsupported nc=%d", nc); return GATRES_ERR_ARG;
   }
   return check_launch("decoder_fwd");
@@ -559,9 +574,9 @@ extern "C" int gatres_decoder_bwd(const float* g_out, const float* x, const floa
   const int atomic = slots <= 0;
   const unsigned grid = atomic ? row_kernel_grid(Mu, kWarps * (32 / (nc / 4)), 8) : (unsigned)slots;
   switch (nc) {
-    case 32: decoder_bwd_kernel<32><<<grid, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
-    case 64: decoder_bwd_kernel<64><<<grid, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
-    case 128: decoder_bwd_kernel<128><<<grid, 256, 0, st>>>(g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
+    case 32: launch_kernel(decoder_bwd_kernel<32>, dim3(grid), dim3(256), 0, st, g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
+    case 64: launch_kernel(decoder_bwd_kernel<64>, dim3(grid), dim3(256), 0, st, g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
+    case 128: launch_kernel(decoder_bwd_kernel<128>, dim3(grid), dim3(256), 0, st, g_out, x, w, dx, partial, P, off_w, off_b, Mu, mask_relu, atomic); break;
     default: set_error("decoder_bwd: unsupported nc=%d", nc); return GATRES_ERR_ARG;
   }
   return check_launch("decoder_bwd");
@@ -571,7 +586,7 @@ extern "C" int gatres_reduce_partials(const float* partial, int64_t P, int32_t s
                                       int64_t p_end, float* grads, void* stream) {
   GATRES_REQUIRE(slots > 0 && p_begin >= 0 && p_end >= p_begin && p_end <= P, "reduce_partials: bad range");
   if (p_end == p_begin) return GATRES_OK;
-  reduce_partials_kernel<<<flat_grid((size_t)(p_end - p_begin)), 256, 0, as_stream(stream)>>>(
+  launch_kernel(reduce_partials_kernel, dim3(flat_grid((size_t)(p_end - p_begin))), dim3(256), 0, as_stream(stream), 
       partial, P, slots, p_begin, p_end, grads);
   return check_launch("reduce_partials");
 }

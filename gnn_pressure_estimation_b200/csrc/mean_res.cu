@@ -19,6 +19,8 @@ mean_res_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, lig = lane % LPR;
   constexpr unsigned rows_per_cta = kWarps * RPW;
+  pdl_launch_dependents();
+  pdl_wait();
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
     if (r >= M) continue;
@@ -54,6 +56,8 @@ mean_res_bwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ rowp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, lig = lane % LPR;
   constexpr unsigned rows_per_cta = kWarps * RPW;
+  pdl_launch_dependents();
+  pdl_wait();
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
     if (r >= M) continue;
@@ -105,9 +109,9 @@ extern "C" int gatres_mean_res_fwd(const int32_t* rowptr, const int32_t* col, co
   const unsigned M = (unsigned)(B * N);
   cudaStream_t st = as_stream(stream);
   switch (C) {
-    case 32: mean_res_fwd_kernel<32><<<row_grid<32>(M), kThreads, 0, st>>>(rowptr, col, z, x0, out, M, N); break;
-    case 64: mean_res_fwd_kernel<64><<<row_grid<64>(M), kThreads, 0, st>>>(rowptr, col, z, x0, out, M, N); break;
-    case 128: mean_res_fwd_kernel<128><<<row_grid<128>(M), kThreads, 0, st>>>(rowptr, col, z, x0, out, M, N); break;
+    case 32: launch_kernel(mean_res_fwd_kernel<32>, dim3(row_grid<32>(M)), dim3(kThreads), 0, st, rowptr, col, z, x0, out, M, N); break;
+    case 64: launch_kernel(mean_res_fwd_kernel<64>, dim3(row_grid<64>(M)), dim3(kThreads), 0, st, rowptr, col, z, x0, out, M, N); break;
+    case 128: launch_kernel(mean_res_fwd_kernel<128>, dim3(row_grid<128>(M)), dim3(kThreads), 0, st, rowptr, col, z, x0, out, M, N); break;
     default: set_error("mean_res_fwd: unsupported channels %d (32, 64, 128)", C); return GATRES_ERR_ARG;
   }
   return check_launch("mean_res_fwd");
@@ -122,9 +126,9 @@ extern "C" int gatres_mean_res_bwd(const int32_t* rowptr, const int32_t* rowptr_
   const unsigned M = (unsigned)(B * N);
   cudaStream_t st = as_stream(stream);
   switch (C) {
-    case 32: mean_res_bwd_kernel<32><<<row_grid<32>(M), kThreads, 0, st>>>(rowptr, rowptr_t, col_t, g_out, out, dz, dres, M, N); break;
-    case 64: mean_res_bwd_kernel<64><<<row_grid<64>(M), kThreads, 0, st>>>(rowptr, rowptr_t, col_t, g_out, out, dz, dres, M, N); break;
-    case 128: mean_res_bwd_kernel<128><<<row_grid<128>(M), kThreads, 0, st>>>(rowptr, rowptr_t, col_t, g_out, out, dz, dres, M, N); break;
+    case 32: launch_kernel(mean_res_bwd_kernel<32>, dim3(row_grid<32>(M)), dim3(kThreads), 0, st, rowptr, rowptr_t, col_t, g_out, out, dz, dres, M, N); break;
+    case 64: launch_kernel(mean_res_bwd_kernel<64>, dim3(row_grid<64>(M)), dim3(kThreads), 0, st, rowptr, rowptr_t, col_t, g_out, out, dz, dres, M, N); break;
+    case 128: launch_kernel(mean_res_bwd_kernel<128>, dim3(row_grid<128>(M)), dim3(kThreads), 0, st, rowptr, rowptr_t, col_t, g_out, out, dz, dres, M, N); break;
     default: set_error("mean_res_bwd: unsupported channels %d (32, 64, 128)", C); return GATRES_ERR_ARG;
   }
   return check_launch("mean_res_bwd");
