@@ -9,6 +9,7 @@
 // HBM-bound, so the kernels are organised around the memory system instead:
 // persistent CTAs keep the whole weight matrix resident in shared memory and
 // stream row tiles through a cp.async double buffer.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gatres {
@@ -484,15 +485,38 @@ reduce_partials_kernel(const float* __restrict__ partial, long long P, int slots
   }
 }
 
+// tensor-core (tcgen05 3xTF32) variants, linear_tc.cu
+int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const float* W, const float* e0,
+                     const float* e1, float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st);
+
+static int g_tensor_core = -1;
+static bool tensor_core_enabled() {
+  if (g_tensor_core < 0) {
+    const char* e = getenv("GATRES_TC");
+    g_tensor_core = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return g_tensor_core == 1;
+}
+
 }  // namespace gatres
 
 using namespace gatres;
+
+extern "C" int gatres_set_tensor_core(int enable) {
+  const int prev = tensor_core_enabled() ? 1 : 0;
+  if (enable >= 0) g_tensor_core = enable ? 1 : 0;
+  return prev;
+}
 
 extern "C" int gatres_linear_att_fwd(const float* x, const float* W, const float* att_src, const float* att_dst,
                                      float* h, float* s_src, float* s_dst, int64_t M, int32_t K, int32_t H,
                                      int32_t C, void* stream) {
   GATRES_REQUIRE(M >= 0 && M < (1ll << 31), "linear_att_fwd: bad M=%lld", (long long)M);
   if (M == 0) return GATRES_OK;
+  if (tensor_core_enabled() && (H == 1 || H == 2)) {
+    const int rc = gemm_tc_dispatch(0, H, K, H * C, x, W, att_src, att_dst, h, s_src, s_dst, (unsigned)M, as_stream(stream));
+    if (rc != 0) return rc < 0 ? rc : GATRES_OK;
+  }
   if (H == 1) return dispatch_gemm<0, 1>(K, H * C, x, W, att_src, att_dst, h, s_src, s_dst, (unsigned)M, as_stream(stream), "linear_att_fwd");
   if (H == 2) return dispatch_gemm<0, 2>(K, H * C, x, W, att_src, att_dst, h, s_src, s_dst, (unsigned)M, as_stream(stream), "linear_att_fwd");
   set_error("linear_att_fwd: heads must be 1 or 2, got %d", H);
@@ -507,7 +531,11 @@ extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W
   cudaStream_t st = as_stream(stream);
   const int NO = H * C;
   if (dx != nullptr) {
-    int rc = dispatch_gemm<1, 1>(NO, K, dh, W, add, relu_ref, dx, nullptr, nullptr, (unsigned)M, st, "linear_bwd_dx");
+    int rc = tensor_core_enabled()
+                 ? gemm_tc_dispatch(1, 1, NO, K, dh, W, add, relu_ref, dx, nullptr, nullptr, (unsigned)M, st)
+                 : 0;
+    if (rc < 0) return rc;
+    rc = rc == 1 ? 0 : dispatch_gemm<1, 1>(NO, K, dh, W, add, relu_ref, dx, nullptr, nullptr, (unsigned)M, st, "linear_bwd_dx");
     if (rc) return rc;
   }
 #define WG(NOv, KIv, TNn, TKk) \

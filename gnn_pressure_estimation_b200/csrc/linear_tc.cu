@@ -1,0 +1,269 @@
+// Projection GEMMs on the 5th-generation tensor cores (sm_100a): tcgen05.mma
+// kind::tf32 with the accumulator in TMEM, error-compensated to fp32 accuracy
+// ("3xTF32":  A B ~= A_hi B_hi + A_lo B_hi + A_hi B_lo, A = A_hi + A_lo with both
+// parts rounded to TF32 by the staging threads, fp32 accumulation in TMEM), because
+// the parity contract is 1e-4 relative through 30 chained projections and a single
+// TF32 pass (2^-11 per operand) does not meet it.
+//
+//   MODE 0  h = x W^T  + attention-score epilogue   (GATConv.forward step 1,
+//           /root/reference/gnn_pressure_estimation/GraphModels.py:464-465)
+//   MODE 1  dx = dh W (+ residual gradient) (* ReLU mask)   (its data gradient)
+//
+// One CTA = 128 threads = one 128-row tile at a time (UMMA M = 128, N = 32 or 64,
+// K = 8 per instruction).  Operands live in shared memory in the canonical K-major
+// SWIZZLE_128B layout (rows of 128 B, 16-byte chunk index XOR row%8, 1024-byte
+// 8-row atoms); thread 0 issues the MMAs, completion is signalled through
+// tcgen05.commit on an mbarrier, and each of the four warps drains its 32 TMEM
+// lanes (= 32 rows) with tcgen05.ld: one thread owns one output row, so the
+// attention scores are in-thread dot products.  Several CTAs share an SM
+// (48-80 KB of shared memory, 32-64 TMEM columns each), which overlaps one CTA's
+// loads with another's MMAs and epilogue.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace gatres {
+
+__device__ __forceinline__ void tc_cp_async16(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {       // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {          // the allocating warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when they complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulator -> 32 registers per thread (thread = lane = row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024>>4 | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// byte offset of element (row, k) of a [rows x KK] fp32 operand tile: KK/32 blocks of [rows x 128 B]
+__device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t k, uint32_t rows) {
+  const uint32_t atom = k >> 5, kk = k & 31u;
+  return atom * rows * 128u + row * 128u + ((((kk >> 2) ^ (row & 7u))) << 4) + ((kk & 3u) << 2);
+}
+
+template <int KK, int NN, int MODE, int H>
+__global__ void __launch_bounds__(128)
+gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ e0,
+               const float* __restrict__ e1, float* __restrict__ Cout, float* __restrict__ s0,
+               float* __restrict__ s1, unsigned M) {
+  constexpr int BM = 128, KA = KK / 32;                       // K atoms of 32 floats (128 B)
+  constexpr uint32_t A_BYTES = BM * KK * 4, B_BYTES = NN * KK * 4;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static_assert(KK % 32 == 0 && NN % 16 == 0 && NN >= 32 && NN <= 64, "unsupported tensor-core shape");
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // SWIZZLE_128B atoms are 1024 B aligned
+  unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_hi = base, a_lo = base + A_BYTES, b_hi = base + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+  float* att = reinterpret_cast<float*>(sm + 2 * A_BYTES + 2 * B_BYTES);  // [2][NN] (MODE 0)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(att + 2 * NN);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned ntiles = (M + BM - 1) / BM;
+
+  // ---- prologue (constant data only: runs under the previous kernel's tail) ----
+  pdl_launch_dependents();
+  if (warp == 0) tmem_alloc(tmem_slot, NN);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  for (int idx = tid; idx < NN * KK; idx += 128) {            // B operand [NN rows x KK], K-major, split hi/lo
+    const int n = idx / KK, k = idx % KK;
+    const float w = MODE == 0 ? __ldg(W + (size_t)n * KK + k) : __ldg(W + (size_t)k * NN + n);
+    const float hi = to_tf32(w), lo = to_tf32(w - hi);
+    const uint32_t off = swz_off(n, k, NN);
+    *reinterpret_cast<float*>(sm + 2 * A_BYTES + off) = hi;
+    *reinterpret_cast<float*>(sm + 2 * A_BYTES + B_BYTES + off) = lo;
+  }
+  if (MODE == 0)
+    for (int idx = tid; idx < NN; idx += 128) {
+      att[idx] = __ldg(e0 + idx);
+      att[NN + idx] = __ldg(e1 + idx);
+    }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  uint32_t phase = 0;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // ---- stage the A tile (raw fp32) with cp.async into the swizzled layout ----
+    constexpr int CHUNKS = BM * KK / 4;                       // 16-byte chunks
+#pragma unroll
+    for (int q = 0; q < CHUNKS / 128; ++q) {
+      const int idx = q * 128 + tid;
+      const uint32_t row = idx / (KK / 4), c = idx % (KK / 4);
+      const unsigned grow = tile * BM + row;
+      const bool ok = grow < M;
+      tc_cp_async16(a_hi + swz_off(row, 4 * c, BM), A + (size_t)(ok ? grow : 0) * KK + 4 * c, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // ---- split every chunk this thread loaded into TF32 hi (in place) and lo ----
+#pragma unroll
+    for (int q = 0; q < CHUNKS / 128; ++q) {
+      const int idx = q * 128 + tid;
+      const uint32_t row = idx / (KK / 4), c = idx % (KK / 4);
+      const uint32_t off = swz_off(row, 4 * c, BM);
+      const float4 x = *reinterpret_cast<const float4*>(sm + off);
+      float4 hi, lo;
+      hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
+      lo.x = to_tf32(x.x - hi.x); lo.y = to_tf32(x.y - hi.y); lo.z = to_tf32(x.z - hi.z); lo.w = to_tf32(x.w - hi.w);
+      *reinterpret_cast<float4*>(sm + off) = hi;
+      *reinterpret_cast<float4*>(sm + A_BYTES + off) = lo;
+    }
+    fence_proxy_async();                                      // generic-proxy smem writes -> tensor-core (async) proxy
+    __syncthreads();
+
+    // ---- one thread issues the 3 x KK/8 MMAs and commits them to the mbarrier ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < KK / 8; ++s) {
+        const uint32_t ka = (uint32_t)(s >> 2) * BM * 128u + (uint32_t)(s & 3) * 32u;     // A: atom block + 32 B per K slice
+        const uint32_t kb = (uint32_t)(s >> 2) * NN * 128u + (uint32_t)(s & 3) * 32u;
+        umma_tf32(tmem, umma_desc_k128(a_hi + ka), umma_desc_k128(b_hi + kb), IDESC, s > 0);
+        umma_tf32(tmem, umma_desc_k128(a_lo + ka), umma_desc_k128(b_hi + kb), IDESC, 1);
+        umma_tf32(tmem, umma_desc_k128(a_hi + ka), umma_desc_k128(b_lo + kb), IDESC, 1);
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+
+    // ---- epilogue: thread = output row; TMEM lanes [32*warp, 32*warp+32) ----
+    const unsigned row = tile * BM + tid;
+    const bool ok = row < M;
+    float ps[H], pd[H];
+#pragma unroll
+    for (int hh = 0; hh < H; ++hh) ps[hh] = pd[hh] = 0.f;
+#pragma unroll
+    for (int cb = 0; cb < NN / 32; ++cb) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+      if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int n = cb * 32 + k, hh = n / (NN / H);
+          ps[hh] = fmaf(v[k], att[n], ps[hh]);
+          pd[hh] = fmaf(v[k], att[NN + n], pd[hh]);
+        }
+      }
+      if (ok) {
+        const size_t o = (size_t)row * NN + cb * 32;
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          float4 t = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+          if (MODE == 1) {
+            if (e0 != nullptr) add4(t, ldg4_stream(e0 + o + k));
+            if (e1 != nullptr) {
+              const float4 r = ldg4_stream(e1 + o + k);
+              t.x = r.x > 0.f ? t.x : 0.f; t.y = r.y > 0.f ? t.y : 0.f;
+              t.z = r.z > 0.f ? t.z : 0.f; t.w = r.w > 0.f ? t.w : 0.f;
+            }
+          }
+          st4(Cout + o + k, t);
+        }
+      }
+    }
+    if (MODE == 0 && ok) {
+#pragma unroll
+      for (int hh = 0; hh < H; ++hh) {
+        s0[(size_t)row * H + hh] = ps[hh];
+        s1[(size_t)row * H + hh] = pd[hh];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                          // TMEM accumulator and the A buffers are free again
+  }
+  if (warp == 0) tmem_dealloc(tmem, NN);
+}
+
+template <int KK, int NN, int MODE, int H>
+static int launch_tc(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
+                     float* s1, unsigned M, cudaStream_t st, const char* what) {
+  constexpr size_t smem = 1024 + 2 * (size_t)128 * KK * 4 + 2 * (size_t)NN * KK * 4 + 2 * NN * 4 + 32;
+  auto kern = gemm_tc_kernel<KK, NN, MODE, H>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch(what);
+    configured = true;
+  }
+  const unsigned ntiles = (M + 127) / 128;
+  unsigned per_sm = (unsigned)((200u * 1024u) / smem);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  unsigned grid = (unsigned)sm_count() * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  launch_kernel(kern, dim3(grid), dim3(128), smem, st, A, W, e0, e1, Cout, s0, s1, M);
+  return check_launch(what);
+}
+
+// -> 1 if handled, 0 if this shape has no tensor-core path (caller falls back to the FFMA kernel), <0 on error
+int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const float* W, const float* e0,
+                     const float* e1, float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st) {
+  int rc = 1;
+#define TC(KKv, NNv, MODEv, Hv)                                                                           \
+  if (mode == MODEv && KK == KKv && NN == NNv && (MODEv == 1 || H == Hv)) {                               \
+    rc = launch_tc<KKv, NNv, MODEv, Hv>(A, W, e0, e1, Cout, s0, s1, M, st, "gemm_tc");                    \
+    return rc ? rc : 1;                                                                                   \
+  }
+  TC(32, 64, 0, 2)      // conv1 projection, nc = 32
+  TC(64, 32, 0, 1)      // conv2 projection, nc = 32
+  TC(32, 64, 1, 1)      // conv2 data gradient (dh2 [M,32] -> dy1 [M,64])
+  TC(64, 32, 1, 1)      // conv1 data gradient (dh1 [M,64] -> dx0 [M,32])
+#undef TC
+  return 0;
+}
+
+}  // namespace gatres

@@ -97,15 +97,18 @@ GRAPHS = {
 }
 
 
-@pytest.fixture(params=["gather", "tile"])
+@pytest.fixture(params=["gather-ffma", "tile-tc"])
 def kernel_variant(request):
-    """run a test with the gather kernels (default for small batches) and with the
-    TMA-staged snapshot-tile kernels forced on (used for batches >= 64 by default)."""
+    """run a test with (a) the gather aggregation kernels + fp32 FFMA projections and (b) the TMA-staged
+    snapshot-tile aggregation kernels (default only for batches >= 64) + tcgen05 3xTF32 projections."""
     from gnn_pressure_estimation_b200 import _lib
     lib = _lib.load()
-    prev = lib.gatres_set_tile_min_batch(1 if request.param == "tile" else 1 << 40)
+    fancy = request.param == "tile-tc"
+    prev_tile = lib.gatres_set_tile_min_batch(1 if fancy else 1 << 40)
+    prev_tc = lib.gatres_set_tensor_core(1 if fancy else 0)
     yield request.param
-    lib.gatres_set_tile_min_batch(prev)
+    lib.gatres_set_tile_min_batch(prev_tile)
+    lib.gatres_set_tensor_core(prev_tc)
 
 
 @pytest.mark.parametrize("graph,B", [("tiny", 1), ("tiny", 5), ("ctown", 3), ("directed", 2)])
