@@ -39,6 +39,11 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 // barrier init) while its predecessor is still draining, and blocks in pdl_wait()
 // until the predecessor's memory is visible.  Only data that is constant within a
 // step (parameters, CSR) may be touched before pdl_wait().
+// A kernel releases its dependents early (pdl_launch_dependents) only when every one
+// of its CTAs makes a single pass (small batches, where launch latency matters).  With
+// multi-pass persistent grids an early release parks the next kernel's CTAs on whichever
+// SMs drain first; its static work split then runs unbalanced (measured: dgrad -> wgrad
+// chain 228 us -> 410 us at 2048 snapshots), so large launches keep plain serialization.
 bool pdl_enabled();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

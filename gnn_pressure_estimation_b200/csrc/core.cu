@@ -47,7 +47,6 @@ int sm_count() {
 // x_masked = mask ? 0 : x   (train.py:174  data.x[batch_mask] = 0)
 __global__ void __launch_bounds__(256)
 apply_mask_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, float* __restrict__ out, size_t M) {
-  pdl_launch_dependents();
   pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x)
     out[i] = mask[i] ? 0.f : x[i];
@@ -58,7 +57,6 @@ __global__ void __launch_bounds__(256)
 masked_mse_kernel(const float* __restrict__ out, const float* __restrict__ y, const uint8_t* __restrict__ mask,
                   size_t M, float inv_count, float* __restrict__ d_out, float* __restrict__ partial_loss) {
   __shared__ float red[kWarps];
-  pdl_launch_dependents();
   pdl_wait();
   float s = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
@@ -79,7 +77,6 @@ masked_mse_kernel(const float* __restrict__ out, const float* __restrict__ y, co
 __global__ void __launch_bounds__(256)
 final_loss_kernel(const float* __restrict__ partial_loss, int n, float inv_count, float* __restrict__ loss) {
   __shared__ float red[kWarps];
-  pdl_launch_dependents();
   pdl_wait();
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial_loss[i];
@@ -94,7 +91,6 @@ final_loss_kernel(const float* __restrict__ partial_loss, int n, float inv_count
 }
 
 __global__ void bump_step_kernel(int* step) {
-  pdl_launch_dependents();
   pdl_wait();
   step[0] += 1;
 }
@@ -104,7 +100,6 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             const int* __restrict__ step, size_t P, float lr, float b1, float b2, float eps, float wd,
             float grad_scale) {
-  pdl_launch_dependents();
   pdl_wait();
   const float t = (float)__ldg(step);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);

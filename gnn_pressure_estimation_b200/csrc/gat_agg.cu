@@ -53,9 +53,9 @@ gat_agg_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
   float4 bv[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) bv[v] = ldg4(bias + 4 * RM::chunk(lig, v));
-  pdl_launch_dependents();
   pdl_wait();                                     // activations of the previous kernel become visible here
 
+  if ((unsigned long long)gridDim.x * rows_per_cta >= M) pdl_launch_dependents();   // single pass: see common.cuh
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     // rows past the end are clamped (their lanes redo the last row and skip the stores) so that every
     // lane of the warp runs the same instruction stream: plain full-mask SHFLs, no convergence barriers
@@ -176,9 +176,9 @@ gat_agg_bwd_p1_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
   float4 bacc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) bacc[v] = f4zero();
-  pdl_launch_dependents();
   pdl_wait();
 
+  if ((unsigned long long)gridDim.x * rows_per_cta >= M) pdl_launch_dependents();   // single pass: see common.cuh
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r_raw = r0 + warp * RPW + sub;
     const bool row_ok = r_raw < M;                // clamped rows recompute the last row and emit nothing
@@ -299,9 +299,9 @@ gat_agg_bwd_p2_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ 
     accs[v] = f4zero();
     accd[v] = f4zero();
   }
-  pdl_launch_dependents();
   pdl_wait();
 
+  if ((unsigned long long)gridDim.x * rows_per_cta >= M) pdl_launch_dependents();   // single pass: see common.cuh
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r_raw = r0 + warp * RPW + sub;
     const bool row_ok = r_raw < M;

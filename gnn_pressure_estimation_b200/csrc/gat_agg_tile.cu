@@ -72,7 +72,6 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   }
   for (unsigned k = tid; k <= N; k += kTileThreads) rp_s[k] = __ldg(rowptr + k);
   for (unsigned k = tid; k < E1; k += kTileThreads) col_s[k] = __ldg(col + k);
-  pdl_launch_dependents();
   __syncthreads();
   pdl_wait();                                     // CSR staging above overlapped the previous kernel's tail
   if (tid == 0) {
@@ -85,6 +84,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   for (int v = 0; v < V; ++v) bv[v] = ldg4(bias + 4 * RM::chunk(lig, v));
 
   unsigned k = 0;
+  if (gridDim.x >= B) pdl_launch_dependents();
   for (unsigned b = blockIdx.x; b < B; b += gridDim.x, ++k) {
     const int stage = k & 1;
     const float* hs = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes) + 4 * lig;
@@ -317,12 +317,12 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     ad[v] = ldg4(att_dst + 4 * RM::chunk(lig, v));
     accs[v] = accd[v] = bacc[v] = f4zero();
   }
-  pdl_launch_dependents();
   __syncthreads();
   pdl_wait();
   if (tid == 0 && blockIdx.x < B) issue(blockIdx.x);
 
   unsigned it = 0;
+  if (gridDim.x >= B) pdl_launch_dependents();
   for (unsigned b = blockIdx.x; b < B; b += gridDim.x, ++it) {
     mbar_wait(full, it & 1);
 

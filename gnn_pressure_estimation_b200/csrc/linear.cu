@@ -58,7 +58,6 @@ gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ W,
   };
 
   // weights / attention vectors are constant within a step: stage them before the dependency wait
-  pdl_launch_dependents();
   if (MODE == 0) {
     for (int idx = tid; idx < NN * (KK / 4); idx += 256) {
       const int n = idx / (KK / 4), kv = idx % (KK / 4);
@@ -89,6 +88,7 @@ gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ W,
   cp_async_commit();
 
   int stage = 0;
+  if (gridDim.x >= ntiles) pdl_launch_dependents();
   for (; tile < ntiles; tile += gridDim.x) {
     const unsigned next = tile + gridDim.x;
     if (STAGES == 2) {
@@ -236,12 +236,12 @@ wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* _
 #pragma unroll
     for (int j = 0; j < TKk; ++j) acc[i][j] = 0.f;
 
-  pdl_launch_dependents();
   pdl_wait();
   unsigned tile = blockIdx.x;
   if (tile < ntiles) load_tile(tile, 0);
   cp_async_commit();
   int stage = 0;
+  if (gridDim.x >= ntiles) pdl_launch_dependents();
   for (; tile < ntiles; tile += gridDim.x) {
     const unsigned next = tile + gridDim.x;
     if (next < ntiles) load_tile(next, stage ^ 1);
@@ -361,7 +361,6 @@ static int dispatch_gemm(int KK, int NN, const float* A, const float* W, const f
 __global__ void __launch_bounds__(256)
 encoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                    float* __restrict__ out, size_t total4, int nc4) {
-  pdl_launch_dependents();
   pdl_wait();
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total4; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t m = idx / nc4;
@@ -379,7 +378,6 @@ encoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, flo
   __shared__ float red[2 * 256 * 4];
   const int c = threadIdx.x % nc4, rl = threadIdx.x / nc4, rows_per_pass = 256 / nc4;
   float4 aw = f4zero(), ab = f4zero();
-  pdl_launch_dependents();
   pdl_wait();
   for (size_t m = (size_t)blockIdx.x * rows_per_pass + rl; m < M; m += (size_t)gridDim.x * rows_per_pass) {
     const float4 gv = ldg4_stream(g + m * (size_t)(nc4 * 4) + 4 * c);
@@ -409,10 +407,10 @@ decoder_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, lig = lane % LPR;
   const float4 wv = ldg4(w + 4 * lig);
   const float bias = __ldg(b);
-  pdl_launch_dependents();
   pdl_wait();
   const bool bad = poison != nullptr && __ldg(poison) != 0;
   constexpr unsigned rows_per_cta = kWarps * RPW;
+  if ((unsigned long long)gridDim.x * rows_per_cta >= M) pdl_launch_dependents();   // single pass: see common.cuh
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
     float p = 0.f;
@@ -435,10 +433,10 @@ decoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, con
   const float4 wv = ldg4(w + 4 * lig);
   float4 aw = f4zero();
   float ab = 0.f;
-  pdl_launch_dependents();
   pdl_wait();
 
   constexpr unsigned rows_per_cta = kWarps * RPW;
+  if ((unsigned long long)gridDim.x * rows_per_cta >= M) pdl_launch_dependents();   // single pass: see common.cuh
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
     if (r >= M) continue;
@@ -468,7 +466,6 @@ decoder_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, con
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, long long P, int slots, long long p_begin,
                        long long p_end, float* __restrict__ grads) {
-  pdl_launch_dependents();
   pdl_wait();
   for (long long p = p_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; p < p_end;
        p += (long long)gridDim.x * blockDim.x) {
@@ -489,22 +486,30 @@ reduce_partials_kernel(const float* __restrict__ partial, long long P, int slots
 int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const float* W, const float* e0,
                      const float* e1, float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st);
 
+// 0 = never, 1 = auto (launches of at least kTcMinRows rows: below that the 128-row UMMA tiles leave
+// most SMs idle and the FFMA kernel with 64-row tiles is faster), 2 = always
 static int g_tensor_core = -1;
-static bool tensor_core_enabled() {
+constexpr long long kTcMinRows = 32768;
+static int tensor_core_mode() {
   if (g_tensor_core < 0) {
     const char* e = getenv("GATRES_TC");
-    g_tensor_core = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    g_tensor_core = e == nullptr ? 1 : atoi(e);
+    if (g_tensor_core < 0 || g_tensor_core > 2) g_tensor_core = 1;
   }
-  return g_tensor_core == 1;
+  return g_tensor_core;
+}
+static bool tensor_core_enabled(long long rows) {
+  const int m = tensor_core_mode();
+  return m == 2 || (m == 1 && rows >= kTcMinRows);
 }
 
 }  // namespace gatres
 
 using namespace gatres;
 
-extern "C" int gatres_set_tensor_core(int enable) {
-  const int prev = tensor_core_enabled() ? 1 : 0;
-  if (enable >= 0) g_tensor_core = enable ? 1 : 0;
+extern "C" int gatres_set_tensor_core(int mode) {
+  const int prev = tensor_core_mode();
+  if (mode >= 0 && mode <= 2) g_tensor_core = mode;
   return prev;
 }
 
@@ -513,7 +518,7 @@ extern "C" int gatres_linear_att_fwd(const float* x, const float* W, const float
                                      int32_t C, void* stream) {
   GATRES_REQUIRE(M >= 0 && M < (1ll << 31), "linear_att_fwd: bad M=%lld", (long long)M);
   if (M == 0) return GATRES_OK;
-  if (tensor_core_enabled() && (H == 1 || H == 2)) {
+  if (tensor_core_enabled(M) && (H == 1 || H == 2)) {
     const int rc = gemm_tc_dispatch(0, H, K, H * C, x, W, att_src, att_dst, h, s_src, s_dst, (unsigned)M, as_stream(stream));
     if (rc != 0) return rc < 0 ? rc : GATRES_OK;
   }
@@ -531,7 +536,7 @@ extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W
   cudaStream_t st = as_stream(stream);
   const int NO = H * C;
   if (dx != nullptr) {
-    int rc = tensor_core_enabled()
+    int rc = tensor_core_enabled(M)
                  ? gemm_tc_dispatch(1, 1, NO, K, dh, W, add, relu_ref, dx, nullptr, nullptr, (unsigned)M, st)
                  : 0;
     if (rc < 0) return rc;

@@ -93,10 +93,10 @@ __global__ void __launch_bounds__(128)
 gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ e0,
                const float* __restrict__ e1, float* __restrict__ Cout, float* __restrict__ s0,
                float* __restrict__ s1, unsigned M) {
-  constexpr int BM = 128, KA = KK / 32;                       // K atoms of 32 floats (128 B)
+  constexpr int BM = 128;
   constexpr uint32_t A_BYTES = BM * KK * 4, B_BYTES = NN * KK * 4;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  static_assert(KK % 32 == 0 && NN % 16 == 0 && NN >= 32 && NN <= 64, "unsupported tensor-core shape");
+  static_assert(KK % 32 == 0 && NN % 16 == 0 && NN >= 32 && NN <= 64 && NN <= 2 * KK, "unsupported tensor-core shape");
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // SWIZZLE_128B atoms are 1024 B aligned
   unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -109,7 +109,6 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
   const unsigned ntiles = (M + BM - 1) / BM;
 
   // ---- prologue (constant data only: runs under the previous kernel's tail) ----
-  pdl_launch_dependents();
   if (warp == 0) tmem_alloc(tmem_slot, NN);
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -135,6 +134,7 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
   pdl_wait();
 
   uint32_t phase = 0;
+  if (gridDim.x >= ntiles) pdl_launch_dependents();
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ---- stage the A tile (raw fp32) with cp.async into the swizzled layout ----
     constexpr int CHUNKS = BM * KK / 4;                       // 16-byte chunks
@@ -182,11 +182,14 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
     tc_fence_after();
 
     // ---- epilogue: thread = output row; TMEM lanes [32*warp, 32*warp+32) ----
+    // The row is parked in shared memory (the operand buffers are dead once the MMAs have completed; 16-byte
+    // chunk index XOR row keeps the column-strided stores at the 4-wavefront minimum) so that the global
+    // stores below are fully coalesced instead of 32 rows x 16 B per instruction.
     const unsigned row = tile * BM + tid;
-    const bool ok = row < M;
     float ps[H], pd[H];
 #pragma unroll
     for (int hh = 0; hh < H; ++hh) ps[hh] = pd[hh] = 0.f;
+    constexpr int NCH = NN / 4;                                // 16-byte chunks per output row
 #pragma unroll
     for (int cb = 0; cb < NN / 32; ++cb) {
       float v[32];
@@ -199,24 +202,14 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
           pd[hh] = fmaf(v[k], att[NN + n], pd[hh]);
         }
       }
-      if (ok) {
-        const size_t o = (size_t)row * NN + cb * 32;
 #pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-          float4 t = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-          if (MODE == 1) {
-            if (e0 != nullptr) add4(t, ldg4_stream(e0 + o + k));
-            if (e1 != nullptr) {
-              const float4 r = ldg4_stream(e1 + o + k);
-              t.x = r.x > 0.f ? t.x : 0.f; t.y = r.y > 0.f ? t.y : 0.f;
-              t.z = r.z > 0.f ? t.z : 0.f; t.w = r.w > 0.f ? t.w : 0.f;
-            }
-          }
-          st4(Cout + o + k, t);
-        }
+      for (int k = 0; k < 32; k += 4) {
+        const int c = cb * 8 + k / 4;
+        *reinterpret_cast<float4*>(sm + (size_t)tid * (NN * 4) + (((c ^ tid) & (NCH - 1)) << 4)) =
+            make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
       }
     }
-    if (MODE == 0 && ok) {
+    if (MODE == 0 && row < M) {
 #pragma unroll
       for (int hh = 0; hh < H; ++hh) {
         s0[(size_t)row * H + hh] = ps[hh];
@@ -224,7 +217,27 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
       }
     }
     tc_fence_before();
-    __syncthreads();                                          // TMEM accumulator and the A buffers are free again
+    __syncthreads();                                          // staging complete; TMEM accumulator free
+#pragma unroll
+    for (int q = 0; q < BM * NCH / 128; ++q) {
+      const int idx = q * 128 + tid;
+      const int r = idx / NCH, c = idx % NCH;
+      const unsigned grow = tile * BM + r;
+      if (grow < M) {
+        float4 t = *reinterpret_cast<const float4*>(sm + (size_t)r * (NN * 4) + (((c ^ r) & (NCH - 1)) << 4));
+        const size_t o = (size_t)grow * NN + 4 * c;
+        if (MODE == 1) {
+          if (e0 != nullptr) add4(t, ldg4_stream(e0 + o));
+          if (e1 != nullptr) {
+            const float4 rr = ldg4_stream(e1 + o);
+            t.x = rr.x > 0.f ? t.x : 0.f; t.y = rr.y > 0.f ? t.y : 0.f;
+            t.z = rr.z > 0.f ? t.z : 0.f; t.w = rr.w > 0.f ? t.w : 0.f;
+          }
+        }
+        st4(Cout + o, t);
+      }
+    }
+    __syncthreads();                                          // staging (= operand buffers) free for the next tile
   }
   if (warp == 0) tmem_dealloc(tmem, NN);
 }

@@ -19,8 +19,8 @@ mean_res_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, lig = lane % LPR;
   constexpr unsigned rows_per_cta = kWarps * RPW;
-  pdl_launch_dependents();
   pdl_wait();
+  if ((unsigned long long)gridDim.x * rows_per_cta >= M) pdl_launch_dependents();   // single pass: see common.cuh
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
     if (r >= M) continue;
@@ -56,8 +56,8 @@ mean_res_bwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ rowp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, lig = lane % LPR;
   constexpr unsigned rows_per_cta = kWarps * RPW;
-  pdl_launch_dependents();
   pdl_wait();
+  if ((unsigned long long)gridDim.x * rows_per_cta >= M) pdl_launch_dependents();   // single pass: see common.cuh
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const unsigned r = r0 + warp * RPW + sub;
     if (r >= M) continue;

@@ -98,12 +98,13 @@ int gatres_check_replicated(const int64_t* edge_index_batch, const int64_t* edge
 int64_t gatres_set_tile_min_batch(int64_t min_batch);
 
 /*
- * Kernel-selection knob: 1 = projections and their data gradients run on the tensor cores
- * (tcgen05.mma kind::tf32, 3xTF32 error-compensated, accumulator in TMEM) for the shapes
- * that have such a kernel (nc = 32), 0 = fp32 FFMA kernels everywhere.  Default 1, or the
- * GATRES_TC environment variable.  Negative = query only.  Returns the previous value.
+ * Kernel-selection knob for the projections and their data gradients: 0 = fp32 FFMA kernels
+ * everywhere; 1 (default) = tensor cores (tcgen05.mma kind::tf32, 3xTF32 error-compensated,
+ * accumulator in TMEM) for launches of >= 32768 rows and the shapes that have such a kernel
+ * (nc = 32); 2 = tensor cores whenever the shape allows.  GATRES_TC environment variable sets
+ * the initial mode.  Negative = query only.  Returns the previous mode.
  */
-int gatres_set_tensor_core(int enable);
+int gatres_set_tensor_core(int mode);
 
 /* --------------------------------------------------------------- operators */
 

@@ -105,7 +105,7 @@ def kernel_variant(request):
     lib = _lib.load()
     fancy = request.param == "tile-tc"
     prev_tile = lib.gatres_set_tile_min_batch(1 if fancy else 1 << 40)
-    prev_tc = lib.gatres_set_tensor_core(1 if fancy else 0)
+    prev_tc = lib.gatres_set_tensor_core(2 if fancy else 0)
     yield request.param
     lib.gatres_set_tile_min_batch(prev_tile)
     lib.gatres_set_tensor_core(prev_tc)
