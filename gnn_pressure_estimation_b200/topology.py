@@ -19,6 +19,10 @@ restated here as three explicit steps:
              the same double loop, ids = position in node order.
 
 tests/test_topology.py checks this against real networkx on random multigraphs.
+Caveat: when fewer than half of the nodes are kept, networkx's subgraph view walks
+the kept-node *set* (string-hash order, different from run to run), so the reference
+has no reproducible order to match there; this module always keeps registry order,
+which is what networkx does for real networks (C-Town keeps 388 of 396 nodes).
 This is host-side, once-per-``.inp`` indexing work (integer only).
 """
 from __future__ import annotations

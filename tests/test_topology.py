@@ -11,7 +11,11 @@ from oracle import topology_oracle as TO
 def test_random_multigraphs_match_networkx_pipeline():
     rnd = random.Random(7)
     for _ in range(200):
-        nj, nt = rnd.randint(2, 12), rnd.randint(0, 3)
+        nj = rnd.randint(2, 12)
+        # networkx's subgraph view iterates the kept-node SET (hash order, not reproducible) when it is
+        # smaller than half of the graph; real networks keep almost every node (C-Town: 388 of 396), so the
+        # contract — and this test — cover the regime where the reference itself is deterministic.
+        nt = rnd.randint(0, min(3, nj))
         j = [f"J{k}" for k in range(nj)]
         tk = [f"T{k}" for k in range(nt)]
         pool = j + tk
