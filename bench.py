@@ -345,7 +345,7 @@ def main():
             ts.step(y, y, m)                                   # x = y unmasked; the mask is applied on the device
             loss_host[slot:slot + 1].copy_(ts.loss, non_blocking=True)
 
-        launches_per_step = ts.kernels_per_step
+        launches_per_step = ts.kernels_per_step             # counted by the library while the step was captured
         h2d = M * (4 + 4 + 1)
         d2h = 4
     else:
@@ -363,7 +363,10 @@ def main():
             with torch.no_grad():
                 out_host.copy_(model(xdev, eib).view(-1), non_blocking=True)
 
-        launches_per_step = 2 + 5 * nb + 1
+        from gnn_pressure_estimation_b200 import _lib as _gl
+        n0 = _gl.load().gatres_launch_count()
+        step_resident(0)
+        launches_per_step = int(_gl.load().gatres_launch_count() - n0)
         h2d, d2h = 4 * M, 4 * M
 
     def barrier():

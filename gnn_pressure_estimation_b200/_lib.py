@@ -35,6 +35,7 @@ _PROTOTYPES = {
     "gatres_abi_version": (C.c_int, []),
     "gatres_last_error": (C.c_char_p, []),
     "gatres_sm_count": (C.c_int, []),
+    "gatres_launch_count": (_i64, []),
     "gatres_set_tile_min_batch": (_i64, [_i64]),
     "gatres_set_tensor_core": (C.c_int, [C.c_int]),
     "gatres_csr_scratch_bytes": (_sz, [_i64, _i32]),

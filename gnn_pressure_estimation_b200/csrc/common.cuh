@@ -45,6 +45,7 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 // SMs drain first; its static work split then runs unbalanced (measured: dgrad -> wgrad
 // chain 228 us -> 410 us at 2048 snapshots), so large launches keep plain serialization.
 bool pdl_enabled();
+void count_launch();                    // bumps the counter behind gatres_launch_count()
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -62,6 +63,7 @@ static inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  count_launch();
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface in check_launch()
 }
 #endif

@@ -22,6 +22,9 @@ int check_launch(const char* what) {
   return GATRES_ERR_CUDA;
 }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -128,6 +131,7 @@ using namespace gatres;
 extern "C" int gatres_abi_version(void) { return GATRES_ABI_VERSION; }
 extern "C" const char* gatres_last_error(void) { return g_err; }
 extern "C" int gatres_sm_count(void) { return sm_count(); }
+extern "C" int64_t gatres_launch_count(void) { return g_launches; }
 
 extern "C" int gatres_apply_mask(const float* x, const uint8_t* mask, float* x_masked, int64_t M, void* stream) {
   GATRES_REQUIRE(M >= 0, "apply_mask: bad M");

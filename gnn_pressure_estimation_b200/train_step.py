@@ -64,11 +64,17 @@ class TrainStep:
         self.scratch = torch.empty(int(lib.gatres_scratch_floats(C.byref(self.desc), 1)), **f32)
         self.partial = torch.empty(self.desc.slots * _gops.a4(P), **f32) if deterministic else None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        # our kernel launches per step: mask, forward, loss, backward (+ final reduction if deterministic), Adam
-        self.kernels_per_step = 1 + (2 + 5 * self.nb) + 2 + (2 + 9 * self.nb + int(deterministic)) + 2
+        # our kernel launches per step (mask, forward, loss, backward, Adam); measured in capture()/first run
+        self.kernels_per_step = 0
 
     # ------------------------------------------------------------------ pieces
     def _enqueue(self) -> None:
+        lib = _lib.load()
+        n0 = lib.gatres_launch_count()
+        self._enqueue_impl()
+        self.kernels_per_step = int(lib.gatres_launch_count() - n0)
+
+    def _enqueue_impl(self) -> None:
         s = stream()
         d = C.byref(self.desc)
         call("gatres_apply_mask", ptr(self.x), ptr(self.mask), ptr(self.xm), self.M, s)

@@ -58,6 +58,9 @@ int gatres_abi_version(void);
 const char* gatres_last_error(void);
 /* Number of SMs of the current device (grid sizing); <0 on error. */
 int gatres_sm_count(void);
+/* Kernels this library has launched so far in this process (step/forward kernels; the one-off CSR build is
+ * not counted).  Benchmarks difference it around one step to report launches per step. */
+int64_t gatres_launch_count(void);
 
 /* ------------------------------------------------------------------ graph */
 
