@@ -31,6 +31,7 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {       // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
                "r"(ncols)
@@ -97,11 +98,13 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
   constexpr uint32_t A_BYTES = BM * KK * 4, B_BYTES = NN * KK * 4;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   static_assert(KK % 32 == 0 && NN % 16 == 0 && NN >= 32 && NN <= 64 && NN <= 2 * KK, "unsupported tensor-core shape");
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // SWIZZLE_128B atoms are 1024 B aligned
-  unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t a_hi = base, a_lo = base + A_BYTES, b_hi = base + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
-  float* att = reinterpret_cast<float*>(sm + 2 * A_BYTES + 2 * B_BYTES);  // [2][NN] (MODE 0)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);                    // SWIZZLE_128B atoms must be 1024 B aligned
+  if ((base & 1023u) != 0) __trap();                           // (no slack is allocated: two CTAs of the K=64 shape fill an SM)
+  unsigned char* sm = smem_raw;
+  const uint32_t a_raw0 = base, a_lo = base + A_BYTES, a_raw1 = base + 2 * A_BYTES, b_hi = base + 3 * A_BYTES,
+                 b_lo = b_hi + B_BYTES;
+  float* att = reinterpret_cast<float*>(sm + 3 * A_BYTES + 2 * B_BYTES);  // [2][NN] (MODE 0)
   uint64_t* bar = reinterpret_cast<uint64_t*>(att + 2 * NN);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -119,8 +122,8 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
     const float w = MODE == 0 ? __ldg(W + (size_t)n * KK + k) : __ldg(W + (size_t)k * NN + n);
     const float hi = to_tf32(w), lo = to_tf32(w - hi);
     const uint32_t off = swz_off(n, k, NN);
-    *reinterpret_cast<float*>(sm + 2 * A_BYTES + off) = hi;
-    *reinterpret_cast<float*>(sm + 2 * A_BYTES + B_BYTES + off) = lo;
+    *reinterpret_cast<float*>(sm + 3 * A_BYTES + off) = hi;
+    *reinterpret_cast<float*>(sm + 3 * A_BYTES + B_BYTES + off) = lo;
   }
   if (MODE == 0)
     for (int idx = tid; idx < NN; idx += 128) {
@@ -133,32 +136,41 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
 
-  uint32_t phase = 0;
-  if (gridDim.x >= ntiles) pdl_launch_dependents();
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    // ---- stage the A tile (raw fp32) with cp.async into the swizzled layout ----
-    constexpr int CHUNKS = BM * KK / 4;                       // 16-byte chunks
+  // ---- software pipeline over this CTA's tiles ----
+  // buffers: [raw0][lo][raw1].  raw_c holds the fp32 tile as loaded (the tensor core reads its TF32 truncation,
+  // hi = trunc(x)), lo = rna(x - trunc(x)) is written by the staging threads, and the NEXT tile's cp.async flies
+  // into the other raw buffer during this tile's MMAs and epilogue.
+  constexpr int CHUNKS = BM * KK / 4;                         // 16-byte chunks per tile
+  auto issue_load = [&](unsigned t, uint32_t raw_addr) {
 #pragma unroll
     for (int q = 0; q < CHUNKS / 128; ++q) {
       const int idx = q * 128 + tid;
       const uint32_t row = idx / (KK / 4), c = idx % (KK / 4);
-      const unsigned grow = tile * BM + row;
+      const unsigned grow = t * BM + row;
       const bool ok = grow < M;
-      tc_cp_async16(a_hi + swz_off(row, 4 * c, BM), A + (size_t)(ok ? grow : 0) * KK + 4 * c, ok ? 16 : 0);
+      tc_cp_async16(raw_addr + swz_off(row, 4 * c, BM), A + (size_t)(ok ? grow : 0) * KK + 4 * c, ok ? 16 : 0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (gridDim.x >= ntiles) pdl_launch_dependents();
+  uint32_t phase = 0, it = 0;
+  if (blockIdx.x < ntiles) issue_load(blockIdx.x, a_raw0);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const uint32_t cur = it & 1u;
+    const uint32_t raw_c = cur ? a_raw1 : a_raw0, raw_n = cur ? a_raw0 : a_raw1;
+    const uint32_t stg = cur ? A_BYTES : 0u;                  // epilogue staging: raw0+lo (even) / lo+raw1 (odd)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // ---- split every chunk this thread loaded into TF32 hi (in place) and lo ----
+    if (tile + gridDim.x < ntiles) issue_load(tile + gridDim.x, raw_n);
+    // ---- lo part of every chunk this thread loaded ----
 #pragma unroll
     for (int q = 0; q < CHUNKS / 128; ++q) {
       const int idx = q * 128 + tid;
       const uint32_t row = idx / (KK / 4), c = idx % (KK / 4);
       const uint32_t off = swz_off(row, 4 * c, BM);
-      const float4 x = *reinterpret_cast<const float4*>(sm + off);
-      float4 hi, lo;
-      hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
-      lo.x = to_tf32(x.x - hi.x); lo.y = to_tf32(x.y - hi.y); lo.z = to_tf32(x.z - hi.z); lo.w = to_tf32(x.w - hi.w);
-      *reinterpret_cast<float4*>(sm + off) = hi;
+      const float4 x = *reinterpret_cast<const float4*>(sm + (raw_c - base) + off);
+      float4 lo;
+      lo.x = to_tf32(x.x - trunc_tf32(x.x)); lo.y = to_tf32(x.y - trunc_tf32(x.y));
+      lo.z = to_tf32(x.z - trunc_tf32(x.z)); lo.w = to_tf32(x.w - trunc_tf32(x.w));
       *reinterpret_cast<float4*>(sm + A_BYTES + off) = lo;
     }
     fence_proxy_async();                                      // generic-proxy smem writes -> tensor-core (async) proxy
@@ -171,9 +183,9 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
       for (int s = 0; s < KK / 8; ++s) {
         const uint32_t ka = (uint32_t)(s >> 2) * BM * 128u + (uint32_t)(s & 3) * 32u;     // A: atom block + 32 B per K slice
         const uint32_t kb = (uint32_t)(s >> 2) * NN * 128u + (uint32_t)(s & 3) * 32u;
-        umma_tf32(tmem, umma_desc_k128(a_hi + ka), umma_desc_k128(b_hi + kb), IDESC, s > 0);
+        umma_tf32(tmem, umma_desc_k128(raw_c + ka), umma_desc_k128(b_hi + kb), IDESC, s > 0);
         umma_tf32(tmem, umma_desc_k128(a_lo + ka), umma_desc_k128(b_hi + kb), IDESC, 1);
-        umma_tf32(tmem, umma_desc_k128(a_hi + ka), umma_desc_k128(b_lo + kb), IDESC, 1);
+        umma_tf32(tmem, umma_desc_k128(raw_c + ka), umma_desc_k128(b_lo + kb), IDESC, 1);
       }
       umma_commit(bar);
     }
@@ -205,7 +217,7 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
 #pragma unroll
       for (int k = 0; k < 32; k += 4) {
         const int c = cb * 8 + k / 4;
-        *reinterpret_cast<float4*>(sm + (size_t)tid * (NN * 4) + (((c ^ tid) & (NCH - 1)) << 4)) =
+        *reinterpret_cast<float4*>(sm + stg + (size_t)tid * (NN * 4) + (((c ^ tid) & (NCH - 1)) << 4)) =
             make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
       }
     }
@@ -224,7 +236,7 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
       const int r = idx / NCH, c = idx % NCH;
       const unsigned grow = tile * BM + r;
       if (grow < M) {
-        float4 t = *reinterpret_cast<const float4*>(sm + (size_t)r * (NN * 4) + (((c ^ r) & (NCH - 1)) << 4));
+        float4 t = *reinterpret_cast<const float4*>(sm + stg + (size_t)r * (NN * 4) + (((c ^ r) & (NCH - 1)) << 4));
         const size_t o = (size_t)grow * NN + 4 * c;
         if (MODE == 1) {
           if (e0 != nullptr) add4(t, ldg4_stream(e0 + o));
@@ -245,7 +257,7 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
 template <int KK, int NN, int MODE, int H>
 static int launch_tc(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
                      float* s1, unsigned M, cudaStream_t st, const char* what) {
-  constexpr size_t smem = 1024 + 2 * (size_t)128 * KK * 4 + 2 * (size_t)NN * KK * 4 + 2 * NN * 4 + 32;
+  constexpr size_t smem = 3 * (size_t)128 * KK * 4 + 2 * (size_t)NN * KK * 4 + 2 * NN * 4 + 32;
   auto kern = gemm_tc_kernel<KK, NN, MODE, H>;
   static bool configured = false;
   if (!configured) {
@@ -254,7 +266,7 @@ static int launch_tc(const float* A, const float* W, const float* e0, const floa
     configured = true;
   }
   const unsigned ntiles = (M + 127) / 128;
-  unsigned per_sm = (unsigned)((200u * 1024u) / smem);
+  unsigned per_sm = (unsigned)((228u * 1024u) / (smem + 1024u));       // +1 KB the system reserves per CTA
   per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
   unsigned grid = (unsigned)sm_count() * per_sm;
   if (grid > ntiles) grid = ntiles;
