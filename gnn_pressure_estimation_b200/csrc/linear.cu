@@ -195,22 +195,24 @@ gemm_rows_kernel(const float* __restrict__ A, const float* __restrict__ W,
 
 // ---------------------------------------------------------------------------
 // Weight gradient dW[NO,KI] = dh^T x, reduced over this CTA's row tiles and
-// written once to its row of `partial` (deterministic two-stage reduction).
-// Thread (tk,tn) owns TNn x TKk outputs.
+// emitted once (row of `partial`, or atomic add into the gradient buffer).
+// The 256 threads form G row groups; within a group thread (tk,tn) owns a
+// TNn x TKk block of dW and group g takes rows g, g+G, ... of every tile, so a
+// thread does TNn*TKk FFMAs per (TNn+TKk)/4 shared-memory loads (32 : 3 for
+// nc = 32) instead of 8 : 1.5; the G partial copies are summed through shared
+// memory at the end.
 // ---------------------------------------------------------------------------
-template <int NO, int KI, int BM, int TNn, int TKk>
+template <int NO, int KI, int BM, int TNn, int TKk, int G>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* __restrict__ partial,
              long long P, long long off_W, unsigned M, int atomic) {
-  constexpr int TKT = KI / TKk, TNT = NO / TNn, LDH = NO + 4, LDX = KI + 4;
-  constexpr int NVn = TNn / 4, CGn = NO / NVn;
-  constexpr int KW = TKk >= 4 ? 4 : TKk;            // contiguous k run per group
-  constexpr int NVk = TKk / KW, CGk = KI / NVk;
-  static_assert(TKT * TNT == 256 && TNn % 4 == 0 && (TKk == 2 || TKk % 4 == 0), "bad wgrad tiling");
+  constexpr int TKT = KI / TKk, TNT = NO / TNn, GT = 256 / G, LDH = NO + 4, LDX = KI + 4;
+  constexpr int NVn = TNn / 4, CGn = NO / NVn, NVk = TKk / 4, CGk = KI / NVk;
+  static_assert(TKT * TNT == GT && TNn % 4 == 0 && TKk % 4 == 0 && BM % G == 0, "bad wgrad tiling");
   extern __shared__ __align__(16) float smem[];
   float* Hs = smem;                         // [2][BM][LDH]
   float* Xs = smem + 2 * BM * LDH;          // [2][BM][LDX]
-  const int tid = threadIdx.x, tk = tid % TKT, tn = tid / TKT;
+  const int tid = threadIdx.x, grp = tid / GT, t = tid % GT, tk = t % TKT, tn = t / TKT;
   const unsigned ntiles = (M + BM - 1) / BM;
 
   auto load_tile = [&](unsigned tile, int stage) {
@@ -250,23 +252,18 @@ wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* _
     __syncthreads();
     const float* hs = Hs + stage * BM * LDH;
     const float* xs = Xs + stage * BM * LDX;
-#pragma unroll 4
-    for (int m = 0; m < BM; ++m) {
+#pragma unroll 2
+    for (int m = grp; m < BM; m += G) {       // rows past M were zero-filled
       float a[TNn], b[TKk];
 #pragma unroll
       for (int jv = 0; jv < NVn; ++jv) {
-        const float4 t = *reinterpret_cast<const float4*>(hs + m * LDH + jv * CGn + 4 * tn);
-        a[jv * 4 + 0] = t.x; a[jv * 4 + 1] = t.y; a[jv * 4 + 2] = t.z; a[jv * 4 + 3] = t.w;
+        const float4 q = *reinterpret_cast<const float4*>(hs + m * LDH + jv * CGn + 4 * tn);
+        a[jv * 4 + 0] = q.x; a[jv * 4 + 1] = q.y; a[jv * 4 + 2] = q.z; a[jv * 4 + 3] = q.w;
       }
 #pragma unroll
       for (int jv = 0; jv < NVk; ++jv) {
-        if constexpr (KW == 4) {
-          const float4 t = *reinterpret_cast<const float4*>(xs + m * LDX + jv * CGk + 4 * tk);
-          b[jv * 4 + 0] = t.x; b[jv * 4 + 1] = t.y; b[jv * 4 + 2] = t.z; b[jv * 4 + 3] = t.w;
-        } else {
-          const float2 t = *reinterpret_cast<const float2*>(xs + m * LDX + 2 * tk);
-          b[0] = t.x; b[1] = t.y;
-        }
+        const float4 q = *reinterpret_cast<const float4*>(xs + m * LDX + jv * CGk + 4 * tk);
+        b[jv * 4 + 0] = q.x; b[jv * 4 + 1] = q.y; b[jv * 4 + 2] = q.z; b[jv * 4 + 3] = q.w;
       }
 #pragma unroll
       for (int i = 0; i < TNn; ++i)
@@ -278,18 +275,32 @@ wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* _
   }
   cp_async_wait<0>();
 
-  float* dst = partial + (atomic ? 0 : (size_t)blockIdx.x * P) + off_W;
+  // ---- sum the G row-group copies through shared memory, then emit ----
+  float* red = smem;                         // [G-1][GT][TNn*TKk], aliases the (now idle) tile buffers
+  if (G > 1) {
+    __syncthreads();
+    if (grp > 0) {
+      float* dst = red + ((size_t)(grp - 1) * GT + t) * (TNn * TKk);
 #pragma unroll
-  for (int i = 0; i < TNn; ++i) {
-    const int n = (i / 4) * CGn + 4 * tn + (i % 4);
+      for (int i = 0; i < TNn; ++i)
 #pragma unroll
-    for (int jv = 0; jv < NVk; ++jv) {
-      if constexpr (KW == 4) {
-        emit4(dst + (size_t)n * KI + jv * CGk + 4 * tk,
-              make_float4(acc[i][jv * 4 + 0], acc[i][jv * 4 + 1], acc[i][jv * 4 + 2], acc[i][jv * 4 + 3]), atomic);
-      } else {
-        emit1(dst + (size_t)n * KI + 2 * tk, acc[i][0], atomic);
-        emit1(dst + (size_t)n * KI + 2 * tk + 1, acc[i][1], atomic);
+        for (int j = 0; j < TKk; j += 4)
+          st4(dst + i * TKk + j, make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]));
+    }
+    __syncthreads();
+  }
+  if (grp == 0) {
+    float* out = partial + (atomic ? 0 : (size_t)blockIdx.x * P) + off_W;
+#pragma unroll
+    for (int i = 0; i < TNn; ++i) {
+      const int n = (i / 4) * CGn + 4 * tn + (i % 4);
+#pragma unroll
+      for (int jv = 0; jv < NVk; ++jv) {
+        float4 v = make_float4(acc[i][jv * 4 + 0], acc[i][jv * 4 + 1], acc[i][jv * 4 + 2], acc[i][jv * 4 + 3]);
+#pragma unroll
+        for (int g2 = 1; g2 < G; ++g2)
+          add4(v, *reinterpret_cast<const float4*>(red + ((size_t)(g2 - 1) * GT + t) * (TNn * TKk) + i * TKk + jv * 4));
+        emit4(out + (size_t)n * KI + jv * CGk + 4 * tk, v, atomic);
       }
     }
   }
@@ -316,12 +327,14 @@ static int launch_gemm(const float* A, const float* W, const float* e0, const fl
   return check_launch(what);
 }
 
-template <int NO, int KI, int TNn, int TKk>
+template <int NO, int KI, int TNn, int TKk, int G>
 static int launch_wgrad(const float* dh, const float* x, float* partial, long long P, int slots, long long off_W,
                         unsigned M, cudaStream_t st) {
   constexpr int BM = 32;
-  constexpr size_t smem = (size_t)(2 * BM * (NO + 4) + 2 * BM * (KI + 4)) * sizeof(float);
-  auto kern = wgrad_kernel<NO, KI, BM, TNn, TKk>;
+  constexpr size_t tiles = (size_t)(2 * BM * (NO + 4) + 2 * BM * (KI + 4)) * sizeof(float);
+  constexpr size_t red = (size_t)(G - 1) * NO * KI * sizeof(float);
+  constexpr size_t smem = tiles > red ? tiles : red;
+  auto kern = wgrad_kernel<NO, KI, BM, TNn, TKk, G>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -543,14 +556,14 @@ extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W
     rc = rc == 1 ? 0 : dispatch_gemm<1, 1>(NO, K, dh, W, add, relu_ref, dx, nullptr, nullptr, (unsigned)M, st, "linear_bwd_dx");
     if (rc) return rc;
   }
-#define WG(NOv, KIv, TNn, TKk) \
-  if (NO == NOv && K == KIv) return launch_wgrad<NOv, KIv, TNn, TKk>(dh, x, partial, P, slots, off_W, (unsigned)M, st)
-  WG(64, 32, 4, 2);
-  WG(32, 64, 4, 2);
-  WG(128, 64, 8, 4);
-  WG(64, 128, 4, 8);
-  WG(256, 128, 16, 8);
-  WG(128, 256, 8, 16);
+#define WG(NOv, KIv, TNn, TKk, G) \
+  if (NO == NOv && K == KIv) return launch_wgrad<NOv, KIv, TNn, TKk, G>(dh, x, partial, P, slots, off_W, (unsigned)M, st)
+  WG(64, 32, 8, 4, 4);
+  WG(32, 64, 4, 8, 4);
+  WG(128, 64, 8, 8, 2);
+  WG(64, 128, 8, 8, 2);
+  WG(256, 128, 16, 8, 1);
+  WG(128, 256, 8, 16, 1);
 #undef WG
   set_error("linear_bwd: unsupported weight shape [%d,%d]", NO, K);
   return GATRES_ERR_ARG;
