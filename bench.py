@@ -426,8 +426,15 @@ def main():
         hbm = kernel_table(hbm_B, N, topo, nc, True, dev)
         dom = max((r for r in hbm if r["kernel"].startswith("gat_agg")), key=lambda r: r["us"])
         dom_l2 = next(r for r in in_step if r["kernel"] == dom["kernel"])
+        traffic = None
+        try:                                   # DRAM bytes per launch from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+            if tj.get("hbm_batch") == hbm_B:
+                traffic = tj["bytes_per_launch"].get(dom["kernel"])
+        except Exception:
+            pass
         line["roofline"] = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak,
-                            "unit": "GB/s", "frac": dom["GBps"] / peak, "traffic": None, "peak_source": which,
+                            "unit": "GB/s", "frac": dom["GBps"] / peak, "traffic": traffic, "peak_source": which,
                             "workload": f"{hbm_B} snapshots x {N} nodes per launch (tensors larger than L2), "
                                         f"{dom['bytes_per_node']} algorithmic B/node, {dom['us']:.1f} us/launch"}
         line["roofline_in_step"] = {"bound": "hbm", "kernel": dom_l2["kernel"], "achieved": dom_l2["GBps"], "peak": peak,
