@@ -57,6 +57,8 @@ _PROTOTYPES = {
     "gatres_scratch_floats": (_i64, [C.POINTER(ModelDesc), _i32]),
     "gatres_forward": (C.c_int, [C.POINTER(ModelDesc), _p, _p, _p, _p, _p, _p]),
     "gatres_backward": (C.c_int, [C.POINTER(ModelDesc), _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gatres_backward_range": (C.c_int, [C.POINTER(ModelDesc), _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
+    "gatres_param_offset_of_block": (_i64, [_i32, _i32, _i32]),
     "gatres_masked_mse": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "gatres_apply_mask": (C.c_int, [_p, _p, _p, _i64, _p]),
     "gatres_adam_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p]),

@@ -136,36 +136,47 @@ extern "C" int gatres_forward(const gatres_model_desc* d, const float* params, c
   return gatres_decoder_fwd(x0, params + pl.lin1_w(), params + pl.lin1_b(), out, d->poison, M, C, stream);
 }
 
-extern "C" int gatres_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
-                               const float* d_out, float* partial, float* grads, float* scratch, void* stream) {
+// Backward of blocks k_hi .. k_lo (descending).  The first range (k_hi == num_blocks-1) also runs the
+// decoder backward and zeroes the gradient buffer (atomic mode); the last one (k_lo == 0) also runs the
+// encoder backward and, in deterministic mode, the final reduction.  The gradient w.r.t. a block's output
+// lives in scratch slot (num_blocks-1-k) & 1, so consecutive ranges chain without extra state.
+extern "C" int gatres_backward_range(const gatres_model_desc* d, const float* params, const float* x,
+                                     const float* saved, const float* d_out, float* partial, float* grads,
+                                     float* scratch, int32_t k_hi, int32_t k_lo, void* stream) {
   TRY(validate(d, "backward"));
   GATRES_REQUIRE(params && x && saved && d_out && grads && scratch, "backward: null buffer");
   GATRES_REQUIRE(d->slots <= 0 || partial != nullptr, "backward: deterministic mode (slots > 0) needs `partial`");
   const int64_t M = d->B * (int64_t)d->N, nc = d->nc;
   const int32_t N = d->N, C = d->nc, S = d->slots, nb = d->num_blocks;
+  GATRES_REQUIRE(nb == 0 || (k_hi < nb && k_lo >= 0 && k_lo <= k_hi), "backward_range: bad block range [%d, %d]", k_lo,
+                 k_hi);
+  const bool head = nb == 0 || k_hi == nb - 1, tail = nb == 0 || k_lo == 0;
   const ParamLayout pl(nb, d->nc);
   const SavedLayout sl(M, nc);
   const int64_t P = a4(pl.count());                      // row stride of `partial`
   if (S <= 0) {
     // atomic mode: every kernel adds its contribution straight into `grads`
-    if (cudaMemsetAsync(grads, 0, (size_t)pl.count() * sizeof(float), as_stream(stream)) != cudaSuccess)
+    if (head && cudaMemsetAsync(grads, 0, (size_t)pl.count() * sizeof(float), as_stream(stream)) != cudaSuccess)
       return check_launch("backward: zero grads");
     partial = grads;
   }
 
-  float* gA = scratch;
-  float* gB = gA + M * nc;
-  float* dz = gB + M * nc;
+  float* gbuf[2] = {scratch, scratch + M * nc};
+  float* dz = scratch + 2 * M * nc;
   float* dh2 = dz + M * nc;
   float* dy1 = dh2 + M * nc;
   float* dh1 = dy1 + 2 * M * nc;
   float* rec = dh1 + 2 * M * nc;
   float* dsd = rec + 8 * M;
 
-  const float* x_last = nb > 0 ? saved + sl.xout(nb - 1) : saved + sl.x_enc();
-  TRY(gatres_decoder_bwd(d_out, x_last, params + pl.lin1_w(), gA, partial, P, S, pl.lin1_w(), pl.lin1_b(), M, C,
-                         nb > 0 ? 1 : 0, stream));
-  for (int k = nb - 1; k >= 0; --k) {
+  if (head) {
+    const float* x_last = nb > 0 ? saved + sl.xout(nb - 1) : saved + sl.x_enc();
+    TRY(gatres_decoder_bwd(d_out, x_last, params + pl.lin1_w(), gbuf[0], partial, P, S, pl.lin1_w(), pl.lin1_b(), M, C,
+                           nb > 0 ? 1 : 0, stream));
+  }
+  for (int k = nb > 0 ? k_hi : -1; k >= k_lo && k >= 0; --k) {
+    float* gA = gbuf[(nb - 1 - k) & 1];
+    float* gB = gbuf[(nb - k) & 1];
     const float* x0 = k > 0 ? saved + sl.xout(k - 1) : saved + sl.x_enc();
     // SimpleConv(mean) + residual: gA already carries the ReLU mask of this block's output
     TRY(gatres_mean_res_bwd(d->rowptr, d->rowptr_t, d->col_t, gA, nullptr, dz, nullptr, d->B, N, C, stream));
@@ -184,9 +195,20 @@ extern "C" int gatres_backward(const gatres_model_desc* d, const float* params, 
     // dx0 = dh1 W1 + (residual branch gA), masked by the previous block's ReLU (none before block 0)
     TRY(gatres_linear_bwd(dh1, x0, params + pl.c1_W(k), gA, k > 0 ? x0 : nullptr, gB, partial, P, S, pl.c1_W(k), M, C,
                           2, C, stream));
-    float* t = gA; gA = gB; gB = t;
   }
-  TRY(gatres_encoder_bwd(gA, x, partial, P, S, pl.lin0_w(), pl.lin0_b(), M, C, stream));
+  if (!tail) return GATRES_OK;
+  TRY(gatres_encoder_bwd(gbuf[nb & 1], x, partial, P, S, pl.lin0_w(), pl.lin0_b(), M, C, stream));
   if (S <= 0) return GATRES_OK;
   return gatres_reduce_partials(partial, P, S, 0, pl.count(), grads, stream);
+}
+
+extern "C" int64_t gatres_param_offset_of_block(int32_t num_blocks, int32_t nc, int32_t k) {
+  const ParamLayout pl(num_blocks, nc);
+  return k >= num_blocks ? pl.lin1_w() : (k < 0 ? 0 : pl.block(k));
+}
+
+extern "C" int gatres_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
+                               const float* d_out, float* partial, float* grads, float* scratch, void* stream) {
+  TRY(validate(d, "backward"));
+  return gatres_backward_range(d, params, x, saved, d_out, partial, grads, scratch, d->num_blocks - 1, 0, stream);
 }

@@ -14,7 +14,7 @@ Only host logic lives here (works with gloo on CPU for tests and NCCL on GPUs).
 from __future__ import annotations
 
 import os
-from typing import Optional, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -29,6 +29,31 @@ def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
                          "(equal shards keep mean-of-means == global mean)")
     per = global_batch // world
     return rank * per, (rank + 1) * per
+
+
+def bucket_ranges(num_blocks: int, buckets: int) -> List[Tuple[int, int]]:
+    """Split the backward walk over blocks num_blocks-1 .. 0 into `buckets` contiguous descending ranges
+    [(k_hi, k_lo), ...] of near-equal length (earlier = later blocks; the first range also carries the decoder,
+    the last one the encoder).  A model without blocks has the single range (-1, 0)."""
+    if num_blocks <= 0:
+        return [(-1, 0)]
+    buckets = max(1, min(int(buckets), num_blocks))
+    out, hi = [], num_blocks - 1
+    for i in range(buckets):
+        n = (num_blocks - (num_blocks - 1 - hi)) // (buckets - i)    # blocks left / ranges left
+        out.append((hi, hi - n + 1))
+        hi -= n
+    return out
+
+
+def bucket_slice(num_blocks: int, param_count: int, k_hi: int, k_lo: int, offset_of_block) -> Tuple[int, int]:
+    """[lo, hi) of the flat gradient buffer that is final once blocks k_hi..k_lo have been back-propagated
+    (layout lin0 | block 0 | ... | block nb-1 | lin1; `offset_of_block(k)` = start of block k, k == nb -> lin1)."""
+    head = num_blocks <= 0 or k_hi == num_blocks - 1
+    tail = num_blocks <= 0 or k_lo == 0
+    lo = 0 if tail else offset_of_block(k_lo)
+    hi = param_count if head else offset_of_block(k_hi + 1)
+    return lo, hi
 
 
 def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:

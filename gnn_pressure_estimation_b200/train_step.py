@@ -28,7 +28,8 @@ from .graph import Topology
 class TrainStep:
     def __init__(self, model: GATResMeanConv, topo: Topology, batch: int, mask_count_per_snapshot: int,
                  lr: float = 5e-4, weight_decay: float = 6e-6, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None, use_graph: bool = True, deterministic: bool = False):
+                 process_group=None, use_graph: bool = True, deterministic: bool = False,
+                 grad_buckets: Optional[int] = None):
         self.model, self.topo, self.B = model, topo, int(batch)
         self.N, self.nc, self.nb = topo.N, model.nc, model.num_blocks
         self.M = self.B * self.N
@@ -37,6 +38,13 @@ class TrainStep:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.use_graph = use_graph
+        # gradient buckets for the data-parallel all-reduce: backward walks blocks nb-1 .. 0, and a bucket's
+        # slice of the flat gradient buffer is reduced on a side stream while the next range still computes.
+        # (deterministic mode finishes every gradient in one final reduction, so it has a single bucket.)
+        if grad_buckets is None:
+            grad_buckets = 3 if (self.world > 1 and not deterministic) else 1
+        self.block_ranges = _dp.bucket_ranges(self.nb, 1 if deterministic else grad_buckets)
+        self._comm_stream: Optional[torch.cuda.Stream] = None
         dev = topo.rowptr.device
         self.device = dev
         self.flat = model.flat_parameters()
@@ -81,14 +89,37 @@ class TrainStep:
         call("gatres_forward", d, ptr(self.flat), ptr(self.xm), ptr(self.out), ptr(self.saved), ptr(self.scratch), s)
         call("gatres_masked_mse", ptr(self.out), ptr(self.y), ptr(self.mask), self.M, self.count, ptr(self.d_out),
              ptr(self.loss), ptr(self._loss_part), s)
-        call("gatres_backward", d, ptr(self.flat), ptr(self.xm), ptr(self.saved), ptr(self.d_out), ptr(self.partial),
-             ptr(self.grads), ptr(self.scratch), s)
-        if self.pg is not None and self.world > 1:
-            # equal shard sizes and equal masked counts per snapshot -> mean of local means == global mean
-            torch.distributed.all_reduce(self.grads, group=self.pg)
+        # equal shard sizes and equal masked counts per snapshot -> mean of local means == global mean, so the
+        # collective is a plain SUM (the 1/world factor is folded into the Adam kernel)
+        dp = self.pg is not None and self.world > 1
+        if not dp or len(self.block_ranges) == 1:
+            call("gatres_backward", d, ptr(self.flat), ptr(self.xm), ptr(self.saved), ptr(self.d_out),
+                 ptr(self.partial), ptr(self.grads), ptr(self.scratch), s)
+            if dp:
+                torch.distributed.all_reduce(self.grads, group=self.pg)
+        else:
+            self._backward_overlapped(d, s)
         call("gatres_adam_step", ptr(self.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              ptr(self.step_count), self.P, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
              1.0 / self.world, s)
+
+    def _backward_overlapped(self, d, s) -> None:
+        """Backward in block ranges; each range's finished slice of the flat gradient buffer is all-reduced
+        on a communication stream while the compute stream continues with the next range.  Only the last
+        bucket (block 0 + lin0) is exposed.  Works eagerly and under CUDA-graph capture (fork/join by events)."""
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        comm, compute = self._comm_stream, torch.cuda.current_stream()
+        lib = _lib.load()
+        for (k_hi, k_lo) in self.block_ranges:
+            call("gatres_backward_range", d, ptr(self.flat), ptr(self.xm), ptr(self.saved), ptr(self.d_out),
+                 ptr(self.partial), ptr(self.grads), ptr(self.scratch), k_hi, k_lo, s)
+            lo, hi = _dp.bucket_slice(self.nb, self.P, k_hi, k_lo,
+                                      lambda k: int(lib.gatres_param_offset_of_block(self.nb, self.nc, k)))
+            comm.wait_stream(compute)
+            with torch.cuda.stream(comm):
+                torch.distributed.all_reduce(self.grads[lo:hi], group=self.pg)
+        compute.wait_stream(comm)
 
     def capture(self, warmup: int = 1) -> None:
         """Run the step eagerly on a side stream (lazy CUDA/NCCL initialisation must

@@ -235,6 +235,21 @@ int gatres_backward(const gatres_model_desc* d, const float* params, const float
                     const float* saved, const float* d_out, float* partial, float* grads,
                     float* scratch, void* stream);
 
+/*
+ * The same backward in pieces, for overlapping the data-parallel gradient all-reduce with the rest of
+ * the backward pass: blocks k_hi .. k_lo (descending).  The range that starts at num_blocks-1 also runs
+ * the decoder backward (and zeroes `grads` in atomic mode); the range that ends at 0 also runs the
+ * encoder backward (and the final reduction in deterministic mode).  Ranges must be issued in
+ * descending order on one stream.  In atomic mode the gradients of blocks [k_lo, k_hi] (and lin1 / lin0
+ * for the first / last range) are final when the call's kernels complete:
+ * grads[gatres_param_offset_of_block(k_lo) .. gatres_param_offset_of_block(k_hi + 1)).
+ */
+int gatres_backward_range(const gatres_model_desc* d, const float* params, const float* x,
+                          const float* saved, const float* d_out, float* partial, float* grads,
+                          float* scratch, int32_t k_hi, int32_t k_lo, void* stream);
+/* Offset (floats) of block k's parameters in the flat layout; k >= num_blocks -> lin1.weight, k < 0 -> 0. */
+int64_t gatres_param_offset_of_block(int32_t num_blocks, int32_t nc, int32_t k);
+
 /* ------------------------------------------------------- caller-side fusions */
 
 /*

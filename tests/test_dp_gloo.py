@@ -83,3 +83,26 @@ def test_shard_bounds():
     assert dp.shard_bounds(16384, 3, 8) == (6144, 8192)
     with pytest.raises(ValueError):
         dp.shard_bounds(10, 0, 4)
+
+
+@pytest.mark.parametrize("nb,buckets", [(15, 3), (15, 4), (25, 5), (2, 3), (1, 1), (0, 2), (15, 1)])
+def test_gradient_buckets_partition_the_flat_buffer(nb, buckets):
+    """Backward walks blocks nb-1..0; the slices that become final after each range must tile [0, P)
+    from the top down (layout: lin0 | block 0 .. nb-1 | lin1), with no gap and no overlap."""
+    nc = 32
+    block = 4 * nc * nc + 9 * nc
+    P = 2 * nc + nb * block + nc + 1
+    off = lambda k: 2 * nc + min(max(k, 0), nb) * block if k >= 0 else 0   # same rule as gatres_param_offset_of_block
+    ranges = dp.bucket_ranges(nb, buckets)
+    assert len(ranges) == (max(1, min(buckets, nb)) if nb > 0 else 1)
+    if nb > 0:
+        assert ranges[0][0] == nb - 1 and ranges[-1][1] == 0
+        assert all(a[1] == b[0] + 1 for a, b in zip(ranges, ranges[1:]))        # descending, contiguous
+        sizes = [hi - lo + 1 for hi, lo in ranges]
+        assert max(sizes) - min(sizes) <= 1
+    top = P
+    for k_hi, k_lo in ranges:
+        lo, hi = dp.bucket_slice(nb, P, k_hi, k_lo, off)
+        assert hi == top and lo < hi
+        top = lo
+    assert top == 0

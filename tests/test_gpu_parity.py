@@ -281,6 +281,46 @@ def test_gradient_is_mean_over_shards(dev, G):
     assert_close(0.5 * (grads[1] + grads[2]), grads[0], 1e-4, "shard-mean gradient")
 
 
+def test_backward_in_block_ranges_equals_one_call(dev, G):
+    """gatres_backward_range (the pieces the DP all-reduce overlaps with) == gatres_backward, and each range's
+    slice of the flat gradient buffer is final when the range returns."""
+    import ctypes as C
+    from gnn_pressure_estimation_b200 import _lib, dp
+    from gnn_pressure_estimation_b200.train_step import TrainStep
+    c = load_case("ctown_small_15b_32c_B8")
+    model, _ = _cuda_model_from_case(c, G, dev)
+    N, B = c["N"], c["B"]
+    topo = model.set_topology(c["edge_index"].to(dev), N)
+    ts = TrainStep(model, topo, B, mask_count_per_snapshot=int(N * 0.95), use_graph=False)
+    ts.load_inputs(c["y"].to(dev), c["y"].to(dev), c["mask"].to(dev))
+    lib = _lib.load()
+    s, d = _lib.stream(), C.byref(ts.desc)
+    p = _lib.ptr
+    _lib.call("gatres_apply_mask", p(ts.x), p(ts.mask), p(ts.xm), ts.M, s)
+    _lib.call("gatres_forward", d, p(ts.flat), p(ts.xm), p(ts.out), p(ts.saved), p(ts.scratch), s)
+    _lib.call("gatres_masked_mse", p(ts.out), p(ts.y), p(ts.mask), ts.M, ts.count, p(ts.d_out), p(ts.loss),
+              p(ts._loss_part), s)
+    _lib.call("gatres_backward", d, p(ts.flat), p(ts.xm), p(ts.saved), p(ts.d_out), None, p(ts.grads), p(ts.scratch), s)
+    whole = ts.grads.clone()
+    off = lambda k: int(lib.gatres_param_offset_of_block(ts.nb, ts.nc, k))
+    assert off(0) == 2 * ts.nc and off(ts.nb) == ts.P - ts.nc - 1 and off(-1) == 0
+    for buckets in (2, 3, 15):
+        ts.grads.fill_(float("nan"))                       # the head range must zero the buffer itself
+        done_from = ts.P
+        for k_hi, k_lo in dp.bucket_ranges(ts.nb, buckets):
+            _lib.call("gatres_backward_range", d, p(ts.flat), p(ts.xm), p(ts.saved), p(ts.d_out), None, p(ts.grads),
+                      p(ts.scratch), k_hi, k_lo, s)
+            lo, hi = dp.bucket_slice(ts.nb, ts.P, k_hi, k_lo, off)
+            assert hi == done_from
+            done_from = lo
+            # atomic accumulation order differs between runs -> tolerance, not equality
+            assert_close(ts.grads[lo:], whole[lo:], 1e-4, f"{buckets} buckets, final slice after blocks {k_hi}..{k_lo}")
+        assert done_from == 0
+    with pytest.raises(_lib.GatresError):
+        _lib.call("gatres_backward_range", d, p(ts.flat), p(ts.xm), p(ts.saved), p(ts.d_out), None, p(ts.grads),
+                  p(ts.scratch), 3, 5, s)
+
+
 # --------------------------------------------------------------- train step
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_train_step_matches_oracle_adam(use_graph, dev, G):
