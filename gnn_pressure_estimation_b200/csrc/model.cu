@@ -5,52 +5,17 @@
 // stream, so the Python host pays two FFI crossings per training step and the
 // whole step can be captured into a CUDA graph.
 #include "common.cuh"
+#include "layout.cuh"
 
 namespace gatres {
 
-static inline int64_t a4(int64_t n) { return (n + 3) & ~(int64_t)3; }
-
-struct ParamLayout {
-  int64_t nc, nb;
-  explicit ParamLayout(int32_t num_blocks, int32_t nc_) : nc(nc_), nb(num_blocks) {}
-  int64_t lin0_w() const { return 0; }
-  int64_t lin0_b() const { return nc; }
-  int64_t block_size() const { return 4 * nc * nc + 9 * nc; }
-  int64_t block(int64_t k) const { return 2 * nc + k * block_size(); }
-  int64_t c1_W(int64_t k) const { return block(k); }
-  int64_t c1_as(int64_t k) const { return block(k) + 2 * nc * nc; }
-  int64_t c1_ad(int64_t k) const { return c1_as(k) + 2 * nc; }
-  int64_t c1_b(int64_t k) const { return c1_ad(k) + 2 * nc; }
-  int64_t c2_W(int64_t k) const { return c1_b(k) + 2 * nc; }
-  int64_t c2_as(int64_t k) const { return c2_W(k) + 2 * nc * nc; }
-  int64_t c2_ad(int64_t k) const { return c2_as(k) + nc; }
-  int64_t c2_b(int64_t k) const { return c2_ad(k) + nc; }
-  int64_t lin1_w() const { return block(nb); }
-  int64_t lin1_b() const { return lin1_w() + nc; }
-  int64_t count() const { return lin1_b() + 1; }
-};
-
-// activations forward(training) keeps for backward
-struct SavedLayout {
-  int64_t M, nc;
-  SavedLayout(int64_t M_, int64_t nc_) : M(M_), nc(nc_) {}
-  int64_t x_enc() const { return 0; }
-  int64_t block_size() const { return 6 * M * nc + 4 * a4(2 * M) + 4 * a4(M); }
-  int64_t block(int64_t k) const { return M * nc + k * block_size(); }
-  int64_t h1(int64_t k) const { return block(k); }
-  int64_t ss1(int64_t k) const { return h1(k) + 2 * M * nc; }
-  int64_t sd1(int64_t k) const { return ss1(k) + a4(2 * M); }
-  int64_t m1(int64_t k) const { return sd1(k) + a4(2 * M); }
-  int64_t l1(int64_t k) const { return m1(k) + a4(2 * M); }
-  int64_t y1(int64_t k) const { return l1(k) + a4(2 * M); }
-  int64_t h2(int64_t k) const { return y1(k) + 2 * M * nc; }
-  int64_t ss2(int64_t k) const { return h2(k) + M * nc; }
-  int64_t sd2(int64_t k) const { return ss2(k) + a4(M); }
-  int64_t m2(int64_t k) const { return sd2(k) + a4(M); }
-  int64_t l2(int64_t k) const { return m2(k) + a4(M); }
-  int64_t xout(int64_t k) const { return l2(k) + a4(M); }
-  int64_t total(int64_t nb) const { return block(nb); }
-};
+// snapshot-resident cluster kernels for small batches (resident.cu)
+bool resident_eligible(const gatres_model_desc* d, bool backward);
+int resident_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
+                     float* scratch, cudaStream_t st);
+int resident_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
+                      const float* d_out, float* grads, float* scratch, int k_hi, int k_lo, bool head, bool tail,
+                      cudaStream_t st);
 
 static int validate(const gatres_model_desc* d, const char* who) {
   GATRES_REQUIRE(d != nullptr, "%s: null model descriptor", who);
@@ -97,6 +62,7 @@ extern "C" int gatres_forward(const gatres_model_desc* d, const float* params, c
   const ParamLayout pl(d->num_blocks, d->nc);
   const SavedLayout sl(M, nc);
   const bool train = saved != nullptr;
+  if (resident_eligible(d, false)) return resident_forward(d, params, x, out, saved, scratch, as_stream(stream));
 
   // inference: rolling buffers carved from scratch
   float* xa = scratch;
@@ -160,6 +126,9 @@ extern "C" int gatres_backward_range(const gatres_model_desc* d, const float* pa
       return check_launch("backward: zero grads");
     partial = grads;
   }
+  if (resident_eligible(d, true))
+    return resident_backward(d, params, x, saved, d_out, grads, scratch, nb > 0 ? k_hi : -1, nb > 0 ? k_lo : 0, head,
+                             tail, as_stream(stream));
 
   float* gbuf[2] = {scratch, scratch + M * nc};
   float* dz = scratch + 2 * M * nc;

@@ -101,6 +101,20 @@ int gatres_check_replicated(const int64_t* edge_index_batch, const int64_t* edge
 int64_t gatres_set_tile_min_batch(int64_t min_batch);
 
 /*
+ * Kernel-selection knob for gatres_forward / gatres_backward[_range]: batches of at most `max_batch`
+ * snapshots (nc = 32, gradient mode slots = 0 for the backward, graph slice fits shared memory) run the
+ * snapshot-resident cluster kernels — one thread-block cluster per snapshot carries the whole stack, layers
+ * separated by cluster barriers instead of kernel launches; larger batches run layer by layer.  Default
+ * 256, or the GATRES_RESIDENT_MAX_B environment variable; 0 disables.  Negative = query only.  Returns
+ * the previous value.
+ */
+int64_t gatres_set_resident_max_batch(int64_t max_batch);
+/* CTAs per snapshot cluster of the resident kernels: 1, 2, 4 or 8; 0 = automatic (as many as keeps the batch
+ * co-resident at two CTAs per SM; GATRES_RESIDENT_CLUSTER presets it).  Other values only query.  Returns
+ * the previous setting. */
+int32_t gatres_set_resident_cluster(int32_t ctas);
+
+/*
  * Kernel-selection knob for the projections and their data gradients: 0 = fp32 FFMA kernels
  * everywhere; 1 (default) = tensor cores (tcgen05.mma kind::tf32, 3xTF32 error-compensated,
  * accumulator in TMEM) for launches of >= 32768 rows and the shapes that have such a kernel

@@ -97,18 +97,22 @@ GRAPHS = {
 }
 
 
-@pytest.fixture(params=["gather-ffma", "tile-tc"])
+@pytest.fixture(params=["gather-ffma", "tile-tc", "resident"])
 def kernel_variant(request):
-    """run a test with (a) the gather aggregation kernels + fp32 FFMA projections and (b) the TMA-staged
-    snapshot-tile aggregation kernels (default only for batches >= 64) + tcgen05 3xTF32 projections."""
+    """run a test with (a) the gather aggregation kernels + fp32 FFMA projections, (b) the TMA-staged
+    snapshot-tile aggregation kernels (default only for batches >= 64) + tcgen05 3xTF32 projections, and
+    (c) the snapshot-resident cluster kernels (whole-model calls of small batches; op-level calls are
+    unaffected).  (a) and (b) switch the resident path off so that the layer kernels stay covered."""
     from gnn_pressure_estimation_b200 import _lib
     lib = _lib.load()
     fancy = request.param == "tile-tc"
     prev_tile = lib.gatres_set_tile_min_batch(1 if fancy else 1 << 40)
     prev_tc = lib.gatres_set_tensor_core(2 if fancy else 0)
+    prev_res = lib.gatres_set_resident_max_batch(256 if request.param == "resident" else 0)
     yield request.param
     lib.gatres_set_tile_min_batch(prev_tile)
     lib.gatres_set_tensor_core(prev_tc)
+    lib.gatres_set_resident_max_batch(prev_res)
 
 
 @pytest.mark.parametrize("graph,B", [("tiny", 1), ("tiny", 5), ("ctown", 3), ("directed", 2)])
@@ -228,6 +232,54 @@ def test_model_matches_golden(name, deterministic, dev, G, kernel_variant):
         if "grads" in c:
             ref = c["grads"][k]
             assert float((p.grad.cpu() - ref).abs().max()) <= GRAD_TOL * max(float(ref.abs().max()), floor), k
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 0])
+@pytest.mark.parametrize("graph,B,blocks", [("tiny", 5, 2), ("directed", 3, 3), ("ctown", 4, 4), ("ctown", 40, 2)])
+def test_resident_kernels_equal_layer_kernels(graph, B, blocks, cluster, dev, G):
+    """The snapshot-resident cluster kernels (small batches) against the layer-by-layer kernels on the same
+    weights and inputs: forward (training and inference) and every parameter gradient, for each cluster size.
+    `directed` has in-degrees above 8 (chunked online softmax) and an asymmetric transposed CSR; `tiny` leaves
+    CTAs of the cluster without rows."""
+    from gnn_pressure_estimation_b200 import _lib
+    lib = _lib.load()
+    ei, names = GRAPHS[graph]() if graph != "directed" else (random_directed_graph(50, 420, 3).numpy(), list(range(50)))
+    ei = torch.as_tensor(ei)
+    N = len(names)
+    ref = O.make_oracle(blocks, 32, seed=11)
+    x, y, mask = O.synthetic_snapshots(N, B, seed=5)
+    eib = O.collate_edge_index(ei, N, B).to(dev)
+    results = []
+    prev_c = lib.gatres_set_resident_cluster(cluster)
+    prev = lib.gatres_set_resident_max_batch(-1)
+    try:
+        for max_b in (0, 256):
+            lib.gatres_set_resident_max_batch(max_b)
+            model = G.GATResMeanConv(num_blocks=blocks, nc=32)
+            model.load_state_dict(ref.state_dict())
+            model = model.to(dev)
+            batch = torch.arange(B, device=dev).repeat_interleave(N)
+            out = model(x.to(dev), eib, batch, None)
+            torch.nn.functional.mse_loss(out[mask.to(dev)], y.to(dev)[mask.to(dev)]).backward()
+            with torch.no_grad():
+                out_inf = model(x.to(dev), eib, batch, None)
+            assert torch.equal(out.detach(), out_inf)
+            results.append((out.detach(), {k: p.grad.clone() for k, p in model.named_parameters()}))
+    finally:
+        lib.gatres_set_resident_max_batch(prev)
+        lib.gatres_set_resident_cluster(prev_c)
+    (out_l, g_l), (out_r, g_r) = results
+    assert_close(out_r, out_l, 1e-5, "resident forward vs layer kernels")
+    floor = 1e-3 * max(float(g.norm()) for g in g_l.values())
+    for k in g_l:
+        err = float((g_r[k] - g_l[k]).abs().max())
+        assert err <= 1e-4 * max(float(g_l[k].abs().max()), floor), f"{k}: {err}"
+    # and against the CPU oracle
+    out_ref, _, grads_ref = O.train_step_loss_and_grads(ref, x, y, mask, O.collate_edge_index(ei, N, B))
+    assert_close(out_r, out_ref, FWD_TOL, "resident forward vs oracle")
+    floor = 1e-3 * max(float(g.norm()) for g in grads_ref.values())
+    for k, g in grads_ref.items():
+        assert float((g_r[k].cpu() - g).abs().max()) <= GRAD_TOL * max(float(g.abs().max()), floor), k
 
 
 def test_model_inference_equals_training_forward_and_batch_hint(dev, G):
