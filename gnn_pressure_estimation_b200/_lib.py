@@ -39,6 +39,8 @@ _PROTOTYPES = {
     "gatres_set_tile_min_batch": (_i64, [_i64]),
     "gatres_set_resident_max_batch": (_i64, [_i64]),
     "gatres_set_resident_cluster": (_i32, [_i32]),
+    "gatres_set_resident_threads": (_i32, [_i32]),
+    "gatres_set_resident_profile": (None, [_p, _i32]),
     "gatres_set_tensor_core": (C.c_int, [C.c_int]),
     "gatres_csr_scratch_bytes": (_sz, [_i64, _i32]),
     "gatres_csr_build": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -27,710 +27,6 @@
 
 namespace gatres {
 namespace res {
-
-constexpr int NC = 32;             // channels (gatres_small); other widths use the layer kernels
-constexpr int T = 256;             // threads per CTA
-constexpr int LDX = NC + 4;        // padded row of a [*, 32] shared tile
-constexpr int LDY = 2 * NC + 4;    // padded row of a [*, 64] shared tile
-constexpr int W1F = 2 * NC * LDX;  // conv1 weight [64][32] padded
-constexpr int W2F = NC * LDY;      // conv2 weight [32][64] padded
-constexpr int VECF = 9 * NC;       // as1 ad1 b1 (64 each) as2 ad2 b2 (32 each)
-constexpr unsigned FULL = 0xffffffffu;
-
-struct Args {
-  const int* rowptr;
-  const int* col;
-  const int* rowptr_t;
-  const int* col_t;
-  const float* params;
-  const float* x;        // [M] model input (masked nodes already zeroed)
-  float* out;            // fwd: [M]
-  float* saved;          // fwd: training activations or NULL; bwd: the same buffer
-  float* scratch;
-  const float* d_out;    // bwd: [M]
-  float* grads;          // bwd: flat gradient buffer (atomic accumulation)
-  const int* poison;
-  long long M;
-  int N, nb, R, B;
-  int k_hi, k_lo, head, tail;
-};
-
-// ---- cluster / memory primitives ------------------------------------------------
-__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
-// all threads of all CTAs of the cluster; global writes before it are visible cluster-wide after it
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// coherent loads: tensors produced inside this kernel by other CTAs of the cluster (never ld.global.nc)
-__device__ __forceinline__ float4 ldc4(const float* p) {
-  float4 r;
-  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float ldc1(const float* p) {
-  float r;
-  asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
-  return r;
-}
-template <bool COH> __device__ __forceinline__ float4 ld4(const float* p) { return COH ? ldc4(p) : ldg4(p); }
-template <bool COH> __device__ __forceinline__ float ld1(const float* p) { return COH ? ldc1(p) : __ldg(p); }
-__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
-
-__device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ float gmax8(float v) {
-  v = fmaxf(v, __shfl_xor_sync(FULL, v, 4));
-  v = fmaxf(v, __shfl_xor_sync(FULL, v, 2));
-  return fmaxf(v, __shfl_xor_sync(FULL, v, 1));
-}
-__device__ __forceinline__ float4 relu4(float4 v) {
-  return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-}
-__device__ __forceinline__ float4 mask4(float4 v, float4 ref) {
-  return make_float4(ref.x > 0.f ? v.x : 0.f, ref.y > 0.f ? v.y : 0.f, ref.z > 0.f ? v.z : 0.f, ref.w > 0.f ? v.w : 0.f);
-}
-
-// one block's parameters (contiguous W1 as1 ad1 b1 W2 as2 ad2 b2) -> padded shared tiles, 16 B per cp.async
-__device__ __forceinline__ void stage_block_params(const float* blk, float* W1s, float* W2s, float* vec) {
-  constexpr int C_W1 = 2 * NC * NC / 4, C_V1 = 6 * NC / 4, C_W2 = 2 * NC * NC / 4, C_V2 = 3 * NC / 4;
-  for (int c = threadIdx.x; c < C_W1 + C_V1 + C_W2 + C_V2; c += T) {
-    float* dst;
-    if (c < C_W1) dst = W1s + (c / (NC / 4)) * LDX + 4 * (c % (NC / 4));
-    else if (c < C_W1 + C_V1) dst = vec + 4 * (c - C_W1);
-    else if (c < C_W1 + C_V1 + C_W2) {
-      const int q = c - C_W1 - C_V1;
-      dst = W2s + (q / (2 * NC / 4)) * LDY + 4 * (q % (2 * NC / 4));
-    } else dst = vec + 6 * NC + 4 * (c - C_W1 - C_V1 - C_W2);
-    cp16(dst, blk + 4 * c);
-  }
-}
-
-// own rows [0, n) of a row-major global tensor -> padded shared tile (cp.async, 16 B chunks)
-template <int F, int LD>
-__device__ __forceinline__ void stage_rows(const float* g, float* s, int n) {
-  for (int c = threadIdx.x; c < n * (F / 4); c += T) cp16(s + (c / (F / 4)) * LD + 4 * (c % (F / 4)), g + 4 * c);
-}
-
-// ---- row-local projections (A operand resident in shared memory) ---------------------
-// out[m][n] = sum_k A[m][k] W[n][k]  (W [NOUT][K] as stored by PyG Linear), + attention scores.
-// Thread (tx, ty): output columns {tx + TX j}, rows {m0 + ty + TY i}; k ascending like linear.cu.
-template <int K, int NOUT, int H, int LDA, int LDW>
-__device__ __forceinline__ void project_rows(const float* As, const float* Ws, const float* att_s, const float* att_d,
-                                             float* h_own, float* ss_own, float* sd_own, int n) {
-  constexpr int TN = 4, TX = NOUT / TN, TY = T / TX, TM = 64 / TY;
-  static_assert(TM * TY == 64 && (TX == 8 || TX == 16), "tiling");
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  float as_[TN], ad_[TN];
-#pragma unroll
-  for (int j = 0; j < TN; ++j) { as_[j] = att_s[tx + TX * j]; ad_[j] = att_d[tx + TX * j]; }
-  for (int m0 = 0; m0 < n; m0 += 64) {
-    float acc[TM][TN];
-    int row[TM];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      row[i] = min(m0 + ty + TY * i, n - 1);
-#pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    }
-#pragma unroll 2
-    for (int k4 = 0; k4 < K / 4; ++k4) {
-      float4 a[TM], w[TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = lds4(As + row[i] * LDA + 4 * k4);
-#pragma unroll
-      for (int j = 0; j < TN; ++j) w[j] = lds4(Ws + (tx + TX * j) * LDW + 4 * k4);
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) {
-          acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
-          acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
-          acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
-          acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int m = m0 + ty + TY * i;
-      const bool ok = m < n;
-      // column tx + TX j belongs to head (tx + TX j) / 32: H = 2 -> j / 2 (TX = 16); H = 1 -> 0
-      float ps[H], pd[H];
-#pragma unroll
-      for (int hh = 0; hh < H; ++hh) ps[hh] = pd[hh] = 0.f;
-#pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int hh = H == 1 ? 0 : j / 2;
-        ps[hh] = fmaf(acc[i][j], as_[j], ps[hh]);
-        pd[hh] = fmaf(acc[i][j], ad_[j], pd[hh]);
-      }
-#pragma unroll
-      for (int hh = 0; hh < H; ++hh) {
-        ps[hh] = group_sum<TX>(ps[hh], FULL);
-        pd[hh] = group_sum<TX>(pd[hh], FULL);
-      }
-      if (ok) {
-#pragma unroll
-        for (int j = 0; j < TN; ++j) h_own[(size_t)m * NOUT + tx + TX * j] = acc[i][j];
-        if (tx == 0) {
-#pragma unroll
-          for (int hh = 0; hh < H; ++hh) { ss_own[m * H + hh] = ps[hh]; sd_own[m * H + hh] = pd[hh]; }
-        }
-      }
-    }
-  }
-}
-
-// dx[m][k] = sum_n G[m][n] W[n][k]   (data gradient; W [NRED][NOUT] as stored).  Thread owns 4 consecutive
-// output columns.  Epilogue supplied by the caller through `fin(m, col4, value)`.
-template <int NRED, int NOUT, int LDG, int LDW, typename Fin>
-__device__ __forceinline__ void dgrad_rows(const float* Gs, const float* Ws, int n, Fin fin) {
-  constexpr int TX = NOUT / 4, TY = T / TX, TM = 64 / TY;
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  for (int m0 = 0; m0 < n; m0 += 64) {
-    float4 acc[TM];
-    int row[TM];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) { row[i] = min(m0 + ty + TY * i, n - 1); acc[i] = f4zero(); }
-#pragma unroll 2
-    for (int n4 = 0; n4 < NRED / 4; ++n4) {
-      float4 a[TM], w[4];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = lds4(Gs + row[i] * LDG + 4 * n4);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = lds4(Ws + (4 * n4 + q) * LDW + 4 * tx);
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        fma4(acc[i], a[i].x, w[0]);
-        fma4(acc[i], a[i].y, w[1]);
-        fma4(acc[i], a[i].z, w[2]);
-        fma4(acc[i], a[i].w, w[3]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int m = m0 + ty + TY * i;
-      if (m < n) fin(m, 4 * tx, acc[i]);
-    }
-  }
-}
-
-// dW[no][ki] += sum_m G[m][no] X[m][ki]: thread owns a 4 x 2 block, atomics at the end.
-template <int NO, int KI, int LDG, int LDXX>
-__device__ __forceinline__ void wgrad_rows(const float* Gs, const float* Xs, int n, float* dW) {
-  constexpr int TNN = NO / 4;                 // threads along the output rows
-  static_assert(TNN * (KI / 2) == T, "wgrad tiling");
-  const int tn = threadIdx.x % TNN, tk = threadIdx.x / TNN;
-  float2 acc[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
-#pragma unroll 4
-  for (int m = 0; m < n; ++m) {
-    const float4 g = lds4(Gs + m * LDG + 4 * tn);
-    const float2 xv = lds2(Xs + m * LDXX + 2 * tk);
-    acc[0].x = fmaf(g.x, xv.x, acc[0].x); acc[0].y = fmaf(g.x, xv.y, acc[0].y);
-    acc[1].x = fmaf(g.y, xv.x, acc[1].x); acc[1].y = fmaf(g.y, xv.y, acc[1].y);
-    acc[2].x = fmaf(g.z, xv.x, acc[2].x); acc[2].y = fmaf(g.z, xv.y, acc[2].y);
-    acc[3].x = fmaf(g.w, xv.x, acc[3].x); acc[3].y = fmaf(g.w, xv.y, acc[3].y);
-  }
-  if (n > 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<float2*>(dW + (size_t)(4 * tn + i) * KI + 2 * tk), acc[i]);
-  }
-}
-
-// ---- fused GAT aggregation over this CTA's rows (same lane mapping as gat_agg.cu, C = 32) ----------
-// LPR = 8H lanes own a row (one float4 chunk each); lane `slot` of a head group evaluates edge `slot`.
-template <int H, bool TRAIN>
-__device__ __forceinline__ void agg_fwd_rows(const int* __restrict__ rowptr, const int* __restrict__ col,
-                                             const float* hsnap, const float* sssnap, const float* sd_own,
-                                             const float* bias_s, float* out_g, float* out_s, int lds_out,
-                                             float* m_own, float* l_own, int lo, int n, bool relu) {
-  constexpr int F = 32 * H, LPR = 8 * H, RPW = 32 / LPR, PRE = 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR, slot = lig & 7, hd = lig >> 3;
-  const float4 bv = lds4(bias_s + 4 * lig);
-  for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
-    const int il_raw = i0 + warp * RPW + sub;
-    const bool ok = il_raw < n;
-    const int il = ok ? il_raw : n - 1, i = lo + il;
-    const int beg = __ldg(rowptr + i), deg = __ldg(rowptr + i + 1) - beg;
-    const int deg_max = __reduce_max_sync(FULL, deg);
-    const float sd = ldc1(sd_own + il * H + hd);
-    float mrun = -CUDART_INF_F, lrun = 0.f;
-    float4 acc = f4zero();
-    for (int e0 = 0; e0 < deg_max; e0 += 8) {
-      const bool valid = e0 + slot < deg;
-      const int j = valid ? __ldg(col + beg + e0 + slot) : 0;
-      const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
-      float4 x[PRE];
-#pragma unroll
-      for (int u = 0; u < PRE; ++u) {
-        const int ju = __shfl_sync(FULL, j, u, 8);
-        x[u] = u < cnt ? ldc4(hsnap + (size_t)ju * F + 4 * lig) : f4zero();
-      }
-      const float a = valid ? lrelu(ldc1(sssnap + j * H + hd) + sd) : -CUDART_INF_F;
-      const float nm = fmaxf(mrun, gmax8(a));
-      if (e0 > 0) {
-        const float sc = __expf(mrun - nm);
-        lrun *= sc;
-        acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
-      }
-      const float p = __expf(a - nm);
-      lrun += group_sum<8>(p, FULL);
-      mrun = nm;
-#pragma unroll
-      for (int u = 0; u < PRE; ++u) fma4(acc, __shfl_sync(FULL, p, u, 8), x[u]);
-      for (int t = PRE; t < cnt_max; t += 2) {
-        const int j0 = __shfl_sync(FULL, j, t, 8), j1 = __shfl_sync(FULL, j, t + 1, 8);
-        const float4 x0 = t < cnt ? ldc4(hsnap + (size_t)j0 * F + 4 * lig) : f4zero();
-        const float4 x1 = t + 1 < cnt ? ldc4(hsnap + (size_t)j1 * F + 4 * lig) : f4zero();
-        const float p0 = __shfl_sync(FULL, p, t, 8), p1 = __shfl_sync(FULL, p, t + 1, 8);
-        fma4(acc, p0, x0);
-        fma4(acc, t + 1 < 8 ? p1 : 0.f, x1);
-      }
-    }
-    if (!ok) continue;
-    const float inv = 1.f / (lrun + kSoftmaxEps);
-    float4 o = make_float4(fmaf(acc.x, inv, bv.x), fmaf(acc.y, inv, bv.y), fmaf(acc.z, inv, bv.z), fmaf(acc.w, inv, bv.w));
-    if (relu) o = relu4(o);
-    if (out_g != nullptr) st4(out_g + (size_t)il * F + 4 * lig, o);
-    if (out_s != nullptr) st4(out_s + il * lds_out + 4 * lig, o);
-    if (TRAIN && slot == 0) { m_own[il * H + hd] = mrun; l_own[il * H + hd] = lrun; }
-  }
-}
-
-// sum a per-lane float4 over the row slots of a warp and park it in this warp's row of `vred`
-template <int LPR>
-__device__ __forceinline__ void warp_chunk_park(float4 v, float* dst) {
-#pragma unroll
-  for (int o = LPR; o < 32; o <<= 1) {
-    v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
-    v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
-  }
-  if ((threadIdx.x & 31) < LPR) st4(dst + 4 * (threadIdx.x & 31), v);
-}
-
-// Backward pass 1 over own target rows: D_i, ds_dst[i]; rec = {s_dst, m, 1/(l+eps), D}.
-// MEAN = true (conv2): the incoming gradient is produced on the fly as the SimpleConv(mean) backward
-// of gA (dz[j] = sum_{j->i} gA[i] / max(indeg(i), 1)) and also written to dz_own for pass 2's gathers;
-// MEAN = false (conv1): it is read from the shared tile g_s.
-template <int H, bool MEAN>
-__device__ __forceinline__ void bwd_p1_rows(const int* __restrict__ rowptr, const int* __restrict__ col,
-                                            const int* __restrict__ rowptr_t, const int* __restrict__ col_t,
-                                            const float* gA_snap, float* dz_own, const float* g_s, int ldg_s,
-                                            const float* __restrict__ hsnap, const float* __restrict__ sssnap,
-                                            const float* __restrict__ sd_own, const float* __restrict__ m_own,
-                                            const float* __restrict__ l_own, float* rec_own, float* dsd_own,
-                                            float* vred_bias, int lo, int n) {
-  constexpr int F = 32 * H, LPR = 8 * H, RPW = 32 / LPR, PRE = 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR, slot = lig & 7, hd = lig >> 3;
-  float4 bacc = f4zero();
-  for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
-    const int il_raw = i0 + warp * RPW + sub;
-    const bool ok = il_raw < n;
-    const int il = ok ? il_raw : n - 1, i = lo + il;
-    float4 gv;
-    if (MEAN) {
-      const int tb = __ldg(rowptr_t + i), te = __ldg(rowptr_t + i + 1) - 1;     // out-edges minus the self-loop
-      gv = f4zero();
-#pragma unroll 4
-      for (int e = tb; e < te; ++e) {
-        const int t = __ldg(col_t + e);
-        const int dg = __ldg(rowptr + t + 1) - __ldg(rowptr + t) - 1;
-        fma4(gv, 1.f / (float)(dg > 1 ? dg : 1), ldc4(gA_snap + (size_t)t * F + 4 * lig));
-      }
-      if (ok) st4(dz_own + (size_t)il * F + 4 * lig, gv);
-    } else {
-      gv = lds4(g_s + il * ldg_s + 4 * lig);
-    }
-    if (ok) add4(bacc, gv);
-    const int beg = __ldg(rowptr + i), deg = __ldg(rowptr + i + 1) - beg;
-    const int deg_max = __reduce_max_sync(FULL, deg);
-    const float sd = __ldg(sd_own + il * H + hd), mi = __ldg(m_own + il * H + hd);
-    const float il_ = 1.f / (__ldg(l_own + il * H + hd) + kSoftmaxEps);
-    float S1 = 0.f, S2 = 0.f, S3 = 0.f;
-    for (int e0 = 0; e0 < deg_max; e0 += 8) {
-      const bool valid = e0 + slot < deg;
-      const int j = valid ? __ldg(col + beg + e0 + slot) : 0;
-      const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
-      float4 x[PRE];
-#pragma unroll
-      for (int u = 0; u < PRE; ++u) {
-        const int ju = __shfl_sync(FULL, j, u, 8);
-        x[u] = u < cnt ? ldg4(hsnap + (size_t)ju * F + 4 * lig) : f4zero();
-      }
-      const float z = __ldg(sssnap + j * H + hd) + sd;
-      const float alpha = valid ? __expf(lrelu(z) - mi) * il_ : 0.f;
-      const float sl = lrelu_slope(z);
-      float da = 0.f;
-#pragma unroll
-      for (int u = 0; u < PRE; ++u) {
-        const float d = group_sum<8>(dot4(gv, x[u]), FULL);
-        da = slot == u ? d : da;
-      }
-      for (int t = PRE; t < cnt_max; t += 2) {
-        const int j0 = __shfl_sync(FULL, j, t, 8), j1 = __shfl_sync(FULL, j, t + 1, 8);
-        const float4 x0 = t < cnt ? ldg4(hsnap + (size_t)j0 * F + 4 * lig) : f4zero();
-        const float4 x1 = t + 1 < cnt ? ldg4(hsnap + (size_t)j1 * F + 4 * lig) : f4zero();
-        const float d0 = group_sum<8>(dot4(gv, x0), FULL), d1 = group_sum<8>(dot4(gv, x1), FULL);
-        da = slot == t ? d0 : (slot == t + 1 ? d1 : da);
-      }
-      S1 = fmaf(alpha, da, S1);
-      S2 = fmaf(alpha * sl, da, S2);
-      S3 = fmaf(alpha, sl, S3);
-    }
-    const float D = group_sum<8>(S1, FULL), T2 = group_sum<8>(S2, FULL), T3 = group_sum<8>(S3, FULL);
-    if (slot == 0 && ok) {
-      st4(rec_own + (size_t)(il * H + hd) * 4, make_float4(sd, mi, il_, D));
-      dsd_own[il * H + hd] = T2 - D * T3;
-    }
-  }
-  warp_chunk_park<LPR>(bacc, vred_bias);
-}
-
-// Backward pass 2 over own source rows: dh[j] (-> shared tile), ds_src, datt_src / datt_dst partials.
-template <int H>
-__device__ __forceinline__ void bwd_p2_rows(const int* __restrict__ rowptr_t, const int* __restrict__ col_t,
-                                            const float* gsnap, const float* recsnap, const float* dsd_own,
-                                            const float* __restrict__ h_own, const float* __restrict__ ss_own,
-                                            const float* att_s, const float* att_d, float* dh_s, int ld_dh,
-                                            float* vred_as, float* vred_ad, int lo, int n) {
-  constexpr int F = 32 * H, LPR = 8 * H, RPW = 32 / LPR, PRE = 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR, slot = lig & 7, hd = lig >> 3;
-  const float4 as = lds4(att_s + 4 * lig), ad = lds4(att_d + 4 * lig);
-  float4 accs = f4zero(), accd = f4zero();
-  for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
-    const int il_raw = i0 + warp * RPW + sub;
-    const bool ok = il_raw < n;
-    const int il = ok ? il_raw : n - 1, jn = lo + il;
-    const int beg = __ldg(rowptr_t + jn), deg = __ldg(rowptr_t + jn + 1) - beg;
-    const int deg_max = __reduce_max_sync(FULL, deg);
-    const float4 hv = ldg4(h_own + (size_t)il * F + 4 * lig);
-    const float ss = __ldg(ss_own + il * H + hd);
-    float4 dacc = f4zero();
-    float dsrc = 0.f;
-    for (int e0 = 0; e0 < deg_max; e0 += 8) {
-      const bool valid = e0 + slot < deg;
-      const int i = valid ? __ldg(col_t + beg + e0 + slot) : 0;
-      const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
-      float4 gx[PRE];
-#pragma unroll
-      for (int u = 0; u < PRE; ++u) {
-        const int iu = __shfl_sync(FULL, i, u, 8);
-        gx[u] = u < cnt ? ldc4(gsnap + (size_t)iu * F + 4 * lig) : f4zero();
-      }
-      const float4 t4 = ldc4(recsnap + (size_t)(i * H + hd) * 4);      // {s_dst, m, 1/l, D} of the edge's target
-      const float z = ss + t4.x;
-      const float alpha = valid ? __expf(lrelu(z) - t4.y) * t4.z : 0.f;
-      const float k2 = alpha * lrelu_slope(z);
-      float da = 0.f;
-#pragma unroll
-      for (int u = 0; u < PRE; ++u) {
-        const float d = group_sum<8>(dot4(gx[u], hv), FULL);
-        da = slot == u ? d : da;
-        fma4(dacc, __shfl_sync(FULL, alpha, u, 8), gx[u]);
-      }
-      for (int t = PRE; t < cnt_max; t += 2) {
-        const int i0_ = __shfl_sync(FULL, i, t, 8), i1_ = __shfl_sync(FULL, i, t + 1, 8);
-        const float4 g0 = t < cnt ? ldc4(gsnap + (size_t)i0_ * F + 4 * lig) : f4zero();
-        const float4 g1 = t + 1 < cnt ? ldc4(gsnap + (size_t)i1_ * F + 4 * lig) : f4zero();
-        const float d0 = group_sum<8>(dot4(g0, hv), FULL), d1 = group_sum<8>(dot4(g1, hv), FULL);
-        da = slot == t ? d0 : (slot == t + 1 ? d1 : da);
-        const float a0 = __shfl_sync(FULL, alpha, t, 8), a1 = __shfl_sync(FULL, alpha, t + 1, 8);
-        fma4(dacc, a0, g0);
-        fma4(dacc, t + 1 < 8 ? a1 : 0.f, g1);
-      }
-      dsrc = fmaf(k2, da - t4.w, dsrc);
-    }
-    const float ds = group_sum<8>(dsrc, FULL);
-    const float dd = ldc1(dsd_own + il * H + hd);
-    fma4(dacc, ds, as);
-    fma4(dacc, dd, ad);
-    if (ok) {
-      st4(dh_s + il * ld_dh + 4 * lig, dacc);
-      fma4(accs, ds, hv);
-      fma4(accd, dd, hv);
-    }
-  }
-  warp_chunk_park<LPR>(accs, vred_as);
-  warp_chunk_park<LPR>(accd, vred_ad);
-}
-
-// =============================================================================== forward
-template <bool TRAIN>
-__global__ void __launch_bounds__(T)
-resident_fwd_kernel(const Args a) {
-  extern __shared__ __align__(16) float smem[];
-  const int R = a.R, N = a.N;
-  float* xs = smem;                        // [R][LDX] block input / output (own rows)
-  float* ys = xs + R * LDX;                // [R][LDY] conv1 output (own rows)
-  float* W1s = ys + R * LDY;               // [2][64][LDX]
-  float* W2s = W1s + 2 * W1F;              // [2][32][LDY]
-  float* vec = W2s + 2 * W2F;              // [2][288]
-  const int rank = (int)cluster_ctarank();
-  const long long b = cluster_id_x();
-  const int lo = rank * R, n = max(0, min(R, N - lo));
-  const long long M = a.M, rb = b * N, ro = rb + lo;    // snapshot base row, first own row
-  const ParamLayout pl(a.nb, NC);
-  const SavedLayout sl(M, NC);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  pdl_wait();
-  if (a.nb > 0) stage_block_params(a.params + pl.block(0), W1s, W2s, vec);
-  cp_commit();
-
-  // encoder Linear(1, nc): x0[i][c] = x[i] w[c] + b[c]
-  {
-    const int lig = lane & 7, sub = lane >> 3;
-    const float4 wv = ldg4(a.params + pl.lin0_w() + 4 * lig), bv = ldg4(a.params + pl.lin0_b() + 4 * lig);
-    for (int il = warp * 4 + sub; il < n; il += 32) {
-      const float xv = __ldg(a.x + ro + il);
-      const float4 o = make_float4(fmaf(xv, wv.x, bv.x), fmaf(xv, wv.y, bv.y), fmaf(xv, wv.z, bv.z), fmaf(xv, wv.w, bv.w));
-      st4(xs + il * LDX + 4 * lig, o);
-      if (TRAIN) st4(a.saved + sl.x_enc() + (ro + il) * NC + 4 * lig, o);
-    }
-  }
-
-  // inference: rolling buffers carved from scratch (layout of gatres_scratch_floats, training = 0)
-  float* sc = a.scratch;
-  for (int k = 0; k < a.nb; ++k) {
-    const int buf = k & 1;
-    float* W1 = W1s + buf * W1F;
-    float* W2 = W2s + buf * W2F;
-    float* vc = vec + buf * VECF;
-    float* h1 = TRAIN ? a.saved + sl.h1(k) : sc + 2 * M * NC;
-    float* ss1 = TRAIN ? a.saved + sl.ss1(k) : sc + 8 * M * NC;
-    float* sd1 = TRAIN ? a.saved + sl.sd1(k) : sc + 8 * M * NC + a4(2 * M);
-    float* h2 = TRAIN ? a.saved + sl.h2(k) : sc + 6 * M * NC;
-    float* ss2 = TRAIN ? a.saved + sl.ss2(k) : sc;
-    float* sd2 = TRAIN ? a.saved + sl.sd2(k) : sc + a4(M);
-    float* z = TRAIN ? sc : sc + 7 * M * NC;
-
-    cp_wait_all();
-    __syncthreads();                         // parameters of block k and xs are in place
-    if (k + 1 < a.nb) stage_block_params(a.params + pl.block(k + 1), W1s + (buf ^ 1) * W1F, W2s + (buf ^ 1) * W2F, vec + (buf ^ 1) * VECF);
-    cp_commit();
-
-    // conv1 projection + scores  (GraphModels.py:464)
-    project_rows<NC, 2 * NC, 2, LDX, LDX>(xs, W1, vc, vc + 2 * NC, h1 + ro * 2 * NC, ss1 + ro * 2, sd1 + ro * 2, n);
-    cluster_sync();
-    // conv1 aggregation + bias + ReLU -> y1
-    agg_fwd_rows<2, TRAIN>(a.rowptr, a.col, h1 + rb * 2 * NC, ss1 + rb * 2, sd1 + ro * 2, vc + 4 * NC,
-                           TRAIN ? a.saved + sl.y1(k) + ro * 2 * NC : nullptr, ys, LDY,
-                           TRAIN ? a.saved + sl.m1(k) + ro * 2 : nullptr, TRAIN ? a.saved + sl.l1(k) + ro * 2 : nullptr,
-                           lo, n, true);
-    __syncthreads();
-    // conv2 projection + scores  (:465)
-    project_rows<2 * NC, NC, 1, LDY, LDY>(ys, W2, vc + 6 * NC, vc + 7 * NC, h2 + ro * NC, ss2 + ro, sd2 + ro, n);
-    cluster_sync();
-    // conv2 aggregation + bias -> z (neighbours read it in the mean)
-    agg_fwd_rows<1, TRAIN>(a.rowptr, a.col, h2 + rb * NC, ss2 + rb, sd2 + ro, vc + 8 * NC, z + ro * NC, nullptr, 0,
-                           TRAIN ? a.saved + sl.m2(k) + ro : nullptr, TRAIN ? a.saved + sl.l2(k) + ro : nullptr, lo, n,
-                           false);
-    cluster_sync();
-    // SimpleConv(mean) + residual + ReLU  (:466-467)
-    {
-      const int lig = lane & 7, sub = lane >> 3;
-      const float* zs = z + rb * NC;
-      for (int il = warp * 4 + sub; il < n; il += 32) {
-        const int i = lo + il;
-        const int beg = __ldg(a.rowptr + i), end = __ldg(a.rowptr + i + 1) - 1;
-        float4 acc = f4zero();
-#pragma unroll 4
-        for (int e = beg; e < end; ++e) add4(acc, ldc4(zs + (size_t)__ldg(a.col + e) * NC + 4 * lig));
-        const int deg = end - beg;
-        const float inv = 1.f / (float)(deg > 1 ? deg : 1);
-        const float4 xr = lds4(xs + il * LDX + 4 * lig);
-        const float4 o = relu4(make_float4(fmaf(acc.x, inv, xr.x), fmaf(acc.y, inv, xr.y), fmaf(acc.z, inv, xr.z), fmaf(acc.w, inv, xr.w)));
-        st4(xs + il * LDX + 4 * lig, o);
-        if (TRAIN) st4(a.saved + sl.xout(k) + (ro + il) * NC + 4 * lig, o);
-      }
-    }
-  }
-  cp_wait_all();
-  __syncthreads();
-  // decoder Linear(nc, 1)  (:492)
-  {
-    const int lig = lane & 7, sub = lane >> 3;
-    const float4 wv = ldg4(a.params + pl.lin1_w() + 4 * lig);
-    const float bias = __ldg(a.params + pl.lin1_b());
-    const bool bad = a.poison != nullptr && __ldg(a.poison) != 0;
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      const int il = i0 + warp * 4 + sub;
-      float p = il < n ? dot4(lds4(xs + il * LDX + 4 * lig), wv) : 0.f;
-      p = group_sum<8>(p, FULL);
-      if (il < n && lig == 0) a.out[ro + il] = bad ? __int_as_float(0x7fc00000) : p + bias;
-    }
-  }
-}
-
-// =============================================================================== backward
-__global__ void __launch_bounds__(T)
-resident_bwd_kernel(const Args a) {
-  extern __shared__ __align__(16) float smem[];
-  const int R = a.R, N = a.N, nb = a.nb;
-  float* xs = smem;                        // [R][LDX] x0 of the block (own rows)
-  float* ys = xs + R * LDX;                // [R][LDY] y1 -> dy1 -> dh1 (own rows)
-  float* d2s = ys + R * LDY;               // [R][LDX] dh2 (own rows)
-  float* W1s = d2s + R * LDX;              // [2][64][LDX]
-  float* W2s = W1s + 2 * W1F;              // [2][32][LDY]
-  float* vec = W2s + 2 * W2F;              // [2][288]
-  float* vred = vec + 2 * VECF;            // [8 warps][288] parameter-vector gradient partials
-  float* red = vred + (T / 32) * VECF;     // [T*4] scratch of cta_chunk_sum_store
-  const int rank = (int)cluster_ctarank();
-  const long long b = cluster_id_x();
-  const int lo = rank * R, n = max(0, min(R, N - lo));
-  const long long M = a.M, rb = b * N, ro = rb + lo;
-  const ParamLayout pl(nb, NC);
-  const SavedLayout sl(M, NC);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  // scratch carve-up (gatres_scratch_floats, training = 1): gbuf[2] dz (dh2) dy1 (dh1) rec dsd
-  float* gbuf[2] = {a.scratch, a.scratch + M * NC};
-  float* dz = a.scratch + 2 * M * NC;
-  float* rec2 = a.scratch + 3 * M * NC;            // dh2 region: rec of conv2 [M][4] + ds_dst of conv2 [M]
-  float* dsd2 = rec2 + 4 * M;
-  float* dy1 = a.scratch + 4 * M * NC;
-  float* rec1 = a.scratch + 8 * M * NC;            // [M][2][4]
-  float* dsd1 = rec1 + 8 * M;                      // [M][2]
-
-  pdl_wait();
-  const int k_first = nb > 0 ? a.k_hi : -1;
-  if (nb > 0) stage_block_params(a.params + pl.block(k_first), W1s + (k_first & 1) * W1F, W2s + (k_first & 1) * W2F, vec + (k_first & 1) * VECF);
-  if (nb > 0) {
-    stage_rows<2 * NC, LDY>(a.saved + sl.y1(k_first) + ro * 2 * NC, ys, n);
-    stage_rows<NC, LDX>(a.saved + (k_first > 0 ? sl.xout(k_first - 1) : sl.x_enc()) + ro * NC, xs, n);
-  }
-  cp_commit();
-
-  if (a.head) {
-    // decoder backward: g[i][c] = d_out[i] w[c] (masked by the last ReLU), dw = sum d_out x, db = sum d_out
-    const int lig = lane & 7, sub = lane >> 3;
-    const float* xl = a.saved + (nb > 0 ? sl.xout(nb - 1) : sl.x_enc());
-    const float4 wv = ldg4(a.params + pl.lin1_w() + 4 * lig);
-    float4 aw = f4zero();
-    float ab = 0.f;
-    for (int il = warp * 4 + sub; il < n; il += 32) {
-      const float gv = __ldg(a.d_out + ro + il);
-      const float4 xv = ldg4(xl + (ro + il) * NC + 4 * lig);
-      float4 d = make_float4(gv * wv.x, gv * wv.y, gv * wv.z, gv * wv.w);
-      if (nb > 0) d = mask4(d, xv);
-      st4(gbuf[0] + (ro + il) * NC + 4 * lig, d);
-      fma4(aw, gv, xv);
-      if (lig == 0) ab += gv;
-    }
-    cta_chunk_sum_store<8>(aw, red, a.grads + pl.lin1_w(), 0, true);
-    ab = group_sum<32>(ab, FULL);
-    if (lane == 0 && ab != 0.f) atomicAdd(a.grads + pl.lin1_b(), ab);
-  }
-  cluster_sync();                            // gA of the first block is visible cluster-wide
-
-  for (int k = k_first; k >= a.k_lo && k >= 0; --k) {
-    const int buf = k & 1;
-    const float* W1 = W1s + buf * W1F;
-    const float* W2 = W2s + buf * W2F;
-    const float* vc = vec + buf * VECF;
-    float* gA = gbuf[(nb - 1 - k) & 1];
-    float* gB = gbuf[(nb - k) & 1];
-    const float* sv = a.saved;
-
-    // (1) SimpleConv(mean) backward fused with conv2 pass 1 (incoming gradient dz stays in registers)
-    bwd_p1_rows<1, true>(a.rowptr, a.col, a.rowptr_t, a.col_t, gA + rb * NC, dz + ro * NC, nullptr, 0,
-                         sv + sl.h2(k) + rb * NC, sv + sl.ss2(k) + rb, sv + sl.sd2(k) + ro, sv + sl.m2(k) + ro,
-                         sv + sl.l2(k) + ro, rec2 + ro * 4, dsd2 + ro, vred + warp * VECF + 8 * NC, lo, n);
-    cp_wait_all();                           // this block's parameters, y1 and x0 (own rows) have landed ...
-    cluster_sync();                          // ... and are visible CTA-wide; dz / rec2 / dsd2 cluster-wide
-    if (k - 1 >= a.k_lo && k - 1 >= 0)
-      stage_block_params(a.params + pl.block(k - 1), W1s + (buf ^ 1) * W1F, W2s + (buf ^ 1) * W2F, vec + (buf ^ 1) * VECF);
-    cp_commit();
-    // (2) conv2 pass 2 -> dh2 (shared)
-    bwd_p2_rows<1>(a.rowptr_t, a.col_t, dz + rb * NC, rec2 + rb * 4, dsd2 + ro, sv + sl.h2(k) + ro * NC,
-                   sv + sl.ss2(k) + ro, vc + 6 * NC, vc + 7 * NC, d2s, LDX, vred + warp * VECF + 6 * NC,
-                   vred + warp * VECF + 7 * NC, lo, n);
-    __syncthreads();                         // dh2 is in shared memory
-    // (3) conv2 projection backward: dW2 = dh2^T y1 ; dy1 = (dh2 W2) masked by y1 > 0 (in place over y1)
-    wgrad_rows<NC, 2 * NC, LDX, LDY>(d2s, ys, n, a.grads + pl.c2_W(k));
-    __syncthreads();
-    {
-      float* dy1o = dy1 + ro * 2 * NC;
-      dgrad_rows<NC, 2 * NC, LDX, LDY>(d2s, W2, n, [&](int m, int c, float4 v) {
-        float* p = ys + m * LDY + c;
-        v = mask4(v, lds4(p));
-        st4(p, v);
-        st4(dy1o + (size_t)m * 2 * NC + c, v);
-      });
-    }
-    __syncthreads();
-    // (4) conv1 pass 1 (incoming gradient = dy1 from shared memory)
-    bwd_p1_rows<2, false>(a.rowptr, a.col, a.rowptr_t, a.col_t, nullptr, nullptr, ys, LDY, sv + sl.h1(k) + rb * 2 * NC,
-                          sv + sl.ss1(k) + rb * 2, sv + sl.sd1(k) + ro * 2, sv + sl.m1(k) + ro * 2,
-                          sv + sl.l1(k) + ro * 2, rec1 + ro * 8, dsd1 + ro * 2, vred + warp * VECF + 4 * NC, lo, n);
-    cluster_sync();
-    // (5) conv1 pass 2 -> dh1 (shared, over the dy1 tile)
-    bwd_p2_rows<2>(a.rowptr_t, a.col_t, dy1 + rb * 2 * NC, rec1 + rb * 8, dsd1 + ro * 2, sv + sl.h1(k) + ro * 2 * NC,
-                   sv + sl.ss1(k) + ro * 2, vc, vc + 2 * NC, ys, LDY, vred + warp * VECF, vred + warp * VECF + 2 * NC,
-                   lo, n);
-    __syncthreads();
-    // (6) conv1 projection backward: dW1 = dh1^T x0 ; gB = dh1 W1 + gA (residual), masked by x0 > 0 for k > 0
-    wgrad_rows<2 * NC, NC, LDY, LDX>(ys, xs, n, a.grads + pl.c1_W(k));
-    {
-      const float* gAo = gA + ro * NC;
-      float* gBo = gB + ro * NC;
-      const bool mask = k > 0;
-      dgrad_rows<2 * NC, NC, LDY, LDX>(ys, W1, n, [&](int m, int c, float4 v) {
-        add4(v, ldc4(gAo + (size_t)m * NC + c));
-        if (mask) v = mask4(v, lds4(xs + m * LDX + c));
-        st4(gBo + (size_t)m * NC + c, v);
-      });
-    }
-    // parameter-vector gradients of the block: sum the 8 warp rows, one 128-bit red per chunk
-    for (int c = threadIdx.x; c < VECF / 4; c += T) {
-      float4 s = f4zero();
-#pragma unroll
-      for (int w = 0; w < T / 32; ++w) add4(s, lds4(vred + w * VECF + 4 * c));
-      const long long off = c < 6 * NC / 4 ? pl.c1_as(k) + 4 * c : pl.c2_as(k) + 4 * (c - 6 * NC / 4);
-      if (n > 0) atomicAdd(reinterpret_cast<float4*>(a.grads + off), s);
-    }
-    __syncthreads();                         // xs / ys / vred are free again
-    if (k - 1 >= a.k_lo && k - 1 >= 0) {
-      stage_rows<2 * NC, LDY>(sv + sl.y1(k - 1) + ro * 2 * NC, ys, n);
-      stage_rows<NC, LDX>(sv + (k - 1 > 0 ? sl.xout(k - 2) : sl.x_enc()) + ro * NC, xs, n);
-    }
-    cp_commit();
-    cluster_sync();                          // gB is visible to the next block's gathers
-  }
-  cp_wait_all();
-
-  if (a.tail) {
-    // encoder backward: dw[c] = sum_i g[i][c] x[i], db[c] = sum_i g[i][c]
-    const int lig = lane & 7, sub = lane >> 3;
-    const float* g = gbuf[nb & 1];
-    float4 aw = f4zero(), ab = f4zero();
-    for (int il = warp * 4 + sub; il < n; il += 32) {
-      const float4 gv = ldc4(g + (ro + il) * NC + 4 * lig);
-      fma4(aw, __ldg(a.x + ro + il), gv);
-      add4(ab, gv);
-    }
-    cta_chunk_sum_store<8>(aw, red, a.grads + pl.lin0_w(), 0, true);
-    cta_chunk_sum_store<8>(ab, red, a.grads + pl.lin0_b(), 0, true);
-  }
-}
-
-// ------------------------------------------------------------------------- host side
-static size_t fwd_smem(int R) { return sizeof(float) * ((size_t)R * (LDX + LDY) + 2 * (W1F + W2F + VECF)); }
-static size_t bwd_smem(int R) {
-  return sizeof(float) * ((size_t)R * (2 * LDX + LDY) + 2 * (W1F + W2F + VECF) + (T / 32) * VECF + T * 4);
-}
-
 static long long g_max_batch = -1;
 static long long max_batch() {
   if (g_max_batch < 0) {
@@ -741,6 +37,7 @@ static long long max_batch() {
 }
 
 // cluster size: as many CTAs per snapshot as keeps the whole batch co-resident (2 CTAs per SM), power of two <= 8
+constexpr size_t kMaxSmem = 200 * 1024;    // per-CTA shared-memory budget of the resident kernels
 static int g_forced_cluster = -2;
 static int forced_cluster() {
   if (g_forced_cluster == -2) {
@@ -750,78 +47,57 @@ static int forced_cluster() {
   }
   return g_forced_cluster;
 }
-static int pick_cluster(long long B, int N, size_t (*smem_of)(int)) {
-  int cs = 8;
-  if (forced_cluster() > 0) cs = forced_cluster();
-  else
-    while (cs > 1 && B * cs > 2ll * sm_count()) cs >>= 1;
-  // rows per CTA must fit the shared-memory budget (227 KB per CTA)
-  while (cs < 8 && smem_of((N + cs - 1) / cs) > 200 * 1024) cs <<= 1;
-  return cs;
-}
-
-template <void (*kern)(const Args)>
-static int launch_cluster(const char* what, int cs, long long B, size_t smem, cudaStream_t st, const Args& a) {
-  static size_t configured = 0;             // one instance per kernel (the kernel is a template argument)
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch(what);
-    configured = smem;
+static long long* g_prof = nullptr;       // phase-timestamp buffer of the profiling tool (NULL = off)
+static int g_prof_slots = 0;
+static int g_threads = -1;
+static int threads() {
+  if (g_threads < 0) {
+    const char* e = getenv("GATRES_RESIDENT_THREADS");
+    g_threads = e ? atoi(e) : 256;
+    if (g_threads != 256 && g_threads != 512) g_threads = 256;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(B * cs));
-  cfg.blockDim = dim3(T);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  count_launch();
-  cudaLaunchKernelEx(&cfg, kern, a);
-  return check_launch(what);
+  return g_threads;
 }
-
 }  // namespace res
+}  // namespace gatres
 
-// Is the snapshot-resident path applicable?  nc = 32, a batch small enough that clusters cover it in about one wave,
-// and a graph whose per-CTA row slice fits shared memory.
+#define RES_NS res256
+#define RES_T 256
+#define RES_MIN_CTAS 2
+#include "resident_impl.cuh"
+#undef RES_NS
+#undef RES_T
+#undef RES_MIN_CTAS
+
+#define RES_NS res512
+#define RES_T 512
+#define RES_MIN_CTAS 2
+#include "resident_impl.cuh"
+#undef RES_NS
+#undef RES_T
+#undef RES_MIN_CTAS
+
+namespace gatres {
+
+// Is the snapshot-resident path applicable?  nc = 32, the network has its self-loop CSR (E1 > 0), a batch small
+// enough that clusters cover it in about one wave, and a graph whose CSR + per-CTA row slice fit shared memory.
 bool resident_eligible(const gatres_model_desc* d, bool backward) {
-  if (d->nc != res::NC || d->B > res::max_batch() || d->B * 8ll >= (1ll << 31)) return false;
+  if (d->nc != 32 || d->E1 <= 0 || d->B > res::max_batch() || d->B * 8ll >= (1ll << 31)) return false;
   if (backward && d->slots > 0) return false;                       // deterministic two-stage reduction: layer path
-  const int R = (d->N + 7) / 8;
-  return (backward ? res::bwd_smem(R) : res::fwd_smem(R)) <= 200 * 1024;
+  return res::threads() == 512 ? res512::fits(d->N, d->E1, backward) : res256::fits(d->N, d->E1, backward);
 }
 
 int resident_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
                      float* scratch, cudaStream_t st) {
-  res::Args a = {};
-  a.rowptr = d->rowptr; a.col = d->col; a.rowptr_t = d->rowptr_t; a.col_t = d->col_t;
-  a.params = params; a.x = x; a.out = out; a.saved = saved; a.scratch = scratch; a.poison = d->poison;
-  a.M = d->B * (long long)d->N; a.N = d->N; a.nb = d->num_blocks; a.B = (int)d->B;
-  const int cs = res::pick_cluster(d->B, d->N, res::fwd_smem);
-  a.R = (d->N + cs - 1) / cs;
-  const size_t smem = res::fwd_smem(a.R);
-  return saved != nullptr ? res::launch_cluster<res::resident_fwd_kernel<true>>("resident_forward(train)", cs, d->B, smem, st, a)
-                          : res::launch_cluster<res::resident_fwd_kernel<false>>("resident_forward", cs, d->B, smem, st, a);
+  return res::threads() == 512 ? res512::forward(d, params, x, out, saved, scratch, st)
+                               : res256::forward(d, params, x, out, saved, scratch, st);
 }
 
 int resident_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
                       const float* d_out, float* grads, float* scratch, int k_hi, int k_lo, bool head, bool tail,
                       cudaStream_t st) {
-  res::Args a = {};
-  a.rowptr = d->rowptr; a.col = d->col; a.rowptr_t = d->rowptr_t; a.col_t = d->col_t;
-  a.params = params; a.x = x; a.saved = const_cast<float*>(saved); a.scratch = scratch; a.d_out = d_out; a.grads = grads;
-  a.M = d->B * (long long)d->N; a.N = d->N; a.nb = d->num_blocks; a.B = (int)d->B;
-  a.k_hi = k_hi; a.k_lo = k_lo; a.head = head; a.tail = tail;
-  const int cs = res::pick_cluster(d->B, d->N, res::bwd_smem);
-  a.R = (d->N + cs - 1) / cs;
-  return res::launch_cluster<res::resident_bwd_kernel>("resident_backward", cs, d->B, res::bwd_smem(a.R), st, a);
+  return res::threads() == 512 ? res512::backward(d, params, x, saved, d_out, grads, scratch, k_hi, k_lo, head, tail, st)
+                               : res256::backward(d, params, x, saved, d_out, grads, scratch, k_hi, k_lo, head, tail, st);
 }
 
 }  // namespace gatres
@@ -829,6 +105,17 @@ int resident_backward(const gatres_model_desc* d, const float* params, const flo
 extern "C" int32_t gatres_set_resident_cluster(int32_t ctas) {
   const int prev = gatres::res::forced_cluster();
   if (ctas == 0 || ctas == 1 || ctas == 2 || ctas == 4 || ctas == 8) gatres::res::g_forced_cluster = ctas;
+  return prev;
+}
+
+extern "C" void gatres_set_resident_profile(int64_t* device_buf, int32_t slots_per_cta) {
+  gatres::res::g_prof = reinterpret_cast<long long*>(device_buf);
+  gatres::res::g_prof_slots = device_buf != nullptr ? slots_per_cta : 0;
+}
+
+extern "C" int32_t gatres_set_resident_threads(int32_t threads) {
+  const int prev = gatres::res::threads();
+  if (threads == 256 || threads == 512) gatres::res::g_threads = threads;
   return prev;
 }
 

@@ -113,6 +113,13 @@ int64_t gatres_set_resident_max_batch(int64_t max_batch);
  * co-resident at two CTAs per SM; GATRES_RESIDENT_CLUSTER presets it).  Other values only query.  Returns
  * the previous setting. */
 int32_t gatres_set_resident_cluster(int32_t ctas);
+/* Threads per CTA of the resident kernels: 256 or 512 (GATRES_RESIDENT_THREADS presets it).  Other values only
+ * query.  Returns the previous setting. */
+int32_t gatres_set_resident_threads(int32_t threads);
+/* Profiling aid (tools/resident_probe.py): when device_buf is not NULL, thread 0 of CTA c of every resident kernel
+ * writes %globaltimer at its phase boundaries to device_buf[c * slots_per_cta ...] (at most slots_per_cta stamps).
+ * NULL switches it off (default). */
+void gatres_set_resident_profile(int64_t* device_buf, int32_t slots_per_cta);
 
 /*
  * Kernel-selection knob for the projections and their data gradients: 0 = fp32 FFMA kernels

@@ -234,9 +234,9 @@ def test_model_matches_golden(name, deterministic, dev, G, kernel_variant):
             assert float((p.grad.cpu() - ref).abs().max()) <= GRAD_TOL * max(float(ref.abs().max()), floor), k
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 0])
+@pytest.mark.parametrize("cluster,threads", [(1, 256), (2, 512), (4, 256), (8, 256), (8, 512), (0, 512), (0, 256)])
 @pytest.mark.parametrize("graph,B,blocks", [("tiny", 5, 2), ("directed", 3, 3), ("ctown", 4, 4), ("ctown", 40, 2)])
-def test_resident_kernels_equal_layer_kernels(graph, B, blocks, cluster, dev, G):
+def test_resident_kernels_equal_layer_kernels(graph, B, blocks, cluster, threads, dev, G):
     """The snapshot-resident cluster kernels (small batches) against the layer-by-layer kernels on the same
     weights and inputs: forward (training and inference) and every parameter gradient, for each cluster size.
     `directed` has in-degrees above 8 (chunked online softmax) and an asymmetric transposed CSR; `tiny` leaves
@@ -251,6 +251,7 @@ def test_resident_kernels_equal_layer_kernels(graph, B, blocks, cluster, dev, G)
     eib = O.collate_edge_index(ei, N, B).to(dev)
     results = []
     prev_c = lib.gatres_set_resident_cluster(cluster)
+    prev_t = lib.gatres_set_resident_threads(threads)
     prev = lib.gatres_set_resident_max_batch(-1)
     try:
         for max_b in (0, 256):
@@ -268,6 +269,7 @@ def test_resident_kernels_equal_layer_kernels(graph, B, blocks, cluster, dev, G)
     finally:
         lib.gatres_set_resident_max_batch(prev)
         lib.gatres_set_resident_cluster(prev_c)
+        lib.gatres_set_resident_threads(prev_t)
     (out_l, g_l), (out_r, g_r) = results
     assert_close(out_r, out_l, 1e-5, "resident forward vs layer kernels")
     floor = 1e-3 * max(float(g.norm()) for g in g_l.values())
