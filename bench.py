@@ -346,7 +346,7 @@ def main():
             loss_host[slot:slot + 1].copy_(ts.loss, non_blocking=True)
 
         launches_per_step = ts.kernels_per_step             # counted by the library while the step was captured
-        h2d = M * (4 + 4 + 1)
+        h2d = M * (4 + 1)           # x (= y, copied once; auxil.py:96-97) + the uint8 mask
         d2h = 4
     else:
         eib = O.collate_edge_index(ei, N, B).to(dev)

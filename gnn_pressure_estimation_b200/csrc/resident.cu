@@ -27,11 +27,15 @@
 
 namespace gatres {
 namespace res {
+// Largest batch that takes the resident path.  Measured on B200 (tools/resident_probe.py, C-Town-shaped graph):
+// the cluster kernels win while a batch fits one wave of 4-CTA clusters at two CTAs per SM (32 snapshots: 0.70 ms
+// per training step against 1.19 ms layer by layer; 64: 1.30 against 1.66 ms); from 128 snapshots on the
+// layer-by-layer kernels are faster (2.23 against 2.59 ms).
 static long long g_max_batch = -1;
 static long long max_batch() {
   if (g_max_batch < 0) {
     const char* e = getenv("GATRES_RESIDENT_MAX_B");
-    g_max_batch = e ? atoll(e) : 256;
+    g_max_batch = e ? atoll(e) : (2ll * sm_count()) / 4;
   }
   return g_max_batch;
 }

@@ -19,7 +19,7 @@ from typing import Optional
 import torch
 from torch import Tensor
 
-from . import _lib, dp as _dp, ops as _gops
+from . import _lib, dp as _dp, metrics as _metrics, ops as _gops
 from ._lib import ModelDesc, call, ptr, stream
 from .GraphModels import GATResMeanConv
 from .graph import Topology
@@ -29,13 +29,19 @@ class TrainStep:
     def __init__(self, model: GATResMeanConv, topo: Topology, batch: int, mask_count_per_snapshot: int,
                  lr: float = 5e-4, weight_decay: float = 6e-6, betas=(0.9, 0.999), eps: float = 1e-8,
                  process_group=None, use_graph: bool = True, deterministic: bool = False,
-                 grad_buckets: Optional[int] = None):
+                 grad_buckets: Optional[int] = None, device_mask_seed: Optional[int] = None,
+                 metrics: Optional["_metrics.MaskedMetrics"] = None):
         self.model, self.topo, self.B = model, topo, int(batch)
         self.N, self.nc, self.nb = topo.N, model.nc, model.num_blocks
         self.M = self.B * self.N
         self.count = self.B * int(mask_count_per_snapshot)        # masked nodes per local batch
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.pg = process_group
+        # device_mask_seed: draw the per-snapshot exact-count mask on the device every step (keyed by the seed and
+        # the Adam step counter) instead of receiving a host mask; metrics: the seven reference metrics per step
+        self.mask_count_per_snapshot = int(mask_count_per_snapshot)
+        self.device_mask_seed = device_mask_seed
+        self.metrics = metrics
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.use_graph = use_graph
         # gradient buckets for the data-parallel all-reduce: backward walks blocks nb-1 .. 0, and a bucket's
@@ -85,10 +91,17 @@ class TrainStep:
     def _enqueue_impl(self) -> None:
         s = stream()
         d = C.byref(self.desc)
+        if self.device_mask_seed is not None:
+            # rank-distinct streams: every rank masks its own shard independently (train.py:172 draws per batch)
+            rank = torch.distributed.get_rank(self.pg) if self.pg is not None else 0
+            call("gatres_generate_mask", (self.device_mask_seed + 0x9E3779B9 * rank) & (2 ** 64 - 1), 0,
+                 ptr(self.step_count), self.B, self.N, self.mask_count_per_snapshot, ptr(self.mask), s)
         call("gatres_apply_mask", ptr(self.x), ptr(self.mask), ptr(self.xm), self.M, s)
         call("gatres_forward", d, ptr(self.flat), ptr(self.xm), ptr(self.out), ptr(self.saved), ptr(self.scratch), s)
         call("gatres_masked_mse", ptr(self.out), ptr(self.y), ptr(self.mask), self.M, self.count, ptr(self.d_out),
              ptr(self.loss), ptr(self._loss_part), s)
+        if self.metrics is not None:
+            self.metrics.update(self.out, self.y, self.mask)                # train.py:191-198, on the device
         # equal shard sizes and equal masked counts per snapshot -> mean of local means == global mean, so the
         # collective is a plain SUM (the 1/world factor is folded into the Adam kernel)
         dp = self.pg is not None and self.world > 1
@@ -143,11 +156,21 @@ class TrainStep:
         self.graph = g
 
     # ------------------------------------------------------------------- steps
-    def load_inputs(self, x: Tensor, y: Tensor, mask: Tensor) -> None:
+    def load_inputs(self, x: Tensor, y: Tensor, mask: Optional[Tensor] = None) -> None:
         """H2D (or D2D) copy of one batch into the static buffers; x/y are the
-        UNMASKED z-normed pressures ([B*N] or [B*N,1]), mask is bool/uint8 [B*N]."""
+        UNMASKED z-normed pressures ([B*N] or [B*N,1]), mask is bool/uint8 [B*N]
+        (omit it when the mask is drawn on the device)."""
         self.x.copy_(x.reshape(-1), non_blocking=True)
-        self.y.copy_(y.reshape(-1), non_blocking=True)
+        if y is not x:
+            self.y.copy_(y.reshape(-1), non_blocking=True)
+        else:
+            self.y.copy_(self.x, non_blocking=True)                        # x = y in the reference (auxil.py:96-97)
+        if mask is None:
+            if self.device_mask_seed is None:
+                raise ValueError("no mask given and no device_mask_seed configured")
+            return
+        if self.device_mask_seed is not None:
+            raise ValueError("a host mask was given but this TrainStep draws its masks on the device")
         m = mask.reshape(-1)
         self.mask.copy_(m.view(torch.uint8) if m.dtype == torch.bool else m, non_blocking=True)
 
@@ -159,6 +182,6 @@ class TrainStep:
             self._enqueue()
         return self.loss
 
-    def step(self, x: Tensor, y: Tensor, mask: Tensor) -> Tensor:
+    def step(self, x: Tensor, y: Tensor, mask: Optional[Tensor] = None) -> Tensor:
         self.load_inputs(x, y, mask)
         return self.run()

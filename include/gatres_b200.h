@@ -105,7 +105,8 @@ int64_t gatres_set_tile_min_batch(int64_t min_batch);
  * snapshots (nc = 32, gradient mode slots = 0 for the backward, graph slice fits shared memory) run the
  * snapshot-resident cluster kernels — one thread-block cluster per snapshot carries the whole stack, layers
  * separated by cluster barriers instead of kernel launches; larger batches run layer by layer.  Default
- * 256, or the GATRES_RESIDENT_MAX_B environment variable; 0 disables.  Negative = query only.  Returns
+ * SM count / 2 (74 on B200: one wave of 4-CTA clusters at two CTAs per SM), or the GATRES_RESIDENT_MAX_B
+ * environment variable; 0 disables.  Negative = query only.  Returns
  * the previous value.
  */
 int64_t gatres_set_resident_max_batch(int64_t max_batch);
@@ -282,6 +283,34 @@ int gatres_masked_mse(const float* out, const float* y, const uint8_t* mask, int
                       float* d_out, float* loss_out, float* partial_loss, void* stream);
 /* x_masked[m] = mask[m] ? 0 : x[m]  (train.py:174) */
 int gatres_apply_mask(const float* x, const uint8_t* mask, float* x_masked, int64_t M, void* stream);
+
+/*
+ * Per-snapshot exact-count random mask on the device, replacing the host-side
+ * generate_batch_mask(num_nodes, mask_rate, required_idx=[]) of utils/auxil.py:143-182 (called per batch at
+ * train.py:171-172): for each of the B snapshots exactly `count` (= int(N * mask_rate)) of its N nodes get
+ * mask = 1, uniformly at random without replacement.  Node (b, i) draws the 32-bit key
+ * gatres_mask_key(seed, step, b*N + i); the `count` smallest keys of a snapshot are selected (ties by node
+ * index), so the result is a pure function of (seed, step) - reproducible, replayable from a CUDA graph.
+ * step_dev: optional device int32[1] added to `step` at run time (pass the Adam step counter so that a
+ * captured graph draws a fresh mask every replay); NULL = use `step` alone.  mask: uint8 [B*N] (overwritten).
+ */
+int gatres_generate_mask(uint64_t seed, uint64_t step, const int32_t* step_dev, int64_t B, int32_t N,
+                         int32_t count, uint8_t* mask, void* stream);
+/* The key function above, on the host (splitmix64 of the counter; for tests and host-side replication). */
+uint32_t gatres_mask_key(uint64_t seed, uint64_t step, uint64_t row);
+
+/*
+ * The seven metrics of get_metric_fn_collection (utils/auxil.py:185-203) as train.py:177-198 and
+ * evaluation.py:326-338 apply them: over the entries with mask != 0 (mask NULL = all M entries) of the DESCALED
+ * prediction / target, descaled = v * scale + shift (znorm: scale = std, shift = mean; minmax: scale = max - min,
+ * shift = min; none: 1, 0 - utils/auxil.py:42-64).
+ * metrics_out: device float[8] = { rel. error (|t| > 0.01 only), accuracy(|e| <= t * threshold), correlation
+ * (clamped to [-1, 1]), r2 = corr^2, MAE, RMSE, NSE, number of entries }.  Two passes with fp64 accumulators.
+ * scratch: gatres_metrics_scratch_doubles() doubles of device memory.
+ */
+int64_t gatres_metrics_scratch_doubles(void);
+int gatres_masked_metrics(const float* out, const float* y, const uint8_t* mask, int64_t M, float scale,
+                          float shift, float threshold, double* scratch, float* metrics_out, void* stream);
 
 /*
  * torch.optim.Adam step (train.py:348: lr 5e-4, weight_decay 6e-6 as L2 added to the
