@@ -403,6 +403,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"dp{world}",
                        "cuda_graph": not args.no_graph,
+                       "kernels": ("snapshot-resident cluster kernels (whole forward / backward stack per launch)"
+                                   if args.mode == "train" and launches_per_step < 20 else "layer-by-layer kernels"),
                        "l2": f"no flush: inputs rotate over {pool} resident batches and one step streams "
                              f"~{(ts.saved.numel() + ts.scratch.numel()) * 4 / 1e6:.0f} MB of "
                              "saved activations + scratch (L2 is 126 MB)" if args.mode == "train" else
@@ -440,6 +442,36 @@ def main():
         line["roofline_in_step"] = {"bound": "hbm", "kernel": dom_l2["kernel"], "achieved": dom_l2["GBps"], "peak": peak,
                                     "unit": "GB/s", "frac": dom_l2["GBps"] / peak,
                                     "workload": f"bench batch ({B} snapshots, L2-resident, {dom_l2['us']:.1f} us/launch)"}
+        if args.mode == "train" and ts.kernels_per_step < 20:
+            # the timed step ran the snapshot-resident cluster kernels: its dominant launch is the whole-stack backward
+            # (one kernel).  Algorithmic bytes = the per-kernel figures of SURVEY 8d summed over the stack.
+            import ctypes as C
+            from gnn_pressure_estimation_b200 import _lib as gl
+            F1, F2 = 2 * nc, nc
+            blk_fwd = (4 * nc + 4 * F1 + 16) + (8 * F1 + 32) + (4 * F1 + 4 * F2 + 8) + (8 * F2 + 16) + 12 * nc
+            blk_bwd = (20 * F1 + 104) + (20 * F2 + 52) + (4 * F1 + 8 * nc) + (4 * F2 + 8 * F1) + 8 * nc
+            bpn = {"fwd": nb * blk_fwd + 2 * (4 + 4 * nc), "bwd": nb * blk_bwd + (4 + 8 * nc) + (4 + 4 * nc)}
+            d = C.byref(ts.desc)
+            calls = {
+                "fwd": lambda k: gl.call("gatres_forward", d, gl.ptr(ts.flat), gl.ptr(ts.xm), gl.ptr(ts.out), gl.ptr(ts.saved),
+                                         gl.ptr(ts.scratch), gl.stream()),
+                "bwd": lambda k: gl.call("gatres_backward", d, gl.ptr(ts.flat), gl.ptr(ts.xm), gl.ptr(ts.saved), gl.ptr(ts.d_out),
+                                         None, gl.ptr(ts.grads), gl.ptr(ts.scratch), gl.stream()),
+            }
+            res = {}
+            for name in ("fwd", "bwd"):
+                t = time_launches(calls[name], 20, 1)
+                res[name] = {"us": t * 1e6, "bytes_per_node": bpn[name], "GBps": M * bpn[name] / t / 1e9}
+            step_us = ms_res / K * 1e3
+            line["roofline_in_step"] = {
+                "bound": "hbm", "kernel": f"resident_bwd_kernel (whole backward stack, {nb} blocks, one launch)",
+                "achieved": res["bwd"]["GBps"], "peak": peak, "unit": "GB/s", "frac": res["bwd"]["GBps"] / peak,
+                "share_of_step": res["bwd"]["us"] / step_us,
+                "workload": f"bench batch ({B} snapshots, L2-resident): {res['bwd']['us']:.0f} us/launch for "
+                            f"{bpn['bwd']} algorithmic B/node (SURVEY 8d per-kernel accounting summed over the stack); "
+                            f"forward stack {res['fwd']['us']:.0f} us/launch, {bpn['fwd']} B/node, "
+                            f"{res['fwd']['GBps']:.0f} GB/s.  Cluster-barrier / issue bound, not HBM bound "
+                            "(profiles/r1_resident.md)"}
         if args.kernels_json:
             os.makedirs(os.path.dirname(os.path.abspath(args.kernels_json)), exist_ok=True)
             json.dump({"in_step_batch": B, "in_step": in_step, "hbm_batch": hbm_B, "hbm": hbm, "peak_gbs": peak},

@@ -65,7 +65,7 @@ _PROTOTYPES = {
     "gatres_param_offset_of_block": (_i64, [_i32, _i32, _i32]),
     "gatres_masked_mse": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "gatres_apply_mask": (C.c_int, [_p, _p, _p, _i64, _p]),
-    "gatres_generate_mask": (C.c_int, [C.c_uint64, C.c_uint64, _p, _i64, _i32, _i32, _p, _p]),
+    "gatres_generate_mask": (C.c_int, [C.c_uint64, C.c_uint64, _p, _p, _i64, _i32, _i32, _p, _p]),
     "gatres_mask_key": (C.c_uint32, [C.c_uint64, C.c_uint64, C.c_uint64]),
     "gatres_metrics_scratch_doubles": (_i64, []),
     "gatres_masked_metrics": (C.c_int, [_p, _p, _p, _i64, _f32, _f32, _f32, _p, _p, _p]),

@@ -7,7 +7,9 @@
 //             ships a bool mask to the GPU every step; here every node gets a counter-based 32-bit random key
 //             and the `count` smallest keys of a snapshot are selected with a 4-pass radix select (ties by
 //             node index), so the set is uniform, exact-count, reproducible from (seed, step) and never leaves
-//             the device.  (A host mask is still accepted everywhere: NumPy-compatible mode.)
+//             the device.  Nodes flagged in `required` (the sensors of evaluation.py:288-291) take key 0 and
+//             are therefore always in the set, as mask_nodes(..., required_idx) guarantees.  (A host mask is still
+//             accepted everywhere: NumPy-compatible mode.)
 //   metrics   utils/auxil.py:101-140,185-203 applied as in train.py:177-198 / evaluation.py:326-338: relative
 //             error, accuracy@threshold, correlation, R2, MAE, RMSE, NSE over the DESCALED predictions and
 //             targets of the masked nodes.  Two passes (means first, then centred sums) with fp64 accumulators,
@@ -22,14 +24,15 @@ __host__ __device__ __forceinline__ uint32_t mask_key(uint64_t seed, uint64_t st
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z ^= z >> 31;
-  return (uint32_t)(z >> 32);
+  const uint32_t k = (uint32_t)(z >> 32);
+  return k != 0 ? k : 1u;                 // key 0 is reserved for the nodes that must be masked
 }
 
 // One CTA per snapshot.  Keys are recomputed from the counter in every pass (cheaper than staging them, and it
 // keeps the kernel independent of the graph size).
 __global__ void __launch_bounds__(256)
-generate_mask_kernel(uint64_t seed, uint64_t step0, const int* __restrict__ step_dev, unsigned N, unsigned count,
-                     uint8_t* __restrict__ mask) {
+generate_mask_kernel(uint64_t seed, uint64_t step0, const int* __restrict__ step_dev,
+                     const uint8_t* __restrict__ required, unsigned N, unsigned count, uint8_t* __restrict__ mask) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_need, s_base;
   __shared__ unsigned warp_tot[8];
@@ -44,7 +47,7 @@ generate_mask_kernel(uint64_t seed, uint64_t step0, const int* __restrict__ step
     __syncthreads();
     const unsigned prefix = s_prefix, hi_mask = p == 3 ? 0u : (0xffffffffu << (8 * (p + 1)));
     for (unsigned i = tid; i < N; i += 256) {
-      const unsigned k = mask_key(seed, step, row0 + i);
+      const unsigned k = (required != nullptr && required[i]) ? 0u : mask_key(seed, step, row0 + i);
       if ((k & hi_mask) == prefix) atomicAdd(&hist[(k >> (8 * p)) & 255u], 1u);
     }
     __syncthreads();
@@ -81,7 +84,7 @@ generate_mask_kernel(uint64_t seed, uint64_t step0, const int* __restrict__ step
   __syncthreads();
   for (unsigned i0 = 0; i0 < N; i0 += 256) {
     const unsigned i = i0 + tid;
-    const unsigned k = i < N ? mask_key(seed, step, row0 + i) : 0xffffffffu;
+    const unsigned k = i < N ? ((required != nullptr && required[i]) ? 0u : mask_key(seed, step, row0 + i)) : 0xffffffffu;
     const bool tie = i < N && k == K;
     const unsigned bal = __ballot_sync(0xffffffffu, tie);
     if (lane == 0) warp_tot[warp] = __popc(bal);
@@ -101,6 +104,9 @@ generate_mask_kernel(uint64_t seed, uint64_t step0, const int* __restrict__ step
 
 // ------------------------------------------------------------------------------ metrics
 constexpr int kMetricSums = 8;   // pass B: sum|e|, sum e^2, sum rel, n_rel, n_acc, sum vx^2, sum vy^2, sum vx vy
+
+// descale as the reference rounds it: one fp32 multiply, then one fp32 add (auxil.py:58-61), never fused
+__device__ __forceinline__ float descale1(float v, float scale, float shift) { return __fadd_rn(__fmul_rn(v, scale), shift); }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -134,8 +140,8 @@ metrics_pass_a_kernel(const float* __restrict__ out, const float* __restrict__ y
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
     if (mask != nullptr && mask[i] == 0) continue;
     acc[0] += 1.0;
-    acc[1] += (double)fmaf(out[i], scale, shift);
-    acc[2] += (double)fmaf(y[i], scale, shift);
+    acc[1] += (double)descale1(out[i], scale, shift);
+    acc[2] += (double)descale1(y[i], scale, shift);
   }
   cta_sum_store<3>(acc, red, part_a + (size_t)blockIdx.x * 3);
 }
@@ -162,7 +168,7 @@ metrics_pass_b_kernel(const float* __restrict__ out, const float* __restrict__ y
   for (int k = 0; k < kMetricSums; ++k) acc[k] = 0.0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
     if (mask != nullptr && mask[i] == 0) continue;
-    const float p = fmaf(out[i], scale, shift), t = fmaf(y[i], scale, shift);
+    const float p = descale1(out[i], scale, shift), t = descale1(y[i], scale, shift);
     const float e = fabsf(t - p);                       // auxil.py:115,122
     acc[0] += (double)e;
     acc[1] += (double)(p - t) * (double)(p - t);
@@ -220,8 +226,8 @@ using namespace gatres;
 
 extern "C" uint32_t gatres_mask_key(uint64_t seed, uint64_t step, uint64_t row) { return mask_key(seed, step, row); }
 
-extern "C" int gatres_generate_mask(uint64_t seed, uint64_t step, const int32_t* step_dev, int64_t B, int32_t N,
-                                    int32_t count, uint8_t* mask, void* stream) {
+extern "C" int gatres_generate_mask(uint64_t seed, uint64_t step, const int32_t* step_dev, const uint8_t* required,
+                                    int64_t B, int32_t N, int32_t count, uint8_t* mask, void* stream) {
   GATRES_REQUIRE(B >= 0 && N > 0 && count >= 0 && count <= N, "generate_mask: bad B=%lld N=%d count=%d", (long long)B, N, count);
   GATRES_REQUIRE(B < (1ll << 31) && mask != nullptr, "generate_mask: bad batch or null mask");
   if (B == 0) return GATRES_OK;
@@ -229,8 +235,8 @@ extern "C" int gatres_generate_mask(uint64_t seed, uint64_t step, const int32_t*
     if (cudaMemsetAsync(mask, 0, (size_t)B * N, as_stream(stream)) != cudaSuccess) return check_launch("generate_mask");
     return GATRES_OK;
   }
-  launch_kernel(generate_mask_kernel, dim3((unsigned)B), dim3(256), 0, as_stream(stream), seed, step, step_dev, (unsigned)N,
-                (unsigned)count, mask);
+  launch_kernel(generate_mask_kernel, dim3((unsigned)B), dim3(256), 0, as_stream(stream), seed, step, step_dev, required,
+                (unsigned)N, (unsigned)count, mask);
   return check_launch("generate_mask");
 }
 

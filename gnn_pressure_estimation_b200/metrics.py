@@ -15,8 +15,9 @@ CUDA only: there is no CPU path (the oracle in oracle/caller_oracle.py is test i
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 from torch import Tensor
 
@@ -44,18 +45,46 @@ def mask_count(num_nodes: int, mask_rate: float) -> int:
     return int(num_nodes * mask_rate)
 
 
+def required_flags(num_nodes: int, required_idx: Sequence[int], device) -> Optional[Tensor]:
+    """uint8 [num_nodes] flags of the nodes every mask must contain (`required_idx`, auxil.py:143-161)"""
+    if len(required_idx) == 0:
+        return None
+    f = torch.zeros(num_nodes, dtype=torch.uint8)
+    f[torch.as_tensor(list(required_idx), dtype=torch.long)] = 1
+    return f.to(device)
+
+
 def generate_batch_mask(batch: int, num_nodes: int, mask_rate: float, seed: int, step: int = 0,
                         out: Optional[Tensor] = None, step_dev: Optional[Tensor] = None,
-                        device=None) -> Tensor:
-    """uint8 [batch*num_nodes]: exactly int(num_nodes*mask_rate) ones per snapshot, chosen on the device."""
+                        required: Optional[Tensor] = None, device=None) -> Tensor:
+    """uint8 [batch*num_nodes]: exactly int(num_nodes*mask_rate) ones per snapshot, chosen on the device;
+    `required` = required_flags(...) of the nodes that are always masked."""
     count = mask_count(num_nodes, mask_rate)
-    if count <= 0:
-        raise ValueError("mask_rate selects no node (the reference asserts mask_length > 0)")
+    n_req = int(required.sum()) if required is not None else 0
+    if count - n_req <= 0:
+        raise ValueError("mask_rate leaves no node to draw (the reference asserts mask_length > 0)")
     if out is None:
         out = torch.empty(batch * num_nodes, dtype=torch.uint8, device=device if device is not None else "cuda")
-    call("gatres_generate_mask", seed & (2 ** 64 - 1), step & (2 ** 64 - 1), ptr(step_dev), batch, num_nodes, count,
-         ptr(out), stream())
+    call("gatres_generate_mask", seed & (2 ** 64 - 1), step & (2 ** 64 - 1), ptr(step_dev), ptr(required), batch,
+         num_nodes, count, ptr(out), stream())
     return out
+
+
+def numpy_batch_mask(num_nodes: Sequence[int], mask_rate: float, required_idx: Sequence[int] = ()) -> np.ndarray:
+    """NumPy-compatible mode: the reference's own host procedure (auxil.py:143-182) on the global NumPy RNG,
+    for runs that must reproduce the reference's mask stream draw for draw."""
+    req = list(required_idx)
+    parts = []
+    for n in num_nodes:
+        n = int(n)
+        length = int(n * mask_rate) - len(req)
+        assert length > 0
+        candidates = [i for i in range(n) if i not in set(req)]
+        m = np.zeros(n, dtype=bool)
+        m[np.random.choice(candidates, length, replace=False)] = True
+        m[req] = True
+        parts.append(m)
+    return np.hstack(parts)
 
 
 class MaskedMetrics:

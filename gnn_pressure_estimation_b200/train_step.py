@@ -95,7 +95,7 @@ class TrainStep:
             # rank-distinct streams: every rank masks its own shard independently (train.py:172 draws per batch)
             rank = torch.distributed.get_rank(self.pg) if self.pg is not None else 0
             call("gatres_generate_mask", (self.device_mask_seed + 0x9E3779B9 * rank) & (2 ** 64 - 1), 0,
-                 ptr(self.step_count), self.B, self.N, self.mask_count_per_snapshot, ptr(self.mask), s)
+                 ptr(self.step_count), None, self.B, self.N, self.mask_count_per_snapshot, ptr(self.mask), s)
         call("gatres_apply_mask", ptr(self.x), ptr(self.mask), ptr(self.xm), self.M, s)
         call("gatres_forward", d, ptr(self.flat), ptr(self.xm), ptr(self.out), ptr(self.saved), ptr(self.scratch), s)
         call("gatres_masked_mse", ptr(self.out), ptr(self.y), ptr(self.mask), self.M, self.count, ptr(self.d_out),

@@ -292,10 +292,13 @@ int gatres_apply_mask(const float* x, const uint8_t* mask, float* x_masked, int6
  * gatres_mask_key(seed, step, b*N + i); the `count` smallest keys of a snapshot are selected (ties by node
  * index), so the result is a pure function of (seed, step) - reproducible, replayable from a CUDA graph.
  * step_dev: optional device int32[1] added to `step` at run time (pass the Adam step counter so that a
- * captured graph draws a fresh mask every replay); NULL = use `step` alone.  mask: uint8 [B*N] (overwritten).
+ * captured graph draws a fresh mask every replay); NULL = use `step` alone.
+ * required: optional device uint8[N] flags of template nodes that must be masked in every snapshot
+ * (`required_idx`, the sensor nodes of evaluation.py:288-291); they take key 0 (hashed keys are >= 1), so they
+ * are always selected while count >= their number; NULL = none.  mask: uint8 [B*N] (overwritten).
  */
-int gatres_generate_mask(uint64_t seed, uint64_t step, const int32_t* step_dev, int64_t B, int32_t N,
-                         int32_t count, uint8_t* mask, void* stream);
+int gatres_generate_mask(uint64_t seed, uint64_t step, const int32_t* step_dev, const uint8_t* required,
+                         int64_t B, int32_t N, int32_t count, uint8_t* mask, void* stream);
 /* The key function above, on the host (splitmix64 of the counter; for tests and host-side replication). */
 uint32_t gatres_mask_key(uint64_t seed, uint64_t step, uint64_t row);
 

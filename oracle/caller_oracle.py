@@ -96,12 +96,43 @@ def device_mask_keys(seed: int, step: int, rows: np.ndarray) -> np.ndarray:
         z = (z ^ (z >> _U64(30))) * _U64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> _U64(27))) * _U64(0x94D049BB133111EB)
         z = z ^ (z >> _U64(31))
-    return (z >> _U64(32)).astype(np.uint32)
+    return np.maximum((z >> _U64(32)).astype(np.uint32), np.uint32(1))      # key 0 is reserved for required nodes
 
 
-def device_mask_reference(seed: int, step: int, batch: int, num_nodes: int, count: int) -> np.ndarray:
+def device_mask_reference(seed: int, step: int, batch: int, num_nodes: int, count: int,
+                          required_idx: Sequence[int] = ()) -> np.ndarray:
     keys = device_mask_keys(seed, step, np.arange(batch * num_nodes)).reshape(batch, num_nodes)
+    keys[:, list(required_idx)] = 0
     order = np.argsort(keys, axis=1, kind="stable")                  # ties keep node order
     mask = np.zeros((batch, num_nodes), dtype=bool)
     np.put_along_axis(mask, order[:, :count], True, axis=1)
     return mask.reshape(-1)
+
+
+def test_one_epoch_oracle(model, snapshots: Tensor, edge_index: Tensor, batch_size: int, mask_rate: float,
+                          norm_type=None, mean=None, std=None, min_val=None, max_val=None,
+                          required_idx: Sequence[int] = (), use_same_mask: bool = False):
+    """evaluation.py:300-341 on a [S, N] snapshot set with a CPU model (the GATRes oracle): per batch a mask from the
+    global numpy RNG, x[mask] = 0, forward, MSE and the seven metrics on the (descaled) masked nodes, every per-batch
+    value weighted by num_graphs and divided by the dataset length.  -> (loss, {metric: value})"""
+    S, N = snapshots.shape
+    total_loss, totals = 0.0, {k: 0.0 for k in METRIC_NAMES}
+    all_mask = None
+    with torch.no_grad():
+        for s0 in range(0, S, batch_size):
+            y = snapshots[s0:s0 + batch_size].reshape(-1, 1)
+            B = y.numel() // N
+            if all_mask is None or not use_same_mask:
+                all_mask = torch.from_numpy(generate_batch_mask([N] * B, mask_rate, required_idx))
+            mask = all_mask[:B * N]
+            x1 = y.clone()
+            x1[mask] = 0
+            ei = torch.cat([edge_index + b * N for b in range(B)], dim=1)
+            out = model(x1, ei, None, None)
+            y_pred, y_true = out[mask], y[mask]
+            kw = dict(norm_type=norm_type, mean=mean, std=std, min=min_val, max=max_val)
+            m = metrics(descale(y_pred, **kw), descale(y_true, **kw))
+            total_loss += float(torch.nn.functional.mse_loss(y_pred, y_true)) * B
+            for k in METRIC_NAMES:
+                totals[k] += float(m[k]) * B
+    return total_loss / S, {k: v / S for k, v in totals.items()}

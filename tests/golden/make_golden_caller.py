@@ -51,6 +51,13 @@ def main():
     blob["mask/ctown_B6"] = A.generate_batch_mask(num_nodes=torch.tensor([388] * 6), mask_rate=0.95, required_idx=[])
     np.random.seed(7)
     blob["mask/ragged_required"] = A.generate_batch_mask(num_nodes=[7, 40, 388], mask_rate=0.6, required_idx=[0, 3])
+    # Timer arithmetic (utils/timer.py:43-66) without CUDA events: fill the recorded lists directly
+    import utils.timer as TM
+    tm = object.__new__(TM.Timer)
+    tm.timings = [3.25, 3.5, 3.125, 1.75]
+    tm.num_graphs = [32, 32, 32, 11]
+    blob["timer/timings"], blob["timer/num_graphs"] = np.array(tm.timings), np.array(tm.num_graphs)
+    blob["timer/time_throughput"] = np.array([tm.compute_time(107), tm.compute_throughput(107)])
     np.savez_compressed(os.path.join(HERE, "caller_ref.npz"), **blob)
     print({k: v.shape for k, v in blob.items()})
 

@@ -67,6 +67,15 @@ def test_device_mask_key_function_matches_its_restatement():
     assert m.sum(1).tolist() == [368] * 4 and not np.array_equal(m[0], m[1])
 
 
+def test_numpy_compatible_mask_mode_equals_reference():
+    """the product's host-side NumPy mode draws the reference's mask stream bit for bit"""
+    from gnn_pressure_estimation_b200.metrics import numpy_batch_mask
+    np.random.seed(1234)
+    assert np.array_equal(numpy_batch_mask([388] * 6, 0.95), GOLD["mask/ctown_B6"])
+    np.random.seed(7)
+    assert np.array_equal(numpy_batch_mask([7, 40, 388], 0.6, [0, 3]), GOLD["mask/ragged_required"])
+
+
 # ------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES)
@@ -125,6 +134,13 @@ def test_cuda_mask_is_exact_count_and_bit_exact(B, N, rate):
         m = generate_batch_mask(B, N, rate, seed, step, device=dev).cpu().numpy().astype(bool)
         assert m.reshape(B, N).sum(1).tolist() == [count] * B                       # auxil.py:160 assertion
         assert np.array_equal(m, CO.device_mask_reference(seed, step, B, N, count))
+    # required nodes (evaluation.py:288-291 sensors) are in every snapshot's mask, the rest is drawn around them
+    if N >= 40 and count >= 4:
+        from gnn_pressure_estimation_b200.metrics import required_flags
+        req = [0, 3, N - 1]
+        m = generate_batch_mask(B, N, rate, 5, 2, required=required_flags(N, req, dev), device=dev).cpu().numpy().astype(bool)
+        assert m.reshape(B, N).sum(1).tolist() == [count] * B and m.reshape(B, N)[:, req].all()
+        assert np.array_equal(m, CO.device_mask_reference(5, 2, B, N, count, req))
     # step_dev is added to step on the device (CUDA-graph replay draws a fresh mask)
     sd = torch.tensor([5], dtype=torch.int32, device=dev)
     a = generate_batch_mask(B, N, rate, 7, 10, step_dev=sd, device=dev)
@@ -187,3 +203,46 @@ def test_train_step_with_device_mask_and_metrics():
     assert runs[0][0] == pytest.approx(runs[1][0], rel=1e-5)
     # (d/d att_dst is rounding noise whose sign Adam amplifies to +-lr per step: see test_train_step_matches_oracle_adam)
     assert float((runs[0][1] - runs[1][1]).abs().max()) <= 2 * 5e-4 * 3 + 1e-6
+
+
+def test_timer_arithmetic_equals_reference():
+    """compute_time / compute_throughput (utils/timer.py:43-66, incl. its batch-count quirk) vs the real reference"""
+    from gnn_pressure_estimation_b200 import evaluation as E
+    t, g = GOLD["timer/timings"].tolist(), GOLD["timer/num_graphs"].tolist()
+    ref_time, ref_thr = GOLD["timer/time_throughput"]
+    assert E.compute_time(t, g, 107) == pytest.approx(ref_time, rel=1e-12)
+    assert E.compute_throughput(t, g, 107) == pytest.approx(ref_thr, rel=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("required,use_same_mask", [((), False), ((3, 17, 200), False), ((), True)])
+def test_evaluation_epoch_matches_oracle(required, use_same_mask):
+    """test_one_epoch on the CUDA kernels vs the oracle loop with the same NumPy mask stream (evaluation.py:300-351)"""
+    import gnn_pressure_estimation_b200.GraphModels as G
+    from gnn_pressure_estimation_b200 import evaluation as E
+    from helpers import load_case
+    dev = torch.device("cuda:0")
+    c = load_case("ctown_small_15b_32c_B8")
+    N, ei = c["N"], c["edge_index"]
+    ref = O.make_oracle(3, 32, seed=0)
+    model = G.GATResMeanConv(num_blocks=3, nc=32)
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(9)
+    S, bs = 20, 8 if not use_same_mask else 10                       # 8 + 8 + 4: a smaller last batch, as without drop_last
+    snaps = torch.randn(S, N, generator=g)
+    kw = dict(norm_type="znorm", mean=57.3, std=21.9)
+    np.random.seed(77)
+    loss_ref, m_ref = CO.test_one_epoch_oracle(ref, snaps, ei, bs, 0.95, required_idx=required, use_same_mask=use_same_mask, **kw)
+    np.random.seed(77)
+    loss, m = E.test_one_epoch(model, snaps.to(dev), ei, bs, 0.95, required_idx=required, use_same_mask=use_same_mask,
+                               gpu_warmup_times=2, mask_source="numpy", **kw)
+    post = "_sensor" if required else ""
+    assert loss == pytest.approx(loss_ref, rel=2e-4)
+    for k in CO.METRIC_NAMES:
+        assert m[f"test_{k}{post}"] == pytest.approx(m_ref[k], rel=2e-4, abs=1e-6), k
+    assert m[f"test_time{post}"] > 0 and m[f"test_throughput{post}"] > 0 and m[f"test_snapshots_per_s{post}"] > 0
+    # device masks: same contract, different stream -> statistically the same figures
+    loss_d, m_d = E.test_one_epoch(model, snaps.to(dev), ei, bs, 0.95, required_idx=required, use_same_mask=use_same_mask,
+                                   gpu_warmup_times=0, mask_source="device", seed=5, **kw)
+    assert loss_d == pytest.approx(loss_ref, rel=0.1) and m_d[f"test_rmse{post}"] == pytest.approx(m_ref["rmse"], rel=0.1)
