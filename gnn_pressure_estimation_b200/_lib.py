@@ -70,6 +70,8 @@ _PROTOTYPES = {
     "gatres_metrics_scratch_doubles": (_i64, []),
     "gatres_masked_metrics": (C.c_int, [_p, _p, _p, _i64, _f32, _f32, _f32, _p, _p, _p]),
     "gatres_adam_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p]),
+    "gatres_adam_step_peer": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), _i32, _i32, _p, _p, _p, _p, _i64, _f32, _f32, _f32,
+                                        _f32, _f32, _f32, _p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -118,6 +118,93 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// ---- gradient all-reduce fused into the Adam step, over NVLink peer memory -------------------------------------
+// Data-parallel training needs exactly one collective per step: the SUM of the flat gradient buffer.
+// Instead of all-reduce -> Adam (two passes over the gradients plus a collective launch), every rank's Adam kernel
+// reads the gradient buffers of ALL ranks directly through peer pointers (symmetric memory over NVLink / NVSwitch),
+// sums them in rank order (so every replica computes bit-identical updates) and applies the update: the collective
+// costs one cross-GPU flag barrier plus (world - 1) x P floats of peer loads inside a kernel that had to run anyway.
+//   flags[r][q] (uint32, one array per rank r, symmetric) = last epoch for which rank q announced "my backward is done".
+// The gradient buffers are double-buffered by the caller (step parity), so one barrier per step also orders the
+// re-zeroing of a buffer after every peer has finished reading it.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys4(const float* p) {
+  float4 r;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+  const float* grads[kMaxPeers];
+  unsigned* flags[kMaxPeers];
+};
+
+__global__ void bump2_kernel(int* step, int* epoch) {
+  pdl_wait();
+  step[0] += 1;
+  epoch[0] += 1;
+}
+
+__global__ void __launch_bounds__(256)
+adam_peer_kernel(float* __restrict__ p, const PeerTable peers, float* __restrict__ m, float* __restrict__ v,
+                 const int* __restrict__ step, const int* __restrict__ epoch_dev, size_t P4, size_t P, float lr, float b1,
+                 float b2, float eps, float wd, float grad_scale, int rank, int world) {
+  pdl_wait();
+  const unsigned epoch = (unsigned)__ldg(epoch_dev);
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();                                   // this rank's backward (previous kernels) is complete
+    st_release_sys(peers.flags[threadIdx.x] + rank, epoch);   // announce it in every peer's flag array
+  }
+  if (threadIdx.x < world) {
+    const unsigned* f = peers.flags[rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < epoch)
+      if (clock64() - t0 > (20ll << 30)) __trap();            // ~10 s at 2 GHz: a lost peer must not hang the GPU
+  }
+  __syncthreads();
+  const float t = (float)__ldg(step);
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  auto update = [&](float pi, float g, float& mi, float& vi) {
+    const float gi = fmaf(wd, pi, g * grad_scale);
+    mi = fmaf(1.f - b1, gi - mi, mi);
+    vi = fmaf(b2, vi, (1.f - b2) * gi * gi);
+    return pi - step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+  };
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < P4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 g = ld_relaxed_sys4(peers.grads[0] + 4 * i);
+    for (int r = 1; r < world; ++r) add4(g, ld_relaxed_sys4(peers.grads[r] + 4 * i));      // rank order: same sum everywhere
+    float4 pv = *reinterpret_cast<float4*>(p + 4 * i), mv = *reinterpret_cast<float4*>(m + 4 * i), vv = *reinterpret_cast<float4*>(v + 4 * i);
+    pv.x = update(pv.x, g.x, mv.x, vv.x);
+    pv.y = update(pv.y, g.y, mv.y, vv.y);
+    pv.z = update(pv.z, g.z, mv.z, vv.z);
+    pv.w = update(pv.w, g.w, mv.w, vv.w);
+    st4(p + 4 * i, pv); st4(m + 4 * i, mv); st4(v + 4 * i, vv);
+  }
+  if (blockIdx.x == 0) {                                       // tail (P is not a multiple of 4)
+    for (size_t i = 4 * P4 + threadIdx.x; i < P; i += blockDim.x) {
+      float g = 0.f;
+      for (int r = 0; r < world; ++r) {
+        float x;
+        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(peers.grads[r] + i) : "memory");
+        g += x;
+      }
+      float mi = m[i], vi = v[i];
+      p[i] = update(p[i], g, mi, vi);
+      m[i] = mi;
+      v[i] = vi;
+    }
+  }
+}
+
 static unsigned flat_grid(size_t n, unsigned cap_per_sm) {
   size_t g = (n + 255) / 256;
   const size_t cap = (size_t)sm_count() * cap_per_sm;
@@ -164,4 +251,28 @@ extern "C" int gatres_adam_step(float* params, const float* grads, float* exp_av
                                                                       (size_t)P, lr, beta1, beta2, eps, weight_decay,
                                                                       grad_scale);
   return check_launch("adam_step");
+}
+
+extern "C" int gatres_adam_step_peer(float* params, const float* const* peer_grads, uint32_t* const* peer_flags,
+                                     int32_t rank, int32_t world, float* exp_avg, float* exp_avg_sq, int32_t* step_count,
+                                     int32_t* epoch, int64_t P, float lr, float beta1, float beta2, float eps,
+                                     float weight_decay, float grad_scale, void* stream) {
+  GATRES_REQUIRE(P > 0 && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+                 "adam_step_peer: bad P=%lld rank=%d world=%d (at most %d peers)", (long long)P, rank, world, kMaxPeers);
+  GATRES_REQUIRE(peer_grads && peer_flags && epoch && step_count, "adam_step_peer: null table");
+  PeerTable t = {};
+  for (int r = 0; r < world; ++r) {
+    GATRES_REQUIRE(peer_grads[r] != nullptr && peer_flags[r] != nullptr, "adam_step_peer: null pointer for rank %d", r);
+    GATRES_REQUIRE((reinterpret_cast<uintptr_t>(peer_grads[r]) & 15) == 0, "adam_step_peer: gradient buffers must be 16-byte aligned");
+    t.grads[r] = peer_grads[r];
+    t.flags[r] = peer_flags[r];
+  }
+  launch_kernel(bump2_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_count, epoch);
+  int rc = check_launch("adam_peer_bump");
+  if (rc) return rc;
+  const size_t P4 = (size_t)P / 4;
+  launch_kernel(adam_peer_kernel, dim3(flat_grid(P4 ? P4 : 1, 2)), dim3(256), 0, as_stream(stream), params, t, exp_avg, exp_avg_sq,
+                (const int*)step_count, (const int*)epoch, P4, (size_t)P, lr, beta1, beta2, eps, weight_decay, grad_scale,
+                (int)rank, (int)world);
+  return check_launch("adam_step_peer");
 }

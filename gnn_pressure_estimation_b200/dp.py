@@ -56,6 +56,32 @@ def bucket_slice(num_blocks: int, param_count: int, k_hi: int, k_lo: int, offset
     return lo, hi
 
 
+class PeerGradients:
+    """Symmetric (peer-mapped) gradient buffers for the all-reduce that is fused into the Adam kernel
+    (`gatres_adam_step_peer`): two flat fp32 gradient buffers (step parity) and one uint32 flag array per rank,
+    allocated with torch's CUDA symmetric memory so that every rank holds device pointers to every peer's copy
+    (NVLink / NVSwitch loads).  Raises if symmetric memory is unavailable; the caller then keeps the NCCL path."""
+
+    def __init__(self, param_count: int, group, device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n = (param_count + 3) // 4 * 4
+        self.grads = [symm.empty(n, dtype=torch.float32, device=device) for _ in range(2)]
+        self.flags = symm.empty(64, dtype=torch.int32, device=device)
+        for t in self.grads + [self.flags]:
+            t.zero_()
+        torch.cuda.synchronize(device)
+        handles = [symm.rendezvous(t, group) for t in self.grads + [self.flags]]
+        self._handles = handles                                   # keep the mappings alive
+        arr = C.c_void_p * self.world
+        self.grad_tables = [arr(*[int(p) for p in h.buffer_ptrs]) for h in handles[:2]]
+        self.flag_table = arr(*[int(p) for p in handles[2].buffer_ptrs])
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group)                                       # every rank's buffers are zeroed and mapped
+        torch.cuda.synchronize(device)
+
+
 def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     """torchrun-style rendezvous (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).  -> (rank, world, local_rank)"""
     rank = int(os.environ.get("RANK", "0"))

@@ -29,7 +29,8 @@ class TrainStep:
     def __init__(self, model: GATResMeanConv, topo: Topology, batch: int, mask_count_per_snapshot: int,
                  lr: float = 5e-4, weight_decay: float = 6e-6, betas=(0.9, 0.999), eps: float = 1e-8,
                  process_group=None, use_graph: bool = True, deterministic: bool = False,
-                 grad_buckets: Optional[int] = None, device_mask_seed: Optional[int] = None,
+                 grad_buckets: Optional[int] = None, peer_allreduce: Optional[bool] = None,
+                 device_mask_seed: Optional[int] = None,
                  metrics: Optional["_metrics.MaskedMetrics"] = None):
         self.model, self.topo, self.B = model, topo, int(batch)
         self.N, self.nc, self.nb = topo.N, model.nc, model.num_blocks
@@ -67,6 +68,18 @@ class TrainStep:
         self.loss = torch.zeros(1, **f32)
         self._loss_part = torch.empty(1024, **f32)
         self.grads = torch.zeros(P, **f32)
+        # data parallel, atomic gradient mode: fuse the gradient all-reduce into the Adam kernel over NVLink peer
+        # memory (dp.PeerGradients); peer_allreduce=None tries it and falls back to the overlapped NCCL all-reduce
+        self.peer: Optional[_dp.PeerGradients] = None
+        self._parity = 0
+        if self.world > 1 and not deterministic and peer_allreduce is not False and dev.type == "cuda":
+            try:
+                self.peer = _dp.PeerGradients(P, self.pg, dev)
+            except Exception as e:                                 # symmetric memory unavailable on this system
+                if peer_allreduce:
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory gradient all-reduce unavailable ({e!r}); using NCCL all-reduce")
         self.exp_avg = torch.zeros(P, **f32)
         self.exp_avg_sq = torch.zeros(P, **f32)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -78,6 +91,7 @@ class TrainStep:
         self.scratch = torch.empty(int(lib.gatres_scratch_floats(C.byref(self.desc), 1)), **f32)
         self.partial = torch.empty(self.desc.slots * _gops.a4(P), **f32) if deterministic else None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graphs = [None, None]                       # peer mode: one captured step per gradient-buffer parity
         # our kernel launches per step (mask, forward, loss, backward, Adam); measured in capture()/first run
         self.kernels_per_step = 0
 
@@ -91,6 +105,7 @@ class TrainStep:
     def _enqueue_impl(self) -> None:
         s = stream()
         d = C.byref(self.desc)
+        grads = self.grads if self.peer is None else self.peer.grads[self._parity]
         if self.device_mask_seed is not None:
             # rank-distinct streams: every rank masks its own shard independently (train.py:172 draws per batch)
             rank = torch.distributed.get_rank(self.pg) if self.pg is not None else 0
@@ -105,13 +120,21 @@ class TrainStep:
         # equal shard sizes and equal masked counts per snapshot -> mean of local means == global mean, so the
         # collective is a plain SUM (the 1/world factor is folded into the Adam kernel)
         dp = self.pg is not None and self.world > 1
-        if not dp or len(self.block_ranges) == 1:
+        if not dp or len(self.block_ranges) == 1 or self.peer is not None:
             call("gatres_backward", d, ptr(self.flat), ptr(self.xm), ptr(self.saved), ptr(self.d_out),
-                 ptr(self.partial), ptr(self.grads), ptr(self.scratch), s)
-            if dp:
+                 ptr(self.partial), ptr(grads), ptr(self.scratch), s)
+            if dp and self.peer is None:
                 torch.distributed.all_reduce(self.grads, group=self.pg)
         else:
             self._backward_overlapped(d, s)
+        if self.peer is not None:
+            # all-reduce fused into Adam: every rank sums all ranks' gradient buffers through NVLink peer pointers
+            call("gatres_adam_step_peer", ptr(self.flat), self.peer.grad_tables[self._parity], self.peer.flag_table,
+                 self.peer.rank, self.world, ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.step_count),
+                 ptr(self.peer.epoch), self.P, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                 1.0 / self.world, s)
+            self._parity ^= 1
+            return
         call("gatres_adam_step", ptr(self.flat), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              ptr(self.step_count), self.P, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
              1.0 / self.world, s)
@@ -150,10 +173,22 @@ class TrainStep:
         for t, s in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_count), state):
             t.copy_(s)
         torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._enqueue()
-        self.graph = g
+        if self.peer is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.graph = g
+            return
+        start = self._parity                              # the warm-up steps advanced it identically on every rank
+        for k in range(2):
+            par = start ^ k
+            self._parity = par
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()                           # flips self._parity
+            self._graphs[par] = g
+        self._parity = start
+        self.graph = self._graphs[start]
 
     # ------------------------------------------------------------------- steps
     def load_inputs(self, x: Tensor, y: Tensor, mask: Optional[Tensor] = None) -> None:
@@ -176,7 +211,10 @@ class TrainStep:
 
     def run(self) -> Tensor:
         """Enqueue one optimizer step on the resident inputs; returns the device loss scalar."""
-        if self.graph is not None:
+        if self.graph is not None and self.peer is not None:
+            self._graphs[self._parity].replay()
+            self._parity ^= 1
+        elif self.graph is not None:
             self.graph.replay()
         else:
             self._enqueue()

@@ -325,6 +325,23 @@ int gatres_adam_step(float* params, const float* grads, float* exp_avg, float* e
                      int32_t* step_count, int64_t P, float lr, float beta1, float beta2,
                      float eps, float weight_decay, float grad_scale, void* stream);
 
+/*
+ * Data-parallel variant: gradient all-reduce FUSED into the Adam step over NVLink peer memory (no reference
+ * counterpart: the reference is single-process, train.py:306-324; contract = SURVEY 8e, "N-rank step == 1-rank
+ * step on the concatenated batch").  peer_grads[r] / peer_flags[r] (HOST arrays of `world` device pointers) are
+ * rank r's flat gradient buffer (16-byte aligned) and uint32[world] flag array, mapped into this process (CUDA
+ * symmetric memory / IPC).  The kernel announces "rank's backward of this step is done" in every peer's flag array,
+ * waits for all peers, then reads every rank's gradients through the peer pointers, sums them in rank order (all
+ * replicas compute bit-identical updates) and applies Adam with grad_scale (1/world).  epoch: device int32[1],
+ * incremented here (never reset by the caller, unlike step_count).  The caller alternates between two gradient
+ * buffers per step, so this one barrier also protects a buffer from being re-zeroed while a peer still reads it.
+ * world == 1 degenerates to gatres_adam_step.
+ */
+int gatres_adam_step_peer(float* params, const float* const* peer_grads, uint32_t* const* peer_flags,
+                          int32_t rank, int32_t world, float* exp_avg, float* exp_avg_sq, int32_t* step_count,
+                          int32_t* epoch, int64_t P, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
