@@ -32,6 +32,13 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// round-to-nearest (ties away) to TF32 with two integer instructions: add half an ulp of the 10-bit mantissa to the
+// magnitude bits, drop the low 13 bits.  cvt.rna.tf32.f32 is emulated by ptxas with a ~5-instruction sequence
+// (inf/nan guards), which made the per-tile operand split the bottleneck of the staging threads; the operands
+// here are finite residuals of magnitude << FLT_MAX, so the guards are not needed.
+__device__ __forceinline__ float rna_tf32_fast(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// lo part of the 3xTF32 split of x whose hi part is the tensor core's own truncation of x
+__device__ __forceinline__ float lo_tf32(float x) { return rna_tf32_fast(x - trunc_tf32(x)); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {       // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
                "r"(ncols)
@@ -169,8 +176,7 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
       const uint32_t off = swz_off(row, 4 * c, BM);
       const float4 x = *reinterpret_cast<const float4*>(sm + (raw_c - base) + off);
       float4 lo;
-      lo.x = to_tf32(x.x - trunc_tf32(x.x)); lo.y = to_tf32(x.y - trunc_tf32(x.y));
-      lo.z = to_tf32(x.z - trunc_tf32(x.z)); lo.w = to_tf32(x.w - trunc_tf32(x.w));
+      lo.x = lo_tf32(x.x); lo.y = lo_tf32(x.y); lo.z = lo_tf32(x.z); lo.w = lo_tf32(x.w);
       *reinterpret_cast<float4*>(sm + A_BYTES + off) = lo;
     }
     fence_proxy_async();                                      // generic-proxy smem writes -> tensor-core (async) proxy
@@ -274,6 +280,253 @@ static int launch_tc(const float* A, const float* W, const float* e0, const floa
   return check_launch(what);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Wide shapes (nc = 64 / 128: K up to 256, N up to 256): the operands of a whole tile no longer fit shared
+// memory, so K is walked in 32-column chunks (one SWIZZLE_128B atom column) through a software pipeline:
+//   A chunk [128 x 32] fp32 : cp.async into a 3-deep ring two chunks ahead (the tensor core reads its TF32
+//                             truncation as A_hi), A_lo = rna(x - trunc x) written by the staging threads;
+//   B chunk [NN x 32]       : the matching columns of W, read through L2 (the weights of one projection are
+//                             <= 128 KB and shared by every CTA), split into B_hi / B_lo by the staging threads;
+//   12 MMAs per chunk (4 K-steps x {hi*hi, lo*hi, hi*lo}) accumulate into NN TMEM columns; the chunk's commit
+//   arrives on the mbarrier of its stage, so the MMAs of chunk q run under the staging of chunk q + 1.
+// 256 threads: all stage; in the epilogue thread t drains TMEM lane t % 128 (its warp's lane quarter) for the
+// column half t / 128.  FP32 FFMA peaks at ~75 TFLOP/s on B200 and the nc = 128 projections are 4 x 65 kFLOP
+// per node and block, which made the large model FFMA bound (profiles/r1_configs.md); 3xTF32 on tcgen05 puts
+// them back under the HBM roofline.  MODE 0 only (projection + score epilogue).
+// ---------------------------------------------------------------------------------------------------------
+#ifdef GATRES_TC_PROF
+#define TCP_DECL long long tcp_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tcp_last = clock64()
+#define TCP(i) do { const long long now_ = clock64(); tcp_t[i] += now_ - tcp_last; tcp_last = now_; } while (0)
+#else
+#define TCP_DECL
+#define TCP(i)
+#endif
+
+template <int KK, int NN, int H>
+__global__ void __launch_bounds__(256)
+gemm_tc_wide_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ att_src,
+                    const float* __restrict__ att_dst, float* __restrict__ Cout, float* __restrict__ s0,
+                    float* __restrict__ s1, unsigned M) {
+  constexpr int BM = 128, KC = 32, NCHUNK = KK / KC, T = 256;
+  constexpr uint32_t A_CH = BM * KC * 4, B_CH = NN * KC * 4;                 // bytes of one chunk buffer
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static_assert(KK % KC == 0 && (NN == 128 || NN == 256) && (H == 1 || H == 2), "unsupported wide tensor-core shape");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();
+  unsigned char* sm = smem_raw;
+  // [A_raw x3][A_lo x2][B_hi x2][B_lo x2][att 2*NN][score partials 2*T][barriers]
+  constexpr uint32_t OFF_ALO = 3 * A_CH, OFF_BHI = OFF_ALO + 2 * A_CH, OFF_BLO = OFF_BHI + 2 * B_CH,
+                     OFF_END = OFF_BLO + 2 * B_CH;
+  static_assert(OFF_END - OFF_ALO >= (uint32_t)BM * NN * 4, "epilogue staging must fit the A_lo/B buffers");
+  float* att = reinterpret_cast<float*>(sm + OFF_END);
+  float* part = att + 2 * NN;                                               // [2][T] score partials
+  uint64_t* bar = reinterpret_cast<uint64_t*>(part + 2 * T);                // [2] one per stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned ntiles = (M + BM - 1) / BM;
+  if (warp == 0) tmem_alloc(tmem_slot, NN);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    mbar_fence_init();
+  }
+  for (int idx = tid; idx < NN; idx += T) {
+    att[idx] = __ldg(att_src + idx);
+    att[NN + idx] = __ldg(att_dst + idx);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  const unsigned my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const unsigned total = my_tiles * NCHUNK;                                  // flattened (tile, chunk) sequence
+  auto issue_a = [&](unsigned q) {                                           // A chunk of step q -> ring slot q % 3
+    const unsigned tile = blockIdx.x + (q / NCHUNK) * gridDim.x, ch = q % NCHUNK;
+    const uint32_t dst = base + (q % 3) * A_CH;
+#pragma unroll
+    for (int it = 0; it < BM * (KC / 4) / T; ++it) {
+      const int idx = it * T + tid;
+      const uint32_t row = idx / (KC / 4), c = idx % (KC / 4);
+      const unsigned grow = tile * BM + row;
+      const bool ok = grow < M;
+      tc_cp_async16(dst + swz_off(row, 4 * c, BM), A + (size_t)(ok ? grow : 0) * KK + ch * KC + 4 * c, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // W chunk of the NEXT step lives in registers: its L2 latency hides under this step's MMAs instead of stalling
+  // all eight warps at the top of every step (ncu: long-scoreboard bound, tensor pipe 23 % busy without it)
+  constexpr int WPT = NN * (KC / 4) / T;
+  float4 wr[WPT];
+  auto load_w = [&](unsigned q) {
+    const unsigned ch = q % NCHUNK;
+#pragma unroll
+    for (int it = 0; it < WPT; ++it) {
+      const int idx = it * T + tid;
+      wr[it] = ldg4(W + (size_t)(idx / (KC / 4)) * KK + ch * KC + 4 * (idx % (KC / 4)));
+    }
+  };
+  if (total > 0) {
+    issue_a(0);
+    load_w(0);
+  }
+  if (total > 1) issue_a(1);
+  if (gridDim.x >= ntiles) pdl_launch_dependents();
+
+  TCP_DECL;
+  uint32_t ph[2] = {0, 0};                                                   // parity of the next completion of bar[s]
+  bool pending[2] = {false, false};                                          // MMAs committed to bar[s] and not yet waited for
+  auto ensure = [&](uint32_t x) {
+    if (pending[x]) {
+      mbar_wait(bar + x, ph[x]);
+      ph[x] ^= 1u;
+      pending[x] = false;
+    }
+  };
+  for (unsigned q = 0; q < total; ++q) {
+    const unsigned tile = blockIdx.x + (q / NCHUNK) * gridDim.x, ch = q % NCHUNK, s = q & 1u;
+    const uint32_t a_raw = base + (q % 3) * A_CH, a_lo = base + OFF_ALO + s * A_CH, b_hi = base + OFF_BHI + s * B_CH,
+                   b_lo = base + OFF_BLO + s * B_CH;
+    // stage s was last read by the MMAs of step q - 2: they were waited for at step q - 1 (below)
+    if (q + 1 < total) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    TCP(0);
+    // ---- B chunk: W[n][ch*32 .. +32) -> hi / lo, K-major SWIZZLE_128B (values prefetched one step ahead) ----
+#pragma unroll
+    for (int it = 0; it < WPT; ++it) {
+      const int idx = it * T + tid;
+      const uint32_t n = idx / (KC / 4), c = idx % (KC / 4);
+      const float4 w = wr[it];
+      float4 lo;                                       // B_hi = the raw values (the tensor core truncates them to TF32)
+      lo.x = lo_tf32(w.x); lo.y = lo_tf32(w.y); lo.z = lo_tf32(w.z); lo.w = lo_tf32(w.w);
+      const uint32_t off = swz_off(n, 4 * c, NN);
+      *reinterpret_cast<float4*>(sm + OFF_BHI + s * B_CH + off) = w;
+      *reinterpret_cast<float4*>(sm + OFF_BLO + s * B_CH + off) = lo;
+    }
+    // ---- A_lo of the chunks this thread loaded ----
+#pragma unroll
+    for (int it = 0; it < BM * (KC / 4) / T; ++it) {
+      const int idx = it * T + tid;
+      const uint32_t row = idx / (KC / 4), c = idx % (KC / 4);
+      const uint32_t off = swz_off(row, 4 * c, BM);
+      const float4 x = *reinterpret_cast<const float4*>(sm + (q % 3) * A_CH + off);
+      float4 lo;
+      lo.x = lo_tf32(x.x); lo.y = lo_tf32(x.y); lo.z = lo_tf32(x.z); lo.w = lo_tf32(x.w);
+      *reinterpret_cast<float4*>(sm + OFF_ALO + s * A_CH + off) = lo;
+    }
+    TCP(1);
+    fence_proxy_async();
+    __syncthreads();
+    TCP(2);
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < KC / 8; ++ks) {
+        const uint32_t ko = (uint32_t)ks * 32u;
+        umma_tf32(tmem, umma_desc_k128(a_raw + ko), umma_desc_k128(b_hi + ko), IDESC, (ch > 0 || ks > 0) ? 1u : 0u);
+        umma_tf32(tmem, umma_desc_k128(a_lo + ko), umma_desc_k128(b_hi + ko), IDESC, 1);
+        umma_tf32(tmem, umma_desc_k128(a_raw + ko), umma_desc_k128(b_lo + ko), IDESC, 1);
+      }
+      umma_commit(bar + s);
+    }
+    pending[s] = true;
+    if (q + 1 < total) load_w(q + 1);
+    TCP(3);
+    // the MMAs of step q - 1 (other stage, ring slot (q-1) % 3 = (q+2) % 3) must be done before that ring slot is refilled
+    ensure(s ^ 1u);
+    TCP(4);
+    if (q + 2 < total) issue_a(q + 2);
+    TCP(5);
+
+    if (ch == NCHUNK - 1) {
+      // ---- tile complete: wait for this step's MMAs too, then the epilogue ----
+      ensure(s);
+      TCP(6);
+      tc_fence_after();
+      const int lane_row = tid & 127, half = tid >> 7;                      // TMEM lane (= row of the tile), column half
+      const unsigned row = tile * BM + lane_row;
+      constexpr int NCH = NN / 4;
+      unsigned char* stg = sm + OFF_ALO;                                     // [128][NN] floats over A_lo / B buffers
+      float ps = 0.f, pd = 0.f;
+#pragma unroll
+      for (int cb = 0; cb < NN / 64; ++cb) {
+        const int col0 = half * (NN / 2) + cb * 32;
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + col0, v);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          ps = fmaf(v[k], att[col0 + k], ps);
+          pd = fmaf(v[k], att[NN + col0 + k], pd);
+        }
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          const int c = col0 / 4 + k / 4;
+          *reinterpret_cast<float4*>(stg + (size_t)lane_row * (NN * 4) + (((c ^ lane_row) & (NCH - 1)) << 4)) =
+              make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        }
+      }
+      part[tid] = ps;
+      part[T + tid] = pd;
+      tc_fence_before();
+      __syncthreads();
+      if (tid < BM && row < M) {
+        if (H == 2) {                                                         // column half == head
+          s0[(size_t)row * 2 + 0] = part[tid];       s0[(size_t)row * 2 + 1] = part[tid + 128];
+          s1[(size_t)row * 2 + 0] = part[T + tid];   s1[(size_t)row * 2 + 1] = part[T + tid + 128];
+        } else {
+          s0[row] = part[tid] + part[tid + 128];
+          s1[row] = part[T + tid] + part[T + tid + 128];
+        }
+      }
+#pragma unroll 4
+      for (int it = 0; it < BM * NCH / T; ++it) {
+        const int idx = it * T + tid;
+        const int r = idx / NCH, c = idx % NCH;
+        const unsigned grow = tile * BM + r;
+        if (grow < M)
+          st4(Cout + (size_t)grow * NN + 4 * c,
+              *reinterpret_cast<const float4*>(stg + (size_t)r * (NN * 4) + (((c ^ r) & (NCH - 1)) << 4)));
+      }
+      __syncthreads();                                                       // staging area (= stage buffers) free again
+      TCP(7);
+    }
+  }
+#ifdef GATRES_TC_PROF
+  if (blockIdx.x == 0 && (tid == 0 || tid == 200))
+    printf("tc_wide<%d,%d> tid %d steps %u: wait_a %lld stage %lld sync %lld mma_issue+loadw %lld ensure_prev %lld issue_a %lld ensure_tile %lld epilogue %lld (cycles per step)\n",
+           KK, NN, tid, total, tcp_t[0] / total, tcp_t[1] / total, tcp_t[2] / total, tcp_t[3] / total, tcp_t[4] / total, tcp_t[5] / total,
+           tcp_t[6] / total, tcp_t[7] / total);
+#endif
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, NN);
+}
+
+template <int KK, int NN, int H>
+static int launch_tc_wide(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
+                          float* s1, unsigned M, cudaStream_t st) {
+  constexpr size_t smem = 5 * (size_t)128 * 32 * 4 + 4 * (size_t)NN * 32 * 4 + 2 * NN * 4 + 2 * 256 * 4 + 32;
+  auto kern = gemm_tc_wide_kernel<KK, NN, H>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch("gemm_tc_wide");
+    configured = true;
+  }
+  const unsigned ntiles = (M + 127) / 128;
+  unsigned per_sm = (unsigned)((228u * 1024u) / (smem + 1024u));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  if (per_sm * NN > 512) per_sm = 512 / NN;                                 // TMEM columns per SM
+  unsigned grid = (unsigned)sm_count() * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  launch_kernel(kern, dim3(grid), dim3(256), smem, st, A, W, e0, e1, Cout, s0, s1, M);
+  return check_launch("gemm_tc_wide");
+}
+
 // -> 1 if handled, 0 if this shape has no tensor-core path (caller falls back to the FFMA kernel), <0 on error
 int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const float* W, const float* e0,
                      const float* e1, float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st) {
@@ -288,6 +541,15 @@ int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const floa
   TC(32, 64, 1, 1)      // conv2 data gradient (dh2 [M,32] -> dy1 [M,64])
   TC(64, 32, 1, 1)      // conv1 data gradient (dh1 [M,64] -> dx0 [M,32])
 #undef TC
+#define TCW(KKv, NNv, Hv)                                                                                  \
+  if (mode == 0 && KK == KKv && NN == NNv && H == Hv) {                                                    \
+    rc = launch_tc_wide<KKv, NNv, Hv>(A, W, e0, e1, Cout, s0, s1, M, st);                                   \
+    return rc ? rc : 1;                                                                                   \
+  }
+  TCW(64, 128, 2)       // conv1 projection, nc = 64 (its conv2, K = 128 -> N = 64, stays on the FFMA kernel)
+  TCW(128, 256, 2)      // conv1 projection, nc = 128
+  TCW(256, 128, 1)      // conv2 projection, nc = 128
+#undef TCW
   return 0;
 }
 

@@ -146,6 +146,32 @@ def test_gat_conv_forward_backward(graph, B, H, C, fin, concat, relu, dev, kerne
         assert_close(a.grad, b.grad, GRAD_TOL, name)
 
 
+@pytest.mark.parametrize("H,C,fin", [(2, 128, 128), (1, 128, 256), (2, 64, 64), (2, 32, 32), (1, 32, 64)])
+def test_tensor_core_projection_many_tiles(H, C, fin, dev):
+    """tcgen05 3xTF32 projections (whole-K kernel for nc = 32, K-chunked pipeline for the wide shapes) against the
+    fp32 FFMA kernel and an fp64 reference, with several 128-row tiles per CTA and a ragged last tile."""
+    from gnn_pressure_estimation_b200 import _lib, ops as gops  # noqa: F401
+    lib = _lib.load()
+    M = 128 * 148 * 2 + 128 * 37 + 5
+    x, W, a_s, a_d = _layer_inputs(M, fin, H, C, seed=17)
+    res = []
+    prev = lib.gatres_set_tensor_core(-1)
+    try:
+        for mode in (0, 2):
+            lib.gatres_set_tensor_core(mode)
+            h, ss, sd = torch.ops.gatres.linear_att_fwd(x.to(dev), W.to(dev), a_s.reshape(-1).to(dev), a_d.reshape(-1).to(dev), H, C)
+            res.append((h.cpu(), ss.cpu(), sd.cpu()))
+    finally:
+        lib.gatres_set_tensor_core(prev)
+    h64 = x.double() @ W.double().T
+    s64 = (h64.view(M, H, C) * a_s.double()).sum(-1)
+    d64 = (h64.view(M, H, C) * a_d.double()).sum(-1)
+    for name, (h, ss, sd) in zip(("ffma", "tcgen05"), res):
+        assert_close(h, h64.float(), 5e-6, f"{name} h")          # fp32 accumulation over K <= 256
+        assert_close(ss.view(M, H), s64.float(), 1e-5, f"{name} s_src")
+        assert_close(sd.view(M, H), d64.float(), 1e-5, f"{name} s_dst")
+
+
 @pytest.mark.parametrize("graph,B", [("tiny", 4), ("ctown", 2), ("directed", 3)])
 @pytest.mark.parametrize("C", [32, 64, 128])
 def test_mean_res_forward_backward(graph, B, C, dev):
