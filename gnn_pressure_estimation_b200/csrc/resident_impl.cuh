@@ -255,6 +255,10 @@ __device__ __forceinline__ void wgrad_rows(const float* Gs, const float* Xs, int
   }
 }
 
+#if RES_USE_MMA
+#include "resident_mma.cuh"
+#endif
+
 // sum per-lane float4 accumulators over every lane of the CTA that holds the same chunk (lane % LPR) and add
 // the LPR chunk sums into dst (atomic).  red: T*4 floats of shared scratch.  All threads call.
 template <int LPR>
@@ -500,7 +504,8 @@ resident_fwd_kernel(const Args a) {
   float* W1s = ys + R * LDY;               // [2][64][LDX]
   float* W2s = W1s + 2 * W1F;              // [2][32][LDY]
   float* vec = W2s + 2 * W2F;              // [2][288]
-  int* rp_s = reinterpret_cast<int*>(vec + 2 * VECF);     // shared CSR of the water network: rowptr [N+1]
+  float* scr = vec + 2 * VECF;             // [4][R] score partials of the tensor-core conv2 projection
+  int* rp_s = reinterpret_cast<int*>(scr + a4(4 * R));    // shared CSR of the water network: rowptr [N+1]
   int* col_s = rp_s + a4(N + 1);                          //                                   col [E1]
   const int rank = (int)cluster_ctarank();
   const long long b = cluster_id_x();
@@ -554,7 +559,11 @@ resident_fwd_kernel(const Args a) {
 
     // conv1 projection + scores  (GraphModels.py:464)
     stamp();
+#if RES_USE_MMA
+    project_rows_mma<NC, 2 * NC, 2, LDX, LDX>(xs, W1, vc, vc + 2 * NC, h1 + ro * 2 * NC, ss1 + ro * 2, sd1 + ro * 2, scr, n);
+#else
     project_rows<NC, 2 * NC, 2, LDX, LDX>(xs, W1, vc, vc + 2 * NC, h1 + ro * 2 * NC, ss1 + ro * 2, sd1 + ro * 2, n);
+#endif
     stamp();
     cluster_sync();
     stamp();
@@ -566,7 +575,11 @@ resident_fwd_kernel(const Args a) {
     __syncthreads();
     stamp();
     // conv2 projection + scores  (:465)
+#if RES_USE_MMA
+    project_rows_mma<2 * NC, NC, 1, LDY, LDY>(ys, W2, vc + 6 * NC, vc + 7 * NC, h2 + ro * NC, ss2 + ro, sd2 + ro, scr, n);
+#else
     project_rows<2 * NC, NC, 1, LDY, LDY>(ys, W2, vc + 6 * NC, vc + 7 * NC, h2 + ro * NC, ss2 + ro, sd2 + ro, n);
+#endif
     stamp();
     cluster_sync();
     stamp();
@@ -716,6 +729,20 @@ resident_bwd_kernel(const Args a) {
     __syncthreads();                         // dh2 is in shared memory
     stamp();
     // (3) conv2 projection backward: dW2 = dh2^T y1 ; dy1 = (dh2 W2) masked by y1 > 0 (in place over y1)
+#if RES_USE_MMA
+    wgrad_rows_mma<NC, 2 * NC, LDX, LDY>(d2s, ys, n, a.grads + pl.c2_W(k));
+    __syncthreads();
+    {
+      float* dy1o = dy1 + ro * 2 * NC;
+      dgrad_rows_mma<NC, 2 * NC, LDX, LDY>(d2s, W2, n, [&](int m, int c, float2 v) {
+        float2* p = reinterpret_cast<float2*>(ys + m * LDY + c);
+        const float2 y = *p;
+        v = make_float2(y.x > 0.f ? v.x : 0.f, y.y > 0.f ? v.y : 0.f);
+        *p = v;
+        *reinterpret_cast<float2*>(dy1o + (size_t)m * 2 * NC + c) = v;
+      });
+    }
+#else
     wgrad_rows<NC, 2 * NC, LDX, LDY>(d2s, ys, n, a.grads + pl.c2_W(k));
     __syncthreads();
     {
@@ -727,6 +754,7 @@ resident_bwd_kernel(const Args a) {
         st4(dy1o + (size_t)m * 2 * NC + c, v);
       });
     }
+#endif
     __syncthreads();
     stamp();
     // (4) conv1 pass 1 (incoming gradient = dy1 from shared memory)
@@ -743,6 +771,25 @@ resident_bwd_kernel(const Args a) {
     __syncthreads();
     stamp();
     // (6) conv1 projection backward: dW1 = dh1^T x0 ; gB = dh1 W1 + gA (residual), masked by x0 > 0 for k > 0
+#if RES_USE_MMA
+    wgrad_rows_mma<2 * NC, NC, LDY, LDX>(ys, xs, n, a.grads + pl.c1_W(k));
+    {
+      const float* gAo = gA + ro * NC;
+      float* gBo = gB + ro * NC;
+      const bool mask = k > 0;
+      dgrad_rows_mma<2 * NC, NC, LDY, LDX>(ys, W1, n, [&](int m, int c, float2 v) {
+        float gx, gy;
+        asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(gx), "=f"(gy) : "l"(gAo + (size_t)m * NC + c));
+        v.x += gx;
+        v.y += gy;
+        if (mask) {
+          const float2 x0 = lds2(xs + m * LDX + c);
+          v = make_float2(x0.x > 0.f ? v.x : 0.f, x0.y > 0.f ? v.y : 0.f);
+        }
+        *reinterpret_cast<float2*>(gBo + (size_t)m * NC + c) = v;
+      });
+    }
+#else
     wgrad_rows<2 * NC, NC, LDY, LDX>(ys, xs, n, a.grads + pl.c1_W(k));
     {
       const float* gAo = gA + ro * NC;
@@ -754,6 +801,7 @@ resident_bwd_kernel(const Args a) {
         st4(gBo + (size_t)m * NC + c, v);
       });
     }
+#endif
     // parameter-vector gradients of the block: sum the 8 warp rows, one 128-bit red per chunk
     for (int c = threadIdx.x; c < VECF / 4; c += T) {
       float4 s = f4zero();
@@ -791,7 +839,7 @@ resident_bwd_kernel(const Args a) {
 // ------------------------------------------------------------------------- host side
 static size_t csr_ints(int N, int E1) { return (size_t)a4(N + 1) + (size_t)a4(E1); }
 static size_t fwd_smem(int R, int N, int E1) {
-  return sizeof(float) * ((size_t)R * (LDX + LDY) + 2 * (W1F + W2F + VECF) + csr_ints(N, E1));
+  return sizeof(float) * ((size_t)R * (LDX + LDY) + 2 * (W1F + W2F + VECF) + a4(4 * R) + csr_ints(N, E1));
 }
 static size_t bwd_smem(int R, int N, int E1) {
   return sizeof(float) * ((size_t)R * (2 * LDX + LDY) + 2 * (W1F + W2F + VECF) + (T / 32) * VECF + T * 4 + 2 * csr_ints(N, E1));

@@ -114,8 +114,9 @@ int64_t gatres_set_resident_max_batch(int64_t max_batch);
  * co-resident at two CTAs per SM; GATRES_RESIDENT_CLUSTER presets it).  Other values only query.  Returns
  * the previous setting. */
 int32_t gatres_set_resident_cluster(int32_t ctas);
-/* Threads per CTA of the resident kernels: 256 or 512 (GATRES_RESIDENT_THREADS presets it).  Other values only
- * query.  Returns the previous setting. */
+/* Variant of the resident kernels: 256 = 256-thread CTAs with tensor-core (mma.sync 3xTF32) contractions
+ * (default); 255 = the same with fp32 FFMA contractions; 512 = 512-thread CTAs, FFMA (GATRES_RESIDENT_THREADS
+ * presets it).  Other values only query.  Returns the previous setting. */
 int32_t gatres_set_resident_threads(int32_t threads);
 /* Profiling aid (tools/resident_probe.py): when device_buf is not NULL, thread 0 of CTA c of every resident kernel
  * writes %globaltimer at its phase boundaries to device_buf[c * slots_per_cta ...] (at most slots_per_cta stamps).
