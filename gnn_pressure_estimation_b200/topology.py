@@ -135,23 +135,31 @@ def _reinsert(adj: Dict[str, Dict[str, None]], keep: Optional[set] = None) -> Di
     return new
 
 
+def reference_edge_index_for(wn: WaterNetwork, keep: Optional[Sequence[str]]) -> Tuple[np.ndarray, List[str]]:
+    """-> (edge_index int64 [2,E] in the reference's order, kept node names) for an explicit keep list
+    (``graph.subgraph(keep_list).copy()``, DataLoader.py:252; ``None`` keeps every node)."""
+    adj = _collapse(wn.node_names, wn.links)
+    adj = _reinsert(adj)                                        # .to_undirected()
+    if keep is not None:
+        adj = _reinsert(adj, set(keep))                         # .subgraph(keep).copy(): graph order, filtered
+    names = list(adj)
+    idx = {n: k for k, n in enumerate(names)}
+    src = [idx[u] for u, nb in adj.items() for _ in nb]
+    dst = [idx[v] for nb in adj.values() for v in nb]
+    return np.asarray([src, dst], dtype=np.int64).reshape(2, -1), names
+
+
 def reference_edge_index(wn: WaterNetwork, removal: str = "keep_junction") -> Tuple[np.ndarray, List[str]]:
     """-> (edge_index int64 [2,E] in the reference's order, kept node names).
 
     ``removal`` follows DataLoader.get_keep_list (:40-58): ``keep_junction``
     (default, train.py:598-603) or ``keep_all``.
     """
-    adj = _collapse(wn.node_names, wn.links)
-    adj = _reinsert(adj)                                        # .to_undirected()
     if removal == "keep_junction":
-        adj = _reinsert(adj, set(wn.junctions))                 # .subgraph(keep).copy()
-    elif removal != "keep_all":
-        raise ValueError(f"unsupported removal {removal!r}")
-    names = list(adj)
-    idx = {n: k for k, n in enumerate(names)}
-    src = [idx[u] for u, nb in adj.items() for _ in nb]
-    dst = [idx[v] for nb in adj.values() for v in nb]
-    return np.asarray([src, dst], dtype=np.int64).reshape(2, -1), names
+        return reference_edge_index_for(wn, wn.junctions)
+    if removal == "keep_all":
+        return reference_edge_index_for(wn, None)
+    raise ValueError(f"unsupported removal {removal!r}")
 
 
 def edge_index_from_inp(path: str, removal: str = "keep_junction") -> Tuple[np.ndarray, List[str]]:
