@@ -273,80 +273,105 @@ __device__ __forceinline__ void cta_chunk_sum_atomic(float4 acc, float* red, flo
   }
 }
 
-// ---- fused GAT aggregation over this CTA's rows (same lane mapping as gat_agg.cu, C = 32) ----------
-// LPR = 8H lanes own a row (one float4 chunk each); lane `slot` of a head group evaluates edge `slot`.
+// ---- fused GAT aggregation over this CTA's rows (C = 32) -------------------------------------------------
+// Eight lanes own a row: lane `slot` holds the float4 chunk `slot` of EVERY head of the row (H chunks per lane) and
+// evaluates edge `slot` of the row for every head, so a warp covers four rows per pass whatever H is, and the
+// index work (row pointers, neighbour ids, their shuffles) is shared by the heads.  (The first version gave each
+// head its own eight lanes: twice the passes and twice the index instructions for conv1 — these phases are issue
+// bound, profiles/r1_resident.md.)
 template <int H, bool TRAIN>
 __device__ __forceinline__ void agg_fwd_rows(const int* __restrict__ rowptr, const int* __restrict__ col,
                                              const float* hsnap, const float* sssnap, const float* sd_own,
                                              const float* bias_s, float* out_g, float* out_s, int lds_out,
                                              float* m_own, float* l_own, int lo, int n, bool relu) {
-  constexpr int F = 32 * H, LPR = 8 * H, RPW = 32 / LPR, PRE = 4;
+  constexpr int F = 32 * H, RPW = 4, PRE = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR, slot = lig & 7, hd = lig >> 3;
-  const float4 bv = lds4(bias_s + 4 * lig);
+  const int sub = lane >> 3, slot = lane & 7;
+  float4 bv[H];
+#pragma unroll
+  for (int v = 0; v < H; ++v) bv[v] = lds4(bias_s + 32 * v + 4 * slot);
   for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
     const int il_raw = i0 + warp * RPW + sub;
     const bool ok = il_raw < n;
     const int il = ok ? il_raw : n - 1, i = lo + il;
     const int beg = rowptr[i], deg = rowptr[i + 1] - beg;
     const int deg_max = __reduce_max_sync(FULL, deg);
-    const float sd = ldc1(sd_own + il * H + hd);
-    float mrun = -CUDART_INF_F, lrun = 0.f;
-    float4 acc = f4zero();
+    float sd[H], mrun[H], lrun[H];
+    float4 acc[H];
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      sd[v] = ldc1(sd_own + il * H + v);
+      mrun[v] = -CUDART_INF_F;
+      lrun[v] = 0.f;
+      acc[v] = f4zero();
+    }
     for (int e0 = 0; e0 < deg_max; e0 += 8) {
       const bool valid = e0 + slot < deg;
       const int j = valid ? col[beg + e0 + slot] : 0;
       const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
-      float4 x[PRE];
+      float4 x[PRE][H];
 #pragma unroll
       for (int u = 0; u < PRE; ++u) {
         const int ju = __shfl_sync(FULL, j, u, 8);
-        x[u] = u < cnt ? ldc4(hsnap + (size_t)ju * F + 4 * lig) : f4zero();
-      }
-      const float a = valid ? lrelu(ldc1(sssnap + j * H + hd) + sd) : -CUDART_INF_F;
-      const float nm = fmaxf(mrun, gmax8(a));
-      if (e0 > 0) {
-        const float sc = __expf(mrun - nm);
-        lrun *= sc;
-        acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
-      }
-      const float p = __expf(a - nm);
-      lrun += group_sum<8>(p, FULL);
-      mrun = nm;
 #pragma unroll
-      for (int u = 0; u < PRE; ++u) fma4(acc, __shfl_sync(FULL, p, u, 8), x[u]);
+        for (int v = 0; v < H; ++v) x[u][v] = u < cnt ? ldc4(hsnap + (size_t)ju * F + 32 * v + 4 * slot) : f4zero();
+      }
+      float p[H];
+#pragma unroll
+      for (int v = 0; v < H; ++v) {
+        const float a = valid ? lrelu(ldc1(sssnap + j * H + v) + sd[v]) : -CUDART_INF_F;
+        const float nm = fmaxf(mrun[v], gmax8(a));
+        if (e0 > 0) {
+          const float sc = __expf(mrun[v] - nm);
+          lrun[v] *= sc;
+          acc[v].x *= sc; acc[v].y *= sc; acc[v].z *= sc; acc[v].w *= sc;
+        }
+        p[v] = __expf(a - nm);
+        lrun[v] += group_sum<8>(p[v], FULL);
+        mrun[v] = nm;
+      }
+#pragma unroll
+      for (int u = 0; u < PRE; ++u)
+#pragma unroll
+        for (int v = 0; v < H; ++v) fma4(acc[v], __shfl_sync(FULL, p[v], u, 8), x[u][v]);
       for (int t = PRE; t < cnt_max; t += 2) {
         const int j0 = __shfl_sync(FULL, j, t, 8), j1 = __shfl_sync(FULL, j, t + 1, 8);
-        const float4 x0 = t < cnt ? ldc4(hsnap + (size_t)j0 * F + 4 * lig) : f4zero();
-        const float4 x1 = t + 1 < cnt ? ldc4(hsnap + (size_t)j1 * F + 4 * lig) : f4zero();
-        const float p0 = __shfl_sync(FULL, p, t, 8), p1 = __shfl_sync(FULL, p, t + 1, 8);
-        fma4(acc, p0, x0);
-        fma4(acc, t + 1 < 8 ? p1 : 0.f, x1);
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float4 x0 = t < cnt ? ldc4(hsnap + (size_t)j0 * F + 32 * v + 4 * slot) : f4zero();
+          const float4 x1 = t + 1 < cnt ? ldc4(hsnap + (size_t)j1 * F + 32 * v + 4 * slot) : f4zero();
+          const float p0 = __shfl_sync(FULL, p[v], t, 8), p1 = __shfl_sync(FULL, p[v], t + 1, 8);
+          fma4(acc[v], p0, x0);
+          fma4(acc[v], t + 1 < 8 ? p1 : 0.f, x1);
+        }
       }
     }
     if (!ok) continue;
-    const float inv = 1.f / (lrun + kSoftmaxEps);
-    float4 o = make_float4(fmaf(acc.x, inv, bv.x), fmaf(acc.y, inv, bv.y), fmaf(acc.z, inv, bv.z), fmaf(acc.w, inv, bv.w));
-    if (relu) o = relu4(o);
-    if (out_g != nullptr) st4(out_g + (size_t)il * F + 4 * lig, o);
-    if (out_s != nullptr) st4(out_s + il * lds_out + 4 * lig, o);
-    if (TRAIN && slot == 0) { m_own[il * H + hd] = mrun; l_own[il * H + hd] = lrun; }
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      const float inv = 1.f / (lrun[v] + kSoftmaxEps);
+      float4 o = make_float4(fmaf(acc[v].x, inv, bv[v].x), fmaf(acc[v].y, inv, bv[v].y), fmaf(acc[v].z, inv, bv[v].z),
+                             fmaf(acc[v].w, inv, bv[v].w));
+      if (relu) o = relu4(o);
+      if (out_g != nullptr) st4(out_g + (size_t)il * F + 32 * v + 4 * slot, o);
+      if (out_s != nullptr) st4(out_s + il * lds_out + 32 * v + 4 * slot, o);
+      if (TRAIN && slot == 0) { m_own[il * H + v] = mrun[v]; l_own[il * H + v] = lrun[v]; }
+    }
   }
 }
 
-// sum a per-lane float4 over the row slots of a warp and park it in this warp's row of `vred`
-template <int LPR>
+// sum a per-lane float4 over the four row slots of a warp and park it in this warp's row of `vred`
 __device__ __forceinline__ void warp_chunk_park(float4 v, float* dst) {
 #pragma unroll
-  for (int o = LPR; o < 32; o <<= 1) {
+  for (int o = 8; o < 32; o <<= 1) {
     v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
     v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
   }
-  if ((threadIdx.x & 31) < LPR) st4(dst + 4 * (threadIdx.x & 31), v);
+  if ((threadIdx.x & 31) < 8) st4(dst + 4 * (threadIdx.x & 31), v);
 }
 
 // Backward pass 1 over own target rows: D_i, ds_dst[i]; rec = {s_dst, m, 1/(l+eps), D}.
-// MEAN = true (conv2): the incoming gradient is produced on the fly as the SimpleConv(mean) backward
+// MEAN = true (conv2, H = 1): the incoming gradient is produced on the fly as the SimpleConv(mean) backward
 // of gA (dz[j] = sum_{j->i} gA[i] / max(indeg(i), 1)) and also written to dz_own for pass 2's gathers;
 // MEAN = false (conv1): it is read from the shared tile g_s.
 template <int H, bool MEAN>
@@ -357,71 +382,97 @@ __device__ __forceinline__ void bwd_p1_rows(const int* __restrict__ rowptr, cons
                                             const float* __restrict__ sd_own, const float* __restrict__ m_own,
                                             const float* __restrict__ l_own, float* rec_own, float* dsd_own,
                                             float* vred_bias, int lo, int n) {
-  constexpr int F = 32 * H, LPR = 8 * H, RPW = 32 / LPR, PRE = 4;
+  static_assert(!MEAN || H == 1, "the mean backward feeds conv2 (one head)");
+  constexpr int F = 32 * H, RPW = 4, PRE = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR, slot = lig & 7, hd = lig >> 3;
-  float4 bacc = f4zero();
+  const int sub = lane >> 3, slot = lane & 7;
+  float4 bacc[H];
+#pragma unroll
+  for (int v = 0; v < H; ++v) bacc[v] = f4zero();
   for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
     const int il_raw = i0 + warp * RPW + sub;
     const bool ok = il_raw < n;
     const int il = ok ? il_raw : n - 1, i = lo + il;
-    float4 gv;
+    float4 gv[H];
     if (MEAN) {
       const int tb = rowptr_t[i], te = rowptr_t[i + 1] - 1;     // out-edges minus the self-loop
-      gv = f4zero();
+      gv[0] = f4zero();
 #pragma unroll 4
       for (int e = tb; e < te; ++e) {
         const int t = col_t[e];
         const int dg = rowptr[t + 1] - rowptr[t] - 1;
-        fma4(gv, 1.f / (float)(dg > 1 ? dg : 1), ldc4(gA_snap + (size_t)t * F + 4 * lig));
+        fma4(gv[0], 1.f / (float)(dg > 1 ? dg : 1), ldc4(gA_snap + (size_t)t * F + 4 * slot));
       }
-      if (ok) st4(dz_own + (size_t)il * F + 4 * lig, gv);
+      if (ok) st4(dz_own + (size_t)il * F + 4 * slot, gv[0]);
     } else {
-      gv = lds4(g_s + il * ldg_s + 4 * lig);
+#pragma unroll
+      for (int v = 0; v < H; ++v) gv[v] = lds4(g_s + il * ldg_s + 32 * v + 4 * slot);
     }
-    if (ok) add4(bacc, gv);
     const int beg = rowptr[i], deg = rowptr[i + 1] - beg;
     const int deg_max = __reduce_max_sync(FULL, deg);
-    const float sd = __ldg(sd_own + il * H + hd), mi = __ldg(m_own + il * H + hd);
-    const float il_ = 1.f / (__ldg(l_own + il * H + hd) + kSoftmaxEps);
-    float S1 = 0.f, S2 = 0.f, S3 = 0.f;
+    float sd[H], mi[H], il_[H], S1[H], S2[H], S3[H];
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      if (ok) add4(bacc[v], gv[v]);
+      sd[v] = __ldg(sd_own + il * H + v);
+      mi[v] = __ldg(m_own + il * H + v);
+      il_[v] = 1.f / (__ldg(l_own + il * H + v) + kSoftmaxEps);
+      S1[v] = S2[v] = S3[v] = 0.f;
+    }
     for (int e0 = 0; e0 < deg_max; e0 += 8) {
       const bool valid = e0 + slot < deg;
       const int j = valid ? col[beg + e0 + slot] : 0;
       const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
-      float4 x[PRE];
+      float4 x[PRE][H];
 #pragma unroll
       for (int u = 0; u < PRE; ++u) {
         const int ju = __shfl_sync(FULL, j, u, 8);
-        x[u] = u < cnt ? ldg4(hsnap + (size_t)ju * F + 4 * lig) : f4zero();
-      }
-      const float z = __ldg(sssnap + j * H + hd) + sd;
-      const float alpha = valid ? __expf(lrelu(z) - mi) * il_ : 0.f;
-      const float sl = lrelu_slope(z);
-      float da = 0.f;
 #pragma unroll
-      for (int u = 0; u < PRE; ++u) {
-        const float d = group_sum<8>(dot4(gv, x[u]), FULL);
-        da = slot == u ? d : da;
+        for (int v = 0; v < H; ++v) x[u][v] = u < cnt ? ldg4(hsnap + (size_t)ju * F + 32 * v + 4 * slot) : f4zero();
       }
+      float alpha[H], sl[H], da[H];
+#pragma unroll
+      for (int v = 0; v < H; ++v) {
+        const float z = __ldg(sssnap + j * H + v) + sd[v];
+        alpha[v] = valid ? __expf(lrelu(z) - mi[v]) * il_[v] : 0.f;
+        sl[v] = lrelu_slope(z);
+        da[v] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < PRE; ++u)
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float d = group_sum<8>(dot4(gv[v], x[u][v]), FULL);
+          da[v] = slot == u ? d : da[v];
+        }
       for (int t = PRE; t < cnt_max; t += 2) {
         const int j0 = __shfl_sync(FULL, j, t, 8), j1 = __shfl_sync(FULL, j, t + 1, 8);
-        const float4 x0 = t < cnt ? ldg4(hsnap + (size_t)j0 * F + 4 * lig) : f4zero();
-        const float4 x1 = t + 1 < cnt ? ldg4(hsnap + (size_t)j1 * F + 4 * lig) : f4zero();
-        const float d0 = group_sum<8>(dot4(gv, x0), FULL), d1 = group_sum<8>(dot4(gv, x1), FULL);
-        da = slot == t ? d0 : (slot == t + 1 ? d1 : da);
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float4 x0 = t < cnt ? ldg4(hsnap + (size_t)j0 * F + 32 * v + 4 * slot) : f4zero();
+          const float4 x1 = t + 1 < cnt ? ldg4(hsnap + (size_t)j1 * F + 32 * v + 4 * slot) : f4zero();
+          const float d0 = group_sum<8>(dot4(gv[v], x0), FULL), d1 = group_sum<8>(dot4(gv[v], x1), FULL);
+          da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
+        }
       }
-      S1 = fmaf(alpha, da, S1);
-      S2 = fmaf(alpha * sl, da, S2);
-      S3 = fmaf(alpha, sl, S3);
+#pragma unroll
+      for (int v = 0; v < H; ++v) {
+        S1[v] = fmaf(alpha[v], da[v], S1[v]);
+        S2[v] = fmaf(alpha[v] * sl[v], da[v], S2[v]);
+        S3[v] = fmaf(alpha[v], sl[v], S3[v]);
+      }
     }
-    const float D = group_sum<8>(S1, FULL), T2 = group_sum<8>(S2, FULL), T3 = group_sum<8>(S3, FULL);
-    if (slot == 0 && ok) {
-      st4(rec_own + (size_t)(il * H + hd) * 4, make_float4(sd, mi, il_, D));
-      dsd_own[il * H + hd] = T2 - D * T3;
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      const float D = group_sum<8>(S1[v], FULL), T2 = group_sum<8>(S2[v], FULL), T3 = group_sum<8>(S3[v], FULL);
+      if (slot == 0 && ok) {
+        st4(rec_own + (size_t)(il * H + v) * 4, make_float4(sd[v], mi[v], il_[v], D));
+        dsd_own[il * H + v] = T2 - D * T3;
+      }
     }
   }
-  warp_chunk_park<LPR>(bacc, vred_bias);
+#pragma unroll
+  for (int v = 0; v < H; ++v) warp_chunk_park(bacc[v], vred_bias + 32 * v);
 }
 
 // Backward pass 2 over own source rows: dh[j] (-> shared tile), ds_src, datt_src / datt_dst partials.
@@ -431,66 +482,95 @@ __device__ __forceinline__ void bwd_p2_rows(const int* __restrict__ rowptr_t, co
                                             const float* __restrict__ h_own, const float* __restrict__ ss_own,
                                             const float* att_s, const float* att_d, float* dh_s, int ld_dh,
                                             float* vred_as, float* vred_ad, int lo, int n) {
-  constexpr int F = 32 * H, LPR = 8 * H, RPW = 32 / LPR, PRE = 4;
+  constexpr int F = 32 * H, RPW = 4, PRE = H == 1 ? 4 : 2;     // two heads per lane: fewer gathers in flight (registers)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, lig = lane % LPR, slot = lig & 7, hd = lig >> 3;
-  const float4 as = lds4(att_s + 4 * lig), ad = lds4(att_d + 4 * lig);
-  float4 accs = f4zero(), accd = f4zero();
+  const int sub = lane >> 3, slot = lane & 7;
+  float4 as[H], ad[H], accs[H], accd[H];
+#pragma unroll
+  for (int v = 0; v < H; ++v) {
+    as[v] = lds4(att_s + 32 * v + 4 * slot);
+    ad[v] = lds4(att_d + 32 * v + 4 * slot);
+    accs[v] = f4zero();
+    accd[v] = f4zero();
+  }
   for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
     const int il_raw = i0 + warp * RPW + sub;
     const bool ok = il_raw < n;
     const int il = ok ? il_raw : n - 1, jn = lo + il;
     const int beg = rowptr_t[jn], deg = rowptr_t[jn + 1] - beg;
     const int deg_max = __reduce_max_sync(FULL, deg);
-    const float4 hv = ldg4(h_own + (size_t)il * F + 4 * lig);
-    const float ss = __ldg(ss_own + il * H + hd);
-    float4 dacc = f4zero();
-    float dsrc = 0.f;
+    float4 hv[H], dacc[H];
+    float ss[H], dsrc[H];
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      hv[v] = ldg4(h_own + (size_t)il * F + 32 * v + 4 * slot);
+      ss[v] = __ldg(ss_own + il * H + v);
+      dacc[v] = f4zero();
+      dsrc[v] = 0.f;
+    }
     for (int e0 = 0; e0 < deg_max; e0 += 8) {
       const bool valid = e0 + slot < deg;
       const int i = valid ? col_t[beg + e0 + slot] : 0;
       const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
-      float4 gx[PRE];
+      float4 gx[PRE][H];
 #pragma unroll
       for (int u = 0; u < PRE; ++u) {
         const int iu = __shfl_sync(FULL, i, u, 8);
-        gx[u] = u < cnt ? ldc4(gsnap + (size_t)iu * F + 4 * lig) : f4zero();
-      }
-      const float4 t4 = ldc4(recsnap + (size_t)(i * H + hd) * 4);      // {s_dst, m, 1/l, D} of the edge's target
-      const float z = ss + t4.x;
-      const float alpha = valid ? __expf(lrelu(z) - t4.y) * t4.z : 0.f;
-      const float k2 = alpha * lrelu_slope(z);
-      float da = 0.f;
 #pragma unroll
-      for (int u = 0; u < PRE; ++u) {
-        const float d = group_sum<8>(dot4(gx[u], hv), FULL);
-        da = slot == u ? d : da;
-        fma4(dacc, __shfl_sync(FULL, alpha, u, 8), gx[u]);
+        for (int v = 0; v < H; ++v) gx[u][v] = u < cnt ? ldc4(gsnap + (size_t)iu * F + 32 * v + 4 * slot) : f4zero();
       }
+      float alpha[H], k2[H], Dt[H], da[H];
+#pragma unroll
+      for (int v = 0; v < H; ++v) {
+        const float4 t4 = ldc4(recsnap + (size_t)(i * H + v) * 4);      // {s_dst, m, 1/l, D} of the edge's target
+        const float z = ss[v] + t4.x;
+        alpha[v] = valid ? __expf(lrelu(z) - t4.y) * t4.z : 0.f;
+        k2[v] = alpha[v] * lrelu_slope(z);
+        Dt[v] = t4.w;
+        da[v] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < PRE; ++u)
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float d = group_sum<8>(dot4(gx[u][v], hv[v]), FULL);
+          da[v] = slot == u ? d : da[v];
+          fma4(dacc[v], __shfl_sync(FULL, alpha[v], u, 8), gx[u][v]);
+        }
       for (int t = PRE; t < cnt_max; t += 2) {
         const int i0_ = __shfl_sync(FULL, i, t, 8), i1_ = __shfl_sync(FULL, i, t + 1, 8);
-        const float4 g0 = t < cnt ? ldc4(gsnap + (size_t)i0_ * F + 4 * lig) : f4zero();
-        const float4 g1 = t + 1 < cnt ? ldc4(gsnap + (size_t)i1_ * F + 4 * lig) : f4zero();
-        const float d0 = group_sum<8>(dot4(g0, hv), FULL), d1 = group_sum<8>(dot4(g1, hv), FULL);
-        da = slot == t ? d0 : (slot == t + 1 ? d1 : da);
-        const float a0 = __shfl_sync(FULL, alpha, t, 8), a1 = __shfl_sync(FULL, alpha, t + 1, 8);
-        fma4(dacc, a0, g0);
-        fma4(dacc, t + 1 < 8 ? a1 : 0.f, g1);
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float4 g0 = t < cnt ? ldc4(gsnap + (size_t)i0_ * F + 32 * v + 4 * slot) : f4zero();
+          const float4 g1 = t + 1 < cnt ? ldc4(gsnap + (size_t)i1_ * F + 32 * v + 4 * slot) : f4zero();
+          const float d0 = group_sum<8>(dot4(g0, hv[v]), FULL), d1 = group_sum<8>(dot4(g1, hv[v]), FULL);
+          da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
+          const float a0 = __shfl_sync(FULL, alpha[v], t, 8), a1 = __shfl_sync(FULL, alpha[v], t + 1, 8);
+          fma4(dacc[v], a0, g0);
+          fma4(dacc[v], t + 1 < 8 ? a1 : 0.f, g1);
+        }
       }
-      dsrc = fmaf(k2, da - t4.w, dsrc);
+#pragma unroll
+      for (int v = 0; v < H; ++v) dsrc[v] = fmaf(k2[v], da[v] - Dt[v], dsrc[v]);
     }
-    const float ds = group_sum<8>(dsrc, FULL);
-    const float dd = ldc1(dsd_own + il * H + hd);
-    fma4(dacc, ds, as);
-    fma4(dacc, dd, ad);
-    if (ok) {
-      st4(dh_s + il * ld_dh + 4 * lig, dacc);
-      fma4(accs, ds, hv);
-      fma4(accd, dd, hv);
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      const float ds = group_sum<8>(dsrc[v], FULL);
+      const float dd = ldc1(dsd_own + il * H + v);
+      fma4(dacc[v], ds, as[v]);
+      fma4(dacc[v], dd, ad[v]);
+      if (ok) {
+        st4(dh_s + il * ld_dh + 32 * v + 4 * slot, dacc[v]);
+        fma4(accs[v], ds, hv[v]);
+        fma4(accd[v], dd, hv[v]);
+      }
     }
   }
-  warp_chunk_park<LPR>(accs, vred_as);
-  warp_chunk_park<LPR>(accd, vred_ad);
+#pragma unroll
+  for (int v = 0; v < H; ++v) {
+    warp_chunk_park(accs[v], vred_as + 32 * v);
+    warp_chunk_park(accd[v], vred_ad + 32 * v);
+  }
 }
 
 // =============================================================================== forward
