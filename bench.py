@@ -435,13 +435,17 @@ def main():
                 traffic = tj["bytes_per_launch"].get(dom["kernel"])
         except Exception:
             pass
-        line["roofline"] = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak,
-                            "unit": "GB/s", "frac": dom["GBps"] / peak, "traffic": traffic, "peak_source": which,
-                            "workload": f"{hbm_B} snapshots x {N} nodes per launch (tensors larger than L2), "
-                                        f"{dom['bytes_per_node']} algorithmic B/node, {dom['us']:.1f} us/launch"}
-        line["roofline_in_step"] = {"bound": "hbm", "kernel": dom_l2["kernel"], "achieved": dom_l2["GBps"], "peak": peak,
-                                    "unit": "GB/s", "frac": dom_l2["GBps"] / peak,
-                                    "workload": f"bench batch ({B} snapshots, L2-resident, {dom_l2['us']:.1f} us/launch)"}
+        hbm_regime = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak,
+                      "unit": "GB/s", "frac": dom["GBps"] / peak, "traffic": traffic, "peak_source": which,
+                      "workload": f"{hbm_B} snapshots x {N} nodes per launch (tensors larger than L2), "
+                                  f"{dom['bytes_per_node']} algorithmic B/node, {dom['us']:.1f} us/launch"}
+        in_step_layer = {"bound": "hbm", "kernel": dom_l2["kernel"], "achieved": dom_l2["GBps"], "peak": peak,
+                         "unit": "GB/s", "frac": dom_l2["GBps"] / peak, "traffic": None, "peak_source": which,
+                         "workload": f"bench batch ({B} snapshots, L2-resident, {dom_l2['us']:.1f} us/launch)"}
+        # `roofline` = the dominant kernel of the TIMED step (the launch list of this command is under profiles/);
+        # `roofline_hbm_regime` = the dominant layer kernel where an HBM roofline is meaningful (tensors >> L2).
+        line["roofline"] = in_step_layer
+        line["roofline_hbm_regime"] = hbm_regime
         if args.mode == "train" and ts.kernels_per_step < 20:
             # the timed step ran the snapshot-resident cluster kernels: its dominant launch is the whole-stack backward
             # (one kernel).  Algorithmic bytes = the per-kernel figures of SURVEY 8d summed over the stack.
@@ -463,15 +467,23 @@ def main():
                 t = time_launches(calls[name], 20, 1)
                 res[name] = {"us": t * 1e6, "bytes_per_node": bpn[name], "GBps": M * bpn[name] / t / 1e9}
             step_us = ms_res / K * 1e3
-            line["roofline_in_step"] = {
+            rtraffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+                if tj.get("resident_batch") == B:
+                    rtraffic = tj["bytes_per_launch"].get("resident_bwd_kernel")
+            except Exception:
+                pass
+            line["roofline"] = {
                 "bound": "hbm", "kernel": f"resident_bwd_kernel (whole backward stack, {nb} blocks, one launch)",
                 "achieved": res["bwd"]["GBps"], "peak": peak, "unit": "GB/s", "frac": res["bwd"]["GBps"] / peak,
-                "share_of_step": res["bwd"]["us"] / step_us,
-                "workload": f"bench batch ({B} snapshots, L2-resident): {res['bwd']['us']:.0f} us/launch for "
+                "traffic": rtraffic, "peak_source": which, "share_of_step": res["bwd"]["us"] / step_us,
+                "workload": f"bench batch ({B} snapshots): {res['bwd']['us']:.0f} us/launch for "
                             f"{bpn['bwd']} algorithmic B/node (SURVEY 8d per-kernel accounting summed over the stack); "
                             f"forward stack {res['fwd']['us']:.0f} us/launch, {bpn['fwd']} B/node, "
-                            f"{res['fwd']['GBps']:.0f} GB/s.  Cluster-barrier / issue bound, not HBM bound "
-                            "(profiles/r1_resident.md)"}
+                            f"{res['fwd']['GBps']:.0f} GB/s.  The working set of a layer is L2-resident at this batch: the "
+                            "kernel is cluster-barrier / issue bound, not HBM bound (profiles/r1_resident.md); the HBM-regime "
+                            "figure of the aggregation kernels is under roofline_hbm_regime"}
         if args.kernels_json:
             os.makedirs(os.path.dirname(os.path.abspath(args.kernels_json)), exist_ok=True)
             json.dump({"in_step_batch": B, "in_step": in_step, "hbm_batch": hbm_B, "hbm": hbm, "peak_gbs": peak},
