@@ -31,7 +31,8 @@ class TrainStep:
                  process_group=None, use_graph: bool = True, deterministic: bool = False,
                  grad_buckets: Optional[int] = None, peer_allreduce: Optional[bool] = None,
                  device_mask_seed: Optional[int] = None,
-                 metrics: Optional["_metrics.MaskedMetrics"] = None):
+                 metrics: Optional["_metrics.MaskedMetrics"] = None,
+                 share_state_with: Optional["TrainStep"] = None):
         self.model, self.topo, self.B = model, topo, int(batch)
         self.N, self.nc, self.nb = topo.N, model.nc, model.num_blocks
         self.M = self.B * self.N
@@ -80,9 +81,17 @@ class TrainStep:
                     raise
                 import warnings
                 warnings.warn(f"peer-memory gradient all-reduce unavailable ({e!r}); using NCCL all-reduce")
-        self.exp_avg = torch.zeros(P, **f32)
-        self.exp_avg_sq = torch.zeros(P, **f32)
-        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        if share_state_with is not None:
+            # a second step object for another batch size (the smaller last batch of an epoch, train.py:302 has no
+            # drop_last) that continues the same optimisation: same parameters, same Adam moments, same step counter
+            if share_state_with.model is not model:
+                raise ValueError("share_state_with must wrap the same model")
+            self.exp_avg, self.exp_avg_sq = share_state_with.exp_avg, share_state_with.exp_avg_sq
+            self.step_count = share_state_with.step_count
+        else:
+            self.exp_avg = torch.zeros(P, **f32)
+            self.exp_avg_sq = torch.zeros(P, **f32)
+            self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.deterministic = deterministic
         self.desc = ModelDesc(self.nb, self.nc, self.N, _gops.grad_slots(self.M) if deterministic else 0, topo.E1, 0, self.B,
                               ptr(topo.rowptr), ptr(topo.col), ptr(topo.rowptr_t), ptr(topo.col_t), None)

@@ -58,6 +58,13 @@ def main():
     tm.num_graphs = [32, 32, 32, 11]
     blob["timer/timings"], blob["timer/num_graphs"] = np.array(tm.timings), np.array(tm.num_graphs)
     blob["timer/time_throughput"] = np.array([tm.compute_time(107), tm.compute_throughput(107)])
+    # EarlyStopping (utils/early_stopping.py:31-78): stop decisions for a validation-loss sequence
+    import utils.early_stopping as ES
+    seq = [1.0, 0.9, 0.95, 0.91, 0.85, 0.86, 0.87, 0.88, 0.80, float("nan")]
+    for pat in (0, 1, 3):
+        es = ES.EarlyStopping(mode="min", min_delta=0, patience=pat)
+        blob[f"early_stopping/patience{pat}"] = np.array([bool(es.step(torch.tensor(v))) for v in seq])
+    blob["early_stopping/seq"] = np.array(seq)
     np.savez_compressed(os.path.join(HERE, "caller_ref.npz"), **blob)
     print({k: v.shape for k, v in blob.items()})
 
