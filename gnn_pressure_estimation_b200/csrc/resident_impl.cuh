@@ -78,6 +78,7 @@ __device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __device__ __forceinline__ float gmax8(float v) {
   v = fmaxf(v, __shfl_xor_sync(FULL, v, 4));
@@ -393,6 +394,29 @@ __device__ __forceinline__ void bwd_p1_rows(const int* __restrict__ rowptr, cons
     const int il_raw = i0 + warp * RPW + sub;
     const bool ok = il_raw < n;
     const int il = ok ? il_raw : n - 1, i = lo + il;
+    const int beg = rowptr[i], deg = rowptr[i + 1] - beg;
+    const int deg_max = __reduce_max_sync(FULL, deg);
+    // Everything that does not depend on the incoming gradient is requested first: the first chunk's neighbour rows
+    // and scores (saved activations: L2 or HBM) fly while the mean backward below waits for its own gathers of gA.
+    const bool valid0 = slot < deg;
+    const int j0 = valid0 ? col[beg + slot] : 0;
+    const int cnt0 = min(8, deg);
+    float4 x0[PRE][H];
+    float ssv0[H], sd[H], mi[H], il_[H], S1[H], S2[H], S3[H];
+#pragma unroll
+    for (int u = 0; u < PRE; ++u) {
+      const int ju = __shfl_sync(FULL, j0, u, 8);
+#pragma unroll
+      for (int v = 0; v < H; ++v) x0[u][v] = u < cnt0 ? ldg4(hsnap + (size_t)ju * F + 32 * v + 4 * slot) : f4zero();
+    }
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      ssv0[v] = __ldg(sssnap + j0 * H + v);
+      sd[v] = __ldg(sd_own + il * H + v);
+      mi[v] = __ldg(m_own + il * H + v);
+      il_[v] = 1.f / (__ldg(l_own + il * H + v) + kSoftmaxEps);
+      S1[v] = S2[v] = S3[v] = 0.f;
+    }
     float4 gv[H];
     if (MEAN) {
       const int tb = rowptr_t[i], te = rowptr_t[i + 1] - 1;     // out-edges minus the self-loop
@@ -408,32 +432,31 @@ __device__ __forceinline__ void bwd_p1_rows(const int* __restrict__ rowptr, cons
 #pragma unroll
       for (int v = 0; v < H; ++v) gv[v] = lds4(g_s + il * ldg_s + 32 * v + 4 * slot);
     }
-    const int beg = rowptr[i], deg = rowptr[i + 1] - beg;
-    const int deg_max = __reduce_max_sync(FULL, deg);
-    float sd[H], mi[H], il_[H], S1[H], S2[H], S3[H];
 #pragma unroll
-    for (int v = 0; v < H; ++v) {
+    for (int v = 0; v < H; ++v)
       if (ok) add4(bacc[v], gv[v]);
-      sd[v] = __ldg(sd_own + il * H + v);
-      mi[v] = __ldg(m_own + il * H + v);
-      il_[v] = 1.f / (__ldg(l_own + il * H + v) + kSoftmaxEps);
-      S1[v] = S2[v] = S3[v] = 0.f;
-    }
     for (int e0 = 0; e0 < deg_max; e0 += 8) {
       const bool valid = e0 + slot < deg;
-      const int j = valid ? col[beg + e0 + slot] : 0;
+      const int j = e0 == 0 ? j0 : (valid ? col[beg + e0 + slot] : 0);
       const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
       float4 x[PRE][H];
-#pragma unroll
-      for (int u = 0; u < PRE; ++u) {
-        const int ju = __shfl_sync(FULL, j, u, 8);
-#pragma unroll
-        for (int v = 0; v < H; ++v) x[u][v] = u < cnt ? ldg4(hsnap + (size_t)ju * F + 32 * v + 4 * slot) : f4zero();
-      }
       float alpha[H], sl[H], da[H];
+      if (e0 == 0) {
+#pragma unroll
+        for (int u = 0; u < PRE; ++u)
+#pragma unroll
+          for (int v = 0; v < H; ++v) x[u][v] = x0[u][v];
+      } else {
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+          const int ju = __shfl_sync(FULL, j, u, 8);
+#pragma unroll
+          for (int v = 0; v < H; ++v) x[u][v] = u < cnt ? ldg4(hsnap + (size_t)ju * F + 32 * v + 4 * slot) : f4zero();
+        }
+      }
 #pragma unroll
       for (int v = 0; v < H; ++v) {
-        const float z = __ldg(sssnap + j * H + v) + sd[v];
+        const float z = (e0 == 0 ? ssv0[v] : __ldg(sssnap + j * H + v)) + sd[v];
         alpha[v] = valid ? __expf(lrelu(z) - mi[v]) * il_[v] : 0.f;
         sl[v] = lrelu_slope(z);
         da[v] = 0.f;
@@ -446,12 +469,12 @@ __device__ __forceinline__ void bwd_p1_rows(const int* __restrict__ rowptr, cons
           da[v] = slot == u ? d : da[v];
         }
       for (int t = PRE; t < cnt_max; t += 2) {
-        const int j0 = __shfl_sync(FULL, j, t, 8), j1 = __shfl_sync(FULL, j, t + 1, 8);
+        const int j0_ = __shfl_sync(FULL, j, t, 8), j1_ = __shfl_sync(FULL, j, t + 1, 8);
 #pragma unroll
         for (int v = 0; v < H; ++v) {
-          const float4 x0 = t < cnt ? ldg4(hsnap + (size_t)j0 * F + 32 * v + 4 * slot) : f4zero();
-          const float4 x1 = t + 1 < cnt ? ldg4(hsnap + (size_t)j1 * F + 32 * v + 4 * slot) : f4zero();
-          const float d0 = group_sum<8>(dot4(gv[v], x0), FULL), d1 = group_sum<8>(dot4(gv[v], x1), FULL);
+          const float4 xa = t < cnt ? ldg4(hsnap + (size_t)j0_ * F + 32 * v + 4 * slot) : f4zero();
+          const float4 xb = t + 1 < cnt ? ldg4(hsnap + (size_t)j1_ * F + 32 * v + 4 * slot) : f4zero();
+          const float d0 = group_sum<8>(dot4(gv[v], xa), FULL), d1 = group_sum<8>(dot4(gv[v], xb), FULL);
           da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
         }
       }
@@ -752,7 +775,9 @@ resident_bwd_kernel(const Args a) {
   Stamper stamp(a);
   stamp();
   const int k_first = nb > 0 ? a.k_hi : -1;
+  // cp.async groups, oldest first: [parameters of block k] [saved y1 / x0 rows of block k] [parameters of block k - 1]
   if (nb > 0) stage_block_params(a.params + pl.block(k_first), W1s + (k_first & 1) * W1F, W2s + (k_first & 1) * W2F, vec + (k_first & 1) * VECF);
+  cp_commit();
   if (nb > 0) {
     stage_rows<2 * NC, LDY>(a.saved + sl.y1(k_first) + ro * 2 * NC, ys, n);
     stage_rows<NC, LDX>(a.saved + (k_first > 0 ? sl.xout(k_first - 1) : sl.x_enc()) + ro * NC, xs, n);
@@ -795,10 +820,10 @@ resident_bwd_kernel(const Args a) {
     bwd_p1_rows<1, true>(rp_s, col_s, rpt_s, colt_s, gA + rb * NC, dz + ro * NC, nullptr, 0,
                          sv + sl.h2(k) + rb * NC, sv + sl.ss2(k) + rb, sv + sl.sd2(k) + ro, sv + sl.m2(k) + ro,
                          sv + sl.l2(k) + ro, rec2 + ro * 4, dsd2 + ro, vred + warp * VECF + 8 * NC, lo, n);
-    cp_wait_all();                           // this block's parameters, y1 and x0 (own rows) have landed ...
+    cp_wait_but_one();                       // this block's parameters have landed (its y1 / x0 rows may still fly) ...
     stamp();
-    cluster_sync();
-    stamp();                          // ... and are visible CTA-wide; dz / rec2 / dsd2 cluster-wide
+    cluster_sync();                          // ... and are visible CTA-wide; dz / rec2 / dsd2 cluster-wide
+    stamp();
     if (k - 1 >= a.k_lo && k - 1 >= 0)
       stage_block_params(a.params + pl.block(k - 1), W1s + (buf ^ 1) * W1F, W2s + (buf ^ 1) * W2F, vec + (buf ^ 1) * VECF);
     cp_commit();
@@ -806,7 +831,9 @@ resident_bwd_kernel(const Args a) {
     bwd_p2_rows<1>(rpt_s, colt_s, dz + rb * NC, rec2 + rb * 4, dsd2 + ro, sv + sl.h2(k) + ro * NC,
                    sv + sl.ss2(k) + ro, vc + 6 * NC, vc + 7 * NC, d2s, LDX, vred + warp * VECF + 6 * NC,
                    vred + warp * VECF + 7 * NC, lo, n);
-    __syncthreads();                         // dh2 is in shared memory
+    if (k - 1 >= a.k_lo && k - 1 >= 0) cp_wait_but_one();      // y1 / x0 rows of this block (the newest group is the
+    else cp_wait_all();                                        //  next block's parameters, if there is a next block)
+    __syncthreads();                         // dh2, y1 and x0 are in shared memory
     stamp();
     // (3) conv2 projection backward: dW2 = dh2^T y1 ; dy1 = (dh2 W2) masked by y1 > 0 (in place over y1)
 #if RES_USE_MMA
@@ -814,7 +841,7 @@ resident_bwd_kernel(const Args a) {
     __syncthreads();
     {
       float* dy1o = dy1 + ro * 2 * NC;
-      dgrad_rows_mma<NC, 2 * NC, LDX, LDY>(d2s, W2, n, [&](int m, int c, float2 v) {
+      dgrad_rows_mma<NC, 2 * NC, LDX, LDY>(d2s, W2, n, [](int, int) { return make_float2(0.f, 0.f); }, [&](int m, int c, float2 v, float2) {
         float2* p = reinterpret_cast<float2*>(ys + m * LDY + c);
         const float2 y = *p;
         v = make_float2(y.x > 0.f ? v.x : 0.f, y.y > 0.f ? v.y : 0.f);
@@ -857,17 +884,22 @@ resident_bwd_kernel(const Args a) {
       const float* gAo = gA + ro * NC;
       float* gBo = gB + ro * NC;
       const bool mask = k > 0;
-      dgrad_rows_mma<2 * NC, NC, LDY, LDX>(ys, W1, n, [&](int m, int c, float2 v) {
-        float gx, gy;
-        asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(gx), "=f"(gy) : "l"(gAo + (size_t)m * NC + c));
-        v.x += gx;
-        v.y += gy;
-        if (mask) {
-          const float2 x0 = lds2(xs + m * LDX + c);
-          v = make_float2(x0.x > 0.f ? v.x : 0.f, x0.y > 0.f ? v.y : 0.f);
-        }
-        *reinterpret_cast<float2*>(gBo + (size_t)m * NC + c) = v;
-      });
+      dgrad_rows_mma<2 * NC, NC, LDY, LDX>(
+          ys, W1, n,
+          [&](int m, int c) {                 // residual gradient of this fragment: requested before the MMAs
+            float2 r;
+            asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(gAo + (size_t)m * NC + c));
+            return r;
+          },
+          [&](int m, int c, float2 v, float2 r) {
+            v.x += r.x;
+            v.y += r.y;
+            if (mask) {
+              const float2 x0 = lds2(xs + m * LDX + c);
+              v = make_float2(x0.x > 0.f ? v.x : 0.f, x0.y > 0.f ? v.y : 0.f);
+            }
+            *reinterpret_cast<float2*>(gBo + (size_t)m * NC + c) = v;
+          });
     }
 #else
     wgrad_rows<2 * NC, NC, LDY, LDX>(ys, xs, n, a.grads + pl.c1_W(k));

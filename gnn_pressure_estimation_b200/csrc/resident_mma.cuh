@@ -118,9 +118,11 @@ __device__ __forceinline__ void project_rows_mma(const float* As, const float* W
   }
 }
 
-// out[m][c] = sum_r G[m][r] W[r][c]  (data gradient; W [NRED][NOUT] as stored); fin(m, c, float2) gets columns c, c+1
-template <int NRED, int NOUT, int LDG, int LDW, typename Fin>
-__device__ __forceinline__ void dgrad_rows_mma(const float* Gs, const float* Ws, int n, Fin fin) {
+// out[m][c] = sum_r G[m][r] W[r][c]  (data gradient; W [NRED][NOUT] as stored).  pre(m, c) -> float2 is evaluated for
+// every output fragment BEFORE the MMAs (global loads the epilogue needs fly under them); fin(m, c, value, pre value)
+// gets columns c, c+1.
+template <int NRED, int NOUT, int LDG, int LDW, typename Pre, typename Fin>
+__device__ __forceinline__ void dgrad_rows_mma(const float* Gs, const float* Ws, int n, Pre pre, Fin fin) {
   constexpr int NTW = NOUT / 16;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int nbase = (warp >> 2) * (NOUT / 2);
@@ -131,6 +133,13 @@ __device__ __forceinline__ void dgrad_rows_mma(const float* Gs, const float* Ws,
     for (int j = 0; j < NTW; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][i] = acl[j][i] = acm[j][i] = 0.f;
+    float2 pr[NTW][2];
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) {
+      const int c = nbase + 8 * j + 2 * t;
+      pr[j][0] = pre(r0, c);
+      pr[j][1] = pre(r1, c);
+    }
 #pragma unroll 2
     for (int k0 = 0; k0 < NRED; k0 += 8) {
       const float av[4] = {Gs[r0 * LDG + k0 + t], Gs[r1 * LDG + k0 + t], Gs[r0 * LDG + k0 + t + 4], Gs[r1 * LDG + k0 + t + 4]};
@@ -149,8 +158,8 @@ __device__ __forceinline__ void dgrad_rows_mma(const float* Gs, const float* Ws,
     for (int j = 0; j < NTW; ++j) {
       fold3(acc[j], acl[j], acm[j]);
       const int c = nbase + 8 * j + 2 * t;
-      if (m0 + g < n) fin(m0 + g, c, make_float2(acc[j][0], acc[j][1]));
-      if (m0 + g + 8 < n) fin(m0 + g + 8, c, make_float2(acc[j][2], acc[j][3]));
+      if (m0 + g < n) fin(m0 + g, c, make_float2(acc[j][0], acc[j][1]), pr[j][0]);
+      if (m0 + g + 8 < n) fin(m0 + g + 8, c, make_float2(acc[j][2], acc[j][3]), pr[j][1]);
     }
   }
 }
