@@ -110,11 +110,17 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 // row (one chunk each, or V chunks each when F/4 > 32), so a warp works on
 // RPW = 32/LPR rows at a time.  Chunk q covers floats [4q, 4q+4) and belongs to
 // head 4q / C.
-template <int H, int C>
+template <int H, int C, bool PACK = false>
 struct RowMap {
   static constexpr int F = H * C;
   static constexpr int CHUNKS = F / 4;
-  static constexpr int LPR = CHUNKS < 32 ? CHUNKS : 32;   // lanes per row
+  // PACK = false: one chunk per lane while the row fits a warp (two heads of 32 channels = 16 lanes per row).
+  // PACK = true : lanes per row = lanes per head; a lane holds the same chunk of EVERY head (V = H chunks), so the
+  //   index work of a row (row pointers, neighbour ids, their shuffles) is shared by the heads and a warp covers
+  //   32 / LPR rows whatever H is.  Measured (B200, 2048 snapshots): forward snapshot-tile kernel 92.7 -> 86.6 us,
+  //   resident kernels -27 % on the two-head aggregation; the backward tile kernel (64-register budget at 1024
+  //   threads) and the gather kernels on the 100 000-node graph get slower, so they keep PACK = false.
+  static constexpr int LPR = PACK ? ((C / 4) < 32 ? (C / 4) : 32) : (CHUNKS < 32 ? CHUNKS : 32);   // lanes per row
   static constexpr int V = CHUNKS / LPR;                  // chunks per lane
   static constexpr int RPW = 32 / LPR;                    // rows per warp
   static constexpr int LPH = (C / 4) < 32 ? (C / 4) : 32; // lanes holding one head of one row

@@ -9,6 +9,7 @@
 //
 // Same arithmetic and lane mapping as gat_agg.cu (cooperative per-row softmax).
 #include <math_constants.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -44,7 +45,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
                         const float* __restrict__ s_dst, const float* __restrict__ bias,
                         float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ l_out,
                         unsigned B, unsigned N, int relu) {
-  using RM = RowMap<H, C>;
+  using RM = RowMap<H, C, true>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
   constexpr int kTileThreads = THREADS, kTileWarps = THREADS / 32;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -255,8 +256,10 @@ struct BwdTilePlan {
   }
 };
 
-template <int H, int C, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
+// PACK (see RowMap): used when one CTA per SM runs 512 threads with a 128-register budget (two heads, nc = 32:
+// the two slabs fill shared memory); the 2-CTA / 1024-thread shapes have 64 registers per thread and keep PACK off.
+template <int H, int C, int THREADS, bool PACK>
+__global__ void __launch_bounds__(THREADS, (THREADS == 512 && !PACK) ? 2 : 1)
 gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                         const int* __restrict__ rowptr_t, const int* __restrict__ col_t, unsigned E1,
                         const float* __restrict__ g, const float* __restrict__ h,
@@ -266,7 +269,7 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
                         float* __restrict__ dh, float* __restrict__ grads,
                         long long off_att_src, long long off_att_dst, long long off_bias,
                         unsigned B, unsigned N) {
-  using RM = RowMap<H, C>;
+  using RM = RowMap<H, C, PACK>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
   constexpr int kWarpsT = THREADS / 32;
   constexpr unsigned gmask = 0xffffffffu;
@@ -470,6 +473,15 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   }
 }
 
+static bool bwd_tile_pack() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GATRES_BWD_TILE_PACK");     // 0 restores the 1024-thread one-chunk-per-lane variant
+    v = e ? atoi(e) : 1;                                // measured: 277 -> 261 us at 2048 snapshots (two heads, nc = 32)
+  }
+  return v != 0;
+}
+
 template <int H, int C>
 static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_t, const int* col_t, unsigned E1,
                            const float* g, const float* h, const float* s_src, const float* s_dst, const float* m,
@@ -481,9 +493,9 @@ static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
   unsigned grid = (unsigned)sm_count() * per_sm;
   if (grid > B) grid = B;
-#define LAUNCH(THR)                                                                                               \
+#define LAUNCH(THR, PK)                                                                                           \
   do {                                                                                                            \
-    auto kern = gat_agg_bwd_tile_kernel<H, C, THR>;                                                               \
+    auto kern = gat_agg_bwd_tile_kernel<H, C, THR, PK>;                                                            \
     static uint32_t configured = 0;                                                                               \
     if (configured < plan.total) {                                                                                \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
@@ -493,7 +505,9 @@ static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_
     launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, rowptr_t, col_t, E1, g, h, s_src, s_dst, m, l, att_src,      \
                                         att_dst, dh, grads, off_as, off_ad, off_b, B, N);                         \
   } while (0)
-  if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);
+  if (per_sm >= 2) LAUNCH(512, false);
+  else if (H == 2 && C == 32 && bwd_tile_pack()) LAUNCH(512, true);
+  else LAUNCH(1024, false);
 #undef LAUNCH
   return check_launch("gat_agg_bwd_tile");
 }
