@@ -310,6 +310,33 @@ def test_resident_kernels_equal_layer_kernels(graph, B, blocks, cluster, threads
         assert float((g_r[k].cpu() - g).abs().max()) <= GRAD_TOL * max(float(g.abs().max()), floor), k
 
 
+def test_mixed_topology_batch_runs_in_general_mode(dev, G, kernel_variant):
+    """WDNDataset accepts several networks and shuffle=True can collate different graphs into one batch
+    (utils/DataLoader.py:120-129): such an edge_index is not B copies of a template, the model then treats the whole
+    collated graph as one snapshot (B = 1, N = sum of the node counts) on the same kernels."""
+    ei_a, names_a = GRAPHS["tiny"]()
+    ei_b, names_b = GRAPHS["ctown"]()
+    na, nb_ = len(names_a), len(names_b)
+    ei = torch.cat([torch.from_numpy(ei_a), torch.from_numpy(ei_b) + na, torch.from_numpy(ei_a) + na + nb_], dim=1)
+    M = 2 * na + nb_
+    ref = O.make_oracle(3, 32, seed=4)
+    model = G.GATResMeanConv(num_blocks=3, nc=32)
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(M, 1, generator=g)
+    y = torch.randn(M, 1, generator=g)
+    out_ref = ref(x, ei, None, None)
+    torch.nn.functional.mse_loss(out_ref, y).backward()
+    out = model(x.to(dev), ei.to(dev), None, None)
+    torch.nn.functional.mse_loss(out, y.to(dev)).backward()
+    assert_close(out, out_ref, FWD_TOL, "mixed-topology forward")
+    gref = {k: q.grad for k, q in ref.named_parameters()}
+    floor = 1e-3 * max(float(q.norm()) for q in gref.values())
+    for k, p in model.named_parameters():
+        assert float((p.grad.cpu() - gref[k]).abs().max()) <= GRAD_TOL * max(float(gref[k].abs().max()), floor), k
+
+
 def test_model_inference_equals_training_forward_and_batch_hint(dev, G):
     c = load_case("ctown_small_15b_32c_B8")
     model, _ = _cuda_model_from_case(c, G, dev)
