@@ -3,8 +3,8 @@
 
 ``select_model(args, name, reset_model_path)`` keeps the reference's contract:
 it fills ``args.criterion / norm_type / use_data_edge_attrs / model_path`` and
-returns ``(args, model)``.  Only the GATRes family lives on the B200 hot path;
-asking for one of the reference's baseline models raises.
+returns ``(args, model)``.  The GATRes family and the plain ``gat`` baseline (same kernels) are built;
+asking for one of the reference's other baseline models raises.
 """
 from __future__ import annotations
 
@@ -13,7 +13,7 @@ from typing import Callable, Dict, Optional, Tuple
 
 import torch
 
-from .GraphModels import GATResMeanConv
+from .GraphModels import GAT, GATResMeanConv
 
 # (default variant name, num_blocks, nc, the authors' default checkpoint path)
 _GATRES_VARIANTS: Dict[str, Tuple[str, int, int, str]] = {
@@ -26,7 +26,7 @@ _GATRES_VARIANTS: Dict[str, Tuple[str, int, int, str]] = {
                            r"experiments_logs\simple_test\GATRes_small_tough_znorm_15b_32c"
                            r"\best_GATRes_small_tough_znorm_15b_32c_20233629.pth"),
 }
-_NOT_ON_HOT_PATH = ("gin", "graphconvwat", "chebnet", "mgcn", "gcn2", "gat")
+_NOT_ON_HOT_PATH = ("gin", "graphconvwat", "chebnet", "mgcn", "gcn2")
 
 
 def _configure(variant: str) -> Callable[[argparse.Namespace, Optional[str]], Tuple[argparse.Namespace, torch.nn.Module]]:
@@ -48,6 +48,16 @@ config_gatres_large = _configure("gatres_large")
 config_gatres_small_tough = _configure("gatres_small_tough")
 
 
+def config_gat(args: argparse.Namespace, test_model_variant_name: Optional[str] = None):
+    """ConfigModels.py:96-103: the plain GAT baseline (shares the GATRes kernels)"""
+    args.model_path = r"experiments_logs\simple_test\GAT\best_GAT_10b_32c_2h_20231827.pth"
+    args.criterion = "mse"
+    args.use_data_edge_attrs = None
+    args.norm_type = "znorm"
+    return args, GAT(name="GAT_10b_32c_2h" if test_model_variant_name is None else test_model_variant_name,
+                     num_blocks=10, nc=32, in_channels=1, out_channels=1)
+
+
 def select_model(args: argparse.Namespace, test_model_variant_name: Optional[str] = None,
                  reset_model_path: bool = False) -> Tuple[argparse.Namespace, torch.nn.Module]:
     """``args.model`` (default ``gatres_small``) -> (args with the model's defaults, model)."""
@@ -56,9 +66,10 @@ def select_model(args: argparse.Namespace, test_model_variant_name: Optional[str
     if which in _NOT_ON_HOT_PATH:
         raise NotImplementedError(f"model {which!r} is a baseline of the reference and is not part of the "
                                   "B200 GATRes hot path; use gatres_small / gatres_large")
-    if which not in ("gatres_small", "gatres_large"):
+    table = {"gatres_small": config_gatres_small, "gatres_large": config_gatres_large, "gat": config_gat}
+    if which not in table:
         raise NotImplementedError(f"Unknown model! Got {which}!")
-    args, model = (config_gatres_small if which == "gatres_small" else config_gatres_large)(args, test_model_variant_name)
+    args, model = table[which](args, test_model_variant_name)
     if reset_model_path:
         args.model_path = previous_path
     return args, model

@@ -145,6 +145,32 @@ class GResBlockMeanConv(nn.Module):
         return self.mean_conv.forward_residual_relu(x, edge_index, x_0)
 
 
+class GAT(nn.Module):
+    """The reference's plain GAT baseline (/root/reference/gnn_pressure_estimation/GraphModels.py:210-230,
+    `config_gat`, ConfigModels.py:96-103): `num_blocks` GATConv layers, two heads of `nc` channels, no activation
+    between them; first layer from `in_channels`, last layer one head of `out_channels`.  Runs on the same fused
+    kernels as GATRes; the 1-wide first / last layers are zero-padded to built kernel shapes."""
+
+    def __init__(self, name: str = "GAT", num_blocks: int = 10, nc: int = 32, in_channels: int = 1, out_channels: int = 1):
+        super().__init__()
+        self.num_blocks = num_blocks
+        self.name = f"{name}_{num_blocks}b_{nc}c"
+        blocks = []
+        for i in range(num_blocks):
+            if i == 0:
+                blocks.append(GATConv(in_channels, nc, heads=2, concat=True))
+            elif i == num_blocks - 1:
+                blocks.append(GATConv(2 * nc, out_channels, heads=1, concat=True))
+            else:
+                blocks.append(GATConv(2 * nc, nc, heads=2, concat=True))
+        self.blocks = nn.ModuleList(blocks)
+
+    def forward(self, x: Tensor, edge_index: Tensor, batch: Optional[Tensor] = None, edge_attr: Optional[Tensor] = None) -> Tensor:
+        for blk in self.blocks:
+            x = blk(x, edge_index)
+        return x
+
+
 class GATResMeanConv(nn.Module):
     """GraphModels.py:471-494 of the reference; forward runs as one fused-stack op."""
 

@@ -361,6 +361,7 @@ static int dispatch_gemm(int KK, int NN, const float* A, const float* W, const f
   if (KK == KKv && NN == NNv) return launch_gemm<KKv, NNv, BM, TM, TN, ST, MODE, H>(A, W, e0, e1, Cout, s0, s1, M, st, what)
   G(32, 64, 64, 4, 4, 2);
   G(64, 32, 128, 4, 4, 2);
+  G(64, 64, 64, 4, 4, 2);       // sibling GAT model (GraphModels.py:210-230): GATConv(2*32 -> 2 heads x 32)
   G(64, 128, 64, 4, 8, 2);
   G(128, 64, 64, 4, 4, 2);
   G(128, 256, 64, 8, 8, 2);
@@ -560,6 +561,7 @@ extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W
   if (NO == NOv && K == KIv) return launch_wgrad<NOv, KIv, TNn, TKk, G>(dh, x, partial, P, slots, off_W, (unsigned)M, st)
   WG(64, 32, 8, 4, 4);
   WG(32, 64, 4, 8, 4);
+  WG(64, 64, 8, 8, 4);
   WG(128, 64, 8, 8, 2);
   WG(64, 128, 8, 8, 2);
   WG(256, 128, 16, 8, 1);

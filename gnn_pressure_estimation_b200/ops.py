@@ -321,12 +321,34 @@ class _GATConvFn(torch.autograd.Function):
         return dx, dW, das, dad, db, None, None, None, None, None
 
 
+# (heads, channels) -> input widths the projection kernels are built for (linear.cu dispatch tables)
+_SUPPORTED_K = {(2, 32): (32, 64), (1, 32): (64,), (2, 64): (64,), (1, 64): (128,), (2, 128): (128,), (1, 128): (256,)}
+
+
 def gat_conv(x: Tensor, W: Tensor, att_src: Tensor, att_dst: Tensor, bias: Tensor, topo, B: int, heads: int,
              concat: bool, relu: bool = False) -> Tensor:
+    """GATConv on the fused kernels.  Layer shapes outside the kernels' tables (the 1-wide first / last layers of the
+    reference's sibling `GAT` model, GraphModels.py:210-230) are zero-padded to the nearest built shape: padded input
+    columns and padded output channels contribute exact zeros to the projection, the scores and the aggregation,
+    and autograd slices their gradients away."""
     C_ = W.size(0) // heads
     if not concat and heads != 1:
         raise NotImplementedError("concat=False is implemented for heads=1 (the only use in GATRes)")
-    return _GATConvFn.apply(x, W, att_src, att_dst, bias, topo, B, heads, C_, relu)
+    Cp = next((c for c in (32, 64, 128) if c >= C_), None)
+    if Cp is None or (heads, Cp) not in _SUPPORTED_K:
+        raise NotImplementedError(f"GATConv with heads={heads}, out_channels={C_} has no kernel")
+    K = x.size(1)
+    Kp = next((k for k in _SUPPORTED_K[(heads, Cp)] if k >= K), None)
+    if Kp is None:
+        raise NotImplementedError(f"GATConv with in_channels={K}, heads={heads}, out_channels={C_} has no kernel")
+    if Cp == C_ and Kp == K:
+        return _GATConvFn.apply(x, W, att_src, att_dst, bias, topo, B, heads, C_, relu)
+    pad = torch.nn.functional.pad
+    Wp = pad(W.view(heads, C_, K), (0, Kp - K, 0, Cp - C_)).reshape(heads * Cp, Kp)
+    asp, adp = pad(att_src, (0, Cp - C_)), pad(att_dst, (0, Cp - C_))
+    bp = pad(bias.view(-1, C_), (0, Cp - C_)).reshape(-1)
+    out = _GATConvFn.apply(pad(x, (0, Kp - K)), Wp, asp, adp, bp, topo, B, heads, Cp, relu)
+    return out.view(out.size(0), -1, Cp)[:, :, :C_].reshape(out.size(0), -1)
 
 
 class _MeanResFn(torch.autograd.Function):

@@ -258,6 +258,39 @@ class GATResOracle(nn.Module):
         return self.lin1(x)                               # no output activation (:493 commented out)
 
 
+class GATOracle(nn.Module):
+    """The reference's plain GAT baseline, GraphModels.py:210-230 (`config_gat`, ConfigModels.py:96-103): GATConv layers
+    only, two heads of nc channels, no activation in between, last layer one head of out_channels."""
+    def __init__(self, name: str = "GAT", num_blocks: int = 10, nc: int = 32, in_channels: int = 1, out_channels: int = 1):
+        super().__init__()
+        self.num_blocks, self.name = num_blocks, f"{name}_{num_blocks}b_{nc}c"
+        blocks = []
+        for i in range(num_blocks):
+            if i == 0:
+                blocks.append(OracleGATConv(in_channels, nc, 2, True))
+            elif i == num_blocks - 1:
+                blocks.append(OracleGATConv(2 * nc, out_channels, 1, True))
+            else:
+                blocks.append(OracleGATConv(2 * nc, nc, 2, True))
+        self.blocks = nn.ModuleList(blocks)
+
+    def forward(self, x, edge_index, batch=None, edge_attr=None):
+        for blk in self.blocks:
+            x = blk(x, edge_index)
+        return x
+
+
+def make_gat_oracle(num_blocks: int = 10, nc: int = 32, seed: int = 0) -> GATOracle:
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    m = GATOracle(num_blocks=num_blocks, nc=nc)
+    with torch.no_grad():
+        for blk in m.blocks:
+            blk.bias.uniform_(-0.1, 0.1)
+    torch.random.set_rng_state(g)
+    return m
+
+
 def make_oracle(num_blocks: int, nc: int, seed: int = 0, dtype=torch.float32) -> GATResOracle:
     g = torch.random.get_rng_state()
     torch.manual_seed(seed)

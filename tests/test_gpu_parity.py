@@ -310,6 +310,38 @@ def test_resident_kernels_equal_layer_kernels(graph, B, blocks, cluster, threads
         assert float((g_r[k].cpu() - g).abs().max()) <= GRAD_TOL * max(float(g.abs().max()), floor), k
 
 
+@pytest.mark.parametrize("graph,B,blocks", [("ctown", 3, 10), ("tiny", 4, 3), ("ctown", 2, 2)])
+def test_sibling_gat_model_matches_oracle(graph, B, blocks, dev, G):
+    """the reference's plain `GAT` baseline (GraphModels.py:210-230, `select_model("gat")`) on the
+    same fused kernels; its 1 -> 2x32 first layer and 64 -> 1x1 last layer run zero-padded to built shapes."""
+    import argparse
+    from gnn_pressure_estimation_b200 import ConfigModels as CM
+    ei_np, names = GRAPHS[graph]()
+    ei, N = torch.from_numpy(ei_np), len(names)
+    ref = O.make_gat_oracle(blocks, 32, seed=2)
+    if blocks == 10:
+        args, model = CM.select_model(argparse.Namespace(model="gat"))
+        assert (args.criterion, args.norm_type) == ("mse", "znorm") and model.name == "GAT_10b_32c_2h_10b_32c"
+    else:
+        model = G.GAT(num_blocks=blocks, nc=32)
+    assert list(model.state_dict()) == list(ref.state_dict())
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev)
+    x, y, mask = O.synthetic_snapshots(N, B, seed=21)
+    eib = O.collate_edge_index(ei, N, B)
+    out_ref, loss_ref, grads_ref = O.train_step_loss_and_grads(ref, x, y, mask, eib)
+    out = model(x.to(dev), eib.to(dev), None, None)
+    loss = torch.nn.functional.mse_loss(out[mask.to(dev)], y.to(dev)[mask.to(dev)])
+    loss.backward()
+    assert out.shape == out_ref.shape
+    assert_close(out, out_ref, FWD_TOL, "GAT forward")
+    floor = 1e-3 * max(float(g.norm()) for g in grads_ref.values())
+    for k, p in model.named_parameters():
+        g = grads_ref[k]
+        assert p.grad.shape == g.shape, k
+        assert float((p.grad.cpu() - g).abs().max()) <= GRAD_TOL * max(float(g.abs().max()), floor), k
+
+
 def test_mixed_topology_batch_runs_in_general_mode(dev, G, kernel_variant):
     """WDNDataset accepts several networks and shuffle=True can collate different graphs into one batch
     (utils/DataLoader.py:120-129): such an edge_index is not B copies of a template, the model then treats the whole
