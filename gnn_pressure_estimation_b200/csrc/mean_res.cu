@@ -59,25 +59,36 @@ mean_res_bwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ rowp
   pdl_wait();
   if ((unsigned long long)gridDim.x * rows_per_cta >= M) pdl_launch_dependents();   // single pass: see common.cuh
   for (unsigned r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
-    const unsigned r = r0 + warp * RPW + sub;
-    if (r >= M) continue;
+    // rows past the end are clamped (they redo the last row and store nothing): warp-uniform shuffles below
+    const unsigned r_raw = r0 + warp * RPW + sub;
+    const bool row_ok = r_raw < M;
+    const unsigned r = row_ok ? r_raw : M - 1;
     const unsigned b = r / N, jn = r - b * N;
     const size_t base = (size_t)b * N;
-    const int beg = __ldg(rowptr_t + jn), end = __ldg(rowptr_t + jn + 1) - 1;
+    const int beg = __ldg(rowptr_t + jn), deg = __ldg(rowptr_t + jn + 1) - 1 - beg;      // out-edges minus the self-loop
+    const int deg_max = __reduce_max_sync(0xffffffffu, deg);
     float4 acc = f4zero();
-#pragma unroll 4
-    for (int e = beg; e < end; ++e) {
-      const int i = __ldg(col_t + e);
-      const int deg = __ldg(rowptr + i + 1) - __ldg(rowptr + i) - 1;
-      const float inv = 1.f / (float)(deg > 1 ? deg : 1);
-      float4 gv = ldg4(g_out + (base + i) * C + 4 * lig);
-      if (out != nullptr) {
-        const float4 ov = ldg4(out + (base + i) * C + 4 * lig);
-        gv.x = ov.x > 0.f ? gv.x : 0.f; gv.y = ov.y > 0.f ? gv.y : 0.f;
-        gv.z = ov.z > 0.f ? gv.z : 0.f; gv.w = ov.w > 0.f ? gv.w : 0.f;
+    for (int e0 = 0; e0 < deg_max; e0 += LPR) {
+      // lane t of the row's group resolves edge e0 + t (target id and 1 / in-degree of the target) — the index chain
+      // col_t -> rowptr -> rowptr is walked once per edge in parallel instead of once per edge in sequence
+      const bool valid = e0 + lig < deg;
+      const int it = valid ? __ldg(col_t + beg + e0 + lig) : 0;
+      const int dg = valid ? __ldg(rowptr + it + 1) - __ldg(rowptr + it) - 1 : 1;
+      const float inv_t = valid ? 1.f / (float)(dg > 1 ? dg : 1) : 0.f;
+      const int cnt_max = min(LPR, deg_max - e0);
+      for (int t = 0; t < cnt_max; ++t) {
+        const int i = __shfl_sync(0xffffffffu, it, t, LPR);
+        const float inv = __shfl_sync(0xffffffffu, inv_t, t, LPR);              // 0 beyond this row's edges
+        float4 gv = ldg4(g_out + (base + i) * C + 4 * lig);
+        if (out != nullptr) {
+          const float4 ov = ldg4(out + (base + i) * C + 4 * lig);
+          gv.x = ov.x > 0.f ? gv.x : 0.f; gv.y = ov.y > 0.f ? gv.y : 0.f;
+          gv.z = ov.z > 0.f ? gv.z : 0.f; gv.w = ov.w > 0.f ? gv.w : 0.f;
+        }
+        fma4(acc, inv, gv);
       }
-      fma4(acc, inv, gv);
     }
+    if (!row_ok) continue;
     st4(dz + (size_t)r * C + 4 * lig, acc);
     if (out != nullptr && dres != nullptr) {
       float4 gv = ldg4(g_out + (size_t)r * C + 4 * lig);
