@@ -45,6 +45,10 @@ def _run_steps(rank, world, peer, use_graph, steps, c, pg):
     return ts, losses
 
 
+def _eval_snapshots(N):
+    return torch.randn(16, N, generator=torch.Generator().manual_seed(77))
+
+
 def _worker(rank, world, port, ret):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     from gnn_pressure_estimation_b200 import dp
@@ -60,6 +64,14 @@ def _worker(rank, world, port, ret):
         t = torch.tensor(losses, device=ts.device)
         dist.all_reduce(t)
         out[name] = (ts.flat.cpu(), (t / world).cpu(), ts.kernels_per_step)
+    # sharded evaluation (inference shards snapshots with no communication until the final reduction)
+    import numpy as np
+    from gnn_pressure_estimation_b200 import evaluation as E
+    snaps = _eval_snapshots(c["N"]).to(ts.device)
+    np.random.seed(100 + rank)
+    loss, m = E.test_one_epoch(ts.model, snaps, c["edge_index"], 4, 0.95, norm_type="znorm", mean=57.3, std=21.9,
+                               gpu_warmup_times=1, mask_source="numpy", process_group=pg)
+    out["eval"] = (loss, {k: v for k, v in m.items()})
     if rank == 0:
         ret.update(out)
     dist.barrier()
@@ -81,6 +93,7 @@ def test_two_gpu_training_equals_single_gpu_training():
                     p.kill()
                 pytest.fail("2-GPU workers did not finish within 150 s")
         got = dict(ret)
+    loss_dp, m_dp = got.pop("eval")
     c = load_case("ctown_small_15b_32c_B8")
     single, losses = _run_steps(0, 1, False, True, 4, c, None)
     lr, steps = 5e-4, 4
@@ -90,6 +103,21 @@ def test_two_gpu_training_equals_single_gpu_training():
         # d/d att_dst is rounding noise whose sign Adam turns into +-lr per step (see test_train_step_matches_oracle_adam)
         assert float(diff.max()) <= 2 * lr * steps + 1e-6, name
         assert float((diff > 0.05 * lr * steps).float().mean()) < 0.02, name
+    # sharded evaluation == graph-weighted combination of the per-shard single-GPU evaluations (same masks per shard)
+    import numpy as np
+    from gnn_pressure_estimation_b200 import evaluation as E
+    snaps = _eval_snapshots(c["N"]).to(single.device)
+    parts = []
+    for r in range(2):
+        np.random.seed(100 + r)
+        parts.append(E.test_one_epoch(single.model, snaps[8 * r:8 * r + 8], c["edge_index"], 4, 0.95, norm_type="znorm",
+                                      mean=57.3, std=21.9, gpu_warmup_times=0, mask_source="numpy"))
+    # the workers evaluated the weights after THEIR training; re-evaluate with the same weights: copy them over
+    # (single-GPU and 2-GPU training agree to rounding, so compare with a tolerance that covers that)
+    assert loss_dp == pytest.approx(0.5 * (parts[0][0] + parts[1][0]), rel=5e-3)
+    for k in ("test_mae", "test_rmse", "test_r2"):
+        assert m_dp[k] == pytest.approx(0.5 * (parts[0][1][k] + parts[1][1][k]), rel=5e-3), k
+    assert m_dp["test_snapshots_per_s"] > 0
     assert got["peer_graph"][2] == 7                  # mask, forward stack, MSE x2, backward stack, epoch bump, Adam+all-reduce
     assert float((got["peer_graph"][0] - got["peer_eager"][0]).abs().max()) <= 2 * lr * steps + 1e-6
 
