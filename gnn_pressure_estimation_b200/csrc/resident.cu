@@ -58,7 +58,7 @@ static int threads() {
   if (g_threads < 0) {
     const char* e = getenv("GATRES_RESIDENT_THREADS");
     g_threads = e ? atoi(e) : 256;
-    if (g_threads != 256 && g_threads != 512 && g_threads != 255) g_threads = 256;
+    if (g_threads != 256 && g_threads != 255) g_threads = 256;
   }
   return g_threads;
 }
@@ -81,16 +81,6 @@ static int threads() {
 #undef RES_MIN_CTAS
 #undef RES_USE_MMA
 
-#define RES_NS res512
-#define RES_T 512
-#define RES_MIN_CTAS 2
-#define RES_USE_MMA 0
-#include "resident_impl.cuh"
-#undef RES_USE_MMA
-#undef RES_NS
-#undef RES_T
-#undef RES_MIN_CTAS
-
 namespace gatres {
 
 // Is the snapshot-resident path applicable?  nc = 32, the network has its self-loop CSR (E1 > 0), a batch small
@@ -98,14 +88,13 @@ namespace gatres {
 bool resident_eligible(const gatres_model_desc* d, bool backward) {
   if (d->nc != 32 || d->E1 <= 0 || d->B > res::max_batch() || d->B * 8ll >= (1ll << 31)) return false;
   if (backward && d->slots > 0) return false;                       // deterministic two-stage reduction: layer path
-  return res::threads() == 512 ? res512::fits(d->N, d->E1, backward) : res256::fits(d->N, d->E1, backward);   // res256f needs less
+  return res256::fits(d->N, d->E1, backward);                       // res256f needs less
 }
 
 int resident_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
                      float* scratch, cudaStream_t st) {
   if (res::threads() == 255) return res256f::forward(d, params, x, out, saved, scratch, st);
-  return res::threads() == 512 ? res512::forward(d, params, x, out, saved, scratch, st)
-                               : res256::forward(d, params, x, out, saved, scratch, st);
+  return res256::forward(d, params, x, out, saved, scratch, st);
 }
 
 int resident_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
@@ -113,8 +102,7 @@ int resident_backward(const gatres_model_desc* d, const float* params, const flo
                       cudaStream_t st) {
   if (res::threads() == 255)
     return res256f::backward(d, params, x, saved, d_out, grads, scratch, k_hi, k_lo, head, tail, st);
-  return res::threads() == 512 ? res512::backward(d, params, x, saved, d_out, grads, scratch, k_hi, k_lo, head, tail, st)
-                               : res256::backward(d, params, x, saved, d_out, grads, scratch, k_hi, k_lo, head, tail, st);
+  return res256::backward(d, params, x, saved, d_out, grads, scratch, k_hi, k_lo, head, tail, st);
 }
 
 }  // namespace gatres
@@ -132,7 +120,7 @@ extern "C" void gatres_set_resident_profile(int64_t* device_buf, int32_t slots_p
 
 extern "C" int32_t gatres_set_resident_threads(int32_t threads) {
   const int prev = gatres::res::threads();
-  if (threads == 256 || threads == 512 || threads == 255) gatres::res::g_threads = threads;
+  if (threads == 256 || threads == 255) gatres::res::g_threads = threads;
   return prev;
 }
 

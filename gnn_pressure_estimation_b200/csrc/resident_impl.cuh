@@ -67,8 +67,6 @@ __device__ __forceinline__ float ldc1(const float* p) {
   asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
-template <bool COH> __device__ __forceinline__ float4 ld4(const float* p) { return COH ? ldc4(p) : ldg4(p); }
-template <bool COH> __device__ __forceinline__ float ld1(const float* p) { return COH ? ldc1(p) : __ldg(p); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 

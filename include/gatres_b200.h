@@ -114,9 +114,10 @@ int64_t gatres_set_resident_max_batch(int64_t max_batch);
  * co-resident at two CTAs per SM; GATRES_RESIDENT_CLUSTER presets it).  Other values only query.  Returns
  * the previous setting. */
 int32_t gatres_set_resident_cluster(int32_t ctas);
-/* Variant of the resident kernels: 256 = 256-thread CTAs with tensor-core (mma.sync 3xTF32) contractions
- * (default); 255 = the same with fp32 FFMA contractions; 512 = 512-thread CTAs, FFMA (GATRES_RESIDENT_THREADS
- * presets it).  Other values only query.  Returns the previous setting. */
+/* Variant of the resident kernels (256-thread CTAs): 256 = tensor-core (mma.sync 3xTF32) contractions (default);
+ * 255 = the same kernels with fp32 FFMA contractions, kept for A/B measurements (GATRES_RESIDENT_THREADS presets
+ * it).  Other values only query.  Returns the previous setting.  (A 512-thread / 64-register variant was measured
+ * and dropped: it halves the row passes but not the time, profiles/r1_resident.md.) */
 int32_t gatres_set_resident_threads(int32_t threads);
 /* Profiling aid (tools/resident_probe.py): when device_buf is not NULL, thread 0 of CTA c of every resident kernel
  * writes %globaltimer at its phase boundaries to device_buf[c * slots_per_cta ...] (at most slots_per_cta stamps).

@@ -70,7 +70,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", default="32")
     ap.add_argument("--clusters", default="0")
-    ap.add_argument("--threads", default="256")
+    ap.add_argument("--threads", default="256", help="256 = tensor-core contractions, 255 = FFMA contractions")
     ap.add_argument("--blocks", type=int, default=15)
     ap.add_argument("--layer", action="store_true", help="also time the layer-by-layer kernels")
     ap.add_argument("--phases", action="store_true", help="per-phase timestamps of the resident kernels")
