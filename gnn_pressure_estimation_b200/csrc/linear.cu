@@ -306,6 +306,126 @@ wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* _
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Tensor-core weight gradient for the nc = 32 shapes (atomic accumulation mode): the same persistent, cp.async
+// double-buffered tiles as wgrad_kernel, contracted with mma.sync.m16n8k8 TF32 in the error-compensated 3xTF32 form
+// (hi = the tensor core's truncation of the fp32 operand, lo = rna_tf32(x - trunc x); three independent accumulator
+// chains).  dW[NO][KI] is NO/16 x KI/8 output tiles of 16 x 8; the 8 warps own TILES/8 tiles each, a warp's tiles
+// share one A fragment (dh^T) per 8-row step.  The FFMA kernel above is issue bound (2048 FMA per row = 64 warp
+// instructions + loads, ncu: issue 70 %, DRAM 38 %); this form needs ~38 per row.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned wg_lo_bits(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  return (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+}
+__device__ __forceinline__ void wg_mma(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int NO, int KI, int BM>
+__global__ void __launch_bounds__(256)
+wgrad_mma_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* __restrict__ grads, long long off_W,
+                 unsigned M) {
+  constexpr int LDH = NO + 4, LDX = KI + 4, NT = KI / 8, TILES = (NO / 16) * NT, TPW = TILES / 8;
+  static_assert(TILES % 8 == 0 && NT % TPW == 0 && BM % 8 == 0, "wgrad_mma tiling: a warp's tiles share one 16-row A block");
+  extern __shared__ __align__(16) float smem[];
+  float* Hs = smem;                         // [2][BM][LDH]
+  float* Xs = smem + 2 * BM * LDH;          // [2][BM][LDX]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int tile0 = warp * TPW, no0 = (tile0 / NT) * 16, ki0 = (tile0 % NT) * 8;
+  const unsigned ntiles = (M + BM - 1) / BM;
+
+  auto load_tile = [&](unsigned tile, int stage) {
+    float* hd = Hs + stage * BM * LDH;
+    float* xd = Xs + stage * BM * LDX;
+    for (int idx = tid; idx < BM * (NO / 4); idx += 256) {
+      const int m = idx / (NO / 4), v = idx % (NO / 4);
+      const unsigned row = tile * BM + m;
+      const bool ok = row < M;
+      cp_async16(hd + m * LDH + 4 * v, dh + (size_t)(ok ? row : 0) * NO + 4 * v, ok ? 16 : 0);
+    }
+    for (int idx = tid; idx < BM * (KI / 4); idx += 256) {
+      const int m = idx / (KI / 4), v = idx % (KI / 4);
+      const unsigned row = tile * BM + m;
+      const bool ok = row < M;
+      cp_async16(xd + m * LDX + 4 * v, x + (size_t)(ok ? row : 0) * KI + 4 * v, ok ? 16 : 0);
+    }
+  };
+
+  float acc[TPW][4], acl[TPW][4], acm[TPW][4];
+#pragma unroll
+  for (int q = 0; q < TPW; ++q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[q][i] = acl[q][i] = acm[q][i] = 0.f;
+
+  pdl_wait();
+  unsigned tile = blockIdx.x;
+  if (tile < ntiles) load_tile(tile, 0);
+  cp_async_commit();
+  int stage = 0;
+  if (gridDim.x >= ntiles) pdl_launch_dependents();
+  for (; tile < ntiles; tile += gridDim.x) {
+    const unsigned next = tile + gridDim.x;
+    if (next < ntiles) load_tile(next, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* hs = Hs + stage * BM * LDH;
+    const float* xs = Xs + stage * BM * LDX;
+#pragma unroll
+    for (int m0 = 0; m0 < BM; m0 += 8) {      // rows past M were zero-filled
+      // A = dh^T block [16 output rows x 8 data rows]: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4)
+      const float* h0 = hs + (m0 + t) * LDH + no0 + g;
+      const float* h1 = hs + (m0 + t + 4) * LDH + no0 + g;
+      const float av[4] = {h0[0], h0[8], h1[0], h1[8]};
+      unsigned a[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = __float_as_uint(av[i]); al[i] = wg_lo_bits(av[i]); }
+#pragma unroll
+      for (int q = 0; q < TPW; ++q) {
+        const float b0 = xs[(m0 + t) * LDX + ki0 + 8 * q + g], b1 = xs[(m0 + t + 4) * LDX + ki0 + 8 * q + g];
+        const unsigned b[2] = {__float_as_uint(b0), __float_as_uint(b1)}, bl[2] = {wg_lo_bits(b0), wg_lo_bits(b1)};
+        wg_mma(acl[q], al, b);
+        wg_mma(acm[q], a, bl);
+        wg_mma(acc[q], a, b);
+      }
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+  cp_async_wait<0>();
+  float* out = grads + off_W;
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    const int k = ki0 + 8 * q + 2 * t;
+    atomicAdd(reinterpret_cast<float2*>(out + (size_t)(no0 + g) * KI + k),
+              make_float2(acc[q][0] + acl[q][0] + acm[q][0], acc[q][1] + acl[q][1] + acm[q][1]));
+    atomicAdd(reinterpret_cast<float2*>(out + (size_t)(no0 + g + 8) * KI + k),
+              make_float2(acc[q][2] + acl[q][2] + acm[q][2], acc[q][3] + acl[q][3] + acm[q][3]));
+  }
+}
+
+template <int NO, int KI>
+static int launch_wgrad_mma(const float* dh, const float* x, float* grads, long long off_W, unsigned M, cudaStream_t st) {
+  constexpr int BM = 64;
+  constexpr size_t smem = (size_t)(2 * BM * (NO + 4) + 2 * BM * (KI + 4)) * sizeof(float);
+  auto kern = wgrad_mma_kernel<NO, KI, BM>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch("wgrad_mma");
+    configured = true;
+  }
+  const unsigned ntiles = (M + BM - 1) / BM;
+  unsigned grid = (unsigned)sm_count() * 3u;
+  if (grid > ntiles) grid = ntiles;
+  launch_kernel(kern, dim3(grid), dim3(256), smem, st, dh, x, grads, off_W, M);
+  return check_launch("wgrad_mma");
+}
+
 // ------------------------------------------------------------ host launchers
 template <int KK, int NN, int BM, int TM, int TN, int STAGES, int MODE, int H>
 static int launch_gemm(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
@@ -556,6 +676,10 @@ extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W
     if (rc < 0) return rc;
     rc = rc == 1 ? 0 : dispatch_gemm<1, 1>(NO, K, dh, W, add, relu_ref, dx, nullptr, nullptr, (unsigned)M, st, "linear_bwd_dx");
     if (rc) return rc;
+  }
+  if (slots <= 0 && tensor_core_enabled(M)) {          // atomic accumulation mode, large launch: tensor-core form
+    if (NO == 64 && K == 32) return launch_wgrad_mma<64, 32>(dh, x, partial, off_W, (unsigned)M, st);
+    if (NO == 32 && K == 64) return launch_wgrad_mma<32, 64>(dh, x, partial, off_W, (unsigned)M, st);
   }
 #define WG(NOv, KIv, TNn, TKk, G) \
   if (NO == NOv && K == KIv) return launch_wgrad<NOv, KIv, TNn, TKk, G>(dh, x, partial, P, slots, off_W, (unsigned)M, st)
