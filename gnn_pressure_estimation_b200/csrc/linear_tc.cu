@@ -236,23 +236,41 @@ gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
     }
     tc_fence_before();
     __syncthreads();                                          // staging complete; TMEM accumulator free
+    // coalesced write-out in batches of EPB chunks per thread: the residual-gradient / ReLU-reference loads of a whole
+    // batch are issued before any of them is consumed (they were latency-exposed one by one: the data-gradient kernels
+    // ran at 44 % of HBM peak against 55 % for the same GEMM forward)
+    constexpr int EPB = 8, EPI = BM * NCH / 128;
+    static_assert(EPI % EPB == 0, "epilogue batching");
+#pragma unroll 1
+    for (int q0 = 0; q0 < EPI; q0 += EPB) {
+      float4 addv[EPB], refv[EPB];
+      size_t off[EPB];
+      bool okv[EPB];
 #pragma unroll
-    for (int q = 0; q < BM * NCH / 128; ++q) {
-      const int idx = q * 128 + tid;
-      const int r = idx / NCH, c = idx % NCH;
-      const unsigned grow = tile * BM + r;
-      if (grow < M) {
-        float4 t = *reinterpret_cast<const float4*>(sm + stg + (size_t)r * (NN * 4) + (((c ^ r) & (NCH - 1)) << 4));
-        const size_t o = (size_t)grow * NN + 4 * c;
+      for (int u = 0; u < EPB; ++u) {
+        const int idx = (q0 + u) * 128 + tid;
+        const int r = idx / NCH, c = idx % NCH;
+        const unsigned grow = tile * BM + r;
+        okv[u] = grow < M;
+        off[u] = (size_t)grow * NN + 4 * c;
         if (MODE == 1) {
-          if (e0 != nullptr) add4(t, ldg4_stream(e0 + o));
-          if (e1 != nullptr) {
-            const float4 rr = ldg4_stream(e1 + o);
-            t.x = rr.x > 0.f ? t.x : 0.f; t.y = rr.y > 0.f ? t.y : 0.f;
-            t.z = rr.z > 0.f ? t.z : 0.f; t.w = rr.w > 0.f ? t.w : 0.f;
-          }
+          addv[u] = (okv[u] && e0 != nullptr) ? ldg4_stream(e0 + off[u]) : f4zero();
+          refv[u] = (okv[u] && e1 != nullptr) ? ldg4_stream(e1 + off[u]) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
-        st4(Cout + o, t);
+      }
+#pragma unroll
+      for (int u = 0; u < EPB; ++u) {
+        const int idx = (q0 + u) * 128 + tid;
+        const int r = idx / NCH, c = idx % NCH;
+        if (okv[u]) {
+          float4 t = *reinterpret_cast<const float4*>(sm + stg + (size_t)r * (NN * 4) + (((c ^ r) & (NCH - 1)) << 4));
+          if (MODE == 1) {
+            add4(t, addv[u]);
+            t.x = refv[u].x > 0.f ? t.x : 0.f; t.y = refv[u].y > 0.f ? t.y : 0.f;
+            t.z = refv[u].z > 0.f ? t.z : 0.f; t.w = refv[u].w > 0.f ? t.w : 0.f;
+          }
+          st4(Cout + off[u], t);
+        }
       }
     }
     __syncthreads();                                          // staging (= operand buffers) free for the next tile
