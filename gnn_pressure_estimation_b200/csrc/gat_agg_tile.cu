@@ -232,18 +232,21 @@ int gat_agg_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float
 namespace gatres {
 
 struct BwdTilePlan {
-  uint32_t slab, sc, hs_off, gs_off, ss_off, sd_off, mm_off, ll_off, dd_off, dsd_off, rpi_off, ci_off, rpo_off,
-      co_off, bar_off, total, tx_bytes;
-  __host__ __device__ BwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1) {
+  // [inputs of a snapshot: h slab, g slab, s_src, s_dst, m, l] x nbuf, then D, ds_dst, the two CSRs, barriers
+  uint32_t slab, sc, in_bytes, nbuf, hs_off, gs_off, ss_off, sd_off, mm_off, ll_off, dd_off, dsd_off, rpi_off, ci_off,
+      rpo_off, co_off, bar_off, total, tx_bytes;
+  __host__ __device__ BwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1, unsigned nbuf_ = 1) {
     slab = N * F * 4u;
     sc = N * H * 4u;
+    nbuf = nbuf_;
     hs_off = 0;
     gs_off = slab;
     ss_off = 2u * slab;
     sd_off = ss_off + sc;
     mm_off = sd_off + sc;
     ll_off = mm_off + sc;
-    dd_off = ll_off + sc;
+    in_bytes = (ll_off + sc + 127u) & ~127u;              // stride between the input buffers
+    dd_off = nbuf * in_bytes;
     dsd_off = dd_off + sc;
     rpi_off = dsd_off + sc;
     const uint32_t rp = ((N + 1u) * 4u + 15u) & ~15u, cl = (E1 * 2u + 15u) & ~15u;
@@ -258,8 +261,10 @@ struct BwdTilePlan {
 
 // PACK (see RowMap): used when one CTA per SM runs 512 threads with a 128-register budget (two heads, nc = 32:
 // the two slabs fill shared memory); the 2-CTA / 1024-thread shapes have 64 registers per thread and keep PACK off.
-template <int H, int C, int THREADS, bool PACK>
-__global__ void __launch_bounds__(THREADS, (THREADS == 512 && !PACK) ? 2 : 1)
+// NBUF = 2 (one head, nc = 32: two input sets fit one SM): the next snapshot's slabs are loaded while the two passes
+// of the current one run; with NBUF = 1 the load of a snapshot starts when the passes of the previous one are done.
+template <int H, int C, int THREADS, bool PACK, int NBUF>
+__global__ void __launch_bounds__(THREADS, (THREADS == 512 && !PACK && NBUF == 1) ? 2 : 1)
 gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                         const int* __restrict__ rowptr_t, const int* __restrict__ col_t, unsigned E1,
                         const float* __restrict__ g, const float* __restrict__ h,
@@ -274,38 +279,34 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   constexpr int kWarpsT = THREADS / 32;
   constexpr unsigned gmask = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem[];
-  const BwdTilePlan plan(N, F, H, E1);
-  const float* HS = reinterpret_cast<const float*>(smem + plan.hs_off);
-  const float* GS = reinterpret_cast<const float*>(smem + plan.gs_off);
-  const float* SS = reinterpret_cast<const float*>(smem + plan.ss_off);
-  const float* SD = reinterpret_cast<const float*>(smem + plan.sd_off);
-  const float* MM = reinterpret_cast<const float*>(smem + plan.mm_off);
-  const float* LL = reinterpret_cast<const float*>(smem + plan.ll_off);
+  const BwdTilePlan plan(N, F, H, E1, NBUF);
+  const float *HS, *GS, *SS, *SD, *MM, *LL;                 // inputs of the current snapshot (set per iteration)
   float* DD = reinterpret_cast<float*>(smem + plan.dd_off);
   float* DSD = reinterpret_cast<float*>(smem + plan.dsd_off);
   int* rpi = reinterpret_cast<int*>(smem + plan.rpi_off);
   unsigned short* ci = reinterpret_cast<unsigned short*>(smem + plan.ci_off);
   int* rpo = reinterpret_cast<int*>(smem + plan.rpo_off);
   unsigned short* co = reinterpret_cast<unsigned short*>(smem + plan.co_off);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + plan.bar_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + plan.bar_off);        // [NBUF]
   float* red = reinterpret_cast<float*>(smem);     // reused for the final CTA reduction (slabs are dead by then)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
 
-  auto issue = [&](unsigned bb) {
+  auto issue = [&](unsigned bb, unsigned buf) {
     const size_t ro = (size_t)bb * N;
-    mbar_arrive_expect_tx(full, plan.tx_bytes);
-    bulk_g2s(smem + plan.hs_off, h + ro * F, plan.slab, full);
-    bulk_g2s(smem + plan.gs_off, g + ro * F, plan.slab, full);
-    bulk_g2s(smem + plan.ss_off, s_src + ro * H, plan.sc, full);
-    bulk_g2s(smem + plan.sd_off, s_dst + ro * H, plan.sc, full);
-    bulk_g2s(smem + plan.mm_off, m + ro * H, plan.sc, full);
-    bulk_g2s(smem + plan.ll_off, l + ro * H, plan.sc, full);
+    unsigned char* base = smem + buf * plan.in_bytes;
+    mbar_arrive_expect_tx(full + buf, plan.tx_bytes);
+    bulk_g2s(base + plan.hs_off, h + ro * F, plan.slab, full + buf);
+    bulk_g2s(base + plan.gs_off, g + ro * F, plan.slab, full + buf);
+    bulk_g2s(base + plan.ss_off, s_src + ro * H, plan.sc, full + buf);
+    bulk_g2s(base + plan.sd_off, s_dst + ro * H, plan.sc, full + buf);
+    bulk_g2s(base + plan.mm_off, m + ro * H, plan.sc, full + buf);
+    bulk_g2s(base + plan.ll_off, l + ro * H, plan.sc, full + buf);
   };
 
   if (tid == 0) {
-    mbar_init(full, 1);
+    for (int q = 0; q < NBUF; ++q) mbar_init(full + q, 1);
     mbar_fence_init();
   }
   for (unsigned k = tid; k <= N; k += THREADS) { rpi[k] = __ldg(rowptr + k); rpo[k] = __ldg(rowptr_t + k); }
@@ -322,12 +323,26 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   }
   __syncthreads();
   pdl_wait();
-  if (tid == 0 && blockIdx.x < B) issue(blockIdx.x);
+  if (tid == 0 && blockIdx.x < B) issue(blockIdx.x, 0);
 
   unsigned it = 0;
   if (gridDim.x >= B) pdl_launch_dependents();
   for (unsigned b = blockIdx.x; b < B; b += gridDim.x, ++it) {
-    mbar_wait(full, it & 1);
+    const unsigned cur = NBUF == 2 ? (it & 1u) : 0u;
+    if (NBUF == 2 && tid == 0 && b + gridDim.x < B) {       // that buffer's snapshot finished last iteration
+      fence_proxy_async();
+      issue(b + gridDim.x, cur ^ 1u);
+    }
+    {
+      const unsigned char* base = smem + cur * plan.in_bytes;
+      HS = reinterpret_cast<const float*>(base + plan.hs_off);
+      GS = reinterpret_cast<const float*>(base + plan.gs_off);
+      SS = reinterpret_cast<const float*>(base + plan.ss_off);
+      SD = reinterpret_cast<const float*>(base + plan.sd_off);
+      MM = reinterpret_cast<const float*>(base + plan.mm_off);
+      LL = reinterpret_cast<const float*>(base + plan.ll_off);
+    }
+    mbar_wait(full + cur, NBUF == 2 ? ((it >> 1) & 1u) : (it & 1u));
 
     // ---------------- pass 1: per target row, D and ds_dst into shared memory
     for (unsigned i0 = warp * RPW; i0 < N; i0 += kWarpsT * RPW) {
@@ -443,11 +458,11 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
       }
     }
     __syncthreads();                               // both slabs are free again
-    if (tid == 0) {
+    if (NBUF == 1 && tid == 0) {
       const unsigned nb = b + gridDim.x;
       if (nb < B) {
         fence_proxy_async();
-        issue(nb);
+        issue(nb, 0);
       }
     }
   }
@@ -482,20 +497,33 @@ static bool bwd_tile_pack() {
   return v != 0;
 }
 
+static bool bwd_tile_double_buffer() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GATRES_BWD_TILE_DB");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 template <int H, int C>
 static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_t, const int* col_t, unsigned E1,
                            const float* g, const float* h, const float* s_src, const float* s_dst, const float* m,
                            const float* l, const float* att_src, const float* att_dst, float* dh, float* grads,
                            long long off_as, long long off_ad, long long off_b, unsigned B, unsigned N,
                            cudaStream_t st) {
-  const BwdTilePlan plan(N, H * C, H, E1);
+  BwdTilePlan plan(N, H * C, H, E1);
   unsigned per_sm = (unsigned)((227u * 1024u) / (plan.total + 1024u));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  // one CTA per SM but room for a second input set: double-buffer the snapshot loads instead
+  const BwdTilePlan plan2(N, H * C, H, E1, 2);
+  const bool dbl = per_sm == 1 && plan2.total <= 227u * 1024u && bwd_tile_double_buffer();
+  if (dbl) plan = plan2;
   unsigned grid = (unsigned)sm_count() * per_sm;
   if (grid > B) grid = B;
-#define LAUNCH(THR, PK)                                                                                           \
+#define LAUNCH(THR, PK, NB)                                                                                       \
   do {                                                                                                            \
-    auto kern = gat_agg_bwd_tile_kernel<H, C, THR, PK>;                                                            \
+    auto kern = gat_agg_bwd_tile_kernel<H, C, THR, PK, NB>;                                                            \
     static uint32_t configured = 0;                                                                               \
     if (configured < plan.total) {                                                                                \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
@@ -505,9 +533,10 @@ static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_
     launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, rowptr_t, col_t, E1, g, h, s_src, s_dst, m, l, att_src,      \
                                         att_dst, dh, grads, off_as, off_ad, off_b, B, N);                         \
   } while (0)
-  if (per_sm >= 2) LAUNCH(512, false);
-  else if (H == 2 && C == 32 && bwd_tile_pack()) LAUNCH(512, true);
-  else LAUNCH(1024, false);
+  if (per_sm >= 2) LAUNCH(512, false, 1);
+  else if (dbl) LAUNCH(1024, false, 2);
+  else if (H == 2 && C == 32 && bwd_tile_pack()) LAUNCH(512, true, 1);
+  else LAUNCH(1024, false, 1);
 #undef LAUNCH
   return check_launch("gat_agg_bwd_tile");
 }
