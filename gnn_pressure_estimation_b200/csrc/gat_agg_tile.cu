@@ -488,13 +488,14 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   }
 }
 
-static bool bwd_tile_pack() {
+static int bwd_tile_pack() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("GATRES_BWD_TILE_PACK");     // 0 restores the 1024-thread one-chunk-per-lane variant
-    v = e ? atoi(e) : 1;                                // measured: 277 -> 261 us at 2048 snapshots (two heads, nc = 32)
+    const char* e = getenv("GATRES_BWD_TILE_PACK");     // 0 = 1024 threads, one chunk per lane; 1 = packed, 512 threads;
+    v = e ? atoi(e) : 2;                                // 2 = packed, 640 threads (5 passes of 80 rows for 388 nodes).
+                                                        // measured at 2048 snapshots (two heads, nc = 32): 277 / 261 / 251 us
   }
-  return v != 0;
+  return v;
 }
 
 static bool bwd_tile_double_buffer() {
@@ -535,6 +536,7 @@ static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_
   } while (0)
   if (per_sm >= 2) LAUNCH(512, false, 1);
   else if (dbl) LAUNCH(1024, false, 2);
+  else if (H == 2 && C == 32 && bwd_tile_pack() == 2) LAUNCH(640, true, 1);
   else if (H == 2 && C == 32 && bwd_tile_pack()) LAUNCH(512, true, 1);
   else LAUNCH(1024, false, 1);
 #undef LAUNCH
