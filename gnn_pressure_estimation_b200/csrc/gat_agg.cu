@@ -447,6 +447,32 @@ static long long tile_min_batch() {
   return g_tile_min_batch;
 }
 
+// conv2 aggregation fused with SimpleConv(mean) + residual + ReLU (gat_agg_tile.cu); used by gatres_forward
+bool fwd_tile_mean_eligible(unsigned N, unsigned C, unsigned E1);
+int gat_agg_mean_res_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
+                              const float* s_dst, const float* bias, float* m, float* l, const float* x0, float* xout,
+                              unsigned B, unsigned N, int C, cudaStream_t st);
+
+static int fused_mean_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GATRES_FUSE_MEAN");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+// -> 1 if the fused kernel ran, 0 if the shapes / batch do not take the tile path (caller runs the two kernels), < 0 on error
+int gat_agg_mean_res_fwd(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
+                         const float* s_dst, const float* bias, float* m, float* l, const float* x0, float* xout,
+                         long long B, int N, int C, cudaStream_t st) {
+  if (!fused_mean_enabled() || E1 == 0 || B < tile_min_batch() || (C != 32 && C != 64) ||
+      !fwd_tile_mean_eligible((unsigned)N, (unsigned)C, E1))
+    return 0;
+  const int rc = gat_agg_mean_res_fwd_tile(rowptr, col, E1, h, s_src, s_dst, bias, m, l, x0, xout, (unsigned)B, (unsigned)N, C, st);
+  return rc ? rc : 1;
+}
+
 }  // namespace gatres
 
 using namespace gatres;

@@ -26,33 +26,45 @@ __device__ __forceinline__ float tile_group_max(float v, unsigned mask) {
 
 // shared-memory plan of the forward tile kernel (host and device agree through these)
 struct FwdTilePlan {
-  uint32_t h_bytes, ss_bytes, stage_bytes, rp_off, col_off, bar_off, total;
-  __host__ __device__ FwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1) {
+  uint32_t h_bytes, ss_bytes, tx_bytes, stage_bytes, zs_off, xs_off, rp_off, col_off, bar_off, total;
+  // fuse_mean: two more slabs, the layer output z of the snapshot (never written to HBM) and the block input x0
+  __host__ __device__ FwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1, bool fuse_mean = false) {
     h_bytes = N * F * 4u;
     ss_bytes = N * H * 4u;
-    stage_bytes = h_bytes + 2u * ss_bytes;          // slab + source scores + target scores
-    rp_off = 2u * stage_bytes;
+    tx_bytes = h_bytes + 2u * ss_bytes;                       // slab + source scores + target scores (what the TMA delivers)
+    stage_bytes = (tx_bytes + 127u) & ~127u;                  // stride between the two stages
+    zs_off = 2u * stage_bytes;
+    xs_off = zs_off + (fuse_mean ? h_bytes : 0u);
+    rp_off = xs_off + (fuse_mean ? h_bytes : 0u);
     col_off = rp_off + (((N + 1u) * 4u + 15u) & ~15u);
     bar_off = col_off + ((E1 * 4u + 15u) & ~15u);
     total = bar_off + 32u;
   }
 };
 
-template <int H, int C, int THREADS>
+// FUSE_MEAN (one head, concat = False: conv2 of a GATRes block): the layer output z stays in shared memory and the
+// SimpleConv(mean) + residual + ReLU that always follows (GraphModels.py:466-467) runs in the same kernel:
+// xout[i] = relu(mean_{j in N(i)} z[j] + x0[i]).  z is neither written to nor re-read from HBM and one launch
+// disappears: 272 + 384 algorithmic B/node become 400.
+template <int H, int C, int THREADS, bool FUSE_MEAN>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
 gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, unsigned E1,
                         const float* __restrict__ h, const float* __restrict__ s_src,
                         const float* __restrict__ s_dst, const float* __restrict__ bias,
                         float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ l_out,
+                        const float* __restrict__ x0, float* __restrict__ xout,
                         unsigned B, unsigned N, int relu) {
   using RM = RowMap<H, C, true>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
   constexpr int kTileThreads = THREADS, kTileWarps = THREADS / 32;
+  static_assert(!FUSE_MEAN || (H == 1 && V == 1), "the fused mean follows the one-head layer");
   extern __shared__ __align__(128) unsigned char smem[];
-  const FwdTilePlan plan(N, F, H, E1);
+  const FwdTilePlan plan(N, F, H, E1, FUSE_MEAN);
   int* rp_s = reinterpret_cast<int*>(smem + plan.rp_off);
   int* col_s = reinterpret_cast<int*>(smem + plan.col_off);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + plan.bar_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + plan.bar_off);          // [0], [1]: stages; [2]: x0 slab
+  float* ZS = reinterpret_cast<float*>(smem + plan.zs_off);
+  const float* XS = reinterpret_cast<const float*>(smem + plan.xs_off);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
@@ -60,7 +72,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
 
   auto issue = [&](int stage, unsigned bb) {       // one elected thread
     unsigned char* dst = smem + (size_t)stage * plan.stage_bytes;
-    mbar_arrive_expect_tx(&full[stage], plan.stage_bytes);
+    mbar_arrive_expect_tx(&full[stage], plan.tx_bytes);
     bulk_g2s(dst, h + (size_t)bb * N * F, plan.h_bytes, &full[stage]);
     bulk_g2s(dst + plan.h_bytes, s_src + (size_t)bb * N * H, plan.ss_bytes, &full[stage]);
     bulk_g2s(dst + plan.h_bytes + plan.ss_bytes, s_dst + (size_t)bb * N * H, plan.ss_bytes, &full[stage]);
@@ -69,6 +81,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
+    mbar_init(&full[2], 1);
     mbar_fence_init();
   }
   for (unsigned k = tid; k <= N; k += kTileThreads) rp_s[k] = __ldg(rowptr + k);
@@ -91,6 +104,11 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     const float* hs = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes) + 4 * lig;
     const float* sss = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes + plan.h_bytes);
     const float* sds = sss + N * H;
+    if (FUSE_MEAN && tid == 0) {                   // the previous snapshot's mean phase is done with the x0 slab
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&full[2], plan.h_bytes);
+      bulk_g2s(smem + plan.xs_off, x0 + (size_t)b * N * F, plan.h_bytes, &full[2]);
+    }
     mbar_wait(&full[stage], (k >> 1) & 1);
 
     for (unsigned i0 = warp * RPW; i0 < N; i0 += kTileWarps * RPW) {
@@ -148,14 +166,15 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
         if (relu) {
           o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
         }
-        st4(out + r * F + 4 * RM::chunk(lig, v), o);
+        if (FUSE_MEAN) st4(ZS + i * F + 4 * RM::chunk(lig, v), o);
+        else st4(out + r * F + 4 * RM::chunk(lig, v), o);
         if (m_out != nullptr && slot == 0) {
           m_out[r * H + RM::head(lig, v)] = mrun[v];
           l_out[r * H + RM::head(lig, v)] = lrun[v];
         }
       }
     }
-    __syncthreads();                               // every warp is done with this stage
+    __syncthreads();                               // every warp is done with this stage (and z is complete)
     if (tid == 0) {
       const unsigned nb = b + 2u * gridDim.x;
       if (nb < B) {
@@ -163,42 +182,70 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
         issue(stage, nb);
       }
     }
+    if (FUSE_MEAN) {
+      mbar_wait(&full[2], k & 1);
+      for (unsigned i = warp * RPW + sub; i < N; i += kTileWarps * RPW) {
+        const int beg = rp_s[i], end = rp_s[i + 1] - 1;                    // drop the self-loop
+        float4 acc = f4zero();
+#pragma unroll 4
+        for (int e = beg; e < end; ++e) add4(acc, *reinterpret_cast<const float4*>(ZS + col_s[e] * F + 4 * lig));
+        const int deg = end - beg;
+        const float inv = 1.f / (float)(deg > 1 ? deg : 1);
+        const float4 xr = *reinterpret_cast<const float4*>(XS + i * F + 4 * lig);
+        float4 o;
+        o.x = fmaxf(fmaf(acc.x, inv, xr.x), 0.f);
+        o.y = fmaxf(fmaf(acc.y, inv, xr.y), 0.f);
+        o.z = fmaxf(fmaf(acc.z, inv, xr.z), 0.f);
+        o.w = fmaxf(fmaf(acc.w, inv, xr.w), 0.f);
+        st4(xout + ((size_t)b * N + i) * F + 4 * lig, o);
+      }
+      __syncthreads();                             // z and x0 slabs are free for the next snapshot
+    }
   }
 }
 
-template <int H, int C>
+template <int H, int C, bool FUSE>
 static int launch_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
-                           const float* s_dst, const float* bias, float* out, float* m, float* l, unsigned B,
-                           unsigned N, int relu, cudaStream_t st) {
-  const FwdTilePlan plan(N, H * C, H, E1);
+                           const float* s_dst, const float* bias, float* out, float* m, float* l, const float* x0,
+                           float* xout, unsigned B, unsigned N, int relu, cudaStream_t st) {
+  const FwdTilePlan plan(N, H * C, H, E1, FUSE);
   unsigned per_sm = (unsigned)((227u * 1024u) / (plan.total + 1024u));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
   unsigned grid = (unsigned)sm_count() * per_sm;
   if (grid > B) grid = B;
-  if (per_sm >= 2) {
-    auto kern = gat_agg_fwd_tile_kernel<H, C, 512>;
-    static uint32_t configured = 0;
-    if (configured < plan.total) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess)
-        return check_launch("gat_agg_fwd_tile: smem attribute");
-      configured = plan.total;
-    }
-    launch_kernel(kern, dim3(grid), dim3(512), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, B, N, relu);
-  } else {
-    auto kern = gat_agg_fwd_tile_kernel<H, C, 1024>;
-    static uint32_t configured = 0;
-    if (configured < plan.total) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess)
-        return check_launch("gat_agg_fwd_tile: smem attribute");
-      configured = plan.total;
-    }
-    launch_kernel(kern, dim3(grid), dim3(1024), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, B, N, relu);
-  }
+#define LAUNCH(THR)                                                                                               \
+  do {                                                                                                            \
+    auto kern = gat_agg_fwd_tile_kernel<H, C, THR, FUSE>;                                                         \
+    static uint32_t configured = 0;                                                                               \
+    if (configured < plan.total) {                                                                                \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
+        return check_launch("gat_agg_fwd_tile: smem attribute");                                                  \
+      configured = plan.total;                                                                                    \
+    }                                                                                                             \
+    launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, x0, xout, B, N, relu); \
+  } while (0)
+  if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);
+#undef LAUNCH
   return check_launch("gat_agg_fwd_tile");
 }
 
 // Eligibility: slab + scores double-buffered + CSR must fit, and the per-snapshot byte
 // counts must be 16 B multiples (bulk-copy granularity).
+// conv2 aggregation + SimpleConv(mean) + residual + ReLU in one launch (nc = 32 / 64, one head)
+bool fwd_tile_mean_eligible(unsigned N, unsigned C, unsigned E1) {
+  const FwdTilePlan plan(N, C, 1, E1, true);
+  return N % 4u == 0 && plan.total <= 227u * 1024u && (C == 32 || C == 64);
+}
+
+int gat_agg_mean_res_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
+                              const float* s_dst, const float* bias, float* m, float* l, const float* x0, float* xout,
+                              unsigned B, unsigned N, int C, cudaStream_t st) {
+  if (C == 32) return launch_fwd_tile<1, 32, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 0, st);
+  if (C == 64) return launch_fwd_tile<1, 64, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 0, st);
+  set_error("gat_agg_mean_res_fwd_tile: unsupported channels %d", C);
+  return GATRES_ERR_ARG;
+}
+
 bool fwd_tile_eligible(unsigned N, unsigned H, unsigned C, unsigned E1) {
   const FwdTilePlan plan(N, H * C, H, E1);
   return (N * H) % 4u == 0 && plan.total <= 227u * 1024u && (H * C) <= 128;
@@ -208,7 +255,7 @@ int gat_agg_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float
                      const float* s_dst, const float* bias, float* out, float* m, float* l, unsigned B, unsigned N,
                      int H, int C, int relu, cudaStream_t st) {
 #define T(HH, CC) \
-  if (H == HH && C == CC) return launch_fwd_tile<HH, CC>(rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, B, N, relu, st)
+  if (H == HH && C == CC) return launch_fwd_tile<HH, CC, false>(rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, nullptr, nullptr, B, N, relu, st)
   T(1, 32);
   T(2, 32);
   T(1, 64);

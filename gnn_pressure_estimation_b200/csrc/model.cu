@@ -17,6 +17,11 @@ int resident_backward(const gatres_model_desc* d, const float* params, const flo
                       const float* d_out, float* grads, float* scratch, int k_hi, int k_lo, bool head, bool tail,
                       cudaStream_t st);
 
+// conv2 aggregation + SimpleConv(mean) + residual + ReLU in one launch when the snapshot tile path applies (gat_agg.cu)
+int gat_agg_mean_res_fwd(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
+                         const float* s_dst, const float* bias, float* m, float* l, const float* x0, float* xout,
+                         long long B, int N, int C, cudaStream_t st);
+
 static int validate(const gatres_model_desc* d, const char* who) {
   GATRES_REQUIRE(d != nullptr, "%s: null model descriptor", who);
   GATRES_REQUIRE(d->num_blocks >= 0 && (d->nc == 32 || d->nc == 64 || d->nc == 128),
@@ -95,8 +100,13 @@ extern "C" int gatres_forward(const gatres_model_desc* d, const float* params, c
     TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h1, ss1, sd1, params + pl.c1_b(k), y1, m1, l1, d->B, N, d->E1, 2, C, 1, stream));
     TRY(gatres_linear_att_fwd(y1, params + pl.c2_W(k), params + pl.c2_as(k), params + pl.c2_ad(k), h2, ss2, sd2, M,
                               2 * C, 1, C, stream));
-    TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h2, ss2, sd2, params + pl.c2_b(k), z, m2, l2, d->B, N, d->E1, 1, C, 0, stream));
-    TRY(gatres_mean_res_fwd(d->rowptr, d->col, z, x0, xo, d->B, N, C, stream));
+    const int fused = gat_agg_mean_res_fwd(d->rowptr, d->col, (unsigned)d->E1, h2, ss2, sd2, params + pl.c2_b(k), m2, l2, x0, xo,
+                                           d->B, N, C, as_stream(stream));
+    if (fused < 0) return fused;
+    if (fused == 0) {
+      TRY(gatres_gat_agg_fwd(d->rowptr, d->col, h2, ss2, sd2, params + pl.c2_b(k), z, m2, l2, d->B, N, d->E1, 1, C, 0, stream));
+      TRY(gatres_mean_res_fwd(d->rowptr, d->col, z, x0, xo, d->B, N, C, stream));
+    }
     x0 = xo;
   }
   return gatres_decoder_fwd(x0, params + pl.lin1_w(), params + pl.lin1_b(), out, d->poison, M, C, stream);
