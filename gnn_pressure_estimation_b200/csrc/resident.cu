@@ -88,6 +88,10 @@ namespace gatres {
 bool resident_eligible(const gatres_model_desc* d, bool backward) {
   if (d->nc != 32 || d->E1 <= 0 || d->B > res::max_batch() || d->B * 8ll >= (1ll << 31)) return false;
   if (backward && d->slots > 0) return false;                       // deterministic two-stage reduction: layer path
+  // the backward stack only wins with 8 CTAs per snapshot (49 rows per CTA); with 4 (batches of 38..74) its row passes
+  // double and the layer-by-layer backward is faster, while the forward stack still wins (measured at 40 / 48 / 64
+  // snapshots: forward 312-319 us against 369-430, backward 1053-1082 us against 921-1145; profiles/r1_resident.md)
+  if (backward && res::forced_cluster() == 0 && d->B * 8ll > 2ll * sm_count()) return false;
   return res256::fits(d->N, d->E1, backward);                       // res256f needs less
 }
 

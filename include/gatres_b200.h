@@ -106,7 +106,8 @@ int64_t gatres_set_tile_min_batch(int64_t min_batch);
  * snapshot-resident cluster kernels — one thread-block cluster per snapshot carries the whole stack, layers
  * separated by cluster barriers instead of kernel launches; larger batches run layer by layer.  Default
  * SM count / 2 (74 on B200: one wave of 4-CTA clusters at two CTAs per SM), or the GATRES_RESIDENT_MAX_B
- * environment variable; 0 disables.  Negative = query only.  Returns
+ * environment variable; 0 disables.  The backward stack additionally needs 8 CTAs per snapshot to be co-resident
+ * (B <= SM count / 4 = 37): between 38 and 74 snapshots the forward stack is resident and the backward runs layer by layer.  Negative = query only.  Returns
  * the previous value.
  */
 int64_t gatres_set_resident_max_batch(int64_t max_batch);
