@@ -246,3 +246,15 @@ def test_evaluation_epoch_matches_oracle(required, use_same_mask):
     loss_d, m_d = E.test_one_epoch(model, snaps.to(dev), ei, bs, 0.95, required_idx=required, use_same_mask=use_same_mask,
                                    gpu_warmup_times=0, mask_source="device", seed=5, **kw)
     assert loss_d == pytest.approx(loss_ref, rel=0.1) and m_d[f"test_rmse{post}"] == pytest.approx(m_ref["rmse"], rel=0.1)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_descale_affine_equals_reference(case):
+    """every norm of utils/auxil.py:42-64 is v * scale + shift with the product's (scale, shift)"""
+    from gnn_pressure_estimation_b200.metrics import descale_affine
+    kw = _norm_kwargs(case)
+    scale, shift = descale_affine(kw["norm_type"], mean=kw["mean"], std=kw["std"], min=kw["min"], max=kw["max"])
+    p = torch.from_numpy(GOLD[f"{case}/pred"])
+    assert np.array_equal((p * scale + shift).numpy(), GOLD[f"{case}/pred_descaled"])
+    with pytest.raises(ValueError):
+        descale_affine("znorm")

@@ -23,6 +23,18 @@ def test_select_model_contract():
         CM.select_model(argparse.Namespace(model="gin"))
 
 
+def test_select_model_reaches_the_gat_baseline():
+    """ConfigModels.py:96-103: `gat` = 10 GATConv layers, 1 -> 2x32 ... -> 1, PyG-compatible parameter names"""
+    args, model = CM.select_model(argparse.Namespace(model="gat"))
+    assert isinstance(model, G.GAT) and model.num_blocks == 10 and model.name == "GAT_10b_32c_2h_10b_32c"
+    assert (args.criterion, args.norm_type, args.use_data_edge_attrs) == ("mse", "znorm", None)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert shapes["blocks.0.lin_src.weight"] == (64, 1) and shapes["blocks.5.lin_src.weight"] == (64, 64)
+    assert shapes["blocks.9.lin_src.weight"] == (1, 64) and shapes["blocks.9.att_src"] == (1, 1, 1) and shapes["blocks.9.bias"] == (1,)
+    ref = O.make_gat_oracle(10, 32)
+    assert list(model.state_dict()) == list(ref.state_dict())
+
+
 def test_reference_import_paths():
     from gnn_pressure_estimation.GraphModels import GATResMeanConv, GResBlockMeanConv  # noqa: F401
     from gnn_pressure_estimation.ConfigModels import select_model  # noqa: F401

@@ -202,3 +202,21 @@ def test_snapshot_set_mirrors_wdn_dataset(tmp_path):
     assert torch.equal(torch.cat(got), ds.snapshots.reshape(-1))
     with pytest.raises(SS.StoreError):
         SS.SnapshotSet.load(str(inp), root, "head", "train", device="cpu")
+
+
+def test_missing_chunks_fill_value_and_fortran_order(tmp_path):
+    """a chunk that was never written reads as fill_value; order 'F' chunks are transposed back"""
+    root = tmp_path / "s"
+    arr = np.arange(6 * 4, dtype=np.float32).reshape(6, 4)
+    os.makedirs(root / "a")
+    (root / ".zgroup").write_text(json.dumps({"zarr_format": 2}))
+    meta = {"zarr_format": 2, "shape": [6, 4], "chunks": [3, 4], "dtype": "<f4", "order": "F", "compressor": None,
+            "filters": None, "fill_value": "NaN"}
+    (root / "a" / ".zarray").write_text(json.dumps(meta))
+    (root / "a" / "0.0").write_bytes(np.asfortranarray(arr[:3]).tobytes(order="F"))       # chunk 1.0 is missing
+    got = SS.ZarrV2Store(str(root)).read_array("a")
+    assert np.array_equal(got[:3], arr[:3]) and np.isnan(got[3:]).all()
+    meta["zarr_format"] = 3
+    (root / "a" / ".zarray").write_text(json.dumps(meta))
+    with pytest.raises(SS.StoreError, match="v2"):
+        SS.ZarrV2Store(str(root)).read_array("a")
