@@ -408,9 +408,19 @@ wgrad_mma_kernel(const float* __restrict__ dh, const float* __restrict__ x, floa
   }
 }
 
+static unsigned wgrad_mma_ctas_per_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GATRES_WGRAD_CTAS");
+    v = e ? atoi(e) : 6;
+    if (v < 1 || v > 8) v = 6;
+  }
+  return (unsigned)v;
+}
+
 template <int NO, int KI>
 static int launch_wgrad_mma(const float* dh, const float* x, float* grads, long long off_W, unsigned M, cudaStream_t st) {
-  constexpr int BM = 64;
+  constexpr int BM = 32;
   constexpr size_t smem = (size_t)(2 * BM * (NO + 4) + 2 * BM * (KI + 4)) * sizeof(float);
   auto kern = wgrad_mma_kernel<NO, KI, BM>;
   static bool configured = false;
@@ -420,7 +430,7 @@ static int launch_wgrad_mma(const float* dh, const float* x, float* grads, long 
     configured = true;
   }
   const unsigned ntiles = (M + BM - 1) / BM;
-  unsigned grid = (unsigned)sm_count() * 3u;
+  unsigned grid = (unsigned)sm_count() * wgrad_mma_ctas_per_sm();
   if (grid > ntiles) grid = ntiles;
   launch_kernel(kern, dim3(grid), dim3(256), smem, st, dh, x, grads, off_W, M);
   return check_launch("wgrad_mma");
