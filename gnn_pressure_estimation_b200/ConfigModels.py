@@ -66,7 +66,10 @@ def select_model(args: argparse.Namespace, test_model_variant_name: Optional[str
     if which in _NOT_ON_HOT_PATH:
         raise NotImplementedError(f"model {which!r} is a baseline of the reference and is not part of the "
                                   "B200 GATRes hot path; use gatres_small / gatres_large")
-    table = {"gatres_small": config_gatres_small, "gatres_large": config_gatres_large, "gat": config_gat}
+    # the reference's select_model (ConfigModels.py:133-178) cannot reach config_gatres_small_tough (:123-130);
+    # it is selectable here because the training CLI offers it
+    table = {"gatres_small": config_gatres_small, "gatres_large": config_gatres_large, "gat": config_gat,
+             "gatres_small_tough": config_gatres_small_tough}
     if which not in table:
         raise NotImplementedError(f"Unknown model! Got {which}!")
     args, model = table[which](args, test_model_variant_name)

@@ -23,7 +23,8 @@ from torch import Tensor, nn
 from . import ops as _gops
 from .graph import Topology, TopologyCache
 
-__all__ = ["GATResMeanConv", "GResBlockMeanConv", "GATConv", "SimpleConv", "Linear"]
+__all__ = ["GATResMeanConv", "GResBlockMeanConv", "GResBlockConv", "GAT", "GATConvNet", "GATConv", "SimpleConv",
+           "Linear"]
 
 _SHARED_TOPOLOGIES = TopologyCache()
 
@@ -65,9 +66,15 @@ class Linear(nn.Module):
                 self.bias.uniform_(-b, b)
 
     def forward(self, x: Tensor) -> Tensor:
-        # only lin0 / lin1 of GATRes go through here when blocks are composed by hand;
-        # they are rank-1 / GEMV shaped and torch's own CUDA ops are fine for that use.
+        # lin0 / lin1 of GATRes (GraphModels.py:477,484) run on the library's encoder / decoder kernels when a model
+        # is composed module by module; other widths (the skip connections of the sibling GATConvNet) are plain
+        # dense layers off the GATRes path and use torch's own CUDA GEMM.
         _require_cuda(x, "Linear")
+        if self.bias is not None and x.dim() == 2 and x.dtype == torch.float32:
+            if self.in_channels == 1 and self.out_channels in (32, 64, 128):
+                return _gops.encoder(x, self.weight, self.bias)
+            if self.out_channels == 1 and self.in_channels in (32, 64, 128):
+                return _gops.decoder(x, self.weight, self.bias)
         return F.linear(x, self.weight, self.bias)
 
 
@@ -143,6 +150,57 @@ class GResBlockMeanConv(nn.Module):
         x = self.conv1(x, edge_index, edge_attr, _relu=True)
         x = self.conv2(x, edge_index, edge_attr)
         return self.mean_conv.forward_residual_relu(x, edge_index, x_0)
+
+
+class GResBlockConv(nn.Module):
+    """GraphModels.py:548-561 of the reference: the residual block without the mean convolution
+    (conv1 -> ReLU -> conv2 -> + x_0 -> ReLU); same GATConv kernels as `GResBlockMeanConv`."""
+
+    def __init__(self, in_dim: int, out_dim: int, hc: int):
+        super().__init__()
+        self.conv1 = GATConv(in_dim, hc, 2, concat=True)
+        self.conv2 = GATConv(hc * 2, out_dim, 1, concat=False)
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None) -> Tensor:
+        x_0 = x
+        x = self.conv1(x, edge_index, edge_attr, _relu=True)
+        x = self.conv2(x, edge_index, edge_attr)
+        return F.relu(x + x_0)
+
+
+class GATConvNet(nn.Module):
+    """GraphModels.py:15-46 of the reference: `num_layers` GATConv layers (heads x hidden_dim, concat; the last one a
+    single head of out_dim, mean) each with a Linear skip connection, ReLU + dropout(0.5) between layers, sigmoid at
+    the end.  The GATConv layers run on the fused kernels (widths zero-padded to built shapes, see `ops.gat_conv`);
+    skips, dropout and the sigmoid are elementwise / dense torch ops — this model is a baseline next to the hot path.
+    `dropout_masks` (one [M, heads*hidden_dim] 0/1 tensor per hidden layer) replaces the random draw for parity tests."""
+
+    def __init__(self, net_params: dict):
+        super().__init__()
+        self.net_params = net_params
+        heads, hid = net_params["heads"], net_params["hidden_dim"]
+        self.convs = nn.ModuleList()
+        in_channels = net_params["input_dim"]
+        for _ in range(net_params["num_layers"] - 1):
+            self.convs.append(GATConv(in_channels, hid, heads=heads, concat=True))
+            in_channels = heads * hid
+        self.convs.append(GATConv(heads * hid, net_params["out_dim"], heads=1, concat=False))
+        self.skips = nn.ModuleList()
+        self.skips.append(Linear(net_params["input_dim"], heads * hid))
+        for _ in range(net_params["num_layers"] - 2):
+            self.skips.append(Linear(heads * hid, heads * hid))
+        self.skips.append(Linear(heads * hid, net_params["out_dim"]))
+
+    def forward(self, x: Tensor, edge_index: Tensor, batch: Optional[Tensor] = None,
+                dropout_masks: Optional[List[Tensor]] = None) -> Tensor:
+        for i in range(self.net_params["num_layers"] - 1):
+            x = F.relu(self.convs[i](x, edge_index) + self.skips[i](x))
+            if dropout_masks is not None:
+                x = x * dropout_masks[i] * 2.0                       # dropout(p=0.5) with a given keep mask
+            else:
+                x = F.dropout(x, p=0.5, training=self.training)
+        x = self.convs[-1](x, edge_index) + self.skips[-1](x)
+        return torch.sigmoid(x)
 
 
 class GAT(nn.Module):
@@ -224,6 +282,13 @@ class GATResMeanConv(nn.Module):
             self._flat = flat
         return flat
 
+    def _forward_composed(self, x: Tensor, edge_index: Tensor) -> Tensor:
+        """GraphModels.py:486-494 literally: lin0 -> blocks -> lin1, every module on its own kernels."""
+        x = self.lin0(x)
+        for blk in self.blocks:
+            x = blk(x, edge_index, None)
+        return self.lin1(x)
+
     def set_topology(self, edge_index: Tensor, num_nodes: int) -> Topology:
         """Optional: register the template graph up front (otherwise it is inferred
         from the first collated batch)."""
@@ -235,6 +300,10 @@ class GATResMeanConv(nn.Module):
         if x.dim() != 2 or x.size(1) != 1:
             raise ValueError(f"GATResMeanConv expects x of shape [num_nodes, 1], got {tuple(x.shape)}")
         topo, B = self._topologies.resolve(x.size(0), edge_index, batch)
+        if not topo.shares_one_csr:
+            # a template with self loops: GATConv rewrites them, SimpleConv(mean) keeps them, so the
+            # one-CSR fused stack does not apply — run the same kernels module by module (two CSR views)
+            return self._forward_composed(x, edge_index)
         flat = self.flat_parameters()
         out = _gops.gatres_model(x.reshape(-1), flat, self.ordered_parameters(), topo, B, self.num_blocks, self.nc,
                                  poison=self._topologies.mismatch, deterministic=self.deterministic)

@@ -44,6 +44,7 @@ _PROTOTYPES = {
     "gatres_set_tensor_core": (C.c_int, [C.c_int]),
     "gatres_csr_scratch_bytes": (_sz, [_i64, _i32]),
     "gatres_csr_build": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gatres_csr_build_mean": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gatres_check_replicated": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p]),
     "gatres_linear_att_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "gatres_gat_agg_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),

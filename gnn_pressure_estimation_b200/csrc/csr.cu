@@ -21,12 +21,16 @@ __global__ void csr_zero_kernel(int* a, size_t na, int* b, size_t nb, int* c, si
   if (i < 4) info[i] = 0;
 }
 
+// keep_loops = 0: GATConv's view (existing self loops dropped); 1: SimpleConv's view (they stay ordinary edges)
 __global__ void csr_count_kernel(const long long* __restrict__ ei, long long E, int N, int* cnt_in, int* cnt_out,
-                                 int* info) {
+                                 int* info, int keep_loops) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
     const long long s = ei[e], d = ei[E + e];
     if (s < 0 || s >= N || d < 0 || d >= N) { atomicAdd(info + 2, 1); continue; }
-    if (s == d) { atomicAdd(info + 0, 1); continue; }
+    if (s == d) {
+      atomicAdd(info + 0, 1);
+      if (!keep_loops) continue;
+    }
     atomicAdd(cnt_in + d, 1);
     atomicAdd(cnt_out + s, 1);
   }
@@ -65,10 +69,10 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int* a, int* b, int N, i
 
 __global__ void csr_fill_kernel(const long long* __restrict__ ei, long long E, int N,
                                 const int* __restrict__ rowptr, const int* __restrict__ rowptr_t, int* cur_in,
-                                int* cur_out, int* col, int* col_t) {
+                                int* cur_out, int* col, int* col_t, int keep_loops) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
     const long long s = ei[e], d = ei[E + e];
-    if (s < 0 || s >= N || d < 0 || d >= N || s == d) continue;
+    if (s < 0 || s >= N || d < 0 || d >= N || (s == d && !keep_loops)) continue;
     col[rowptr[d] + atomicAdd(cur_in + d, 1)] = (int)e;
     col_t[rowptr_t[s] + atomicAdd(cur_out + s, 1)] = (int)e;
   }
@@ -113,9 +117,9 @@ extern "C" size_t gatres_csr_scratch_bytes(int64_t E, int32_t N) {
   return (size_t)(2 * (int64_t)N + 8) * sizeof(int32_t);
 }
 
-extern "C" int gatres_csr_build(const int64_t* edge_index, int64_t E, int32_t N, int32_t* rowptr, int32_t* col,
-                                int32_t* rowptr_t, int32_t* col_t, int32_t* info, void* scratch,
-                                size_t scratch_bytes, void* stream) {
+static int csr_build_impl(const int64_t* edge_index, int64_t E, int32_t N, int32_t* rowptr, int32_t* col,
+                          int32_t* rowptr_t, int32_t* col_t, int32_t* info, void* scratch, size_t scratch_bytes,
+                          void* stream, int keep_loops) {
   GATRES_REQUIRE(N > 0 && E >= 0 && E + N < (1ll << 31), "csr_build: bad N=%d E=%lld", N, (long long)E);
   GATRES_REQUIRE(scratch_bytes >= gatres_csr_scratch_bytes(E, N), "csr_build: scratch too small");
   cudaStream_t st = as_stream(stream);
@@ -125,11 +129,23 @@ extern "C" int gatres_csr_build(const int64_t* edge_index, int64_t E, int32_t N,
   const unsigned ge = (unsigned)((E + 255) / 256 > 0 ? ((E + 255) / 256 < 4096 ? (E + 255) / 256 : 4096) : 1);
   const unsigned gn = (unsigned)(((long long)N + 255) / 256 < 4096 ? ((long long)N + 255) / 256 : 4096);
   csr_zero_kernel<<<gn, 256, 0, st>>>(rowptr, (size_t)N + 1, rowptr_t, (size_t)N + 1, cur_in, (size_t)2 * N, info);
-  csr_count_kernel<<<ge, 256, 0, st>>>(ei, E, N, rowptr, rowptr_t, info);
+  csr_count_kernel<<<ge, 256, 0, st>>>(ei, E, N, rowptr, rowptr_t, info, keep_loops);
   csr_scan_kernel<<<1, 1024, 0, st>>>(rowptr, rowptr_t, N, info);
-  csr_fill_kernel<<<ge, 256, 0, st>>>(ei, E, N, rowptr, rowptr_t, cur_in, cur_out, col, col_t);
+  csr_fill_kernel<<<ge, 256, 0, st>>>(ei, E, N, rowptr, rowptr_t, cur_in, cur_out, col, col_t, keep_loops);
   csr_finish_kernel<<<gn, 256, 0, st>>>(ei, E, N, rowptr, rowptr_t, col, col_t);
   return check_launch("csr_build");
+}
+
+extern "C" int gatres_csr_build(const int64_t* edge_index, int64_t E, int32_t N, int32_t* rowptr, int32_t* col,
+                                int32_t* rowptr_t, int32_t* col_t, int32_t* info, void* scratch,
+                                size_t scratch_bytes, void* stream) {
+  return csr_build_impl(edge_index, E, N, rowptr, col, rowptr_t, col_t, info, scratch, scratch_bytes, stream, 0);
+}
+
+extern "C" int gatres_csr_build_mean(const int64_t* edge_index, int64_t E, int32_t N, int32_t* rowptr, int32_t* col,
+                                     int32_t* rowptr_t, int32_t* col_t, int32_t* info, void* scratch,
+                                     size_t scratch_bytes, void* stream) {
+  return csr_build_impl(edge_index, E, N, rowptr, col, rowptr_t, col_t, info, scratch, scratch_bytes, stream, 1);
 }
 
 extern "C" int gatres_check_replicated(const int64_t* edge_index_batch, const int64_t* edge_index_tmpl, int64_t B,

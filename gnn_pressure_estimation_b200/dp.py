@@ -31,6 +31,15 @@ def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
+def shard_bounds_uneven(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous range [lo, hi) of `rank` when `total` need not divide by the world size (evaluation: the epoch sums
+    are weighted by graphs per batch and divided by the dataset length after the all-reduce, so unequal — even empty
+    — shards give the right result).  The first `total % world` ranks hold one snapshot more."""
+    per, rem = divmod(int(total), int(world))
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
 def bucket_ranges(num_blocks: int, buckets: int) -> List[Tuple[int, int]]:
     """Split the backward walk over blocks num_blocks-1 .. 0 into `buckets` contiguous descending ranges
     [(k_hi, k_lo), ...] of near-equal length (earlier = later blocks; the first range also carries the decoder,

@@ -6,7 +6,7 @@ S PyG `Data` objects behind a DataLoader: per batch the reference clones x, draw
 masked inputs, runs the timed forward, and computes MSE + seven metrics on the descaled masked nodes with ~50
 micro-kernels and 8 host syncs.  Here a batch is: (device or NumPy-compatible) mask -> `gatres_apply_mask` ->
 the model's forward kernels -> `gatres_masked_mse` + `gatres_masked_metrics`; the per-batch scalars stay on the
-device until the epoch ends.  With a process group the snapshot set is sharded across ranks (equal contiguous
+device until the epoch ends.  With a process group the snapshot set is sharded across ranks (contiguous
 shards, no communication during the forward passes) and the epoch sums are all-reduced once at the end.
 
 Aggregation is the reference's: every per-batch value is weighted by the batch's number of graphs and divided by
@@ -95,7 +95,7 @@ def test_one_epoch(model, snapshots: Tensor, edge_index: Tensor, batch_size: int
     dev = snapshots.device
     S_total, N = snapshots.shape
     rank, world = (dist.get_rank(process_group), dist.get_world_size(process_group)) if process_group is not None else (0, 1)
-    lo, hi = _dp.shard_bounds(S_total, rank, world)
+    lo, hi = _dp.shard_bounds_uneven(S_total, rank, world)     # a validation split need not divide by the world size
     shard = snapshots[lo:hi].contiguous()
     S = hi - lo
     count = _metrics.mask_count(N, mask_rate)
@@ -138,7 +138,10 @@ def test_one_epoch(model, snapshots: Tensor, edge_index: Tensor, batch_size: int
         dist.all_reduce(totals, group=process_group)
     t = (totals / S_total).cpu().tolist()
     result = {f"{prefix}_{k}": t[1 + i] for i, k in enumerate(_metrics.METRIC_NAMES)}
-    time_ms, thr, sps = timer.compute_time(S), timer.compute_throughput(S), timer.snapshots_per_second()
+    if S > 0:
+        time_ms, thr, sps = timer.compute_time(S), timer.compute_throughput(S), timer.snapshots_per_second()
+    else:                                                             # empty shard (fewer snapshots than ranks)
+        time_ms, thr, sps = 0.0, float("inf"), float("inf")
     if world > 1:
         agg = torch.tensor([time_ms, -thr, -sps], dtype=torch.float64, device=dev)
         dist.all_reduce(agg, op=dist.ReduceOp.MAX, group=process_group)                      # slowest rank

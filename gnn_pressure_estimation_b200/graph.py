@@ -6,12 +6,28 @@ SURVEY.md §A.5).  The kernels want the template once (one CSR in int32) plus B,
 so this module recovers (template, N, B) from what the caller passes to
 ``forward(x, edge_index, batch, edge_attr)`` and caches the device CSR per
 template.  Indexing work only; no feature arithmetic happens here.
+
+Validation policy (`TopologyCache.resolve`): a cached (template, B) is only ever
+used for a batch whose CONTENT was checked against it.
+  * the same tensor object at the same version as a batch validated before
+    (evaluation loops, benchmark loops, the three layers of one block) costs
+    nothing — no kernel, no sync;
+  * any other tensor gets one device-side replication check against each cached
+    candidate of its shape and one read of the result (one sync per forward; the
+    reference pays one hidden sync per GATConv call).  A batch of the
+    same shape but another composition (the reference's multi-network
+    ``shuffle=True`` case, utils/DataLoader.py:120-129) therefore misses, is
+    re-inferred (general mode B = 1 if it is not a replication at all) and gets
+    its own cache entry — nothing is poisoned, nothing goes stale;
+  * inside a CUDA-graph capture no sync is possible: the check is enqueued and
+    its flag (zeroed per call) turns the model output into NaN on mismatch.
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 from math import gcd
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -41,6 +57,18 @@ class Topology:
     rowptr_t: Tensor
     col_t: Tensor
     dropped_self_loops: int
+    # SimpleConv's view (gatres_csr_build_mean) when the template has self loops: GATConv drops them and adds its
+    # own, SimpleConv(mean) keeps them as ordinary in-edges.  None = both views coincide.
+    mean_csr: Optional[Tuple[Tensor, Tensor, Tensor, Tensor]] = None
+
+    @property
+    def shares_one_csr(self) -> bool:
+        """True when the fused kernels (one CSR for GATConv and the mean) apply: no self loops in the template."""
+        return self.mean_csr is None
+
+    def mean_view(self) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        """(rowptr, col, rowptr_t, col_t) the SimpleConv(mean) kernels walk (they skip each row's trailing entry)."""
+        return self.mean_csr if self.mean_csr is not None else (self.rowptr, self.col, self.rowptr_t, self.col_t)
 
     @staticmethod
     def build(edge_index: Tensor, num_nodes: int) -> "Topology":
@@ -50,34 +78,39 @@ class Topology:
             raise _lib.GatresError("Topology.build needs a CUDA edge_index (no CPU path exists)")
         ops = _get_ops()
         ei = edge_index.to(torch.int64).contiguous()
-        rowptr, col, rowptr_t, col_t, info = ops.csr_build(ei, int(num_nodes))
+        rowptr, col, rowptr_t, col_t, info = ops.csr_build(ei, int(num_nodes), False)
         dropped, e1, bad, _ = (int(v) for v in info.tolist())
         if bad:
             raise _lib.GatresError(f"edge_index names {bad} node ids outside [0, {num_nodes})")
+        mean = None
         if dropped:
-            # GATConv drops them, SimpleConv(mean) would keep them: the two operators would need
-            # different structures.  WDN templates come from simple graphs and never have any.
-            raise NotImplementedError("template graphs with self-loops are not supported by the fused mean-conv path")
-        return Topology(int(num_nodes), ei.size(1), e1, ei, rowptr, col[:e1], rowptr_t, col_t[:e1], dropped)
+            rp, c, rpt, ct, info_m = ops.csr_build(ei, int(num_nodes), True)
+            e1m = int(info_m[1])
+            mean = (rp, c[:e1m], rpt, ct[:e1m])
+        return Topology(int(num_nodes), ei.size(1), e1, ei, rowptr, col[:e1], rowptr_t, col_t[:e1], dropped, mean)
 
 
 class TopologyCache:
-    """(rows, edge columns) of a collated batch -> (Topology, B).
-
-    First sight of a shape costs one sync (template inference + full check);
-    afterwards each call only enqueues a device-side replication check whose
-    result poisons the model output with NaN on mismatch — no per-step sync
-    (the reference pays one hidden sync per GATConv call).
-    """
+    """(rows, edge columns) of a collated batch -> (Topology, B), validated by content (module docstring)."""
 
     def __init__(self) -> None:
-        self._by_shape: Dict[Tuple[int, int, int], Tuple[Topology, int]] = {}
-        self._templates: Dict[Tuple[int, int], Topology] = {}
+        self._by_shape: Dict[Tuple[int, int, int], List[Tuple[Topology, int]]] = {}
+        self._templates: Dict[Tuple[int, int], List[Topology]] = {}
+        self._validated: Dict[int, Tuple[weakref.ref, int, Tuple[int, int, int], Tuple[Topology, int]]] = {}
+        self._flag: Optional[Tensor] = None
+        # device int32 flag handed to the decoder as `poison`: nonzero only for a batch that failed its (unsynced)
+        # check under CUDA-graph capture; zeroed again by the next call
         self.mismatch: Optional[Tensor] = None
+        self.syncs = 0                                   # host reads of a check result (tests / diagnostics)
 
+    # ------------------------------------------------------------------ templates
     def set_template(self, edge_index: Tensor, num_nodes: int) -> Topology:
-        topo = Topology.build(edge_index, num_nodes)
-        self._templates[(topo.N, topo.E)] = topo
+        ei = edge_index.to(torch.int64).contiguous()
+        for topo in self._templates.get((int(num_nodes), ei.size(1)), []):
+            if topo.edge_index.device == ei.device and torch.equal(topo.edge_index, ei):
+                return topo
+        topo = Topology.build(ei, num_nodes)
+        self._templates.setdefault((topo.N, topo.E), []).append(topo)
         return topo
 
     def _infer(self, M: int, edge_index: Tensor, batch: Optional[Tensor]) -> Tuple[int, int]:
@@ -102,22 +135,71 @@ class TopologyCache:
                 return N, B
         return M, 1
 
+    # -------------------------------------------------------------------- lookup
+    def _flags(self, dev) -> None:
+        if self._flag is None or self._flag.device != dev:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.mismatch = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def _matches(self, edge_index: Tensor, topo: Topology, B: int) -> bool:
+        """device-side replication check of `edge_index` against (topo, B) + one read of the result"""
+        self._flag.zero_()
+        _get_ops().check_replicated(edge_index, topo.edge_index, B, topo.N, self._flag)
+        self.syncs += 1
+        return int(self._flag.item()) == 0
+
+    @staticmethod
+    def _version(t: Tensor) -> Optional[int]:
+        try:
+            return t._version
+        except RuntimeError:                                         # inference tensors do not track versions
+            return None
+
+    def _remember(self, edge_index: Tensor, key, hit) -> None:
+        ident = id(edge_index)
+        if self._version(edge_index) is None:
+            return
+
+        def _drop(_ref, ident=ident, table=self._validated):
+            table.pop(ident, None)
+
+        self._validated[ident] = (weakref.ref(edge_index, _drop), edge_index._version, key, hit)
+
     def resolve(self, x_rows: int, edge_index: Tensor, batch: Optional[Tensor] = None) -> Tuple[Topology, int]:
-        key = (x_rows, edge_index.size(1), edge_index.device.index or 0)
-        hit = self._by_shape.get(key)
-        ops = _get_ops()
-        if self.mismatch is None or self.mismatch.device != edge_index.device:
-            self.mismatch = torch.zeros(1, dtype=torch.int32, device=edge_index.device)
-        if hit is None:
-            N, B = self._infer(x_rows, edge_index, batch)
-            E = edge_index.size(1) // B
-            topo = self._templates.get((N, E))
-            if topo is None or not torch.equal(topo.edge_index, edge_index[:, :E]):
-                topo = self.set_template(edge_index[:, :E].contiguous(), N)
-            hit = (topo, B)
-            self._by_shape[key] = hit
-        topo, B = hit
-        if edge_index.dtype != torch.int64:
-            edge_index = edge_index.to(torch.int64)
-        ops.check_replicated(edge_index, topo.edge_index, B, topo.N, self.mismatch)
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise _lib.GatresError("edge_index must be [2, E]")
+        dev = edge_index.device
+        key = (x_rows, edge_index.size(1), dev.index or 0)
+        self._flags(dev)
+        if self._poisoned:                                           # a captured check may have tripped earlier
+            self.mismatch.zero_()
+            self._poisoned = False
+        seen = self._validated.get(id(edge_index))
+        if seen is not None and seen[0]() is edge_index and seen[1] == self._version(edge_index) and seen[2] == key:
+            return seen[3]
+        ei64 = edge_index if edge_index.dtype == torch.int64 else edge_index.to(torch.int64)
+        ei64 = ei64.contiguous()
+        cands = self._by_shape.setdefault(key, [])
+        if torch.cuda.is_current_stream_capturing():
+            # no host read is possible here: enqueue the check against the newest candidate, NaN on mismatch
+            if not cands:
+                raise _lib.GatresError("first sight of a batch shape inside a CUDA-graph capture: run one eager forward "
+                                       "(or model.set_topology + a warm-up) before capturing")
+            topo, B = cands[-1]
+            self.mismatch.zero_()                                    # captured too: every replay starts clean
+            _get_ops().check_replicated(ei64, topo.edge_index, B, topo.N, self.mismatch)
+            self._poisoned = True
+            return cands[-1]
+        for hit in reversed(cands):                                  # newest first: consecutive batches usually agree
+            if self._matches(ei64, *hit):
+                self._remember(edge_index, key, hit)
+                return hit
+        N, B = self._infer(x_rows, ei64, batch)
+        E = ei64.size(1) // B
+        topo = self.set_template(ei64[:, :E], N)
+        hit = (topo, B)
+        cands.append(hit)
+        self._remember(edge_index, key, hit)
         return hit
+
+    _poisoned = False

@@ -58,7 +58,8 @@ def grad_slots(rows: int) -> int:
 # ----------------------------------------------------------------------------
 # graph
 # ----------------------------------------------------------------------------
-def _csr_build(edge_index: Tensor, N: int) -> List[Tensor]:
+def _csr_build(edge_index: Tensor, N: int, keep_self_loops: bool = False) -> List[Tensor]:
+    """keep_self_loops=False: GATConv's view (gatres_csr_build); True: SimpleConv's view (gatres_csr_build_mean)"""
     ei = edge_index.contiguous()
     if ei.dtype != torch.int64 or ei.dim() != 2 or ei.size(0) != 2:
         raise _lib.GatresError("edge_index must be int64 [2, E]")
@@ -71,12 +72,12 @@ def _csr_build(edge_index: Tensor, N: int) -> List[Tensor]:
     info = torch.empty(4, dtype=torch.int32, device=dev)
     nbytes = int(_lib.load().gatres_csr_scratch_bytes(E, N))
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    call("gatres_csr_build", ptr(ei), E, N, ptr(rowptr), ptr(col), ptr(rowptr_t), ptr(col_t), ptr(info),
-         ptr(scratch), nbytes, stream())
+    call("gatres_csr_build_mean" if keep_self_loops else "gatres_csr_build", ptr(ei), E, N, ptr(rowptr), ptr(col),
+         ptr(rowptr_t), ptr(col_t), ptr(info), ptr(scratch), nbytes, stream())
     return [rowptr, col, rowptr_t, col_t, info]
 
 
-_def("csr_build(Tensor edge_index, int N) -> Tensor[]", _csr_build)
+_def("csr_build(Tensor edge_index, int N, bool keep_self_loops=False) -> Tensor[]", _csr_build)
 
 
 def _check_replicated(ei_batch: Tensor, ei_tmpl: Tensor, B: int, N: int, mismatch: Tensor) -> None:
@@ -351,12 +352,70 @@ def gat_conv(x: Tensor, W: Tensor, att_src: Tensor, att_dst: Tensor, bias: Tenso
     return out.view(out.size(0), -1, Cp)[:, :, :C_].reshape(out.size(0), -1)
 
 
+class _EncoderFn(torch.autograd.Function):
+    """PyG Linear(1, nc) — lin0 of GATRes (GraphModels.py:477,487): out[m, c] = x[m] w[c] + b[c]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _f32(x, "encoder").reshape(-1)
+        nc = w.numel()
+        out = torch.empty(x.numel(), nc, dtype=torch.float32, device=x.device)
+        call("gatres_encoder_fwd", ptr(x), ptr(_f32(w, "encoder").reshape(-1)), ptr(_f32(b, "encoder")), ptr(out), x.numel(), nc, stream())
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        nc = w.numel()
+        g = _f32(g, "encoder_bwd")
+        grads = torch.zeros(2 * nc, dtype=torch.float32, device=g.device)          # [dw | db], atomic accumulation
+        call("gatres_encoder_bwd", ptr(g), ptr(x), ptr(grads), 2 * nc, 0, 0, nc, x.numel(), nc, stream())
+        dx = (g @ w.reshape(nc, 1)) if ctx.needs_input_grad[0] else None           # model inputs never need it
+        return dx, grads[:nc].view_as(w), grads[nc:]
+
+
+class _DecoderFn(torch.autograd.Function):
+    """PyG Linear(nc, 1) — lin1 of GATRes (GraphModels.py:484,492): out[m] = <x[m, :], w> + b."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _f32(x, "decoder")
+        M, nc = x.shape
+        out = torch.empty(M, dtype=torch.float32, device=x.device)
+        call("gatres_decoder_fwd", ptr(x), ptr(_f32(w, "decoder").reshape(-1)), ptr(_f32(b, "decoder")), ptr(out), None, M, nc, stream())
+        ctx.save_for_backward(x, w)
+        return out.view(M, 1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        M, nc = x.shape
+        g = _f32(g, "decoder_bwd").reshape(-1)
+        P = a4(nc + 1)
+        grads = torch.zeros(P, dtype=torch.float32, device=g.device)               # [dw | db]
+        dx = torch.empty_like(x)
+        call("gatres_decoder_bwd", ptr(g), ptr(x), ptr(w.reshape(-1).contiguous()), ptr(dx), ptr(grads), P, 0, 0, nc, M, nc, 0, stream())
+        return dx, grads[:nc].view_as(w), grads[nc:nc + 1]
+
+
+def encoder(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    return _EncoderFn.apply(x, w, b)
+
+
+def decoder(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    return _DecoderFn.apply(x, w, b)
+
+
 class _MeanResFn(torch.autograd.Function):
     """relu(SimpleConv(mean)(z) + x0), GraphModels.py:466-467."""
 
     @staticmethod
     def forward(ctx, z, x0, topo, B):
-        out = _ops.mean_res_fwd(topo.rowptr, topo.col, z, x0, B, topo.N)
+        rp, col, _, _ = topo.mean_view()
+        out = _ops.mean_res_fwd(rp, col, z, x0, B, topo.N)
         ctx.save_for_backward(out)
         ctx.topo, ctx.B = topo, B
         return out
@@ -366,7 +425,8 @@ class _MeanResFn(torch.autograd.Function):
     def backward(ctx, g):
         (out,) = ctx.saved_tensors
         t = ctx.topo
-        dz, dres = _ops.mean_res_bwd(t.rowptr, t.rowptr_t, t.col_t, g.contiguous(), out, ctx.B, t.N)
+        rp, _, rpt, colt = t.mean_view()
+        dz, dres = _ops.mean_res_bwd(rp, rpt, colt, g.contiguous(), out, ctx.B, t.N)
         return dz, dres, None, None
 
 

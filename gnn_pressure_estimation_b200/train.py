@@ -56,14 +56,21 @@ class EarlyStopping:
 
 
 def adam_state_dict(step: TrainStep) -> dict:
-    """the flat Adam buffers in torch.optim.Adam's state_dict layout (what train.py:436 stores)"""
-    state, off = {}, 0
+    """the flat Adam buffers in torch.optim.Adam's state_dict layout (what train.py:436 stores).
+
+    torch.optim.Adam(model.parameters()) numbers its state by position in ``model.parameters()`` (a module's own
+    parameters before its children's: att_src, att_dst, bias, lin_src.weight per GATConv), which is NOT the order of
+    the flat buffer (``ordered_parameters()``: weight first) — so every parameter is looked up by its offset."""
+    offsets, off = {}, 0
+    for p in step.model.ordered_parameters():
+        offsets[id(p)] = off
+        off += p.numel()
+    state = {}
     t = float(step.step_count.item())
-    for i, p in enumerate(step.model.ordered_parameters()):
-        n = p.numel()
-        state[i] = {"step": torch.tensor(t), "exp_avg": step.exp_avg[off:off + n].view_as(p).clone(),
-                    "exp_avg_sq": step.exp_avg_sq[off:off + n].view_as(p).clone()}
-        off += n
+    for i, p in enumerate(step.model.parameters()):
+        o, n = offsets[id(p)], p.numel()
+        state[i] = {"step": torch.tensor(t), "exp_avg": step.exp_avg[o:o + n].view_as(p).clone(),
+                    "exp_avg_sq": step.exp_avg_sq[o:o + n].view_as(p).clone()}
     group = {"lr": step.lr, "betas": tuple(step.betas), "eps": step.eps, "weight_decay": step.wd, "amsgrad": False,
              "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
              "params": list(range(len(state)))}
@@ -173,6 +180,11 @@ def fit(model, train_set: SnapshotSet, valid_set: SnapshotSet, batch_size: int =
     t0 = time.time()
     for epoch in range(1, epochs + 1):
         model.train()
+        if world > 1:
+            # rank 0 may still be writing checkpoints / printing: the peer-memory Adam kernel spins on every rank's
+            # flag inside a captured graph, so ranks enter an epoch's first step together instead of one of them
+            # waiting on the device for a slow filesystem
+            dist.barrier(process_group)
         tr_loss, tr_metrics = train_one_epoch(steps, shard, batch_size, mask_rate, gen, mask_source, drop_last)
         val_loss, val_metrics = _evaluation.test_one_epoch(
             model, valid_set.snapshots, valid_set.edge_index, batch_size, mask_rate, prefix="val", gpu_warmup_times=0,

@@ -33,6 +33,9 @@ class TrainStep:
                  device_mask_seed: Optional[int] = None,
                  metrics: Optional["_metrics.MaskedMetrics"] = None,
                  share_state_with: Optional["TrainStep"] = None):
+        if not topo.shares_one_csr:
+            raise NotImplementedError("TrainStep runs the fused one-CSR stack; a template with self loops needs the "
+                                      "module-by-module path (call the model eagerly: GATResMeanConv.forward)")
         self.model, self.topo, self.B = model, topo, int(batch)
         self.N, self.nc, self.nb = topo.N, model.nc, model.num_blocks
         self.M = self.B * self.N

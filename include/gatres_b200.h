@@ -85,6 +85,18 @@ int gatres_csr_build(const int64_t* edge_index, int64_t E, int32_t N,
                      int32_t* info, void* scratch, size_t scratch_bytes, void* stream);
 
 /*
+ * SimpleConv's view of the same template (GraphModels.py:466): SimpleConv(aggr="mean") aggregates
+ * over the ORIGINAL edge_index, so a self loop (i,i) of the template is an ordinary in-edge of i there, while
+ * GATConv drops it and adds its own.  Same construction and outputs as gatres_csr_build, except that existing
+ * self loops are kept as ordinary entries (info[0] still counts them); the appended trailing entry per row is
+ * what gatres_mean_res_fwd / _bwd skip, so these arrays are passed to them unchanged.  Only needed when
+ * info[0] > 0 (WDN templates come from simple graphs and have none; then both views coincide).
+ */
+int gatres_csr_build_mean(const int64_t* edge_index, int64_t E, int32_t N,
+                          int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t,
+                          int32_t* info, void* scratch, size_t scratch_bytes, void* stream);
+
+/*
  * Check that a collated edge_index (int64 [2, B*E]) is B shifted copies of the
  * template (PyG Batch collation, train.py:302): column b*E+e == template[:,e] + b*N.
  * *mismatch (device int32) is incremented once per violating column.

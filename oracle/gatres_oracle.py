@@ -280,6 +280,49 @@ class GATOracle(nn.Module):
         return x
 
 
+class OracleGResBlockConv(nn.Module):
+    """GraphModels.py:548-561: conv1 -> ReLU -> conv2 -> + x_0 -> ReLU (no mean convolution)."""
+    def __init__(self, in_dim: int, out_dim: int, hc: int):
+        super().__init__()
+        self.conv1 = OracleGATConv(in_dim, hc, 2, concat=True)
+        self.conv2 = OracleGATConv(hc * 2, out_dim, 1, concat=False)
+
+    def forward(self, x, edge_index, edge_attr=None):
+        x0 = x.clone()
+        x = self.conv1(x, edge_index, edge_attr).relu()
+        x = self.conv2(x, edge_index, edge_attr)
+        return F.relu(x + x0)
+
+
+class GATConvNetOracle(nn.Module):
+    """GraphModels.py:15-46: GATConv layers with Linear skips, ReLU + dropout(0.5) between them, sigmoid at the end.
+    `dropout_masks` (keep masks, one per hidden layer) stands in for the random draw so training mode is comparable."""
+    def __init__(self, net_params: dict):
+        super().__init__()
+        self.net_params = net_params
+        heads, hid = net_params["heads"], net_params["hidden_dim"]
+        self.convs = nn.ModuleList()
+        fin = net_params["input_dim"]
+        for _ in range(net_params["num_layers"] - 1):
+            self.convs.append(OracleGATConv(fin, hid, heads, True))
+            fin = heads * hid
+        self.convs.append(OracleGATConv(heads * hid, net_params["out_dim"], 1, False))
+        self.skips = nn.ModuleList([_Affine(net_params["input_dim"], heads * hid)])
+        for _ in range(net_params["num_layers"] - 2):
+            self.skips.append(_Affine(heads * hid, heads * hid))
+        self.skips.append(_Affine(heads * hid, net_params["out_dim"]))
+
+    def forward(self, x, edge_index, batch=None, dropout_masks=None):
+        for i in range(self.net_params["num_layers"] - 1):
+            x = F.relu(self.convs[i](x, edge_index) + self.skips[i](x))
+            if dropout_masks is not None:
+                x = x * dropout_masks[i] * 2.0
+            else:
+                x = F.dropout(x, p=0.5, training=self.training)
+        x = self.convs[-1](x, edge_index) + self.skips[-1](x)
+        return torch.sigmoid(x)
+
+
 def make_gat_oracle(num_blocks: int = 10, nc: int = 32, seed: int = 0) -> GATOracle:
     g = torch.random.get_rng_state()
     torch.manual_seed(seed)

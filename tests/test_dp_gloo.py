@@ -85,6 +85,16 @@ def test_shard_bounds():
         dp.shard_bounds(10, 0, 4)
 
 
+def test_uneven_shards_cover_the_set_once():
+    """evaluation shards (a validation split need not divide by the world size; empty shards are legal)"""
+    for total, world in ((10, 4), (3, 8), (64, 8), (0, 2), (1001, 8)):
+        b = [dp.shard_bounds_uneven(total, r, world) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == total
+        assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
 @pytest.mark.parametrize("nb,buckets", [(15, 3), (15, 4), (25, 5), (2, 3), (1, 1), (0, 2), (15, 1)])
 def test_gradient_buckets_partition_the_flat_buffer(nb, buckets):
     """Backward walks blocks nb-1..0; the slices that become final after each range must tile [0, P)

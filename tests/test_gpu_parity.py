@@ -60,25 +60,55 @@ def test_csr_matches_golden_fixture(dev, golden_dir):
         assert np.array_equal(got.cpu().numpy(), g[key]), key
 
 
-def test_csr_rejects_bad_ids_and_self_loops(dev):
+def test_csr_rejects_bad_ids_and_splits_self_loops(dev):
     from gnn_pressure_estimation_b200._lib import GatresError
     with pytest.raises(GatresError):
         _topology(torch.tensor([[0, 5], [1, 0]]), 3, dev)
-    with pytest.raises(NotImplementedError):
-        _topology(torch.tensor([[0, 1, 1], [1, 0, 1]]), 3, dev)
+    # a template with a self loop gets two views (GATConv drops it, SimpleConv keeps it): tests/test_gpu_robustness.py
+    topo = _topology(torch.tensor([[0, 1, 1], [1, 0, 1]]), 3, dev)
+    assert topo.dropped_self_loops == 1 and not topo.shares_one_csr
+    assert topo.col.tolist() == [1, 0, 0, 1, 2] and topo.mean_view()[1].tolist() == [1, 0, 0, 1, 1, 2]
 
 
 def test_replication_check_and_poison(dev, G):
+    """eager calls validate the batch content and re-infer on a mismatch (correct answer, general mode); only under
+    CUDA-graph capture, where no host read is possible, a mismatching batch poisons the output with NaN"""
     ei, names = T.reference_edge_index(T.ctown_shaped()); n = len(names)
     ei = torch.from_numpy(ei)
-    model = G.GATResMeanConv(num_blocks=1, nc=32).to(dev)
-    x = torch.randn(4 * n, 1, device=dev)
-    good = O.collate_edge_index(ei, n, 4).to(dev)
+    ref = O.make_oracle(1, 32, seed=2)
+    model = G.GATResMeanConv(num_blocks=1, nc=32)
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev)
+    x = torch.randn(4 * n, 1, generator=torch.Generator().manual_seed(3))
+    good = O.collate_edge_index(ei, n, 4)
+    bad = good.clone()
+    bad[0, 2000] = (bad[0, 2000] + 1) % n + 2 * n              # same shape, different wiring
+    xd, goodd, badd = x.to(dev), good.to(dev), bad.to(dev)
     with torch.no_grad():
-        assert torch.isfinite(model(x, good)).all()
-        bad = good.clone()
-        bad[0, 2000] = (bad[0, 2000] + 1) % n + 2 * n          # same shape, different wiring
-        assert torch.isnan(model(x, bad)).all()                # loud, without a per-step sync
+        assert_close(model(xd, goodd), ref(x, good), FWD_TOL, "replicated batch")
+        assert_close(model(xd, badd), ref(x, bad), FWD_TOL, "same shape, other wiring: re-inferred, not stale")
+        assert_close(model(xd, goodd), ref(x, good), FWD_TOL, "and back")
+        # captured: the check is enqueued, its flag is zeroed per replay, NaN on mismatch
+        fresh_model = G.GATResMeanConv(num_blocks=1, nc=32).to(dev)
+        fresh_model(xd, goodd)
+        static_ei = goodd.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fresh_model(xd, static_ei.clone())
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        capt_ei = static_ei.clone()                             # a tensor the cache has not validated
+        with torch.cuda.graph(graph):
+            out = fresh_model(xd, capt_ei)
+        graph.replay()
+        assert torch.isfinite(out).all()
+        capt_ei.copy_(badd)
+        graph.replay()
+        assert torch.isnan(out).all()
+        capt_ei.copy_(goodd)
+        graph.replay()
+        assert torch.isfinite(out).all()                        # the flag does not stick
 
 
 # ----------------------------------------------------------------- operators

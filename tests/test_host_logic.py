@@ -37,8 +37,33 @@ def test_select_model_reaches_the_gat_baseline():
 
 def test_reference_import_paths():
     from gnn_pressure_estimation.GraphModels import GATResMeanConv, GResBlockMeanConv  # noqa: F401
-    from gnn_pressure_estimation.ConfigModels import select_model  # noqa: F401
-    assert GATResMeanConv is G.GATResMeanConv
+    from gnn_pressure_estimation.GraphModels import GAT, GATConvNet, GResBlockConv  # noqa: F401  (reference's own import line)
+    from gnn_pressure_estimation.ConfigModels import config_gat, select_model  # noqa: F401
+    assert GATResMeanConv is G.GATResMeanConv and GAT is G.GAT
+    ns = {}
+    exec("from gnn_pressure_estimation.GraphModels import *", ns)
+    assert {"GAT", "GATConvNet", "GResBlockConv", "GATResMeanConv"} <= set(ns)
+
+
+def test_every_cli_model_choice_is_selectable():
+    """train.py's --model choices must all resolve (gatres_small_tough once raised 'Unknown model')"""
+    for which in ("gatres_small", "gatres_large", "gatres_small_tough", "gat"):
+        args, model = CM.select_model(argparse.Namespace(model=which))
+        assert model is not None and args.criterion == "mse"
+    _, tough = CM.select_model(argparse.Namespace(model="gatres_small_tough"))
+    assert tough.num_blocks == 15 and tough.nc == 32 and tough.name == "GATResMeanConv_small_tough_znorm_15b_32c"
+
+
+def test_sibling_models_have_pyg_compatible_parameters():
+    """GATConvNet (GraphModels.py:15-46) and GResBlockConv (:548-561): same parameter names / shapes as the oracle
+    restatement, so reference checkpoints of those baselines load"""
+    net = dict(input_dim=1, hidden_dim=32, heads=2, out_dim=1, num_layers=4)
+    m, ref = G.GATConvNet(net), O.GATConvNetOracle(net)
+    assert list(m.state_dict()) == list(ref.state_dict())
+    assert [tuple(v.shape) for v in m.state_dict().values()] == [tuple(v.shape) for v in ref.state_dict().values()]
+    m.load_state_dict(ref.state_dict())
+    b, rb = G.GResBlockConv(32, 32, 32), O.OracleGResBlockConv(32, 32, 32)
+    assert list(b.state_dict()) == list(rb.state_dict())
 
 
 def test_state_dict_is_pyg_compatible_both_schemes():

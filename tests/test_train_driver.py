@@ -26,6 +26,39 @@ def test_synthetic_snapshots_are_smooth_on_the_graph():
     assert data.shape == (32, 388) and edge_var < 0.5          # neighbours agree far better than independent nodes (2.0)
 
 
+def test_adam_state_export_follows_model_parameters_order():
+    """torch.optim.Adam numbers its state by position in model.parameters() (att_src, att_dst, bias, lin_src.weight
+    per GATConv), not by the flat buffer's order: the exported state must attach to the right parameters, and one
+    optimizer step after loading it must run (train.py:436 stores optimizer.state_dict())."""
+    from types import SimpleNamespace
+    import gnn_pressure_estimation_b200.GraphModels as G
+    from gnn_pressure_estimation_b200.train import adam_state_dict
+    model = G.GATResMeanConv(num_blocks=2, nc=32)
+    ordered = model.ordered_parameters()
+    P = sum(p.numel() for p in ordered)
+    exp_avg = torch.arange(P, dtype=torch.float32)                  # value = offset in the flat buffer
+    step = SimpleNamespace(model=model, exp_avg=exp_avg, exp_avg_sq=exp_avg * 2 + 1, step_count=torch.tensor([7]),
+                           lr=5e-4, betas=(0.9, 0.999), eps=1e-8, wd=6e-6)
+    sd = adam_state_dict(step)
+    offsets, off = {}, 0
+    for p in ordered:
+        offsets[id(p)] = off
+        off += p.numel()
+    params = list(model.parameters())
+    assert len(sd["state"]) == len(params) == len(ordered)
+    for i, p in enumerate(params):
+        st = sd["state"][i]
+        assert st["exp_avg"].shape == p.shape and st["exp_avg_sq"].shape == p.shape
+        assert float(st["exp_avg"].reshape(-1)[0]) == offsets[id(p)], i
+        assert float(st["step"]) == 7.0
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=6e-6)
+    opt.load_state_dict(sd)
+    for p in params:
+        p.grad = torch.ones_like(p)
+    opt.step()                                                        # shapes line up -> no broadcasting error
+    assert all(opt.state[p]["exp_avg"].shape == p.shape for p in params)
+
+
 @pytest.mark.gpu
 def test_fit_learns_and_checkpoints(tmp_path):
     """a few epochs on smooth synthetic pressures: validation loss falls below the predict-the-mean level, the last
@@ -57,6 +90,10 @@ def test_fit_learns_and_checkpoints(tmp_path):
         assert k in cp, k
     opt = torch.optim.Adam(fresh.parameters(), lr=5e-4, weight_decay=6e-6)
     opt.load_state_dict(cp["optimizer_state_dict"])                     # torch.optim.Adam accepts the exported state
+    for p in fresh.parameters():
+        assert opt.state[p]["exp_avg"].shape == p.shape
+        p.grad = torch.zeros_like(p)
+    opt.step()
     assert cp["epoch"] == out["best"]["epoch"] and cp["loss"] == pytest.approx(out["best"]["loss"])
     # NumPy-compatible masks drive the same loop
     out2 = TR.fit(G.GATResMeanConv(num_blocks=2, nc=32), train_set, valid_set, batch_size=64, epochs=1, mask_source="numpy",
