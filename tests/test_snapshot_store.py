@@ -39,7 +39,8 @@ def lz4_block_encode(data: bytes) -> bytes:
                     out.append(255); r -= 255
                 out.append(r)
 
-    while i + 4 <= n - 5:                                  # the last 5 bytes are always literals
+    while i <= n - 12:                                     # LZ4 end rules: no match starts in the last 12 bytes,
+                                                           # the last 5 bytes are always literals
         key = data[i:i + 4]
         cand = table.get(key)
         table[key] = i
@@ -220,3 +221,51 @@ def test_missing_chunks_fill_value_and_fortran_order(tmp_path):
     (root / "a" / ".zarray").write_text(json.dumps(meta))
     with pytest.raises(SS.StoreError, match="v2"):
         SS.ZarrV2Store(str(root)).read_array("a")
+
+
+# ------------------------------------------------------------- fixtures whose compressed bytes come from real libraries
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_lz4_decoder_on_blocks_written_by_liblz4():
+    """known answers from the real liblz4 (pyarrow's lz4_raw codec; tests/golden/make_golden_store.py): the decoder is
+    held to bytes it did not produce itself"""
+    kat = np.load(os.path.join(GOLDEN, "liblz4_blocks.npz"))
+    n = len([k for k in kat.files if k.startswith("plain")])
+    assert n >= 8
+    for i in range(n):
+        plain, comp = kat[f"plain{i}"].tobytes(), kat[f"lz4_{i}"].tobytes()
+        assert SS.lz4_block_decode(comp, len(plain)) == plain, i
+    try:                                                     # live cross-check when pyarrow is importable
+        import pyarrow as pa
+    except Exception:
+        return
+    rng = np.random.RandomState(3)
+    for size in (1, 13, 64, 4096, 70000):
+        data = bytes(rng.randint(0, 3, size).astype(np.uint8))
+        assert SS.lz4_block_decode(pa.Codec("lz4_raw").compress(data, asbytes=True), size) == data
+        ours = lz4_block_encode(data)                        # and the test-side encoder is valid LZ4 for liblz4
+        assert pa.Codec("lz4_raw").decompress(ours, decompressed_size=size, asbytes=True) == data
+
+
+def test_store_with_liblz4_and_zlib_streams(tmp_path):
+    """the committed ZipStore (reference generator layout, scenegenv7.py:664-725; Blosc frames around liblz4 / zlib
+    streams) reads back exactly, through ZarrV2Store and through SnapshotSet.load"""
+    want = np.load(os.path.join(GOLDEN, "store_liblz4_expected.npz"))
+    st = SS.ZarrV2Store(os.path.join(GOLDEN, "store_liblz4.zip"))
+    assert st.group_keys() == ["head", "pressure"] and st.group_keys("pressure") == ["test", "train", "valid"]
+    names = [str(s) for s in want["names"]]
+    assert st.attrs()["ordered_names_by_attr"]["pressure"] == names and st.attrs()["batch_size"] == 16
+    for key in ("pressure/train", "pressure/valid", "pressure/test", "head/train", "head/valid"):
+        got = st.read_array(key)
+        exp = want[key.replace("/", "__")]
+        assert got.dtype == exp.dtype and np.array_equal(got, exp), key
+    # the same file through the dataset mirror (utils/DataLoader.py:206-258): junction columns, z-norm
+    wn = T.WaterNetwork(junctions=names[:-2], reservoirs=["R1"], tanks=["T1"],
+                        links=[(f"P{i}", names[i], names[i + 1]) for i in range(len(names) - 1)])
+    inp = tmp_path / "line.inp"
+    inp.write_text(T.write_inp(wn))
+    ds = SS.SnapshotSet.load(str(inp), os.path.join(GOLDEN, "store_liblz4.zip"), "pressure", "valid", device="cpu")
+    kept = want["pressure__valid"][:, :len(names) - 2]
+    assert len(ds) == 16 and ds.num_nodes == len(names) - 2
+    assert np.allclose(ds.snapshots.numpy(), ((kept - kept.mean()) / (kept.std() + 1e-8)).astype(np.float32))
