@@ -167,7 +167,7 @@ adam_peer_kernel(float* __restrict__ p, const PeerTable peers, float* __restrict
     const unsigned* f = peers.flags[rank] + threadIdx.x;
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < epoch)
-      if (clock64() - t0 > (20ll << 30)) __trap();            // ~10 s at 2 GHz: a lost peer must not hang the GPU
+      if (clock64() - t0 > (240ll << 30)) __trap();           // ~2 min at 2 GHz: a lost peer must not hang the GPU forever
   }
   __syncthreads();
   const float t = (float)__ldg(step);
