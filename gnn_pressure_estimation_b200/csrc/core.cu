@@ -147,10 +147,38 @@ struct PeerTable {
   unsigned* flags[kMaxPeers];
 };
 
-__global__ void bump2_kernel(int* step, int* epoch) {
-  pdl_wait();
-  step[0] += 1;
-  epoch[0] += 1;
+// Runs right after the last backward kernel of the step: bumps the Adam step counter and the barrier epoch and
+// ANNOUNCES "this rank's gradients of epoch e are complete" in every peer's flag array — one launch gap earlier than
+// the Adam kernel could, so the flags travel over NVLink while the Adam kernel is being launched and loads its state.
+__global__ void __launch_bounds__(32)
+bump_publish_kernel(int* step, int* epoch, const PeerTable peers, int rank, int world) {
+  pdl_wait();                                                   // the backward kernels' writes are visible
+  const unsigned e = (unsigned)epoch[0] + 1u;
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    step[0] += 1;
+    epoch[0] = (int)e;
+  }
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(peers.flags[threadIdx.x] + rank, e);
+  }
+}
+
+// sum of the `world` ranks' gradient chunk i in rank order; the peer loads are issued together (eight in flight per
+// thread) — a rank-by-rank loop would pay one NVLink round trip per peer
+__device__ __forceinline__ float4 peer_sum4(const PeerTable& peers, size_t i, int world) {
+  float4 acc = f4zero();
+  for (int r0 = 0; r0 < world; r0 += 8) {
+    float4 g[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r0 + u < world) g[u] = ld_relaxed_sys4(peers.grads[r0 + u] + 4 * i);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r0 + u < world) add4(acc, g[u]);
+  }
+  return acc;
 }
 
 __global__ void __launch_bounds__(256)
@@ -159,30 +187,39 @@ adam_peer_kernel(float* __restrict__ p, const PeerTable peers, float* __restrict
                  float b2, float eps, float wd, float grad_scale, int rank, int world) {
   pdl_wait();
   const unsigned epoch = (unsigned)__ldg(epoch_dev);
-  if (blockIdx.x == 0 && threadIdx.x < world) {
-    __threadfence_system();                                   // this rank's backward (previous kernels) is complete
-    st_release_sys(peers.flags[threadIdx.x] + rank, epoch);   // announce it in every peer's flag array
+  // everything that does not depend on the peers is loaded BEFORE the flag wait: this thread's first chunk of the
+  // parameters and moments, the step count and the bias corrections
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  float4 pv0 = f4zero(), mv0 = f4zero(), vv0 = f4zero();
+  if (i0 < P4) {
+    pv0 = *reinterpret_cast<const float4*>(p + 4 * i0);
+    mv0 = *reinterpret_cast<const float4*>(m + 4 * i0);
+    vv0 = *reinterpret_cast<const float4*>(v + 4 * i0);
   }
-  if (threadIdx.x < world) {
-    const unsigned* f = peers.flags[rank] + threadIdx.x;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) < epoch)
-      if (clock64() - t0 > (240ll << 30)) __trap();           // ~2 min at 2 GHz: a lost peer must not hang the GPU forever
-  }
-  __syncthreads();
   const float t = (float)__ldg(step);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  if (threadIdx.x < world) {
+    const unsigned* f = peers.flags[rank] + threadIdx.x;        // own (local) flag array; peers write into it
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < epoch)
+      if (clock64() - t0 > (240ll << 30)) __trap();             // ~2 min at 2 GHz: a lost peer must not hang the GPU forever
+  }
+  __syncthreads();
   auto update = [&](float pi, float g, float& mi, float& vi) {
     const float gi = fmaf(wd, pi, g * grad_scale);
     mi = fmaf(1.f - b1, gi - mi, mi);
     vi = fmaf(b2, vi, (1.f - b2) * gi * gi);
     return pi - step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
   };
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < P4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 g = ld_relaxed_sys4(peers.grads[0] + 4 * i);
-    for (int r = 1; r < world; ++r) add4(g, ld_relaxed_sys4(peers.grads[r] + 4 * i));      // rank order: same sum everywhere
-    float4 pv = *reinterpret_cast<float4*>(p + 4 * i), mv = *reinterpret_cast<float4*>(m + 4 * i), vv = *reinterpret_cast<float4*>(v + 4 * i);
+  for (size_t i = i0; i < P4; i += stride) {
+    const float4 g = peer_sum4(peers, i, world);                // rank order: same sum on every replica
+    float4 pv, mv, vv;
+    if (i == i0) { pv = pv0; mv = mv0; vv = vv0; }
+    else {
+      pv = *reinterpret_cast<float4*>(p + 4 * i); mv = *reinterpret_cast<float4*>(m + 4 * i); vv = *reinterpret_cast<float4*>(v + 4 * i);
+    }
     pv.x = update(pv.x, g.x, mv.x, vv.x);
     pv.y = update(pv.y, g.y, mv.y, vv.y);
     pv.z = update(pv.z, g.z, mv.z, vv.z);
@@ -267,7 +304,7 @@ extern "C" int gatres_adam_step_peer(float* params, const float* const* peer_gra
     t.grads[r] = peer_grads[r];
     t.flags[r] = peer_flags[r];
   }
-  launch_kernel(bump2_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_count, epoch);
+  launch_kernel(bump_publish_kernel, dim3(1), dim3(32), 0, as_stream(stream), step_count, epoch, t, (int)rank, (int)world);
   int rc = check_launch("adam_peer_bump");
   if (rc) return rc;
   const size_t P4 = (size_t)P / 4;
