@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgatres_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -27,7 +27,8 @@ class ModelDesc(C.Structure):
     """struct gatres_model_desc"""
     _fields_ = [("num_blocks", _i32), ("nc", _i32), ("N", _i32), ("slots", _i32), ("E1", _i32), ("reserved", _i32),
                 ("B", _i64),
-                ("rowptr", _p), ("col", _p), ("rowptr_t", _p), ("col_t", _p), ("poison", _p)]
+                ("rowptr", _p), ("col", _p), ("rowptr_t", _p), ("col_t", _p), ("poison", _p),
+                ("perm", _p), ("p_rowptr", _p), ("p_col", _p), ("p_rowptr_t", _p), ("p_col_t", _p), ("p_ecap", _i32 * 4)]
 
 
 # name -> (restype, argtypes); mirrors include/gatres_b200.h one to one
@@ -42,6 +43,7 @@ _PROTOTYPES = {
     "gatres_set_resident_threads": (_i32, [_i32]),
     "gatres_set_resident_profile": (None, [_p, _i32]),
     "gatres_set_tensor_core": (C.c_int, [C.c_int]),
+    "gatres_set_resident_dsm": (C.c_int, [C.c_int]),
     "gatres_csr_scratch_bytes": (_sz, [_i64, _i32]),
     "gatres_csr_build": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gatres_csr_build_mean": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),

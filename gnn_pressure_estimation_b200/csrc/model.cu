@@ -17,6 +17,12 @@ int resident_backward(const gatres_model_desc* d, const float* params, const flo
                       const float* d_out, float* grads, float* scratch, int k_hi, int k_lo, bool head, bool tail,
                       cudaStream_t st);
 
+// second generation (resident2.cu): exchange tensors in distributed shared memory, rows in a locality order
+bool resident2_eligible(const gatres_model_desc* d, bool training, long long max_batch);
+long long resident_max_batch();
+int resident2_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
+                      cudaStream_t st);
+
 // conv2 aggregation + SimpleConv(mean) + residual + ReLU in one launch when the snapshot tile path applies (gat_agg.cu)
 int gat_agg_mean_res_fwd(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
                          const float* s_dst, const float* bias, float* m, float* l, const float* x0, float* xout,
@@ -67,6 +73,7 @@ extern "C" int gatres_forward(const gatres_model_desc* d, const float* params, c
   const ParamLayout pl(d->num_blocks, d->nc);
   const SavedLayout sl(M, nc);
   const bool train = saved != nullptr;
+  if (resident2_eligible(d, train, resident_max_batch())) return resident2_forward(d, params, x, out, saved, as_stream(stream));
   if (resident_eligible(d, false)) return resident_forward(d, params, x, out, saved, scratch, as_stream(stream));
 
   // inference: rolling buffers carved from scratch

@@ -95,6 +95,9 @@ bool resident_eligible(const gatres_model_desc* d, bool backward) {
   return res256::fits(d->N, d->E1, backward);                       // res256f needs less
 }
 
+int resident_forced_cluster() { return res::forced_cluster(); }
+long long resident_max_batch() { return res::max_batch(); }
+
 int resident_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
                      float* scratch, cudaStream_t st) {
   if (res::threads() == 255) return res256f::forward(d, params, x, out, saved, scratch, st);

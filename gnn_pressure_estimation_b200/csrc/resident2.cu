@@ -1,0 +1,594 @@
+// Snapshot-resident GATRes stacks, second generation: the tensors neighbours must see live in DISTRIBUTED SHARED
+// MEMORY (sm_100a thread-block clusters), not in L2.
+//
+// Same decomposition as resident.cu — one cluster per snapshot carries all blocks of GATResMeanConv.forward
+// (/root/reference/gnn_pressure_estimation/GraphModels.py:486-494; block :462-468) and of its autograd backward
+// (train.py:185), each CTA owning a contiguous slice of the rows — but:
+//   * the rows are numbered by a locality order (recursive spectral bisection of the water network, computed once
+//     per template on the host: graph.py) so that ~85-90 % of a row's neighbours belong to the same CTA;
+//   * h1 / h2 / z (forward) and the gradient rows and per-row softmax records (backward) are written to the
+//     owner's shared memory only; a neighbour row is read with ld.shared::cluster through mapa — a plain shared
+//     load (~40 cycles) when the owner is this CTA, a DSMEM load (~215 cycles) otherwise — instead of an L2 round
+//     trip under load after every cluster barrier invalidated L1;
+//   * saved activations for the backward are streamed to HBM AFTER the barrier arrival that follows their
+//     production, so the release fence of a barrier never waits for them.
+// The first generation measured 1.0 us per cluster barrier (MEMBAR.ALL.GPU waiting on the global exchange stores +
+// CCTL.IVALL) and ~1 us per row pass of L2 gathers (profiles/r1_resident.md).
+//
+// Arithmetic is identical to resident.cu / the layer kernels: 3xTF32 mma.sync projections, cooperative per-row
+// softmax with the heads packed per lane, in-row summation in the reference's edge order (ascending original source
+// id, self-loop last — the permuted CSR keeps each row's entry order), recompute backward, atomic parameter gradients.
+// The saved-activation buffer uses the locality row order, so the two kernels of this file are always used as a pair.
+#include <math_constants.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "layout.cuh"
+
+namespace gatres {
+namespace res2 {
+
+constexpr int NC = 32;
+constexpr int T = 256;             // threads per CTA (8 warps: the mma tiling below assumes it)
+constexpr int LDX = NC + 4;        // padded row of a [*, 32] shared tile
+constexpr int LDY = 2 * NC + 4;    // padded row of a [*, 64] shared tile
+constexpr int W1F = 2 * NC * LDX;  // conv1 weight [64][32] padded
+constexpr int W2F = NC * LDY;      // conv2 weight [32][64] padded
+constexpr int VECF = 9 * NC;       // as1 ad1 b1 (64 each) as2 ad2 b2 (32 each)
+constexpr unsigned FULL = 0xffffffffu;
+constexpr size_t kMaxSmem = 110 * 1024;     // two CTAs per SM
+
+struct Args {
+  const int* rowptr;     // in-edge CSR in LOCALITY numbering (self-loop last in every row)
+  const int* col;
+  const int* rowptr_t;   // out-edge CSR, same numbering
+  const int* col_t;
+  const int* perm;       // locality row -> original node id
+  const float* params;
+  const float* x;        // [M] model input, original row order
+  float* out;            // fwd: [M], original row order
+  float* saved;          // training activations (locality row order) or NULL
+  const float* d_out;    // bwd: [M], original row order
+  float* grads;
+  const int* poison;
+  long long M;
+  int N, nb, R, ecap;    // ecap: shared-memory capacity (ints) of one CTA's slice of a CSR (max over the cluster)
+  int k_hi, k_lo, head, tail;
+};
+
+// ---- cluster / distributed shared memory primitives ---------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// address of `local_addr` (a shared-window address of THIS CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ unsigned mapa(unsigned local_addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ldsc4(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 ldsc2(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float ldsc1(unsigned a) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+// a CSR entry in shared memory: owner CTA in the high half, row inside the owner's slice in the low half
+__device__ __forceinline__ unsigned row_addr(unsigned base, int packed, int ld_bytes) {
+  return mapa(base + (unsigned)(packed & 0xffff) * (unsigned)ld_bytes, (unsigned)packed >> 16);
+}
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp4(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void st4_stream(float* p, float4 v) {        // saved activations: written once, read by another kernel
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float gmax8(float v) {
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 2));
+  return fmaxf(v, __shfl_xor_sync(FULL, v, 1));
+}
+__device__ __forceinline__ float4 relu4(float4 v) {
+  return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+}
+__device__ __forceinline__ float4 mask4(float4 v, float4 ref) {
+  return make_float4(ref.x > 0.f ? v.x : 0.f, ref.y > 0.f ? v.y : 0.f, ref.z > 0.f ? v.z : 0.f, ref.w > 0.f ? v.w : 0.f);
+}
+
+// one block's parameters (contiguous W1 as1 ad1 b1 W2 as2 ad2 b2) -> padded shared tiles, 16 B per cp.async
+__device__ __forceinline__ void stage_block_params(const float* blk, float* W1s, float* W2s, float* vec) {
+  constexpr int C_W1 = 2 * NC * NC / 4, C_V1 = 6 * NC / 4, C_W2 = 2 * NC * NC / 4, C_V2 = 3 * NC / 4;
+  for (int c = threadIdx.x; c < C_W1 + C_V1 + C_W2 + C_V2; c += T) {
+    float* dst;
+    if (c < C_W1) dst = W1s + (c / (NC / 4)) * LDX + 4 * (c % (NC / 4));
+    else if (c < C_W1 + C_V1) dst = vec + 4 * (c - C_W1);
+    else if (c < C_W1 + C_V1 + C_W2) {
+      const int q = c - C_W1 - C_V1;
+      dst = W2s + (q / (2 * NC / 4)) * LDY + 4 * (q % (2 * NC / 4));
+    } else dst = vec + 6 * NC + 4 * (c - C_W1 - C_V1 - C_W2);
+    cp16(dst, blk + 4 * c);
+  }
+}
+// own rows [0, n) of a row-major global tensor -> padded shared tile (cp.async, 16 B chunks)
+template <int F, int LD>
+__device__ __forceinline__ void stage_rows(const float* g, float* s, int n) {
+  for (int c = threadIdx.x; c < n * (F / 4); c += T) cp16(s + (c / (F / 4)) * LD + 4 * (c % (F / 4)), g + 4 * c);
+}
+__device__ __forceinline__ void stage_scalars(const float* g, float* s, int cnt) {      // g 16-byte aligned, cnt floats
+  for (int c = threadIdx.x; c < (cnt + 3) / 4; c += T) cp16(s + 4 * c, g + 4 * c);
+}
+// padded shared tile -> own rows of a row-major global tensor (streaming stores)
+template <int F, int LD>
+__device__ __forceinline__ void store_rows(const float* s, float* g, int n) {
+  for (int c = threadIdx.x; c < n * (F / 4); c += T) st4_stream(g + 4 * c, lds4(s + (c / (F / 4)) * LD + 4 * (c % (F / 4))));
+}
+__device__ __forceinline__ void store_scalars(const float* s, float* g, int cnt) {
+  for (int c = threadIdx.x; c < cnt; c += T) g[c] = s[c];
+}
+
+// this CTA's slice of a CSR -> shared memory: row pointers relative to the slice, entries packed (owner << 16 | row)
+__device__ __forceinline__ void stage_csr_slice(const int* __restrict__ rowptr, const int* __restrict__ col, int lo, int n,
+                                                int R, int* rp_s, int* col_s, int ecap) {
+  const int e_lo = __ldg(rowptr + lo), cnt = min(__ldg(rowptr + lo + n) - e_lo, ecap);
+  for (int c = threadIdx.x; c <= n; c += T) rp_s[c] = __ldg(rowptr + lo + c) - e_lo;
+  for (int c = threadIdx.x; c < cnt; c += T) {
+    const int j = __ldg(col + e_lo + c);
+    const int owner = j / R;
+    col_s[c] = (owner << 16) | (j - owner * R);
+  }
+}
+
+// ---- tensor-core contractions (mma.sync m16n8k8 TF32, 3xTF32 error compensated; see resident_mma.cuh) --------------
+__device__ __forceinline__ unsigned tf32_lo_bits(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  return (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], float (&cl)[4], float (&cm)[4], const unsigned (&a)[4],
+                                           const unsigned (&al)[4], const unsigned (&b)[2], const unsigned (&bl)[2]) {
+  mma_tf32(cl, al, b);
+  mma_tf32(cm, a, bl);
+  mma_tf32(c, a, b);
+}
+__device__ __forceinline__ void fold3(float (&c)[4], const float (&cl)[4], const float (&cm)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] += cl[i] + cm[i];
+}
+template <int NF>
+__device__ __forceinline__ void split_frag(const float (&x)[NF], unsigned (&hi)[NF], unsigned (&lo)[NF]) {
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {
+    hi[i] = __float_as_uint(x[i]);
+    lo[i] = tf32_lo_bits(x[i]);
+  }
+}
+
+// h[m][n] = sum_k A[m][k] W[n][k] into a padded SHARED tile (row stride LDO) + attention scores into shared arrays.
+// Warp w: 16-row tile (w % 4) of every 64-row group, column half w / 4 (for H = 2 the half is the head).
+template <int K, int NOUT, int H, int LDA, int LDW, int LDO>
+__device__ __forceinline__ void project_mma(const float* As, const float* Ws, const float* att_s, const float* att_d,
+                                            float* h_s, float* ss_s, float* sd_s, float* scr, int n) {
+  constexpr int NTW = NOUT / 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int half = warp >> 2, nbase = half * (NOUT / 2);
+  for (int m0 = (warp & 3) * 16; m0 < n; m0 += 64) {
+    const int r0 = min(m0 + g, n - 1), r1 = min(m0 + g + 8, n - 1);
+    float acc[NTW][4], acl[NTW][4], acm[NTW][4];
+#pragma unroll
+    for (int j = 0; j < NTW; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = acl[j][i] = acm[j][i] = 0.f;
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      const float av[4] = {As[r0 * LDA + k0 + t], As[r1 * LDA + k0 + t], As[r0 * LDA + k0 + t + 4], As[r1 * LDA + k0 + t + 4]};
+      unsigned a[4], al[4];
+      split_frag<4>(av, a, al);
+#pragma unroll
+      for (int j = 0; j < NTW; ++j) {
+        const float* wp = Ws + (nbase + 8 * j + g) * LDW + k0 + t;
+        const float bv[2] = {wp[0], wp[4]};
+        unsigned b[2], bl[2];
+        split_frag<2>(bv, b, bl);
+        mma_3xtf32(acc[j], acl[j], acm[j], a, al, b, bl);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) fold3(acc[j], acl[j], acm[j]);
+    float ps[2] = {0.f, 0.f}, pd[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) {
+      const int c = nbase + 8 * j + 2 * t;
+      const float s0 = att_s[c], s1 = att_s[c + 1], d0 = att_d[c], d1 = att_d[c + 1];
+      ps[0] = fmaf(acc[j][0], s0, fmaf(acc[j][1], s1, ps[0]));
+      ps[1] = fmaf(acc[j][2], s0, fmaf(acc[j][3], s1, ps[1]));
+      pd[0] = fmaf(acc[j][0], d0, fmaf(acc[j][1], d1, pd[0]));
+      pd[1] = fmaf(acc[j][2], d0, fmaf(acc[j][3], d1, pd[1]));
+      if (m0 + g < n) *reinterpret_cast<float2*>(h_s + (m0 + g) * LDO + c) = make_float2(acc[j][0], acc[j][1]);
+      if (m0 + g + 8 < n) *reinterpret_cast<float2*>(h_s + (m0 + g + 8) * LDO + c) = make_float2(acc[j][2], acc[j][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      ps[i] += __shfl_xor_sync(FULL, ps[i], 1); ps[i] += __shfl_xor_sync(FULL, ps[i], 2);
+      pd[i] += __shfl_xor_sync(FULL, pd[i], 1); pd[i] += __shfl_xor_sync(FULL, pd[i], 2);
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int m = m0 + g + 8 * i;
+        if (m < n) {
+          if (H == 2) {                          // column half == head
+            ss_s[m * 2 + half] = ps[i];
+            sd_s[m * 2 + half] = pd[i];
+          } else {                               // the two halves of the single head meet in shared memory
+            scr[(half * 2 + 0) * n + m] = ps[i];
+            scr[(half * 2 + 1) * n + m] = pd[i];
+          }
+        }
+      }
+    }
+  }
+  if (H == 1) {
+    __syncthreads();
+    for (int m = threadIdx.x; m < n; m += T) {
+      ss_s[m] = scr[0 * n + m] + scr[2 * n + m];
+      sd_s[m] = scr[1 * n + m] + scr[3 * n + m];
+    }
+  }
+}
+
+// ---- fused GAT aggregation over this CTA's rows (C = 32), neighbour rows through distributed shared memory ---------
+// Eight lanes own a row: lane `slot` holds the float4 chunk `slot` of EVERY head of the row and evaluates edge `slot`
+// of the row for every head (resident_impl.cuh: agg_fwd_rows).  h_base / ss_base: shared-window addresses of the h tile
+// (row stride ldh bytes) and of the source-score array ([row][H]) — the same offsets in every CTA of the cluster.
+template <int H>
+__device__ __forceinline__ void agg_fwd(const int* rp_s, const int* col_s, unsigned h_base, int ldh, unsigned ss_base,
+                                        const float* sd_s, const float* bias_s, float* out_s, int ld_out, float* out_g,
+                                        float* m_dst, float* l_dst, int n, int self_owner, bool relu) {
+  constexpr int F = 32 * H, RPW = 4, PRE = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, slot = lane & 7;
+  float4 bv[H];
+#pragma unroll
+  for (int v = 0; v < H; ++v) bv[v] = lds4(bias_s + 32 * v + 4 * slot);
+  for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
+    const int il_raw = i0 + warp * RPW + sub;
+    const bool ok = il_raw < n;
+    const int il = ok ? il_raw : n - 1;
+    const int beg = rp_s[il], deg = rp_s[il + 1] - beg;
+    const int deg_max = __reduce_max_sync(FULL, deg);
+    float sd[H], mrun[H], lrun[H];
+    float4 acc[H];
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      sd[v] = sd_s[il * H + v];
+      mrun[v] = -CUDART_INF_F;
+      lrun[v] = 0.f;
+      acc[v] = f4zero();
+    }
+    for (int e0 = 0; e0 < deg_max; e0 += 8) {
+      const bool valid = e0 + slot < deg;
+      const int j = valid ? col_s[beg + e0 + slot] : ((self_owner << 16) | il);
+      const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
+      float4 x[PRE][H];
+#pragma unroll
+      for (int u = 0; u < PRE; ++u) {
+        const int ju = __shfl_sync(FULL, j, u, 8);
+        const unsigned au = row_addr(h_base, ju, ldh) + 16u * slot;
+#pragma unroll
+        for (int v = 0; v < H; ++v) x[u][v] = u < cnt ? ldsc4(au + 128u * v) : f4zero();
+      }
+      float sj[H];
+      {
+        const unsigned as_ = row_addr(ss_base, j, 4 * H);
+        if (H == 2) {
+          const float2 t2 = ldsc2(as_);
+          sj[0] = t2.x; sj[H - 1] = t2.y;
+        } else sj[0] = ldsc1(as_);
+      }
+      float p[H];
+#pragma unroll
+      for (int v = 0; v < H; ++v) {
+        const float a = valid ? lrelu(sj[v] + sd[v]) : -CUDART_INF_F;
+        const float nm = fmaxf(mrun[v], gmax8(a));
+        if (e0 > 0) {
+          const float sc = __expf(mrun[v] - nm);
+          lrun[v] *= sc;
+          acc[v].x *= sc; acc[v].y *= sc; acc[v].z *= sc; acc[v].w *= sc;
+        }
+        p[v] = __expf(a - nm);
+        lrun[v] += group_sum<8>(p[v], FULL);
+        mrun[v] = nm;
+      }
+#pragma unroll
+      for (int u = 0; u < PRE; ++u)
+#pragma unroll
+        for (int v = 0; v < H; ++v) fma4(acc[v], __shfl_sync(FULL, p[v], u, 8), x[u][v]);
+      for (int t = PRE; t < cnt_max; t += 2) {
+        const int j0 = __shfl_sync(FULL, j, t, 8), j1 = __shfl_sync(FULL, j, t + 1, 8);
+        const unsigned a0 = row_addr(h_base, j0, ldh) + 16u * slot, a1 = row_addr(h_base, j1, ldh) + 16u * slot;
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float4 x0 = t < cnt ? ldsc4(a0 + 128u * v) : f4zero();
+          const float4 x1 = t + 1 < cnt ? ldsc4(a1 + 128u * v) : f4zero();
+          const float p0 = __shfl_sync(FULL, p[v], t, 8), p1 = __shfl_sync(FULL, p[v], t + 1, 8);
+          fma4(acc[v], p0, x0);
+          fma4(acc[v], t + 1 < 8 ? p1 : 0.f, x1);
+        }
+      }
+    }
+    if (!ok) continue;
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      const float inv = 1.f / (lrun[v] + kSoftmaxEps);
+      float4 o = make_float4(fmaf(acc[v].x, inv, bv[v].x), fmaf(acc[v].y, inv, bv[v].y), fmaf(acc[v].z, inv, bv[v].z),
+                             fmaf(acc[v].w, inv, bv[v].w));
+      if (relu) o = relu4(o);
+      st4(out_s + il * ld_out + 32 * v + 4 * slot, o);
+      if (out_g != nullptr) st4_stream(out_g + (size_t)il * F + 32 * v + 4 * slot, o);
+      if (m_dst != nullptr && slot == 0) { m_dst[il * H + v] = mrun[v]; l_dst[il * H + v] = lrun[v]; }
+    }
+  }
+}
+
+// =============================================================================== forward
+// Shared memory (floats): xs[R][LDX] h1s[R][LDY] ys[R][LDY] h2s[R][LDX] zs[R][LDX] ss1[2R] sd1[2R] ss2[R] sd2[R] ml2[2R]
+//                         W1s[2][W1F] W2s[2][W2F] vec[2][VECF] scr[4R] | ints: rp_s[R+1] col_s[ecap]
+struct FwdSmem {
+  int xs, h1s, ys, h2s, zs, ss1, sd1, ss2, sd2, ml2, W1s, W2s, vec, scr, rp, col, total;
+  __host__ __device__ FwdSmem(int R, int ecap) {
+    int o = 0;
+    auto take = [&](int nfl) { const int at = o; o += (int)a4(nfl); return at; };
+    xs = take(R * LDX); h1s = take(R * LDY); ys = take(R * LDY); h2s = take(R * LDX); zs = take(R * LDX);
+    ss1 = take(2 * R); sd1 = take(2 * R); ss2 = take(R); sd2 = take(R); ml2 = take(2 * R);
+    W1s = take(2 * W1F); W2s = take(2 * W2F); vec = take(2 * VECF); scr = take(4 * R);
+    rp = take(R + 1); col = take(ecap);
+    total = o;
+  }
+};
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(T, 2)
+fwd_kernel(const Args a) {
+  extern __shared__ __align__(16) float smem[];
+  const int R = a.R, N = a.N;
+  const FwdSmem L(R, a.ecap);
+  float* xs = smem + L.xs;
+  float* h1s = smem + L.h1s;
+  float* ys = smem + L.ys;
+  float* h2s = smem + L.h2s;
+  float* zs = smem + L.zs;
+  float* ss1 = smem + L.ss1;
+  float* sd1 = smem + L.sd1;
+  float* ss2 = smem + L.ss2;
+  float* sd2 = smem + L.sd2;
+  float* ml2 = smem + L.ml2;
+  float* W1s = smem + L.W1s;
+  float* W2s = smem + L.W2s;
+  float* vec = smem + L.vec;
+  float* scr = smem + L.scr;
+  int* rp_s = reinterpret_cast<int*>(smem + L.rp);
+  int* col_s = reinterpret_cast<int*>(smem + L.col);
+  const int rank = (int)cluster_ctarank();
+  const long long b = cluster_id_x();
+  const int lo = rank * R, n = max(0, min(R, N - lo));
+  const long long M = a.M, rb = b * N, ro = rb + lo;    // snapshot base row, first own row (locality order)
+  const ParamLayout pl(a.nb, NC);
+  const SavedLayout sl(M, NC);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // the topology is constant across steps: stage this CTA's slice before the dependency wait
+  if (n > 0) stage_csr_slice(a.rowptr, a.col, lo, n, R, rp_s, col_s, a.ecap);
+  pdl_wait();
+  if (a.nb > 0) stage_block_params(a.params + pl.block(0), W1s, W2s, vec);
+  cp_commit();
+
+  // encoder Linear(1, nc): x0[i][c] = x[i] w[c] + b[c]   (GraphModels.py:487)
+  {
+    const int lig = lane & 7, sub = lane >> 3;
+    const float4 wv = ldg4(a.params + pl.lin0_w() + 4 * lig), bv = ldg4(a.params + pl.lin0_b() + 4 * lig);
+    for (int il = warp * 4 + sub; il < n; il += T / 8) {
+      const float xv = __ldg(a.x + rb + __ldg(a.perm + lo + il));
+      st4(xs + il * LDX + 4 * lig, make_float4(fmaf(xv, wv.x, bv.x), fmaf(xv, wv.y, bv.y), fmaf(xv, wv.z, bv.z), fmaf(xv, wv.w, bv.w)));
+    }
+  }
+  const unsigned h1_base = smem_u32(h1s), h2_base = smem_u32(h2s), z_base = smem_u32(zs);
+  const unsigned ss1_base = smem_u32(ss1), ss2_base = smem_u32(ss2);
+
+  for (int k = 0; k < a.nb; ++k) {
+    const int buf = k & 1;
+    float* W1 = W1s + buf * W1F;
+    float* W2 = W2s + buf * W2F;
+    float* vc = vec + buf * VECF;
+    cp_wait_all();
+    __syncthreads();                         // parameters of block k and xs are in place
+    if (k + 1 < a.nb) stage_block_params(a.params + pl.block(k + 1), W1s + (buf ^ 1) * W1F, W2s + (buf ^ 1) * W2F, vec + (buf ^ 1) * VECF);
+    cp_commit();
+
+    // conv1 projection + scores  (GraphModels.py:464) -> own shared tiles
+    project_mma<NC, 2 * NC, 2, LDX, LDX, LDY>(xs, W1, vc, vc + 2 * NC, h1s, ss1, sd1, scr, n);
+    cluster_arrive();
+    // behind the arrival: the block input (encoder output / previous block's output) goes to HBM for the backward
+    if (TRAIN) store_rows<NC, LDX>(xs, a.saved + (k > 0 ? sl.xout(k - 1) : sl.x_enc()) + ro * NC, n);
+    cluster_wait();
+    if (TRAIN) {
+      store_rows<2 * NC, LDY>(h1s, a.saved + sl.h1(k) + ro * 2 * NC, n);
+      store_scalars(ss1, a.saved + sl.ss1(k) + ro * 2, 2 * n);
+      store_scalars(sd1, a.saved + sl.sd1(k) + ro * 2, 2 * n);
+    }
+    // conv1 aggregation + bias + ReLU -> y1 (row-local from here on)
+    agg_fwd<2>(rp_s, col_s, h1_base, LDY * 4, ss1_base, sd1, vc + 4 * NC, ys, LDY,
+               TRAIN ? a.saved + sl.y1(k) + ro * 2 * NC : nullptr, TRAIN ? a.saved + sl.m1(k) + ro * 2 : nullptr,
+               TRAIN ? a.saved + sl.l1(k) + ro * 2 : nullptr, n, rank, true);
+    __syncthreads();
+    // conv2 projection + scores  (:465)
+    project_mma<2 * NC, NC, 1, LDY, LDY, LDX>(ys, W2, vc + 6 * NC, vc + 7 * NC, h2s, ss2, sd2, scr, n);
+    cluster_arrive();
+    cluster_wait();
+    if (TRAIN) {
+      store_rows<NC, LDX>(h2s, a.saved + sl.h2(k) + ro * NC, n);
+      store_scalars(ss2, a.saved + sl.ss2(k) + ro, n);
+      store_scalars(sd2, a.saved + sl.sd2(k) + ro, n);
+    }
+    // conv2 aggregation + bias -> z (neighbours read it in the mean); (m, l) wait in shared memory
+    agg_fwd<1>(rp_s, col_s, h2_base, LDX * 4, ss2_base, sd2, vc + 8 * NC, zs, LDX, nullptr, TRAIN ? ml2 : nullptr,
+               TRAIN ? ml2 + R : nullptr, n, rank, false);
+    cluster_arrive();
+    if (TRAIN) {
+      __syncthreads();
+      store_scalars(ml2, a.saved + sl.m2(k) + ro, n);
+      store_scalars(ml2 + R, a.saved + sl.l2(k) + ro, n);
+    }
+    cluster_wait();
+    // SimpleConv(mean) + residual + ReLU  (:466-467): in-neighbours minus the trailing self-loop
+    {
+      const int lig = lane & 7, sub = lane >> 3;
+      for (int il = warp * 4 + sub; il < n; il += T / 8) {
+        const int beg = rp_s[il], end = rp_s[il + 1] - 1;
+        float4 acc = f4zero();
+#pragma unroll 4
+        for (int e = beg; e < end; ++e) add4(acc, ldsc4(row_addr(z_base, col_s[e], LDX * 4) + 16u * lig));
+        const int deg = end - beg;
+        const float inv = 1.f / (float)(deg > 1 ? deg : 1);
+        const float4 xr = lds4(xs + il * LDX + 4 * lig);
+        st4(xs + il * LDX + 4 * lig,
+            relu4(make_float4(fmaf(acc.x, inv, xr.x), fmaf(acc.y, inv, xr.y), fmaf(acc.z, inv, xr.z), fmaf(acc.w, inv, xr.w))));
+      }
+    }
+  }
+  cp_wait_all();
+  __syncthreads();
+  // no CTA may leave while a neighbour still reads its shared memory
+  cluster_arrive();
+  if (TRAIN && a.nb > 0) store_rows<NC, LDX>(xs, a.saved + sl.xout(a.nb - 1) + ro * NC, n);
+  if (TRAIN && a.nb == 0) store_rows<NC, LDX>(xs, a.saved + sl.x_enc() + ro * NC, n);
+  // decoder Linear(nc, 1)  (:492)
+  {
+    const int lig = lane & 7, sub = lane >> 3;
+    const float4 wv = ldg4(a.params + pl.lin1_w() + 4 * lig);
+    const float bias = __ldg(a.params + pl.lin1_b());
+    const bool bad = a.poison != nullptr && __ldg(a.poison) != 0;
+    for (int i0 = 0; i0 < n; i0 += T / 8) {
+      const int il = i0 + warp * 4 + sub;
+      float p = il < n ? dot4(lds4(xs + il * LDX + 4 * lig), wv) : 0.f;
+      p = group_sum<8>(p, FULL);
+      if (il < n && lig == 0) a.out[rb + __ldg(a.perm + lo + il)] = bad ? __int_as_float(0x7fc00000) : p + bias;
+    }
+  }
+  cluster_wait();
+}
+
+// ------------------------------------------------------------------------- host side
+static int g_enabled = -1;
+static bool enabled() {
+  if (g_enabled < 0) {
+    const char* e = getenv("GATRES_RESIDENT_DSM");
+    g_enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return g_enabled == 1;
+}
+
+static size_t fwd_smem(int R, int ecap) { return sizeof(float) * (size_t)FwdSmem(R, ecap).total; }
+
+template <void (*kern)(const Args)>
+static int launch_cluster(const char* what, int cs, long long B, size_t smem, cudaStream_t st, const Args& a) {
+  static size_t configured = 0;             // one instance per kernel (the kernel is a template argument)
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch(what);
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * cs));
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  count_launch();
+  cudaLaunchKernelEx(&cfg, kern, a);
+  return check_launch(what);
+}
+
+}  // namespace res2
+
+int resident_forced_cluster();      // resident.cu (gatres_set_resident_cluster)
+
+// cluster size: as many CTAs per snapshot as keeps the whole batch co-resident at two CTAs per SM
+static int res2_cluster(long long B) {
+  int cs = 8;
+  if (resident_forced_cluster() > 0) cs = resident_forced_cluster();
+  else
+    while (cs > 1 && B * cs > 2ll * sm_count()) cs >>= 1;
+  return cs;
+}
+
+static int res2_ecap(const gatres_model_desc* d, int cs) { return d->p_ecap[cs == 8 ? 3 : (cs == 4 ? 2 : (cs == 2 ? 1 : 0))]; }
+
+// Applicable when the descriptor carries a locality plan, nc = 32, atomics mode, and the slices fit shared memory.
+// `training` = the forward / backward PAIR (same predicate on both sides: the saved buffer is in locality order).
+bool resident2_eligible(const gatres_model_desc* d, bool training, long long max_batch) {
+  if (!res2::enabled() || d->perm == nullptr || d->p_rowptr == nullptr || d->p_col == nullptr) return false;
+  if (d->nc != 32 || d->E1 <= 0 || d->slots > 0) return false;
+  if (d->B > max_batch) return false;
+  if (training) return false;               // backward pair: see resident2_backward (enabled below once built)
+  const int cs = res2_cluster(d->B);
+  const int R = (d->N + cs - 1) / cs, ecap = res2_ecap(d, cs);
+  if (R >= 65536 || ecap <= 0) return false;
+  // two CTAs per SM while the batch needs them, one otherwise
+  const size_t budget = d->B * cs > (long long)sm_count() ? res2::kMaxSmem : 200 * 1024;
+  return res2::fwd_smem(R, ecap) <= budget;
+}
+
+int resident2_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
+                      cudaStream_t st) {
+  res2::Args a = {};
+  a.rowptr = d->p_rowptr; a.col = d->p_col; a.rowptr_t = d->p_rowptr_t; a.col_t = d->p_col_t; a.perm = d->perm;
+  a.params = params; a.x = x; a.out = out; a.saved = saved; a.poison = d->poison;
+  a.M = d->B * (long long)d->N; a.N = d->N; a.nb = d->num_blocks;
+  const int cs = res2_cluster(d->B);
+  a.R = (d->N + cs - 1) / cs;
+  a.ecap = res2_ecap(d, cs);
+  const size_t smem = res2::fwd_smem(a.R, a.ecap);
+  return saved != nullptr ? res2::launch_cluster<res2::fwd_kernel<true>>("resident2_forward(train)", cs, d->B, smem, st, a)
+                          : res2::launch_cluster<res2::fwd_kernel<false>>("resident2_forward", cs, d->B, smem, st, a);
+}
+
+}  // namespace gatres
+
+extern "C" int gatres_set_resident_dsm(int on) {
+  const int prev = gatres::res2::enabled() ? 1 : 0;
+  if (on == 0 || on == 1) gatres::res2::g_enabled = on;
+  return prev;
+}

@@ -52,7 +52,7 @@ extern "C" {
 #define GATRES_ERR_ARG (-1)       /* bad argument / unsupported shape */
 #define GATRES_ERR_CUDA (-2)      /* a CUDA runtime call failed        */
 
-#define GATRES_ABI_VERSION 1
+#define GATRES_ABI_VERSION 2
 
 int gatres_abi_version(void);
 const char* gatres_last_error(void);
@@ -136,6 +136,11 @@ int32_t gatres_set_resident_threads(int32_t threads);
  * writes %globaltimer at its phase boundaries to device_buf[c * slots_per_cta ...] (at most slots_per_cta stamps).
  * NULL switches it off (default). */
 void gatres_set_resident_profile(int64_t* device_buf, int32_t slots_per_cta);
+
+/* Second generation of the resident kernels (exchange tensors in distributed shared memory; needs the locality plan
+ * of gatres_model_desc): 1 = use it when applicable (default; GATRES_RESIDENT_DSM presets it), 0 = never.  Other
+ * values only query.  Returns the previous setting. */
+int gatres_set_resident_dsm(int on);
 
 /*
  * Kernel-selection knob for the projections and their data gradients: 0 = fp32 FFMA kernels
@@ -255,6 +260,20 @@ typedef struct gatres_model_desc {
   const int32_t* rowptr_t;       /* out-edge CSR incl. self loops */
   const int32_t* col_t;
   const int32_t* poison;         /* optional device flag: nonzero -> NaN output */
+  /* Optional locality plan of the template (all NULL / 0 = none; the snapshot-resident kernels of small batches then
+   * exchange rows through L2 instead of distributed shared memory).  perm[r] = original node id of locality row r
+   * (a permutation of 0..N-1 that puts neighbours close together, e.g. recursive bisection of the network); p_* = the
+   * same two CSR structures as above in locality numbering (row r = node perm[r], entries = locality ids of the
+   * neighbours IN THE SAME ORDER as the original row, self-loop last); p_ecap[q] = largest number of CSR entries
+   * owned by one CTA when the rows are cut into 2^q equal slices of ceil(N / 2^q) rows (q = 0..3), taken over both
+   * CSRs.  Model inputs / outputs / gradients keep the original row order; only the saved-activation buffer between
+   * gatres_forward(training) and gatres_backward is in locality order when the plan is used. */
+  const int32_t* perm;
+  const int32_t* p_rowptr;
+  const int32_t* p_col;
+  const int32_t* p_rowptr_t;
+  const int32_t* p_col_t;
+  int32_t p_ecap[4];
 } gatres_model_desc;
 
 int64_t gatres_param_count(int32_t num_blocks, int32_t nc);
