@@ -22,6 +22,9 @@ bool resident2_eligible(const gatres_model_desc* d, bool training, long long max
 long long resident_max_batch();
 int resident2_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
                       cudaStream_t st);
+int resident2_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
+                       const float* d_out, float* grads, float* scratch, int k_hi, int k_lo, bool head, bool tail,
+                       cudaStream_t st);
 
 // conv2 aggregation + SimpleConv(mean) + residual + ReLU in one launch when the snapshot tile path applies (gat_agg.cu)
 int gat_agg_mean_res_fwd(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
@@ -143,6 +146,9 @@ extern "C" int gatres_backward_range(const gatres_model_desc* d, const float* pa
       return check_launch("backward: zero grads");
     partial = grads;
   }
+  if (resident2_eligible(d, true, resident_max_batch()))      // the same predicate gatres_forward(training) evaluated
+    return resident2_backward(d, params, x, saved, d_out, grads, scratch, nb > 0 ? k_hi : -1, nb > 0 ? k_lo : 0, head,
+                              tail, as_stream(stream));
   if (resident_eligible(d, true))
     return resident_backward(d, params, x, saved, d_out, grads, scratch, nb > 0 ? k_hi : -1, nb > 0 ? k_lo : 0, head,
                              tail, as_stream(stream));

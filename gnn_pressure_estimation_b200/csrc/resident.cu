@@ -97,6 +97,7 @@ bool resident_eligible(const gatres_model_desc* d, bool backward) {
 
 int resident_forced_cluster() { return res::forced_cluster(); }
 long long resident_max_batch() { return res::max_batch(); }
+void resident_profile(long long** buf, int* slots) { *buf = res::g_prof; *slots = res::g_prof_slots; }
 
 int resident_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
                      float* scratch, cudaStream_t st) {

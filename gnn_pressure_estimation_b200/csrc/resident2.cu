@@ -49,10 +49,31 @@ struct Args {
   float* saved;          // training activations (locality row order) or NULL
   const float* d_out;    // bwd: [M], original row order
   float* grads;
+  float* scratch;        // bwd: running gradient between the ranges of a split backward ([M][32], locality order)
   const int* poison;
   long long M;
   int N, nb, R, ecap;    // ecap: shared-memory capacity (ints) of one CTA's slice of a CSR (max over the cluster)
   int k_hi, k_lo, head, tail;
+  long long* prof;       // optional phase-timestamp buffer [CTA][prof_slots] (tools/resident_probe.py), else NULL
+  int prof_slots;
+};
+
+// phase timestamps for the profiling tool: thread 0 of every CTA records the global timer
+struct Stamper {
+  long long* p;
+  int left;
+  __device__ __forceinline__ Stamper(const Args& a) {
+    p = (a.prof != nullptr && threadIdx.x == 0) ? a.prof + (size_t)blockIdx.x * a.prof_slots : nullptr;
+    left = a.prof_slots;
+  }
+  __device__ __forceinline__ void operator()() {
+    if (p != nullptr && left > 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      *p++ = t;
+      --left;
+    }
+  }
 };
 
 // ---- cluster / distributed shared memory primitives ---------------------------------------------------------------
@@ -404,6 +425,8 @@ fwd_kernel(const Args a) {
   // the topology is constant across steps: stage this CTA's slice before the dependency wait
   if (n > 0) stage_csr_slice(a.rowptr, a.col, lo, n, R, rp_s, col_s, a.ecap);
   pdl_wait();
+  Stamper stamp(a);
+  stamp();
   if (a.nb > 0) stage_block_params(a.params + pl.block(0), W1s, W2s, vec);
   cp_commit();
 
@@ -430,11 +453,14 @@ fwd_kernel(const Args a) {
     cp_commit();
 
     // conv1 projection + scores  (GraphModels.py:464) -> own shared tiles
+    stamp();
     project_mma<NC, 2 * NC, 2, LDX, LDX, LDY>(xs, W1, vc, vc + 2 * NC, h1s, ss1, sd1, scr, n);
+    stamp();
     cluster_arrive();
     // behind the arrival: the block input (encoder output / previous block's output) goes to HBM for the backward
     if (TRAIN) store_rows<NC, LDX>(xs, a.saved + (k > 0 ? sl.xout(k - 1) : sl.x_enc()) + ro * NC, n);
     cluster_wait();
+    stamp();
     if (TRAIN) {
       store_rows<2 * NC, LDY>(h1s, a.saved + sl.h1(k) + ro * 2 * NC, n);
       store_scalars(ss1, a.saved + sl.ss1(k) + ro * 2, 2 * n);
@@ -445,10 +471,13 @@ fwd_kernel(const Args a) {
                TRAIN ? a.saved + sl.y1(k) + ro * 2 * NC : nullptr, TRAIN ? a.saved + sl.m1(k) + ro * 2 : nullptr,
                TRAIN ? a.saved + sl.l1(k) + ro * 2 : nullptr, n, rank, true);
     __syncthreads();
+    stamp();
     // conv2 projection + scores  (:465)
     project_mma<2 * NC, NC, 1, LDY, LDY, LDX>(ys, W2, vc + 6 * NC, vc + 7 * NC, h2s, ss2, sd2, scr, n);
+    stamp();
     cluster_arrive();
     cluster_wait();
+    stamp();
     if (TRAIN) {
       store_rows<NC, LDX>(h2s, a.saved + sl.h2(k) + ro * NC, n);
       store_scalars(ss2, a.saved + sl.ss2(k) + ro, n);
@@ -457,6 +486,7 @@ fwd_kernel(const Args a) {
     // conv2 aggregation + bias -> z (neighbours read it in the mean); (m, l) wait in shared memory
     agg_fwd<1>(rp_s, col_s, h2_base, LDX * 4, ss2_base, sd2, vc + 8 * NC, zs, LDX, nullptr, TRAIN ? ml2 : nullptr,
                TRAIN ? ml2 + R : nullptr, n, rank, false);
+    stamp();
     cluster_arrive();
     if (TRAIN) {
       __syncthreads();
@@ -464,6 +494,7 @@ fwd_kernel(const Args a) {
       store_scalars(ml2 + R, a.saved + sl.l2(k) + ro, n);
     }
     cluster_wait();
+    stamp();
     // SimpleConv(mean) + residual + ReLU  (:466-467): in-neighbours minus the trailing self-loop
     {
       const int lig = lane & 7, sub = lane >> 3;
@@ -502,6 +533,594 @@ fwd_kernel(const Args a) {
   cluster_wait();
 }
 
+// =============================================================================== backward
+// dx[m][c] = sum_r G[m][r] W[r][c]  (data gradient; W [NRED][NOUT] as stored).  pre(m, c) -> float2 is evaluated for
+// every output fragment BEFORE the MMAs; fin(m, c, value, pre value) gets columns c, c+1.
+template <int NRED, int NOUT, int LDG, int LDW, typename Pre, typename Fin>
+__device__ __forceinline__ void dgrad_mma(const float* Gs, const float* Ws, int n, Pre pre, Fin fin) {
+  constexpr int NTW = NOUT / 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int nbase = (warp >> 2) * (NOUT / 2);
+  for (int m0 = (warp & 3) * 16; m0 < n; m0 += 64) {
+    const int r0 = min(m0 + g, n - 1), r1 = min(m0 + g + 8, n - 1);
+    float acc[NTW][4], acl[NTW][4], acm[NTW][4];
+#pragma unroll
+    for (int j = 0; j < NTW; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = acl[j][i] = acm[j][i] = 0.f;
+    float2 pr[NTW][2];
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) {
+      const int c = nbase + 8 * j + 2 * t;
+      pr[j][0] = pre(r0, c);
+      pr[j][1] = pre(r1, c);
+    }
+#pragma unroll 2
+    for (int k0 = 0; k0 < NRED; k0 += 8) {
+      const float av[4] = {Gs[r0 * LDG + k0 + t], Gs[r1 * LDG + k0 + t], Gs[r0 * LDG + k0 + t + 4], Gs[r1 * LDG + k0 + t + 4]};
+      unsigned a[4], al[4];
+      split_frag<4>(av, a, al);
+#pragma unroll
+      for (int j = 0; j < NTW; ++j) {
+        const float* wp = Ws + (k0 + t) * LDW + nbase + 8 * j + g;
+        const float bv[2] = {wp[0], wp[4 * LDW]};
+        unsigned b[2], bl[2];
+        split_frag<2>(bv, b, bl);
+        mma_3xtf32(acc[j], acl[j], acm[j], a, al, b, bl);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) {
+      fold3(acc[j], acl[j], acm[j]);
+      const int c = nbase + 8 * j + 2 * t;
+      if (m0 + g < n) fin(m0 + g, c, make_float2(acc[j][0], acc[j][1]), pr[j][0]);
+      if (m0 + g + 8 < n) fin(m0 + g + 8, c, make_float2(acc[j][2], acc[j][3]), pr[j][1]);
+    }
+  }
+}
+
+// dW[no][ki] += sum_m G[m][no] X[m][ki]: 16 x 8 output tiles, the reduction runs over this CTA's rows (zero padded)
+template <int NO, int KI, int LDG, int LDXX>
+__device__ __forceinline__ void wgrad_mma(const float* Gs, const float* Xs, int n, float* dW) {
+  constexpr int TILES = (NO / 16) * (KI / 8), TPW = TILES / (T / 32);
+  static_assert(TILES % (T / 32) == 0, "wgrad tiles per warp");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  if (n <= 0) return;
+  float acc[TPW][4], acl[TPW][4], acm[TPW][4];
+  int no0[TPW], ki0[TPW];
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    const int tile = warp * TPW + q;
+    no0[q] = (tile / (KI / 8)) * 16;
+    ki0[q] = (tile % (KI / 8)) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[q][i] = acl[q][i] = acm[q][i] = 0.f;
+  }
+#pragma unroll 2
+  for (int m0 = 0; m0 < n; m0 += 8) {
+    const bool k0ok = m0 + t < n, k1ok = m0 + t + 4 < n;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      const float* g0 = Gs + (m0 + t) * LDG + no0[q] + g;
+      const float* g1 = Gs + (m0 + t + 4) * LDG + no0[q] + g;
+      const float av[4] = {k0ok ? g0[0] : 0.f, k0ok ? g0[8] : 0.f, k1ok ? g1[0] : 0.f, k1ok ? g1[8] : 0.f};
+      const float bv[2] = {k0ok ? Xs[(m0 + t) * LDXX + ki0[q] + g] : 0.f, k1ok ? Xs[(m0 + t + 4) * LDXX + ki0[q] + g] : 0.f};
+      unsigned a[4], al[4], b[2], bl[2];
+      split_frag<4>(av, a, al);
+      split_frag<2>(bv, b, bl);
+      mma_3xtf32(acc[q], acl[q], acm[q], a, al, b, bl);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    fold3(acc[q], acl[q], acm[q]);
+    atomicAdd(reinterpret_cast<float2*>(dW + (size_t)(no0[q] + g) * KI + ki0[q] + 2 * t), make_float2(acc[q][0], acc[q][1]));
+    atomicAdd(reinterpret_cast<float2*>(dW + (size_t)(no0[q] + g + 8) * KI + ki0[q] + 2 * t), make_float2(acc[q][2], acc[q][3]));
+  }
+}
+
+// sum per-lane float4 accumulators over every lane of the CTA that holds the same chunk (lane % LPR) and add the LPR
+// chunk sums into dst (atomic).  red: T*4 floats of shared scratch.  All threads call.
+template <int LPR>
+__device__ __forceinline__ void cta_chunk_sum_atomic(float4 acc, float* red, float* dst) {
+  __syncthreads();
+  st4(red + threadIdx.x * 4, acc);
+  __syncthreads();
+  if (threadIdx.x < LPR) {
+    float4 s = f4zero();
+    for (int t = threadIdx.x; t < T; t += LPR) add4(s, lds4(red + t * 4));
+    atomicAdd(reinterpret_cast<float4*>(dst + 4 * threadIdx.x), s);
+  }
+}
+// sum a per-lane float4 over the four row slots of a warp and park it in this warp's row of `vred`
+__device__ __forceinline__ void warp_chunk_park(float4 v, float* dst) {
+#pragma unroll
+  for (int o = 8; o < 32; o <<= 1) {
+    v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
+    v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
+  }
+  if ((threadIdx.x & 31) < 8) st4(dst + 4 * (threadIdx.x & 31), v);
+}
+
+// Backward pass 1 over own target rows: D_i, ds_dst[i]; rec = {s_dst, m, 1/(l+eps), D} (read by the
+// neighbours' pass 2 through DSMEM).  MEAN (conv2, H = 1): the incoming gradient is produced on the fly as the
+// SimpleConv(mean) backward of the running gradient g (dz[j] = sum_{j->i} g[i] / max(indeg(i), 1); wt_s holds the
+// weight of every out-edge) and is also written to dz_s for pass 2's gathers; otherwise it is read from the tile g_s.
+template <int H, bool MEAN>
+__device__ __forceinline__ void bwd_p1(const int* rp_s, const int* col_s, const int* rpt_s, const int* colt_s,
+                                       const float* wt_s, unsigned g_base, float* dz_s, const float* g_s, int ldg_s,
+                                       unsigned h_base, int ldh, unsigned ss_base, const float* sd_s, const float* m_s,
+                                       const float* l_s, float* rec_s, float* dsd_s, float* vred_bias, int n,
+                                       int self_owner) {
+  static_assert(!MEAN || H == 1, "the mean backward feeds conv2 (one head)");
+  constexpr int RPW = 4, PRE = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, slot = lane & 7;
+  float4 bacc[H];
+#pragma unroll
+  for (int v = 0; v < H; ++v) bacc[v] = f4zero();
+  for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
+    const int il_raw = i0 + warp * RPW + sub;
+    const bool ok = il_raw < n;
+    const int il = ok ? il_raw : n - 1;
+    const int beg = rp_s[il], deg = rp_s[il + 1] - beg;
+    const int deg_max = __reduce_max_sync(FULL, deg);
+    const int self = (self_owner << 16) | il;
+    // neighbour rows and scores of the first chunk are requested before the mean backward's own gathers
+    const bool valid0 = slot < deg;
+    const int j0 = valid0 ? col_s[beg + slot] : self;
+    const int cnt0 = min(8, deg);
+    float4 x0[PRE][H];
+    float ssv0[H], sd[H], mi[H], il_[H], S1[H], S2[H], S3[H];
+#pragma unroll
+    for (int u = 0; u < PRE; ++u) {
+      const int ju = __shfl_sync(FULL, j0, u, 8);
+      const unsigned au = row_addr(h_base, ju, ldh) + 16u * slot;
+#pragma unroll
+      for (int v = 0; v < H; ++v) x0[u][v] = u < cnt0 ? ldsc4(au + 128u * v) : f4zero();
+    }
+    {
+      const unsigned as_ = row_addr(ss_base, j0, 4 * H);
+      if (H == 2) {
+        const float2 t2 = ldsc2(as_);
+        ssv0[0] = t2.x; ssv0[H - 1] = t2.y;
+      } else ssv0[0] = ldsc1(as_);
+    }
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      sd[v] = sd_s[il * H + v];
+      mi[v] = m_s[il * H + v];
+      il_[v] = 1.f / (l_s[il * H + v] + kSoftmaxEps);
+      S1[v] = S2[v] = S3[v] = 0.f;
+    }
+    float4 gv[H];
+    if (MEAN) {
+      const int tb = rpt_s[il], te = rpt_s[il + 1] - 1;     // out-edges minus the self-loop
+      gv[0] = f4zero();
+#pragma unroll 4
+      for (int e = tb; e < te; ++e) fma4(gv[0], wt_s[e], ldsc4(row_addr(g_base, colt_s[e], LDX * 4) + 16u * slot));
+      if (ok) st4(dz_s + il * LDX + 4 * slot, gv[0]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < H; ++v) gv[v] = lds4(g_s + il * ldg_s + 32 * v + 4 * slot);
+    }
+#pragma unroll
+    for (int v = 0; v < H; ++v)
+      if (ok) add4(bacc[v], gv[v]);
+    for (int e0 = 0; e0 < deg_max; e0 += 8) {
+      const bool valid = e0 + slot < deg;
+      const int j = e0 == 0 ? j0 : (valid ? col_s[beg + e0 + slot] : self);
+      const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
+      float4 x[PRE][H];
+      float alpha[H], sl[H], da[H], ssv[H];
+      if (e0 == 0) {
+#pragma unroll
+        for (int u = 0; u < PRE; ++u)
+#pragma unroll
+          for (int v = 0; v < H; ++v) x[u][v] = x0[u][v];
+#pragma unroll
+        for (int v = 0; v < H; ++v) ssv[v] = ssv0[v];
+      } else {
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+          const int ju = __shfl_sync(FULL, j, u, 8);
+          const unsigned au = row_addr(h_base, ju, ldh) + 16u * slot;
+#pragma unroll
+          for (int v = 0; v < H; ++v) x[u][v] = u < cnt ? ldsc4(au + 128u * v) : f4zero();
+        }
+        const unsigned as_ = row_addr(ss_base, j, 4 * H);
+        if (H == 2) {
+          const float2 t2 = ldsc2(as_);
+          ssv[0] = t2.x; ssv[H - 1] = t2.y;
+        } else ssv[0] = ldsc1(as_);
+      }
+#pragma unroll
+      for (int v = 0; v < H; ++v) {
+        const float z = ssv[v] + sd[v];
+        alpha[v] = valid ? __expf(lrelu(z) - mi[v]) * il_[v] : 0.f;
+        sl[v] = lrelu_slope(z);
+        da[v] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < PRE; ++u)
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float d = group_sum<8>(dot4(gv[v], x[u][v]), FULL);
+          da[v] = slot == u ? d : da[v];
+        }
+      for (int t = PRE; t < cnt_max; t += 2) {
+        const int j0_ = __shfl_sync(FULL, j, t, 8), j1_ = __shfl_sync(FULL, j, t + 1, 8);
+        const unsigned a0 = row_addr(h_base, j0_, ldh) + 16u * slot, a1 = row_addr(h_base, j1_, ldh) + 16u * slot;
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float4 xa = t < cnt ? ldsc4(a0 + 128u * v) : f4zero();
+          const float4 xb = t + 1 < cnt ? ldsc4(a1 + 128u * v) : f4zero();
+          const float d0 = group_sum<8>(dot4(gv[v], xa), FULL), d1 = group_sum<8>(dot4(gv[v], xb), FULL);
+          da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < H; ++v) {
+        S1[v] = fmaf(alpha[v], da[v], S1[v]);
+        S2[v] = fmaf(alpha[v] * sl[v], da[v], S2[v]);
+        S3[v] = fmaf(alpha[v], sl[v], S3[v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      const float D = group_sum<8>(S1[v], FULL), T2 = group_sum<8>(S2[v], FULL), T3 = group_sum<8>(S3[v], FULL);
+      if (slot == 0 && ok) {
+        st4(rec_s + (il * H + v) * 4, make_float4(sd[v], mi[v], il_[v], D));
+        dsd_s[il * H + v] = T2 - D * T3;
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < H; ++v) warp_chunk_park(bacc[v], vred_bias + 32 * v);
+}
+
+// Backward pass 2 over own source rows: dh[j] (-> own shared tile), ds_src, datt_src / datt_dst partials.  The
+// gradient rows g[i] and the records of the edges' targets come through DSMEM; h, s_src, ds_dst of the row are own.
+template <int H>
+__device__ __forceinline__ void bwd_p2(const int* rpt_s, const int* colt_s, unsigned g_base, int ldg, unsigned rec_base,
+                                       const float* dsd_s, const float* h_s, int ldh_own, const float* ss_s,
+                                       const float* att_s, const float* att_d, float* dh_s, int ld_dh, float* vred_as,
+                                       float* vred_ad, int n, int self_owner) {
+  constexpr int RPW = 4, PRE = H == 1 ? 4 : 2;     // two heads per lane: fewer gathers in flight (registers)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, slot = lane & 7;
+  float4 as[H], ad[H], accs[H], accd[H];
+#pragma unroll
+  for (int v = 0; v < H; ++v) {
+    as[v] = lds4(att_s + 32 * v + 4 * slot);
+    ad[v] = lds4(att_d + 32 * v + 4 * slot);
+    accs[v] = f4zero();
+    accd[v] = f4zero();
+  }
+  for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
+    const int il_raw = i0 + warp * RPW + sub;
+    const bool ok = il_raw < n;
+    const int il = ok ? il_raw : n - 1;
+    const int beg = rpt_s[il], deg = rpt_s[il + 1] - beg;
+    const int deg_max = __reduce_max_sync(FULL, deg);
+    const int self = (self_owner << 16) | il;
+    float4 hv[H], dacc[H];
+    float ss[H], dsrc[H];
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      hv[v] = lds4(h_s + il * ldh_own + 32 * v + 4 * slot);
+      ss[v] = ss_s[il * H + v];
+      dacc[v] = f4zero();
+      dsrc[v] = 0.f;
+    }
+    for (int e0 = 0; e0 < deg_max; e0 += 8) {
+      const bool valid = e0 + slot < deg;
+      const int i = valid ? colt_s[beg + e0 + slot] : self;
+      const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
+      float4 gx[PRE][H];
+#pragma unroll
+      for (int u = 0; u < PRE; ++u) {
+        const int iu = __shfl_sync(FULL, i, u, 8);
+        const unsigned au = row_addr(g_base, iu, ldg) + 16u * slot;
+#pragma unroll
+        for (int v = 0; v < H; ++v) gx[u][v] = u < cnt ? ldsc4(au + 128u * v) : f4zero();
+      }
+      float alpha[H], k2[H], Dt[H], da[H];
+      const unsigned ar = row_addr(rec_base, i, 16 * H);
+#pragma unroll
+      for (int v = 0; v < H; ++v) {
+        const float4 t4 = ldsc4(ar + 16u * v);      // {s_dst, m, 1/l, D} of the edge's target
+        const float z = ss[v] + t4.x;
+        alpha[v] = valid ? __expf(lrelu(z) - t4.y) * t4.z : 0.f;
+        k2[v] = alpha[v] * lrelu_slope(z);
+        Dt[v] = t4.w;
+        da[v] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < PRE; ++u)
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float d = group_sum<8>(dot4(gx[u][v], hv[v]), FULL);
+          da[v] = slot == u ? d : da[v];
+          fma4(dacc[v], __shfl_sync(FULL, alpha[v], u, 8), gx[u][v]);
+        }
+      for (int t = PRE; t < cnt_max; t += 2) {
+        const int i0_ = __shfl_sync(FULL, i, t, 8), i1_ = __shfl_sync(FULL, i, t + 1, 8);
+        const unsigned a0 = row_addr(g_base, i0_, ldg) + 16u * slot, a1 = row_addr(g_base, i1_, ldg) + 16u * slot;
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float4 g0 = t < cnt ? ldsc4(a0 + 128u * v) : f4zero();
+          const float4 g1 = t + 1 < cnt ? ldsc4(a1 + 128u * v) : f4zero();
+          const float d0 = group_sum<8>(dot4(g0, hv[v]), FULL), d1 = group_sum<8>(dot4(g1, hv[v]), FULL);
+          da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
+          const float a0v = __shfl_sync(FULL, alpha[v], t, 8), a1v = __shfl_sync(FULL, alpha[v], t + 1, 8);
+          fma4(dacc[v], a0v, g0);
+          fma4(dacc[v], t + 1 < 8 ? a1v : 0.f, g1);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < H; ++v) dsrc[v] = fmaf(k2[v], da[v] - Dt[v], dsrc[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < H; ++v) {
+      const float ds = group_sum<8>(dsrc[v], FULL);
+      const float dd = dsd_s[il * H + v];
+      fma4(dacc[v], ds, as[v]);
+      fma4(dacc[v], dd, ad[v]);
+      if (ok) {
+        st4(dh_s + il * ld_dh + 32 * v + 4 * slot, dacc[v]);
+        fma4(accs[v], ds, hv[v]);
+        fma4(accd[v], dd, hv[v]);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < H; ++v) {
+    warp_chunk_park(accs[v], vred_as + 32 * v);
+    warp_chunk_park(accd[v], vred_ad + 32 * v);
+  }
+}
+
+// Shared memory (floats): g[R][LDX] h2s[R][LDX] dzd[R][2 LDX] (dz | dh2, later dh1) h1s[R][LDY] ys[R][LDY] xs[R][LDX]
+//   ss2[R] sc2[3R] (sd2 m2 l2) rec2[4R] dsd2[R] ss1[2R] sc1[6R] (sd1 m1 l1) rec1[8R] dsd1[2R]
+//   W1s[W1F] W2s[W2F] vec[VECF] vred[8][VECF] wt[ecap] | ints: rp[R+1] col[ecap] rpt[R+1] colt[ecap]
+struct BwdSmem {
+  int g, h2s, dzd, h1s, ys, xs, ss2, sc2, rec2, dsd2, ss1, sc1, rec1, dsd1, W1s, W2s, vec, vred, wt, rp, col, rpt, colt, total;
+  __host__ __device__ BwdSmem(int R, int ecap) {
+    int o = 0;
+    auto take = [&](int nfl) { const int at = o; o += (int)a4(nfl); return at; };
+    g = take(R * LDX); h2s = take(R * LDX); dzd = take(R * 2 * LDX > T * 4 ? R * 2 * LDX : T * 4); h1s = take(R * LDY); ys = take(R * LDY); xs = take(R * LDX);
+    ss2 = take(R); sc2 = take(3 * (int)a4(R)); rec2 = take(4 * R); dsd2 = take(R);
+    ss1 = take(2 * R); sc1 = take(3 * (int)a4(2 * R)); rec1 = take(8 * R); dsd1 = take(2 * R);
+    W1s = take(W1F); W2s = take(W2F); vec = take(VECF); vred = take((T / 32) * VECF); wt = take(ecap);
+    rp = take(R + 1); col = take(ecap); rpt = take(R + 1); colt = take(ecap);
+    total = o;
+  }
+};
+
+__global__ void __launch_bounds__(T, 2)
+bwd_kernel(const Args a) {
+  extern __shared__ __align__(16) float smem[];
+  const int R = a.R, N = a.N, nb = a.nb;
+  const BwdSmem L(R, a.ecap);
+  float* gs = smem + L.g;                  // running gradient w.r.t. the block output (own rows; neighbours read it)
+  float* h2s = smem + L.h2s;
+  float* dz = smem + L.dzd;                // [R][LDX] mean-backward output (neighbours read it in conv2's pass 2)
+  float* d2s = dz + R * LDX;               // [R][LDX] dh2 (own)
+  float* dh1 = dz;                         // [R][LDY] dh1 (own) over dz | dh2 once both are dead
+  float* h1s = smem + L.h1s;
+  float* ys = smem + L.ys;                 // y1 -> dy1 (own rows; neighbours read dy1 in conv1's pass 2)
+  float* xs = smem + L.xs;                 // x0 of the block
+  float* ss2 = smem + L.ss2;
+  float* sd2 = smem + L.sc2;
+  float* m2 = sd2 + a4(R);
+  float* l2 = m2 + a4(R);
+  float* rec2 = smem + L.rec2;
+  float* dsd2 = smem + L.dsd2;
+  float* ss1 = smem + L.ss1;
+  float* sd1 = smem + L.sc1;
+  float* m1 = sd1 + a4(2 * R);
+  float* l1 = m1 + a4(2 * R);
+  float* rec1 = smem + L.rec1;
+  float* dsd1 = smem + L.dsd1;
+  float* W1 = smem + L.W1s;
+  float* W2 = smem + L.W2s;
+  float* vc = smem + L.vec;
+  float* vred = smem + L.vred;
+  float* wt = smem + L.wt;
+  float* red = dz;                         // T*4 floats of reduction scratch for the decoder / encoder gradients
+  int* rp_s = reinterpret_cast<int*>(smem + L.rp);
+  int* col_s = reinterpret_cast<int*>(smem + L.col);
+  int* rpt_s = reinterpret_cast<int*>(smem + L.rpt);
+  int* colt_s = reinterpret_cast<int*>(smem + L.colt);
+  const int rank = (int)cluster_ctarank();
+  const long long b = cluster_id_x();
+  const int lo = rank * R, n = max(0, min(R, N - lo));
+  const long long M = a.M, rb = b * N, ro = rb + lo;
+  const ParamLayout pl(nb, NC);
+  const SavedLayout sl(M, NC);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* sv = a.saved;
+
+  if (n > 0) {
+    stage_csr_slice(a.rowptr, a.col, lo, n, R, rp_s, col_s, a.ecap);
+    // out-edge slice + the SimpleConv(mean) weight of every out-edge: 1 / max(in-degree of its target, 1)
+    const int e_lo = __ldg(a.rowptr_t + lo), cnt = min(__ldg(a.rowptr_t + lo + n) - e_lo, a.ecap);
+    for (int c = threadIdx.x; c <= n; c += T) rpt_s[c] = __ldg(a.rowptr_t + lo + c) - e_lo;
+    for (int c = threadIdx.x; c < cnt; c += T) {
+      const int t = __ldg(a.col_t + e_lo + c);
+      const int owner = t / R;
+      colt_s[c] = (owner << 16) | (t - owner * R);
+      const int dg = __ldg(a.rowptr + t + 1) - __ldg(a.rowptr + t) - 1;
+      wt[c] = 1.f / (float)(dg > 1 ? dg : 1);
+    }
+  }
+  pdl_wait();
+  Stamper stamp(a);
+  stamp();
+  const int k_first = nb > 0 ? a.k_hi : -1;
+  const bool any = nb > 0 && k_first >= a.k_lo && k_first >= 0;
+
+  // cp.async groups in flight (oldest first) while block k runs:
+  //   [A: h2 / s2 scalars of k-1, after phase 2] [B: h1 / s1 scalars of k-1, after phase 5] [C: parameters of k-1, after
+  //   phase 6] | cluster barrier | [D: y1 / x0 of k-1]
+  auto load_conv2_side = [&](int k) {
+    stage_rows<NC, LDX>(sv + sl.h2(k) + ro * NC, h2s, n);
+    // scalar arrays start at ro (not 16-byte aligned in general): 4-byte copies
+    for (int c = threadIdx.x; c < n; c += T) {
+      cp4(ss2 + c, sv + sl.ss2(k) + ro + c);
+      cp4(sd2 + c, sv + sl.sd2(k) + ro + c);
+      cp4(m2 + c, sv + sl.m2(k) + ro + c);
+      cp4(l2 + c, sv + sl.l2(k) + ro + c);
+    }
+  };
+  auto load_conv1_side = [&](int k) {
+    stage_rows<2 * NC, LDY>(sv + sl.h1(k) + ro * 2 * NC, h1s, n);
+    for (int c = threadIdx.x; c < 2 * n; c += T) {
+      cp4(ss1 + c, sv + sl.ss1(k) + ro * 2 + c);
+      cp4(sd1 + c, sv + sl.sd1(k) + ro * 2 + c);
+      cp4(m1 + c, sv + sl.m1(k) + ro * 2 + c);
+      cp4(l1 + c, sv + sl.l1(k) + ro * 2 + c);
+    }
+  };
+  auto load_row_local = [&](int k) {
+    stage_rows<2 * NC, LDY>(sv + sl.y1(k) + ro * 2 * NC, ys, n);
+    stage_rows<NC, LDX>(sv + (k > 0 ? sl.xout(k - 1) : sl.x_enc()) + ro * NC, xs, n);
+  };
+  if (any) {
+    stage_block_params(a.params + pl.block(k_first), W1, W2, vc);
+    load_conv2_side(k_first);
+    load_conv1_side(k_first);
+  }
+  cp_commit();
+
+  if (a.head) {
+    // decoder backward: g[i][c] = d_out[i] w[c] (masked by the last ReLU), dw = sum d_out x, db = sum d_out
+    const int lig = lane & 7, sub = lane >> 3;
+    const float* xl = sv + (nb > 0 ? sl.xout(nb - 1) : sl.x_enc());
+    const float4 wv = ldg4(a.params + pl.lin1_w() + 4 * lig);
+    float4 aw = f4zero();
+    float ab = 0.f;
+    for (int il = warp * 4 + sub; il < n; il += T / 8) {
+      const float gv = __ldg(a.d_out + rb + __ldg(a.perm + lo + il));
+      const float4 xv = ldg4(xl + (ro + il) * NC + 4 * lig);
+      float4 d = make_float4(gv * wv.x, gv * wv.y, gv * wv.z, gv * wv.w);
+      if (nb > 0) d = mask4(d, xv);
+      st4(gs + il * LDX + 4 * lig, d);
+      fma4(aw, gv, xv);
+      if (lig == 0) ab += gv;
+    }
+    cta_chunk_sum_atomic<8>(aw, red, a.grads + pl.lin1_w());
+    ab = group_sum<32>(ab, FULL);
+    if (lane == 0 && ab != 0.f) atomicAdd(a.grads + pl.lin1_b(), ab);
+  } else {
+    // a later range of a split backward: the running gradient comes back from the scratch buffer (locality order)
+    for (int c = threadIdx.x; c < n * (NC / 4); c += T)
+      st4(gs + (c / (NC / 4)) * LDX + 4 * (c % (NC / 4)), ldg4_stream(a.scratch + (ro * NC) + 4 * c));
+  }
+  cp_wait_all();
+  cluster_arrive();
+  cluster_wait();                            // g, h2 / h1 and their source scores are visible cluster-wide
+
+  const unsigned g_base = smem_u32(gs), h2_base = smem_u32(h2s), h1_base = smem_u32(h1s), dz_base = smem_u32(dz);
+  const unsigned y_base = smem_u32(ys), ss2_base = smem_u32(ss2), ss1_base = smem_u32(ss1);
+  const unsigned rec2_base = smem_u32(rec2), rec1_base = smem_u32(rec1);
+
+  for (int k = k_first; k >= a.k_lo && k >= 0; --k) {
+    const bool more = k - 1 >= a.k_lo && k - 1 >= 0;
+    load_row_local(k);                       // group D of this block: y1 / x0 (own rows only), needed from phase 3 on
+    cp_commit();
+    stamp();
+    // (1) SimpleConv(mean) backward fused with conv2 pass 1 (incoming gradient dz stays in registers)
+    bwd_p1<1, true>(rp_s, col_s, rpt_s, colt_s, wt, g_base, dz, nullptr, 0, h2_base, LDX * 4, ss2_base, sd2, m2, l2, rec2,
+                    dsd2, vred + warp * VECF + 8 * NC, n, rank);
+    cp_wait_but_one();                       // this block's parameters have landed (group D may still fly)
+    stamp();
+    cluster_arrive();
+    cluster_wait();                          // dz / rec2 cluster-wide, parameters CTA-wide
+    stamp();
+    // (2) conv2 pass 2 -> dh2 (own)
+    bwd_p2<1>(rpt_s, colt_s, dz_base, LDX * 4, rec2_base, dsd2, h2s, LDX, ss2, vc + 6 * NC, vc + 7 * NC, d2s, LDX,
+              vred + warp * VECF + 6 * NC, vred + warp * VECF + 7 * NC, n, rank);
+    cp_wait_all();                           // y1 / x0 rows of this block
+    __syncthreads();                         // dh2, y1 and x0 are in shared memory; h2 / s2 buffers are free
+    if (more) load_conv2_side(k - 1);        // group A
+    cp_commit();
+    stamp();
+    // (3) conv2 projection backward: dW2 = dh2^T y1 ; dy1 = (dh2 W2) masked by y1 > 0 (in place over y1)
+    wgrad_mma<NC, 2 * NC, LDX, LDY>(d2s, ys, n, a.grads + pl.c2_W(k));
+    __syncthreads();
+    dgrad_mma<NC, 2 * NC, LDX, LDY>(d2s, W2, n, [](int, int) { return make_float2(0.f, 0.f); }, [&](int m, int c, float2 v, float2) {
+      float2* p = reinterpret_cast<float2*>(ys + m * LDY + c);
+      const float2 y = *p;
+      *p = make_float2(y.x > 0.f ? v.x : 0.f, y.y > 0.f ? v.y : 0.f);
+    });
+    __syncthreads();
+    stamp();
+    // (4) conv1 pass 1 (incoming gradient = dy1 from the own tile)
+    bwd_p1<2, false>(rp_s, col_s, rpt_s, colt_s, wt, 0u, nullptr, ys, LDY, h1_base, LDY * 4, ss1_base, sd1, m1, l1, rec1,
+                     dsd1, vred + warp * VECF + 4 * NC, n, rank);
+    stamp();
+    cluster_arrive();
+    cluster_wait();                          // dy1 / rec1 cluster-wide
+    stamp();
+    // (5) conv1 pass 2 -> dh1 (own, over dz | dh2: every CTA is past its pass 2 of conv2)
+    bwd_p2<2>(rpt_s, colt_s, y_base, LDY * 4, rec1_base, dsd1, h1s, LDY, ss1, vc, vc + 2 * NC, dh1, LDY,
+              vred + warp * VECF, vred + warp * VECF + 2 * NC, n, rank);
+    __syncthreads();                         // dh1 complete; h1 / s1 buffers are free
+    if (more) load_conv1_side(k - 1);        // group B
+    cp_commit();
+    stamp();
+    // (6) conv1 projection backward: dW1 = dh1^T x0 ; g = dh1 W1 + g (residual), masked by x0 > 0 for k > 0 (in place)
+    wgrad_mma<2 * NC, NC, LDY, LDX>(dh1, xs, n, a.grads + pl.c1_W(k));
+    {
+      const bool mask = k > 0;
+      dgrad_mma<2 * NC, NC, LDY, LDX>(
+          dh1, W1, n, [&](int m, int c) { return lds2(gs + m * LDX + c); },
+          [&](int m, int c, float2 v, float2 r) {
+            v.x += r.x;
+            v.y += r.y;
+            if (mask) {
+              const float2 x0 = lds2(xs + m * LDX + c);
+              v = make_float2(x0.x > 0.f ? v.x : 0.f, x0.y > 0.f ? v.y : 0.f);
+            }
+            *reinterpret_cast<float2*>(gs + m * LDX + c) = v;
+          });
+    }
+    // parameter-vector gradients of the block: sum the 8 warp rows, one 128-bit red per chunk
+    for (int c = threadIdx.x; c < VECF / 4; c += T) {
+      float4 s = f4zero();
+#pragma unroll
+      for (int w = 0; w < T / 32; ++w) add4(s, lds4(vred + w * VECF + 4 * c));
+      const long long off = c < 6 * NC / 4 ? pl.c1_as(k) + 4 * c : pl.c2_as(k) + 4 * (c - 6 * NC / 4);
+      if (n > 0) atomicAdd(reinterpret_cast<float4*>(a.grads + off), s);
+    }
+    __syncthreads();                         // W1 / W2 / vec / vred are free again
+    if (more) stage_block_params(a.params + pl.block(k - 1), W1, W2, vc);      // group C
+    cp_commit();
+    cp_wait_but_one();                       // groups A and B (what neighbours read) have landed
+    stamp();
+    cluster_arrive();
+    cluster_wait();                          // the new g and the next block's h2 / h1 / scores are visible
+  }
+  cp_wait_all();
+
+  if (a.tail) {
+    // encoder backward: dw[c] = sum_i g[i][c] x[i], db[c] = sum_i g[i][c]
+    const int lig = lane & 7, sub = lane >> 3;
+    float4 aw = f4zero(), ab = f4zero();
+    for (int il = warp * 4 + sub; il < n; il += T / 8) {
+      const float4 gv = lds4(gs + il * LDX + 4 * lig);
+      fma4(aw, __ldg(a.x + rb + __ldg(a.perm + lo + il)), gv);
+      add4(ab, gv);
+    }
+    cta_chunk_sum_atomic<8>(aw, red, a.grads + pl.lin0_w());
+    cta_chunk_sum_atomic<8>(ab, red, a.grads + pl.lin0_b());
+  } else {
+    store_rows<NC, LDX>(gs, a.scratch + ro * NC, n);      // the next range of a split backward continues from here
+  }
+}
+
 // ------------------------------------------------------------------------- host side
 static int g_enabled = -1;
 static bool enabled() {
@@ -513,6 +1132,7 @@ static bool enabled() {
 }
 
 static size_t fwd_smem(int R, int ecap) { return sizeof(float) * (size_t)FwdSmem(R, ecap).total; }
+static size_t bwd_smem(int R, int ecap) { return sizeof(float) * (size_t)BwdSmem(R, ecap).total; }
 
 template <void (*kern)(const Args)>
 static int launch_cluster(const char* what, int cs, long long B, size_t smem, cudaStream_t st, const Args& a) {
@@ -544,6 +1164,7 @@ static int launch_cluster(const char* what, int cs, long long B, size_t smem, cu
 }  // namespace res2
 
 int resident_forced_cluster();      // resident.cu (gatres_set_resident_cluster)
+void resident_profile(long long** buf, int* slots);      // resident.cu (gatres_set_resident_profile)
 
 // cluster size: as many CTAs per snapshot as keeps the whole batch co-resident at two CTAs per SM
 static int res2_cluster(long long B) {
@@ -562,13 +1183,16 @@ bool resident2_eligible(const gatres_model_desc* d, bool training, long long max
   if (!res2::enabled() || d->perm == nullptr || d->p_rowptr == nullptr || d->p_col == nullptr) return false;
   if (d->nc != 32 || d->E1 <= 0 || d->slots > 0) return false;
   if (d->B > max_batch) return false;
-  if (training) return false;               // backward pair: see resident2_backward (enabled below once built)
   const int cs = res2_cluster(d->B);
+  // the backward stack only pays off with 8 CTAs per snapshot (profiles/r1_resident.md); larger batches keep the
+  // first-generation forward + layer-by-layer backward pair
+  if (training && resident_forced_cluster() == 0 && cs < 8) return false;
   const int R = (d->N + cs - 1) / cs, ecap = res2_ecap(d, cs);
   if (R >= 65536 || ecap <= 0) return false;
   // two CTAs per SM while the batch needs them, one otherwise
   const size_t budget = d->B * cs > (long long)sm_count() ? res2::kMaxSmem : 200 * 1024;
-  return res2::fwd_smem(R, ecap) <= budget;
+  if (res2::fwd_smem(R, ecap) > budget) return false;
+  return !training || res2::bwd_smem(R, ecap) <= budget;
 }
 
 int resident2_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
@@ -577,12 +1201,28 @@ int resident2_forward(const gatres_model_desc* d, const float* params, const flo
   a.rowptr = d->p_rowptr; a.col = d->p_col; a.rowptr_t = d->p_rowptr_t; a.col_t = d->p_col_t; a.perm = d->perm;
   a.params = params; a.x = x; a.out = out; a.saved = saved; a.poison = d->poison;
   a.M = d->B * (long long)d->N; a.N = d->N; a.nb = d->num_blocks;
+  resident_profile(&a.prof, &a.prof_slots);
   const int cs = res2_cluster(d->B);
   a.R = (d->N + cs - 1) / cs;
   a.ecap = res2_ecap(d, cs);
   const size_t smem = res2::fwd_smem(a.R, a.ecap);
   return saved != nullptr ? res2::launch_cluster<res2::fwd_kernel<true>>("resident2_forward(train)", cs, d->B, smem, st, a)
                           : res2::launch_cluster<res2::fwd_kernel<false>>("resident2_forward", cs, d->B, smem, st, a);
+}
+
+int resident2_backward(const gatres_model_desc* d, const float* params, const float* x, const float* saved,
+                       const float* d_out, float* grads, float* scratch, int k_hi, int k_lo, bool head, bool tail,
+                       cudaStream_t st) {
+  res2::Args a = {};
+  a.rowptr = d->p_rowptr; a.col = d->p_col; a.rowptr_t = d->p_rowptr_t; a.col_t = d->p_col_t; a.perm = d->perm;
+  a.params = params; a.x = x; a.saved = const_cast<float*>(saved); a.d_out = d_out; a.grads = grads; a.scratch = scratch;
+  a.M = d->B * (long long)d->N; a.N = d->N; a.nb = d->num_blocks;
+  a.k_hi = k_hi; a.k_lo = k_lo; a.head = head; a.tail = tail;
+  resident_profile(&a.prof, &a.prof_slots);
+  const int cs = res2_cluster(d->B);
+  a.R = (d->N + cs - 1) / cs;
+  a.ecap = res2_ecap(d, cs);
+  return res2::launch_cluster<res2::bwd_kernel>("resident2_backward", cs, d->B, res2::bwd_smem(a.R, a.ecap), st, a);
 }
 
 }  // namespace gatres

@@ -32,9 +32,138 @@ from typing import Dict, List, Optional, Tuple
 import torch
 from torch import Tensor
 
+import numpy as np
+
 from . import _lib
 
 _ops = None
+
+# templates up to this many nodes get a locality plan (the snapshot-resident kernels only run on graphs whose row
+# slices fit shared memory; the dense eigen-decomposition below is O(N^3))
+LOCALITY_MAX_NODES = 2048
+
+
+def _components(sub: np.ndarray) -> np.ndarray:
+    """connected-component label of every node of a dense symmetric adjacency matrix (labels in order of the
+    smallest member)"""
+    m = sub.shape[0]
+    lab = np.full(m, -1, dtype=np.int64)
+    c = 0
+    for start in range(m):
+        if lab[start] >= 0:
+            continue
+        lab[start] = c
+        frontier = np.array([start])
+        while frontier.size:
+            nxt = np.where((sub[frontier].sum(0) > 0) & (lab < 0))[0]
+            lab[nxt] = c
+            frontier = nxt
+        c += 1
+    return lab
+
+
+def locality_order(edge_index: np.ndarray, num_nodes: int, leaf: int = 6, slices: int = 8) -> np.ndarray:
+    """Permutation (locality row -> original node id) that puts neighbours close together: recursive spectral
+    bisection of the undirected template.  Every sub-graph is laid out along its Fiedler vector (component by
+    component, so a disconnected piece never yields a null-space vector), cut in two, and the halves are oriented
+    towards the segments already placed on either side.  The top levels cut at the row-slice boundaries the resident
+    kernels use (`slices` equal slices of ceil(N / slices) rows), so most of a row's neighbours belong to the same
+    CTA whatever the original numbering was (C-Town-shaped synthetic network with random ids: 11 % of the neighbours
+    local at 8 CTAs per snapshot before, 96 % after).  Deterministic: ties by node id."""
+    N = int(num_nodes)
+    s, d = np.asarray(edge_index[0], dtype=np.int64), np.asarray(edge_index[1], dtype=np.int64)
+    keep = s != d
+    A = np.zeros((N, N), dtype=np.float64)
+    A[s[keep], d[keep]] = 1.0
+    A[d[keep], s[keep]] = 1.0
+    R = -(-N // slices)
+    order: List[int] = []
+    placed = np.zeros(N, dtype=bool)
+
+    def spectral_sequence(nodes: np.ndarray) -> np.ndarray:
+        sub = A[np.ix_(nodes, nodes)]
+        lab = _components(sub)
+        seq: List[int] = []
+        for c in range(int(lab.max()) + 1):
+            loc = np.where(lab == c)[0]
+            if len(loc) <= 2:
+                seq.extend(nodes[loc].tolist())
+                continue
+            part = sub[np.ix_(loc, loc)]
+            _, vec = np.linalg.eigh(np.diag(part.sum(1)) - part)
+            f = vec[:, 1]
+            f = f * (1.0 if f[np.argmax(np.abs(f))] > 0 else -1.0)        # fix the eigenvector's sign
+            seq.extend(nodes[loc][np.lexsort((nodes[loc], np.round(f, 9)))].tolist())
+        return np.asarray(seq, dtype=np.int64)
+
+    def rec(nodes: np.ndarray, aligned: bool) -> None:
+        m = len(nodes)
+        if m <= leaf:
+            order.extend(nodes.tolist())
+            placed[nodes] = True
+            return
+        seq = spectral_sequence(nodes)
+        cut = -(-(-(-m // R)) // 2) * R if (aligned and m > R) else (m + 1) // 2    # a multiple of the slice length
+        first, second = seq[:cut], seq[cut:]
+        inseg = np.zeros(N, dtype=bool)
+        inseg[nodes] = True
+        left, right = np.where(placed)[0], np.where(~(placed | inseg))[0]
+        rev = seq[::-1]
+        keep_score = A[np.ix_(first, left)].sum() + A[np.ix_(second, right)].sum()
+        flip_score = A[np.ix_(rev[:cut], left)].sum() + A[np.ix_(rev[cut:], right)].sum()
+        if flip_score > keep_score:
+            first, second = rev[:cut], rev[cut:]
+        rec(first, aligned)
+        rec(second, aligned and m - cut > R)
+
+    rec(np.arange(N), True)
+    return np.asarray(order, dtype=np.int64)
+
+
+def permute_csr(rowptr: np.ndarray, col: np.ndarray, perm: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """the same CSR in locality numbering: row r = node perm[r]; its entries are the locality ids of that node's
+    neighbours IN THE SAME ORDER (the reference's summation order: ascending original source id, self-loop last)"""
+    N = len(perm)
+    inv = np.empty(N, dtype=np.int64)
+    inv[perm] = np.arange(N)
+    deg = (rowptr[1:] - rowptr[:-1])[perm]
+    rp = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(deg, out=rp[1:])
+    out = np.empty(int(rp[-1]), dtype=np.int64)
+    for r in range(N):
+        i = perm[r]
+        out[rp[r]:rp[r + 1]] = inv[col[rowptr[i]:rowptr[i + 1]]]
+    return rp.astype(np.int32), out.astype(np.int32)
+
+
+@dataclass
+class LocalityPlan:
+    """Row order + CSR pair for the distributed-shared-memory resident kernels (gatres_model_desc.perm / p_*)."""
+    perm: Tensor                 # int32 [N], locality row -> original node id
+    rowptr: Tensor
+    col: Tensor
+    rowptr_t: Tensor
+    col_t: Tensor
+    ecap: Tuple[int, int, int, int]      # largest CSR slice of one CTA at 1 / 2 / 4 / 8 CTAs per snapshot
+
+    @staticmethod
+    def build(topo: "Topology") -> "LocalityPlan":
+        N = topo.N
+        dev = topo.rowptr.device
+        ei = topo.edge_index.cpu().numpy()
+        perm = locality_order(ei, N)
+        rp, col = permute_csr(topo.rowptr.cpu().numpy().astype(np.int64), topo.col.cpu().numpy().astype(np.int64), perm)
+        rpt, colt = permute_csr(topo.rowptr_t.cpu().numpy().astype(np.int64), topo.col_t.cpu().numpy().astype(np.int64), perm)
+        ecap = []
+        for cs in (1, 2, 4, 8):
+            R = -(-N // cs)
+            worst = 0
+            for r in range(cs):
+                lo, hi = min(N, r * R), min(N, (r + 1) * R)
+                worst = max(worst, int(rp[hi] - rp[lo]), int(rpt[hi] - rpt[lo]))
+            ecap.append(worst)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        return LocalityPlan(t(perm.astype(np.int32)), t(rp), t(col), t(rpt), t(colt), tuple(ecap))
 
 
 def _get_ops():
@@ -60,6 +189,18 @@ class Topology:
     # SimpleConv's view (gatres_csr_build_mean) when the template has self loops: GATConv drops them and adds its
     # own, SimpleConv(mean) keeps them as ordinary in-edges.  None = both views coincide.
     mean_csr: Optional[Tuple[Tensor, Tensor, Tensor, Tensor]] = None
+    _plan: Optional["LocalityPlan"] = None
+    _plan_tried: bool = False
+
+    @property
+    def plan(self) -> Optional["LocalityPlan"]:
+        """locality plan for the resident kernels, built on first use (host-side, one device read per template);
+        None for templates that never take that path (too large, or with self loops)"""
+        if not self._plan_tried:
+            self._plan_tried = True
+            if self.N <= LOCALITY_MAX_NODES and self.mean_csr is None and self.N >= 2:
+                self._plan = LocalityPlan.build(self)
+        return self._plan
 
     @property
     def shares_one_csr(self) -> bool:

@@ -196,11 +196,25 @@ _def("mean_res_bwd(Tensor rowptr, Tensor rowptr_t, Tensor col_t, Tensor g_out, T
 # whole model
 # ----------------------------------------------------------------------------
 def _desc(num_blocks: int, nc: int, N: int, B: int, rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor,
-          poison: Optional[Tensor], deterministic: bool = False) -> ModelDesc:
+          poison: Optional[Tensor], deterministic: bool = False, plan: Optional[List[Tensor]] = None) -> ModelDesc:
     """slots > 0: parameter gradients via per-CTA partial rows + a fixed-order reduction (bitwise
-    reproducible, small grids); slots = 0: atomic accumulation into the gradient buffer (full grids)."""
-    return ModelDesc(num_blocks, nc, N, grad_slots(B * N) if deterministic else 0, col.numel(), 0, B, ptr(rowptr), ptr(col),
-                     ptr(rowptr_t), ptr(col_t), ptr(poison))
+    reproducible, small grids); slots = 0: atomic accumulation into the gradient buffer (full grids).
+    plan: [perm, p_rowptr, p_col, p_rowptr_t, p_col_t, ecap(int32[4], host)] of graph.LocalityPlan, or None."""
+    d = ModelDesc(num_blocks, nc, N, grad_slots(B * N) if deterministic else 0, col.numel(), 0, B, ptr(rowptr), ptr(col),
+                  ptr(rowptr_t), ptr(col_t), ptr(poison))
+    if plan:
+        d.perm, d.p_rowptr, d.p_col, d.p_rowptr_t, d.p_col_t = (ptr(t) for t in plan[:5])
+        for q, v in enumerate(plan[5].tolist()):
+            d.p_ecap[q] = int(v)
+    return d
+
+
+def plan_tensors(topo) -> List[Tensor]:
+    """graph.LocalityPlan of a Topology as the tensor list the model ops take ([] = no plan)"""
+    p = topo.plan
+    if p is None:
+        return []
+    return [p.perm, p.rowptr, p.col, p.rowptr_t, p.col_t, torch.tensor(p.ecap, dtype=torch.int32)]
 
 
 def param_count(num_blocks: int, nc: int) -> int:
@@ -208,7 +222,8 @@ def param_count(num_blocks: int, nc: int) -> int:
 
 
 def _model_forward(params: Tensor, x: Tensor, rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor,
-                   poison: Optional[Tensor], num_blocks: int, nc: int, N: int, B: int, training: bool) -> List[Tensor]:
+                   poison: Optional[Tensor], num_blocks: int, nc: int, N: int, B: int, training: bool,
+                   deterministic: bool, plan: List[Tensor]) -> List[Tensor]:
     params, x = _f32(params, "model_forward"), _f32(x, "model_forward")
     M = B * N
     if x.numel() != M:
@@ -216,7 +231,8 @@ def _model_forward(params: Tensor, x: Tensor, rowptr: Tensor, col: Tensor, rowpt
     if params.numel() != param_count(num_blocks, nc):
         raise _lib.GatresError("model_forward: flat parameter buffer has the wrong size")
     lib = _lib.load()
-    d = _desc(num_blocks, nc, N, B, rowptr, col, rowptr_t, col_t, poison)
+    # the same descriptor (gradient mode, locality plan) as the backward: both sides must pick the same kernels
+    d = _desc(num_blocks, nc, N, B, rowptr, col, rowptr_t, col_t, poison, deterministic, plan)
     dev = x.device
     out = torch.empty(M, dtype=torch.float32, device=dev)
     saved = torch.empty(int(lib.gatres_saved_floats(C.byref(d))) if training else 0, dtype=torch.float32, device=dev)
@@ -228,15 +244,16 @@ def _model_forward(params: Tensor, x: Tensor, rowptr: Tensor, col: Tensor, rowpt
 
 
 _def("model_forward(Tensor params, Tensor x, Tensor rowptr, Tensor col, Tensor rowptr_t, Tensor col_t, "
-     "Tensor? poison, int num_blocks, int nc, int N, int B, bool training) -> Tensor[]", _model_forward)
+     "Tensor? poison, int num_blocks, int nc, int N, int B, bool training, bool deterministic, Tensor[] plan) -> Tensor[]",
+     _model_forward)
 
 
 def _model_backward(params: Tensor, x: Tensor, saved: Tensor, d_out: Tensor, rowptr: Tensor, col: Tensor,
                     rowptr_t: Tensor, col_t: Tensor, num_blocks: int, nc: int, N: int, B: int,
-                    deterministic: bool) -> Tensor:
+                    deterministic: bool, plan: List[Tensor]) -> Tensor:
     params, x, d_out = _f32(params, "model_backward"), _f32(x, "model_backward"), _f32(d_out, "model_backward")
     lib = _lib.load()
-    d = _desc(num_blocks, nc, N, B, rowptr, col, rowptr_t, col_t, None, deterministic)
+    d = _desc(num_blocks, nc, N, B, rowptr, col, rowptr_t, col_t, None, deterministic, plan)
     dev = x.device
     P = params.numel()
     grads = torch.empty(P, dtype=torch.float32, device=dev)
@@ -248,7 +265,7 @@ def _model_backward(params: Tensor, x: Tensor, saved: Tensor, d_out: Tensor, row
 
 
 _def("model_backward(Tensor params, Tensor x, Tensor saved, Tensor d_out, Tensor rowptr, Tensor col, "
-     "Tensor rowptr_t, Tensor col_t, int num_blocks, int nc, int N, int B, bool deterministic) -> Tensor",
+     "Tensor rowptr_t, Tensor col_t, int num_blocks, int nc, int N, int B, bool deterministic, Tensor[] plan) -> Tensor",
      _model_backward)
 
 
@@ -441,20 +458,21 @@ class _ModelFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, flat, topo, B, num_blocks, nc, poison, shapes, deterministic, *params):
         training = any(ctx.needs_input_grad[9:]) or ctx.needs_input_grad[1]
+        plan = plan_tensors(topo)
         out, saved = _ops.model_forward(flat, x, topo.rowptr, topo.col, topo.rowptr_t, topo.col_t, poison, num_blocks,
-                                        nc, topo.N, B, training)
+                                        nc, topo.N, B, training, deterministic, plan)
         if training:
             ctx.save_for_backward(x, flat, saved)
-            ctx.cfg = (topo, B, num_blocks, nc, shapes, deterministic)
+            ctx.cfg = (topo, B, num_blocks, nc, shapes, deterministic, plan)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         x, flat, saved = ctx.saved_tensors
-        topo, B, num_blocks, nc, shapes, deterministic = ctx.cfg
+        topo, B, num_blocks, nc, shapes, deterministic, plan = ctx.cfg
         grads = _ops.model_backward(flat, x, saved, g.contiguous(), topo.rowptr, topo.col, topo.rowptr_t, topo.col_t,
-                                    num_blocks, nc, topo.N, B, deterministic)
+                                    num_blocks, nc, topo.N, B, deterministic, plan)
         outs, off = [], 0
         for shp in shapes:
             n = 1

@@ -96,8 +96,9 @@ class TrainStep:
             self.exp_avg_sq = torch.zeros(P, **f32)
             self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.deterministic = deterministic
-        self.desc = ModelDesc(self.nb, self.nc, self.N, _gops.grad_slots(self.M) if deterministic else 0, topo.E1, 0, self.B,
-                              ptr(topo.rowptr), ptr(topo.col), ptr(topo.rowptr_t), ptr(topo.col_t), None)
+        self._plan = _gops.plan_tensors(topo)                  # keeps the plan tensors alive behind the raw pointers
+        self.desc = _gops._desc(self.nb, self.nc, self.N, self.B, topo.rowptr, topo.col, topo.rowptr_t, topo.col_t, None,
+                                deterministic, self._plan)
         lib = _lib.load()
         self.saved = torch.empty(int(lib.gatres_saved_floats(C.byref(self.desc))), **f32)
         self.scratch = torch.empty(int(lib.gatres_scratch_floats(C.byref(self.desc), 1)), **f32)

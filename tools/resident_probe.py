@@ -42,12 +42,14 @@ BWD_PHASES = ["mean_bwd+p1(conv2)", "sync", "p2(conv2)", "wgrad2+dgrad2", "p1(co
               "wgrad1+dgrad1+vec", "sync"]
 
 
-def phases(lib, fwd, bwd, blocks, dev):
+def phases(lib, fwd, bwd, blocks, dev, only=None):
     """mean duration (us) of each phase of a block, over blocks 1.. and all CTAs, from %globaltimer stamps"""
     slots, ctas = 1 + 9 * blocks + 2, 4096
     buf = torch.zeros(ctas * slots, dtype=torch.int64, device=dev)
     out = {}
     for name, fn, per, labels in (("fwd", fwd, 8, FWD_PHASES), ("bwd", bwd, 9, BWD_PHASES)):
+        if only is not None and name not in only:
+            continue
         buf.zero_()
         lib.gatres_set_resident_profile(buf.data_ptr(), slots)
         fn()
@@ -110,6 +112,7 @@ def main():
             row["step_us"] = time_graph(ts._enqueue_impl)
             if a.phases and kind == "resident":
                 row["phases"] = phases(lib, fwd, bwd, a.blocks, dev)
+                row["phases_infer"] = phases(lib, inf, bwd, a.blocks, dev, only=("fwd",))
             rows.append(row)
             print(json.dumps(row), flush=True)
     if a.out:
