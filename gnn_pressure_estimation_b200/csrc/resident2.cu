@@ -54,6 +54,7 @@ struct Args {
   long long M;
   int N, nb, R, ecap;    // ecap: shared-memory capacity (ints) of one CTA's slice of a CSR (max over the cluster)
   int k_hi, k_lo, head, tail;
+  int barrier;           // ClusterBarrier flavour
   long long* prof;       // optional phase-timestamp buffer [CTA][prof_slots] (tools/resident_probe.py), else NULL
   int prof_slots;
 };
@@ -79,8 +80,32 @@ struct Stamper {
 // ---- cluster / distributed shared memory primitives ---------------------------------------------------------------
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// Cluster barrier flavours (GATRES_RES2_BARRIER / gatres_set_resident_barrier):
+//   0: every thread arrives with .release — the formally fenced variant.  On sm_100a the cluster-scope release is a
+//      MEMBAR.ALL.GPU per thread: a round trip to L2 (~0.4 us measured with nothing outstanding) that also waits for
+//      the thread's outstanding GLOBAL stores / atomics / cp.async, none of which the exchange needs.
+//   1: __syncthreads, then warp 0 arrives with .release (cumulative over what the CTA barrier ordered before it) and
+//      the other warps with .relaxed.  Measured no faster than 0 (the fence drains the SM's queue, not the warp's).
+//   2 (default): membar.cta + __syncthreads + .relaxed arrival of every thread.  What crosses CTAs here is SHARED
+//      memory only: the owner's stores are performed in its SM's shared memory once the CTA-scope fence and the CTA
+//      barrier have drained them (B300_MICROARCH.md: BAR.SYNC drains pending STS), and a remote ld.shared::cluster
+//      reads that same SRAM through the SM-to-SM network after the cluster barrier completed — there is no cache in
+//      between that a gpu-scope fence would have to flush.  The PTX memory model does not name this case (a relaxed
+//      arrival does not synchronise formally); flavour 0 stays available and both are covered by the parity tests.
+//      Measured at 32 snapshots: forward barriers 0.85 -> 0.43 us each, training step 537 -> 516 us.
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+struct ClusterBarrier {
+  int flavour;
+  __device__ __forceinline__ void arrive() const {
+    if (flavour == 0) { cluster_arrive_release(); return; }
+    if (flavour == 2) __threadfence_block();
+    __syncthreads();
+    if (flavour == 2 || threadIdx.x >= 32) cluster_arrive_relaxed();
+    else cluster_arrive_release();
+  }
+};
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // address of `local_addr` (a shared-window address of THIS CTA) inside CTA `rank` of the cluster
 __device__ __forceinline__ unsigned mapa(unsigned local_addr, unsigned rank) {
@@ -283,82 +308,111 @@ __device__ __forceinline__ void project_mma(const float* As, const float* Ws, co
 }
 
 // ---- fused GAT aggregation over this CTA's rows (C = 32), neighbour rows through distributed shared memory ---------
-// Eight lanes own a row: lane `slot` holds the float4 chunk `slot` of EVERY head of the row and evaluates edge `slot`
-// of the row for every head (resident_impl.cuh: agg_fwd_rows).  h_base / ss_base: shared-window addresses of the h tile
-// (row stride ldh bytes) and of the source-score array ([row][H]) — the same offsets in every CTA of the cluster.
+// FOUR lanes own a row, so a warp covers eight rows and the 49-row slice of a CTA is ONE pass of its eight warps (the
+// phases are bound by the length of a warp's dependent instruction chain, not by issue slots: one chain instead of
+// two).  Lane `slot` holds the float4 chunks {slot, slot + 4} of EVERY head of the row and evaluates the edges
+// {slot, slot + 4} of each group of eight in-edges for every head (logit, LeakyReLU, exp); row max / sum are two-level
+// butterflies over the four lanes; the accumulation loop broadcasts (neighbour, weight) with two shuffles per edge.
+// h_base / ss_base: shared-window addresses of the h tile (row stride ldh bytes) and of the source-score array
+// ([row][H]) — the same offsets in every CTA of the cluster.
+__device__ __forceinline__ float gmax4(float v) {
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 2));
+  return fmaxf(v, __shfl_xor_sync(FULL, v, 1));
+}
+template <int H>
+__device__ __forceinline__ void load_scores(unsigned ss_base, int packed, float (&s)[H]) {
+  const unsigned a = row_addr(ss_base, packed, 4 * H);
+  if (H == 2) {
+    const float2 t2 = ldsc2(a);
+    s[0] = t2.x; s[H - 1] = t2.y;
+  } else s[0] = ldsc1(a);
+}
+
 template <int H>
 __device__ __forceinline__ void agg_fwd(const int* rp_s, const int* col_s, unsigned h_base, int ldh, unsigned ss_base,
-                                        const float* sd_s, const float* bias_s, float* out_s, int ld_out, float* out_g,
+                                        const float* sd_s, const float* bias_s, float* out_s, int ld_out,
                                         float* m_dst, float* l_dst, int n, int self_owner, bool relu) {
-  constexpr int F = 32 * H, RPW = 4, PRE = 4;
+  constexpr int RPW = 8, PRE = H == 1 ? 4 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane >> 3, slot = lane & 7;
-  float4 bv[H];
+  const int sub = lane >> 2, slot = lane & 3;
+  float4 bv[H][2];
 #pragma unroll
-  for (int v = 0; v < H; ++v) bv[v] = lds4(bias_s + 32 * v + 4 * slot);
+  for (int v = 0; v < H; ++v)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) bv[v][c] = lds4(bias_s + 32 * v + 16 * c + 4 * slot);
   for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
     const int il_raw = i0 + warp * RPW + sub;
     const bool ok = il_raw < n;
     const int il = ok ? il_raw : n - 1;
     const int beg = rp_s[il], deg = rp_s[il + 1] - beg;
     const int deg_max = __reduce_max_sync(FULL, deg);
+    const int self = (self_owner << 16) | il;
     float sd[H], mrun[H], lrun[H];
-    float4 acc[H];
+    float4 acc[H][2];
 #pragma unroll
     for (int v = 0; v < H; ++v) {
       sd[v] = sd_s[il * H + v];
       mrun[v] = -CUDART_INF_F;
       lrun[v] = 0.f;
-      acc[v] = f4zero();
+      acc[v][0] = acc[v][1] = f4zero();
     }
     for (int e0 = 0; e0 < deg_max; e0 += 8) {
-      const bool valid = e0 + slot < deg;
-      const int j = valid ? col_s[beg + e0 + slot] : ((self_owner << 16) | il);
+      const bool valid0 = e0 + slot < deg, valid1 = e0 + slot + 4 < deg;
+      const int j0 = valid0 ? col_s[beg + e0 + slot] : self;
+      const int j1 = valid1 ? col_s[beg + e0 + slot + 4] : self;
       const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
-      float4 x[PRE][H];
+      float4 x[PRE][H][2];
 #pragma unroll
       for (int u = 0; u < PRE; ++u) {
-        const int ju = __shfl_sync(FULL, j, u, 8);
+        const int ju = __shfl_sync(FULL, j0, u, 4);
         const unsigned au = row_addr(h_base, ju, ldh) + 16u * slot;
 #pragma unroll
-        for (int v = 0; v < H; ++v) x[u][v] = u < cnt ? ldsc4(au + 128u * v) : f4zero();
+        for (int v = 0; v < H; ++v)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) x[u][v][c] = u < cnt ? ldsc4(au + 128u * v + 64u * c) : f4zero();
       }
-      float sj[H];
-      {
-        const unsigned as_ = row_addr(ss_base, j, 4 * H);
-        if (H == 2) {
-          const float2 t2 = ldsc2(as_);
-          sj[0] = t2.x; sj[H - 1] = t2.y;
-        } else sj[0] = ldsc1(as_);
+      float s0[H], s1[H], p0[H], p1[H];
+      load_scores<H>(ss_base, j0, s0);
+      if (cnt_max > 4) load_scores<H>(ss_base, j1, s1);
+      else {
+#pragma unroll
+        for (int v = 0; v < H; ++v) s1[v] = 0.f;
       }
-      float p[H];
 #pragma unroll
       for (int v = 0; v < H; ++v) {
-        const float a = valid ? lrelu(sj[v] + sd[v]) : -CUDART_INF_F;
-        const float nm = fmaxf(mrun[v], gmax8(a));
+        const float a0 = valid0 ? lrelu(s0[v] + sd[v]) : -CUDART_INF_F;
+        const float a1 = valid1 ? lrelu(s1[v] + sd[v]) : -CUDART_INF_F;
+        const float nm = fmaxf(mrun[v], gmax4(fmaxf(a0, a1)));
         if (e0 > 0) {
           const float sc = __expf(mrun[v] - nm);
           lrun[v] *= sc;
-          acc[v].x *= sc; acc[v].y *= sc; acc[v].z *= sc; acc[v].w *= sc;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) { acc[v][c].x *= sc; acc[v][c].y *= sc; acc[v][c].z *= sc; acc[v][c].w *= sc; }
         }
-        p[v] = __expf(a - nm);
-        lrun[v] += group_sum<8>(p[v], FULL);
+        p0[v] = __expf(a0 - nm);
+        p1[v] = __expf(a1 - nm);
+        lrun[v] += group_sum<4>(p0[v] + p1[v], FULL);
         mrun[v] = nm;
       }
 #pragma unroll
       for (int u = 0; u < PRE; ++u)
 #pragma unroll
-        for (int v = 0; v < H; ++v) fma4(acc[v], __shfl_sync(FULL, p[v], u, 8), x[u][v]);
-      for (int t = PRE; t < cnt_max; t += 2) {
-        const int j0 = __shfl_sync(FULL, j, t, 8), j1 = __shfl_sync(FULL, j, t + 1, 8);
-        const unsigned a0 = row_addr(h_base, j0, ldh) + 16u * slot, a1 = row_addr(h_base, j1, ldh) + 16u * slot;
+        for (int v = 0; v < H; ++v) {
+          const float pu = __shfl_sync(FULL, p0[v], u, 4);
+          fma4(acc[v][0], pu, x[u][v][0]);
+          fma4(acc[v][1], pu, x[u][v][1]);
+        }
+      for (int t = PRE; t < cnt_max; ++t) {
+        const int jt = __shfl_sync(FULL, t < 4 ? j0 : j1, t & 3, 4);
+        const unsigned at = row_addr(h_base, jt, ldh) + 16u * slot;
+        const bool on = t < cnt;
 #pragma unroll
         for (int v = 0; v < H; ++v) {
-          const float4 x0 = t < cnt ? ldsc4(a0 + 128u * v) : f4zero();
-          const float4 x1 = t + 1 < cnt ? ldsc4(a1 + 128u * v) : f4zero();
-          const float p0 = __shfl_sync(FULL, p[v], t, 8), p1 = __shfl_sync(FULL, p[v], t + 1, 8);
-          fma4(acc[v], p0, x0);
-          fma4(acc[v], t + 1 < 8 ? p1 : 0.f, x1);
+          const float4 xa = on ? ldsc4(at + 128u * v) : f4zero();
+          const float4 xb = on ? ldsc4(at + 128u * v + 64u) : f4zero();
+          const float pt = __shfl_sync(FULL, t < 4 ? p0[v] : p1[v], t & 3, 4);
+          fma4(acc[v][0], pt, xa);
+          fma4(acc[v][1], pt, xb);
         }
       }
     }
@@ -366,26 +420,28 @@ __device__ __forceinline__ void agg_fwd(const int* rp_s, const int* col_s, unsig
 #pragma unroll
     for (int v = 0; v < H; ++v) {
       const float inv = 1.f / (lrun[v] + kSoftmaxEps);
-      float4 o = make_float4(fmaf(acc[v].x, inv, bv[v].x), fmaf(acc[v].y, inv, bv[v].y), fmaf(acc[v].z, inv, bv[v].z),
-                             fmaf(acc[v].w, inv, bv[v].w));
-      if (relu) o = relu4(o);
-      st4(out_s + il * ld_out + 32 * v + 4 * slot, o);
-      if (out_g != nullptr) st4_stream(out_g + (size_t)il * F + 32 * v + 4 * slot, o);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float4 o = make_float4(fmaf(acc[v][c].x, inv, bv[v][c].x), fmaf(acc[v][c].y, inv, bv[v][c].y),
+                               fmaf(acc[v][c].z, inv, bv[v][c].z), fmaf(acc[v][c].w, inv, bv[v][c].w));
+        if (relu) o = relu4(o);
+        st4(out_s + il * ld_out + 32 * v + 16 * c + 4 * slot, o);
+      }
       if (m_dst != nullptr && slot == 0) { m_dst[il * H + v] = mrun[v]; l_dst[il * H + v] = lrun[v]; }
     }
   }
 }
 
 // =============================================================================== forward
-// Shared memory (floats): xs[R][LDX] h1s[R][LDY] ys[R][LDY] h2s[R][LDX] zs[R][LDX] ss1[2R] sd1[2R] ss2[R] sd2[R] ml2[2R]
+// Shared memory (floats): xs[R][LDX] h1s[R][LDY] ys[R][LDY] h2s[R][LDX] zs[R][LDX] ss1[2R] sd1[2R] ss2[R] sd2[R] ml1[4R] ml2[2R]
 //                         W1s[2][W1F] W2s[2][W2F] vec[2][VECF] scr[4R] | ints: rp_s[R+1] col_s[ecap]
 struct FwdSmem {
-  int xs, h1s, ys, h2s, zs, ss1, sd1, ss2, sd2, ml2, W1s, W2s, vec, scr, rp, col, total;
+  int xs, h1s, ys, h2s, zs, ss1, sd1, ss2, sd2, ml1, ml2, W1s, W2s, vec, scr, rp, col, total;
   __host__ __device__ FwdSmem(int R, int ecap) {
     int o = 0;
     auto take = [&](int nfl) { const int at = o; o += (int)a4(nfl); return at; };
     xs = take(R * LDX); h1s = take(R * LDY); ys = take(R * LDY); h2s = take(R * LDX); zs = take(R * LDX);
-    ss1 = take(2 * R); sd1 = take(2 * R); ss2 = take(R); sd2 = take(R); ml2 = take(2 * R);
+    ss1 = take(2 * R); sd1 = take(2 * R); ss2 = take(R); sd2 = take(R); ml1 = take(4 * R); ml2 = take(2 * R);
     W1s = take(2 * W1F); W2s = take(2 * W2F); vec = take(2 * VECF); scr = take(4 * R);
     rp = take(R + 1); col = take(ecap);
     total = o;
@@ -407,6 +463,7 @@ fwd_kernel(const Args a) {
   float* sd1 = smem + L.sd1;
   float* ss2 = smem + L.ss2;
   float* sd2 = smem + L.sd2;
+  float* ml1 = smem + L.ml1;
   float* ml2 = smem + L.ml2;
   float* W1s = smem + L.W1s;
   float* W2s = smem + L.W2s;
@@ -415,6 +472,7 @@ fwd_kernel(const Args a) {
   int* rp_s = reinterpret_cast<int*>(smem + L.rp);
   int* col_s = reinterpret_cast<int*>(smem + L.col);
   const int rank = (int)cluster_ctarank();
+  const ClusterBarrier cb = {a.barrier};
   const long long b = cluster_id_x();
   const int lo = rank * R, n = max(0, min(R, N - lo));
   const long long M = a.M, rb = b * N, ro = rb + lo;    // snapshot base row, first own row (locality order)
@@ -449,72 +507,79 @@ fwd_kernel(const Args a) {
     float* vc = vec + buf * VECF;
     cp_wait_all();
     __syncthreads();                         // parameters of block k and xs are in place
-    if (k + 1 < a.nb) stage_block_params(a.params + pl.block(k + 1), W1s + (buf ^ 1) * W1F, W2s + (buf ^ 1) * W2F, vec + (buf ^ 1) * VECF);
-    cp_commit();
 
     // conv1 projection + scores  (GraphModels.py:464) -> own shared tiles
     stamp();
     project_mma<NC, 2 * NC, 2, LDX, LDX, LDY>(xs, W1, vc, vc + 2 * NC, h1s, ss1, sd1, scr, n);
     stamp();
-    cluster_arrive();
-    // behind the arrival: the block input (encoder output / previous block's output) goes to HBM for the backward
+    cb.arrive();
+    // Saved activations go to HBM only in the shadow of a barrier wait, right AFTER an arrival: the release fence of
+    // the next arrival then finds them long complete.  Here: the block input (encoder output / previous block's output).
     if (TRAIN) store_rows<NC, LDX>(xs, a.saved + (k > 0 ? sl.xout(k - 1) : sl.x_enc()) + ro * NC, n);
     cluster_wait();
     stamp();
-    if (TRAIN) {
-      store_rows<2 * NC, LDY>(h1s, a.saved + sl.h1(k) + ro * 2 * NC, n);
-      store_scalars(ss1, a.saved + sl.ss1(k) + ro * 2, 2 * n);
-      store_scalars(sd1, a.saved + sl.sd1(k) + ro * 2, 2 * n);
-    }
-    // conv1 aggregation + bias + ReLU -> y1 (row-local from here on)
-    agg_fwd<2>(rp_s, col_s, h1_base, LDY * 4, ss1_base, sd1, vc + 4 * NC, ys, LDY,
-               TRAIN ? a.saved + sl.y1(k) + ro * 2 * NC : nullptr, TRAIN ? a.saved + sl.m1(k) + ro * 2 : nullptr,
-               TRAIN ? a.saved + sl.l1(k) + ro * 2 : nullptr, n, rank, true);
+    // conv1 aggregation + bias + ReLU -> y1 (row-local from here on); (m, l) wait in shared memory
+    agg_fwd<2>(rp_s, col_s, h1_base, LDY * 4, ss1_base, sd1, vc + 4 * NC, ys, LDY, TRAIN ? ml1 : nullptr,
+               TRAIN ? ml1 + 2 * R : nullptr, n, rank, true);
     __syncthreads();
     stamp();
     // conv2 projection + scores  (:465)
     project_mma<2 * NC, NC, 1, LDY, LDY, LDX>(ys, W2, vc + 6 * NC, vc + 7 * NC, h2s, ss2, sd2, scr, n);
     stamp();
-    cluster_arrive();
+    cb.arrive();
+    // the next block's parameters are requested in the shadow of this barrier (their buffer was last read a block ago)
+    if (k + 1 < a.nb) stage_block_params(a.params + pl.block(k + 1), W1s + (buf ^ 1) * W1F, W2s + (buf ^ 1) * W2F, vec + (buf ^ 1) * VECF);
+    cp_commit();
+    if (TRAIN) {                             // conv1's tensors: all final, none rewritten before the next block
+      store_rows<2 * NC, LDY>(h1s, a.saved + sl.h1(k) + ro * 2 * NC, n);
+      store_rows<2 * NC, LDY>(ys, a.saved + sl.y1(k) + ro * 2 * NC, n);
+      store_scalars(ss1, a.saved + sl.ss1(k) + ro * 2, 2 * n);
+      store_scalars(sd1, a.saved + sl.sd1(k) + ro * 2, 2 * n);
+      store_scalars(ml1, a.saved + sl.m1(k) + ro * 2, 2 * n);
+      store_scalars(ml1 + 2 * R, a.saved + sl.l1(k) + ro * 2, 2 * n);
+    }
     cluster_wait();
     stamp();
+    // conv2 aggregation + bias -> z (neighbours read it in the mean)
+    agg_fwd<1>(rp_s, col_s, h2_base, LDX * 4, ss2_base, sd2, vc + 8 * NC, zs, LDX, TRAIN ? ml2 : nullptr,
+               TRAIN ? ml2 + R : nullptr, n, rank, false);
+    stamp();
+    cb.arrive();
     if (TRAIN) {
       store_rows<NC, LDX>(h2s, a.saved + sl.h2(k) + ro * NC, n);
       store_scalars(ss2, a.saved + sl.ss2(k) + ro, n);
       store_scalars(sd2, a.saved + sl.sd2(k) + ro, n);
-    }
-    // conv2 aggregation + bias -> z (neighbours read it in the mean); (m, l) wait in shared memory
-    agg_fwd<1>(rp_s, col_s, h2_base, LDX * 4, ss2_base, sd2, vc + 8 * NC, zs, LDX, nullptr, TRAIN ? ml2 : nullptr,
-               TRAIN ? ml2 + R : nullptr, n, rank, false);
-    stamp();
-    cluster_arrive();
-    if (TRAIN) {
-      __syncthreads();
+      __syncthreads();                       // (m, l) of conv2 were written by other warps just before the arrival
       store_scalars(ml2, a.saved + sl.m2(k) + ro, n);
       store_scalars(ml2 + R, a.saved + sl.l2(k) + ro, n);
     }
     cluster_wait();
     stamp();
-    // SimpleConv(mean) + residual + ReLU  (:466-467): in-neighbours minus the trailing self-loop
+    // SimpleConv(mean) + residual + ReLU  (:466-467): in-neighbours minus the trailing self-loop; four lanes per row
     {
-      const int lig = lane & 7, sub = lane >> 3;
-      for (int il = warp * 4 + sub; il < n; il += T / 8) {
+      const int slot = lane & 3, sub = lane >> 2;
+      for (int il = warp * 8 + sub; il < n; il += T / 4) {
         const int beg = rp_s[il], end = rp_s[il + 1] - 1;
-        float4 acc = f4zero();
+        float4 acc0 = f4zero(), acc1 = f4zero();
 #pragma unroll 4
-        for (int e = beg; e < end; ++e) add4(acc, ldsc4(row_addr(z_base, col_s[e], LDX * 4) + 16u * lig));
+        for (int e = beg; e < end; ++e) {
+          const unsigned ar = row_addr(z_base, col_s[e], LDX * 4) + 16u * slot;
+          add4(acc0, ldsc4(ar));
+          add4(acc1, ldsc4(ar + 64u));
+        }
         const int deg = end - beg;
         const float inv = 1.f / (float)(deg > 1 ? deg : 1);
-        const float4 xr = lds4(xs + il * LDX + 4 * lig);
-        st4(xs + il * LDX + 4 * lig,
-            relu4(make_float4(fmaf(acc.x, inv, xr.x), fmaf(acc.y, inv, xr.y), fmaf(acc.z, inv, xr.z), fmaf(acc.w, inv, xr.w))));
+        float* xr = xs + il * LDX + 4 * slot;
+        const float4 r0 = lds4(xr), r1 = lds4(xr + 16);
+        st4(xr, relu4(make_float4(fmaf(acc0.x, inv, r0.x), fmaf(acc0.y, inv, r0.y), fmaf(acc0.z, inv, r0.z), fmaf(acc0.w, inv, r0.w))));
+        st4(xr + 16, relu4(make_float4(fmaf(acc1.x, inv, r1.x), fmaf(acc1.y, inv, r1.y), fmaf(acc1.z, inv, r1.z), fmaf(acc1.w, inv, r1.w))));
       }
     }
   }
   cp_wait_all();
   __syncthreads();
   // no CTA may leave while a neighbour still reads its shared memory
-  cluster_arrive();
+  cb.arrive();
   if (TRAIN && a.nb > 0) store_rows<NC, LDX>(xs, a.saved + sl.xout(a.nb - 1) + ro * NC, n);
   if (TRAIN && a.nb == 0) store_rows<NC, LDX>(xs, a.saved + sl.x_enc() + ro * NC, n);
   // decoder Linear(nc, 1)  (:492)
@@ -579,14 +644,19 @@ __device__ __forceinline__ void dgrad_mma(const float* Gs, const float* Ws, int 
   }
 }
 
-// dW[no][ki] += sum_m G[m][no] X[m][ki]: 16 x 8 output tiles, the reduction runs over this CTA's rows (zero padded)
-template <int NO, int KI, int LDG, int LDXX>
-__device__ __forceinline__ void wgrad_mma(const float* Gs, const float* Xs, int n, float* dW) {
-  constexpr int TILES = (NO / 16) * (KI / 8), TPW = TILES / (T / 32);
+// dW[no][ki] += sum_m G[m][no] X[m][ki]: 16 x 8 output tiles, the reduction runs over this CTA's rows (zero padded).
+// Split in two so that the atomics can be issued later than the MMAs (behind a barrier arrival).
+template <int NO, int KI>
+struct WgradAcc {
+  static constexpr int TILES = (NO / 16) * (KI / 8), TPW = TILES / (T / 32);
   static_assert(TILES % (T / 32) == 0, "wgrad tiles per warp");
+  float acc[TPW][4];
+};
+template <int NO, int KI, int LDG, int LDXX>
+__device__ __forceinline__ void wgrad_mma_compute(const float* Gs, const float* Xs, int n, WgradAcc<NO, KI>& out) {
+  constexpr int TPW = WgradAcc<NO, KI>::TPW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  if (n <= 0) return;
-  float acc[TPW][4], acl[TPW][4], acm[TPW][4];
+  float acl[TPW][4], acm[TPW][4];
   int no0[TPW], ki0[TPW];
 #pragma unroll
   for (int q = 0; q < TPW; ++q) {
@@ -594,7 +664,7 @@ __device__ __forceinline__ void wgrad_mma(const float* Gs, const float* Xs, int 
     no0[q] = (tile / (KI / 8)) * 16;
     ki0[q] = (tile % (KI / 8)) * 8;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[q][i] = acl[q][i] = acm[q][i] = 0.f;
+    for (int i = 0; i < 4; ++i) out.acc[q][i] = acl[q][i] = acm[q][i] = 0.f;
   }
 #pragma unroll 2
   for (int m0 = 0; m0 < n; m0 += 8) {
@@ -608,15 +678,30 @@ __device__ __forceinline__ void wgrad_mma(const float* Gs, const float* Xs, int 
       unsigned a[4], al[4], b[2], bl[2];
       split_frag<4>(av, a, al);
       split_frag<2>(bv, b, bl);
-      mma_3xtf32(acc[q], acl[q], acm[q], a, al, b, bl);
+      mma_3xtf32(out.acc[q], acl[q], acm[q], a, al, b, bl);
     }
   }
 #pragma unroll
+  for (int q = 0; q < TPW; ++q) fold3(out.acc[q], acl[q], acm[q]);
+}
+template <int NO, int KI>
+__device__ __forceinline__ void wgrad_mma_flush(const WgradAcc<NO, KI>& in, int n, float* dW) {
+  constexpr int TPW = WgradAcc<NO, KI>::TPW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  if (n <= 0) return;
+#pragma unroll
   for (int q = 0; q < TPW; ++q) {
-    fold3(acc[q], acl[q], acm[q]);
-    atomicAdd(reinterpret_cast<float2*>(dW + (size_t)(no0[q] + g) * KI + ki0[q] + 2 * t), make_float2(acc[q][0], acc[q][1]));
-    atomicAdd(reinterpret_cast<float2*>(dW + (size_t)(no0[q] + g + 8) * KI + ki0[q] + 2 * t), make_float2(acc[q][2], acc[q][3]));
+    const int tile = warp * TPW + q;
+    const int no0 = (tile / (KI / 8)) * 16, ki0 = (tile % (KI / 8)) * 8;
+    atomicAdd(reinterpret_cast<float2*>(dW + (size_t)(no0 + g) * KI + ki0 + 2 * t), make_float2(in.acc[q][0], in.acc[q][1]));
+    atomicAdd(reinterpret_cast<float2*>(dW + (size_t)(no0 + g + 8) * KI + ki0 + 2 * t), make_float2(in.acc[q][2], in.acc[q][3]));
   }
+}
+template <int NO, int KI, int LDG, int LDXX>
+__device__ __forceinline__ void wgrad_mma(const float* Gs, const float* Xs, int n, float* dW) {
+  WgradAcc<NO, KI> acc;
+  wgrad_mma_compute<NO, KI, LDG, LDXX>(Gs, Xs, n, acc);
+  wgrad_mma_flush<NO, KI>(acc, n, dW);
 }
 
 // sum per-lane float4 accumulators over every lane of the CTA that holds the same chunk (lane % LPR) and add the LPR
@@ -934,6 +1019,7 @@ bwd_kernel(const Args a) {
   int* rpt_s = reinterpret_cast<int*>(smem + L.rpt);
   int* colt_s = reinterpret_cast<int*>(smem + L.colt);
   const int rank = (int)cluster_ctarank();
+  const ClusterBarrier cb = {a.barrier};
   const long long b = cluster_id_x();
   const int lo = rank * R, n = max(0, min(R, N - lo));
   const long long M = a.M, rb = b * N, ro = rb + lo;
@@ -1019,7 +1105,7 @@ bwd_kernel(const Args a) {
       st4(gs + (c / (NC / 4)) * LDX + 4 * (c % (NC / 4)), ldg4_stream(a.scratch + (ro * NC) + 4 * c));
   }
   cp_wait_all();
-  cluster_arrive();
+  cb.arrive();
   cluster_wait();                            // g, h2 / h1 and their source scores are visible cluster-wide
 
   const unsigned g_base = smem_u32(gs), h2_base = smem_u32(h2s), h1_base = smem_u32(h1s), dz_base = smem_u32(dz);
@@ -1036,7 +1122,7 @@ bwd_kernel(const Args a) {
                     dsd2, vred + warp * VECF + 8 * NC, n, rank);
     cp_wait_but_one();                       // this block's parameters have landed (group D may still fly)
     stamp();
-    cluster_arrive();
+    cb.arrive();
     cluster_wait();                          // dz / rec2 cluster-wide, parameters CTA-wide
     stamp();
     // (2) conv2 pass 2 -> dh2 (own)
@@ -1061,7 +1147,7 @@ bwd_kernel(const Args a) {
     bwd_p1<2, false>(rp_s, col_s, rpt_s, colt_s, wt, 0u, nullptr, ys, LDY, h1_base, LDY * 4, ss1_base, sd1, m1, l1, rec1,
                      dsd1, vred + warp * VECF + 4 * NC, n, rank);
     stamp();
-    cluster_arrive();
+    cb.arrive();
     cluster_wait();                          // dy1 / rec1 cluster-wide
     stamp();
     // (5) conv1 pass 2 -> dh1 (own, over dz | dh2: every CTA is past its pass 2 of conv2)
@@ -1072,7 +1158,8 @@ bwd_kernel(const Args a) {
     cp_commit();
     stamp();
     // (6) conv1 projection backward: dW1 = dh1^T x0 ; g = dh1 W1 + g (residual), masked by x0 > 0 for k > 0 (in place)
-    wgrad_mma<2 * NC, NC, LDY, LDX>(dh1, xs, n, a.grads + pl.c1_W(k));
+    WgradAcc<2 * NC, NC> dw1;
+    wgrad_mma_compute<2 * NC, NC, LDY, LDX>(dh1, xs, n, dw1);
     {
       const bool mask = k > 0;
       dgrad_mma<2 * NC, NC, LDY, LDX>(
@@ -1087,20 +1174,26 @@ bwd_kernel(const Args a) {
             *reinterpret_cast<float2*>(gs + m * LDX + c) = v;
           });
     }
-    // parameter-vector gradients of the block: sum the 8 warp rows, one 128-bit red per chunk
-    for (int c = threadIdx.x; c < VECF / 4; c += T) {
-      float4 s = f4zero();
+    // parameter-vector gradients of the block: sum the 8 warp rows (one float4 per thread, flushed behind the arrival)
+    float4 vsum = f4zero();
+    if (threadIdx.x < VECF / 4) {
 #pragma unroll
-      for (int w = 0; w < T / 32; ++w) add4(s, lds4(vred + w * VECF + 4 * c));
-      const long long off = c < 6 * NC / 4 ? pl.c1_as(k) + 4 * c : pl.c2_as(k) + 4 * (c - 6 * NC / 4);
-      if (n > 0) atomicAdd(reinterpret_cast<float4*>(a.grads + off), s);
+      for (int w = 0; w < T / 32; ++w) add4(vsum, lds4(vred + w * VECF + 4 * threadIdx.x));
     }
     __syncthreads();                         // W1 / W2 / vec / vred are free again
+    cp_wait_all();                           // groups A and B (what neighbours read next) have landed
+    stamp();
+    cb.arrive();
+    // behind the arrival: nothing below is covered by its release fence, and everything has a whole phase to drain
+    // before the next one — the weight-gradient atomics, the vector-gradient atomics, the next block's parameters
+    wgrad_mma_flush<2 * NC, NC>(dw1, n, a.grads + pl.c1_W(k));
+    if (threadIdx.x < VECF / 4 && n > 0) {
+      const int c = threadIdx.x;
+      const long long off = c < 6 * NC / 4 ? pl.c1_as(k) + 4 * c : pl.c2_as(k) + 4 * (c - 6 * NC / 4);
+      atomicAdd(reinterpret_cast<float4*>(a.grads + off), vsum);
+    }
     if (more) stage_block_params(a.params + pl.block(k - 1), W1, W2, vc);      // group C
     cp_commit();
-    cp_wait_but_one();                       // groups A and B (what neighbours read) have landed
-    stamp();
-    cluster_arrive();
     cluster_wait();                          // the new g and the next block's h2 / h1 / scores are visible
   }
   cp_wait_all();
@@ -1129,6 +1222,16 @@ static bool enabled() {
     g_enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
   return g_enabled == 1;
+}
+
+static int g_barrier = -1;
+static int barrier_flavour() {
+  if (g_barrier < 0) {
+    const char* e = getenv("GATRES_RES2_BARRIER");
+    g_barrier = e ? atoi(e) : 2;
+    if (g_barrier < 0 || g_barrier > 2) g_barrier = 2;
+  }
+  return g_barrier;
 }
 
 static size_t fwd_smem(int R, int ecap) { return sizeof(float) * (size_t)FwdSmem(R, ecap).total; }
@@ -1202,6 +1305,7 @@ int resident2_forward(const gatres_model_desc* d, const float* params, const flo
   a.params = params; a.x = x; a.out = out; a.saved = saved; a.poison = d->poison;
   a.M = d->B * (long long)d->N; a.N = d->N; a.nb = d->num_blocks;
   resident_profile(&a.prof, &a.prof_slots);
+  a.barrier = res2::barrier_flavour();
   const int cs = res2_cluster(d->B);
   a.R = (d->N + cs - 1) / cs;
   a.ecap = res2_ecap(d, cs);
@@ -1219,6 +1323,7 @@ int resident2_backward(const gatres_model_desc* d, const float* params, const fl
   a.M = d->B * (long long)d->N; a.N = d->N; a.nb = d->num_blocks;
   a.k_hi = k_hi; a.k_lo = k_lo; a.head = head; a.tail = tail;
   resident_profile(&a.prof, &a.prof_slots);
+  a.barrier = res2::barrier_flavour();
   const int cs = res2_cluster(d->B);
   a.R = (d->N + cs - 1) / cs;
   a.ecap = res2_ecap(d, cs);
@@ -1226,6 +1331,12 @@ int resident2_backward(const gatres_model_desc* d, const float* params, const fl
 }
 
 }  // namespace gatres
+
+extern "C" int gatres_set_resident_barrier(int flavour) {
+  const int prev = gatres::res2::barrier_flavour();
+  if (flavour >= 0 && flavour <= 2) gatres::res2::g_barrier = flavour;
+  return prev;
+}
 
 extern "C" int gatres_set_resident_dsm(int on) {
   const int prev = gatres::res2::enabled() ? 1 : 0;

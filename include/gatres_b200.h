@@ -141,6 +141,11 @@ void gatres_set_resident_profile(int64_t* device_buf, int32_t slots_per_cta);
  * of gatres_model_desc): 1 = use it when applicable (default; GATRES_RESIDENT_DSM presets it), 0 = never.  Other
  * values only query.  Returns the previous setting. */
 int gatres_set_resident_dsm(int on);
+/* Cluster-barrier flavour of those kernels: 0 = every thread arrives with .release (gpu-scope fence per barrier),
+ * 1 = one releasing warp, 2 = CTA-scope fence + CTA barrier + relaxed arrival (default: the exchange is shared memory
+ * only; rationale and measurements in csrc/resident2.cu).  GATRES_RES2_BARRIER presets it.  Other values only query.
+ * Returns the previous setting. */
+int gatres_set_resident_barrier(int flavour);
 
 /*
  * Kernel-selection knob for the projections and their data gradients: 0 = fp32 FFMA kernels

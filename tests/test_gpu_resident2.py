@@ -48,11 +48,13 @@ def _setup(kind, B, blocks, dev, seed=3):
 def knobs():
     from gnn_pressure_estimation_b200 import _lib
     lib = _lib.load()
-    prev = (lib.gatres_set_resident_dsm(-1), lib.gatres_set_resident_cluster(-1), lib.gatres_set_resident_max_batch(-1))
+    prev = (lib.gatres_set_resident_dsm(-1), lib.gatres_set_resident_cluster(-1), lib.gatres_set_resident_max_batch(-1),
+            lib.gatres_set_resident_barrier(-1))
     yield lib
     lib.gatres_set_resident_dsm(prev[0])
     lib.gatres_set_resident_cluster(prev[1])
     lib.gatres_set_resident_max_batch(prev[2])
+    lib.gatres_set_resident_barrier(prev[3])
 
 
 def test_locality_plan_is_a_relabelled_copy_of_the_csr(dev):
@@ -102,9 +104,10 @@ def test_dsm_inference_forward(kind, B, blocks, cluster, dev, knobs):
     assert rel_err(outs[1], outs[0]) < 2e-5, "dsm vs first-generation resident kernel"
 
 
+@pytest.mark.parametrize("barrier", [2, 0, 1])
 @pytest.mark.parametrize("cluster", [0, 4, 8])
 @pytest.mark.parametrize("kind,B,blocks", [("tiny", 5, 2), ("directed", 3, 3), ("ctown", 4, 4), ("ctown", 32, 15)])
-def test_dsm_training_pair_matches_first_generation_and_oracle(kind, B, blocks, cluster, dev, knobs):
+def test_dsm_training_pair_matches_first_generation_and_oracle(kind, B, blocks, cluster, barrier, dev, knobs):
     """forward(training) + backward through the C ABI with the DSMEM kernels, against the first-generation resident
     kernels (same inputs) and against the CPU oracle (forward 1e-4, gradients 1e-3)"""
     from gnn_pressure_estimation_b200 import _lib
@@ -113,6 +116,7 @@ def test_dsm_training_pair_matches_first_generation_and_oracle(kind, B, blocks, 
     lib = knobs
     lib.gatres_set_resident_max_batch(1 << 30)
     lib.gatres_set_resident_cluster(cluster)
+    lib.gatres_set_resident_barrier(barrier)
     res = {}
     for dsm in (1, 0):
         lib.gatres_set_resident_dsm(dsm)

@@ -1,9 +1,9 @@
-python -m pytest tests/test_gpu_resident2.py -x -q > gpurun_out/r2f_pytest.log 2>&1; tail -15 gpurun_out/r2f_pytest.log
-python tools/resident_probe.py --batches 8,32 --clusters 0 --phases --out gpurun_out/r2f_probe.json > gpurun_out/r2f_probe.log 2>&1; python - <<'PY'
+python -m pytest tests -m gpu -x -q > gpurun_out/r2i_pytest.log 2>&1; tail -4 gpurun_out/r2i_pytest.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err; tail -3 gpurun_out/r2i_bench.err
+python - <<'PY'
 import json
-for r in json.load(open('gpurun_out/r2f_probe.json')):
-    print(r['B'], 'fwd_train', r['fwd_train_us'], 'infer', r['fwd_infer_us'], 'bwd', r['bwd_us'], 'step', r['step_us'])
-    print(' fwd  ', r['phases']['fwd'])
-    print(' bwd  ', r['phases']['bwd'])
+d=json.load(open('gpurun_out/r2i_bench.json'))
+print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'launches', d['gpu_launches'])
+print(json.dumps(d['roofline'])[:1500])
+for l in d['configs']: print(l['config'], l.get('value'), l.get('ms_per_step'), l.get('error'))
 PY
-tail -3 gpurun_out/r2f_probe.log | cut -c1-300
