@@ -727,12 +727,118 @@ __device__ __forceinline__ void warp_chunk_park(float4 v, float* dst) {
   if ((threadIdx.x & 31) < 8) st4(dst + 4 * (threadIdx.x & 31), v);
 }
 
+// sum a per-lane float4 over the eight row slots of a warp (four lanes per row) and park it in this warp's row of vred
+__device__ __forceinline__ void warp_chunk_park4(float4 v, float* dst) {
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
+    v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
+  }
+  if ((threadIdx.x & 31) < 4) st4(dst + 4 * (threadIdx.x & 31), v);
+}
+
+// Backward pass 1 of ONE head over own target rows: D_i, ds_dst[i]; rec = {s_dst, m, 1/(l+eps), D}
+// (read by the neighbours' pass 2 through DSMEM).  Four lanes own a row — a warp covers eight rows, the CTA's slice
+// is one pass — and lane `slot` holds the chunks {slot, slot + 4} of the head and evaluates the edges {slot, slot + 4}
+// of every group of eight in-edges.  Two-head layers call it once per head (the chain of a head is half as long as
+// the packed two-head chain of the first generation, and there is one row pass instead of two).
+// MEAN (conv2, H = 1): the incoming gradient is produced on the fly as the SimpleConv(mean) backward of the running
+// gradient g (dz[j] = sum_{j->i} g[i] / max(indeg(i), 1); wt_s holds the weight of every out-edge) and is also written
+// to dz_s for pass 2's gathers; otherwise it is read from the own tile g_s.
+template <int H, bool MEAN>
+__device__ __forceinline__ void bwd_p1_head(const int v, const int* rp_s, const int* col_s, const int* rpt_s,
+                                            const int* colt_s, const float* wt_s, unsigned g_base, float* dz_s,
+                                            const float* g_s, int ldg_s, unsigned h_base, int ldh, unsigned ss_base,
+                                            const float* sd_s, const float* m_s, const float* l_s, float* rec_s,
+                                            float* dsd_s, float* vred_bias, int n, int self_owner) {
+  static_assert(!MEAN || H == 1, "the mean backward feeds conv2 (one head)");
+  constexpr int RPW = 8, PRE = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 2, slot = lane & 3;
+  const unsigned hoff = 128u * v + 16u * slot;
+  float4 bacc0 = f4zero(), bacc1 = f4zero();
+  for (int i0 = 0; i0 < n; i0 += (T / 32) * RPW) {
+    const int il_raw = i0 + warp * RPW + sub;
+    const bool ok = il_raw < n;
+    const int il = ok ? il_raw : n - 1;
+    const int beg = rp_s[il], deg = rp_s[il + 1] - beg;
+    const int deg_max = __reduce_max_sync(FULL, deg);
+    const int self = (self_owner << 16) | il;
+    const float sd = sd_s[il * H + v], mi = m_s[il * H + v], il_ = 1.f / (l_s[il * H + v] + kSoftmaxEps);
+    float S1 = 0.f, S2 = 0.f, S3 = 0.f;
+    float4 gv0, gv1;
+    if (MEAN) {
+      const int tb = rpt_s[il], te = rpt_s[il + 1] - 1;     // out-edges minus the self-loop
+      gv0 = gv1 = f4zero();
+#pragma unroll 4
+      for (int e = tb; e < te; ++e) {
+        const unsigned ar = row_addr(g_base, colt_s[e], LDX * 4) + 16u * slot;
+        const float w = wt_s[e];
+        fma4(gv0, w, ldsc4(ar));
+        fma4(gv1, w, ldsc4(ar + 64u));
+      }
+      if (ok) {
+        st4(dz_s + il * LDX + 4 * slot, gv0);
+        st4(dz_s + il * LDX + 16 + 4 * slot, gv1);
+      }
+    } else {
+      gv0 = lds4(g_s + il * ldg_s + 32 * v + 4 * slot);
+      gv1 = lds4(g_s + il * ldg_s + 32 * v + 16 + 4 * slot);
+    }
+    if (ok) { add4(bacc0, gv0); add4(bacc1, gv1); }
+    for (int e0 = 0; e0 < deg_max; e0 += 8) {
+      const bool valid0 = e0 + slot < deg, valid1 = e0 + slot + 4 < deg;
+      const int j0 = valid0 ? col_s[beg + e0 + slot] : self;
+      const int j1 = valid1 ? col_s[beg + e0 + slot + 4] : self;
+      const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
+      float4 x[PRE][2];
+#pragma unroll
+      for (int u = 0; u < PRE; ++u) {
+        const int ju = __shfl_sync(FULL, j0, u, 4);
+        const unsigned au = row_addr(h_base, ju, ldh) + hoff;
+        x[u][0] = u < cnt ? ldsc4(au) : f4zero();
+        x[u][1] = u < cnt ? ldsc4(au + 64u) : f4zero();
+      }
+      const float z0 = ldsc1(row_addr(ss_base, j0, 4 * H) + 4u * v) + sd;
+      const float z1 = cnt_max > 4 ? ldsc1(row_addr(ss_base, j1, 4 * H) + 4u * v) + sd : 0.f;
+      const float alpha0 = valid0 ? __expf(lrelu(z0) - mi) * il_ : 0.f;
+      const float alpha1 = valid1 ? __expf(lrelu(z1) - mi) * il_ : 0.f;
+      float da0 = 0.f, da1 = 0.f;
+#pragma unroll
+      for (int u = 0; u < PRE; ++u) {
+        const float d = group_sum<4>(dot4(gv0, x[u][0]) + dot4(gv1, x[u][1]), FULL);
+        da0 = slot == u ? d : da0;
+      }
+      for (int t = PRE; t < cnt_max; ++t) {
+        const int jt = __shfl_sync(FULL, j1, t & 3, 4);
+        const unsigned at = row_addr(h_base, jt, ldh) + hoff;
+        const bool on = t < cnt;
+        const float4 xa = on ? ldsc4(at) : f4zero(), xb = on ? ldsc4(at + 64u) : f4zero();
+        const float d = group_sum<4>(dot4(gv0, xa) + dot4(gv1, xb), FULL);
+        da1 = slot == (t & 3) ? d : da1;
+      }
+      const float sl0 = lrelu_slope(z0), sl1 = lrelu_slope(z1);
+      S1 = fmaf(alpha0, da0, fmaf(alpha1, da1, S1));
+      S2 = fmaf(alpha0 * sl0, da0, fmaf(alpha1 * sl1, da1, S2));
+      S3 = fmaf(alpha0, sl0, fmaf(alpha1, sl1, S3));
+    }
+    const float D = group_sum<4>(S1, FULL), T2 = group_sum<4>(S2, FULL), T3 = group_sum<4>(S3, FULL);
+    if (slot == 0 && ok) {
+      st4(rec_s + (il * H + v) * 4, make_float4(sd, mi, il_, D));
+      dsd_s[il * H + v] = T2 - D * T3;
+    }
+  }
+  warp_chunk_park4(bacc0, vred_bias + 32 * v);
+  warp_chunk_park4(bacc1, vred_bias + 32 * v + 16);
+}
+
+// Packed form of pass 1 (eight lanes per row, the heads of a row packed per lane): used for the two-head layer.
 // Backward pass 1 over own target rows: D_i, ds_dst[i]; rec = {s_dst, m, 1/(l+eps), D} (read by the
 // neighbours' pass 2 through DSMEM).  MEAN (conv2, H = 1): the incoming gradient is produced on the fly as the
 // SimpleConv(mean) backward of the running gradient g (dz[j] = sum_{j->i} g[i] / max(indeg(i), 1); wt_s holds the
 // weight of every out-edge) and is also written to dz_s for pass 2's gathers; otherwise it is read from the tile g_s.
 template <int H, bool MEAN>
-__device__ __forceinline__ void bwd_p1(const int* rp_s, const int* col_s, const int* rpt_s, const int* colt_s,
+__device__ __forceinline__ void bwd_p1_packed(const int* rp_s, const int* col_s, const int* rpt_s, const int* colt_s,
                                        const float* wt_s, unsigned g_base, float* dz_s, const float* g_s, int ldg_s,
                                        unsigned h_base, int ldh, unsigned ss_base, const float* sd_s, const float* m_s,
                                        const float* l_s, float* rec_s, float* dsd_s, float* vred_bias, int n,
@@ -864,7 +970,22 @@ __device__ __forceinline__ void bwd_p1(const int* rp_s, const int* col_s, const 
   for (int v = 0; v < H; ++v) warp_chunk_park(bacc[v], vred_bias + 32 * v);
 }
 
-// Backward pass 2 over own source rows: dh[j] (-> own shared tile), ds_src, datt_src / datt_dst partials.  The
+template <int H, bool MEAN>
+__device__ __forceinline__ void bwd_p1(const int* rp_s, const int* col_s, const int* rpt_s, const int* colt_s,
+                                       const float* wt_s, unsigned g_base, float* dz_s, const float* g_s, int ldg_s,
+                                       unsigned h_base, int ldh, unsigned ss_base, const float* sd_s, const float* m_s,
+                                       const float* l_s, float* rec_s, float* dsd_s, float* vred_bias, int n,
+                                       int self_owner) {
+  if (H == 1)
+    bwd_p1_head<H, MEAN>(0, rp_s, col_s, rpt_s, colt_s, wt_s, g_base, dz_s, g_s, ldg_s, h_base, ldh, ss_base, sd_s, m_s, l_s,
+                         rec_s, dsd_s, vred_bias, n, self_owner);
+  else
+    bwd_p1_packed<H, MEAN>(rp_s, col_s, rpt_s, colt_s, wt_s, g_base, dz_s, g_s, ldg_s, h_base, ldh, ss_base, sd_s, m_s, l_s,
+                           rec_s, dsd_s, vred_bias, n, self_owner);
+}
+// Backward pass 2 over own source rows: dh[j] (-> own shared tile), ds_src, datt_src / datt_dst partials.  Eight lanes
+// per row with the heads packed per lane (measured faster than the four-lane / one-head form for this pass: its chain
+// is dominated by the dependent dot -> softmax-gradient -> accumulate sequence, not by the number of row passes).  The
 // gradient rows g[i] and the records of the edges' targets come through DSMEM; h, s_src, ds_dst of the row are own.
 template <int H>
 __device__ __forceinline__ void bwd_p2(const int* rpt_s, const int* colt_s, unsigned g_base, int ldg, unsigned rec_base,

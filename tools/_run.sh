@@ -1,9 +1,8 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r2i_pytest.log 2>&1; tail -4 gpurun_out/r2i_pytest.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err; tail -3 gpurun_out/r2i_bench.err
-python - <<'PY'
+python -m pytest tests/test_gpu_resident2.py -x -q 2>&1 | tail -2
+python tools/resident_probe.py --batches 8,32 --clusters 0 --phases --out gpurun_out/r2j_probe.json > gpurun_out/r2j_probe.log 2>&1; python - <<PY
 import json
-d=json.load(open('gpurun_out/r2i_bench.json'))
-print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'launches', d['gpu_launches'])
-print(json.dumps(d['roofline'])[:1500])
-for l in d['configs']: print(l['config'], l.get('value'), l.get('ms_per_step'), l.get('error'))
+for r in json.load(open('gpurun_out/r2j_probe.json')):
+    print(r['B'], 'fwd_train', round(r['fwd_train_us'],1), 'infer', round(r['fwd_infer_us'],1), 'bwd', round(r['bwd_us'],1), 'step', round(r['step_us'],1))
+    print(' fwd  ', r['phases']['fwd'])
+    print(' bwd  ', r['phases']['bwd'])
 PY
