@@ -60,6 +60,7 @@ _PROTOTYPES = {
     "gatres_decoder_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _p]),
     "gatres_decoder_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p]),
     "gatres_reduce_partials": (C.c_int, [_p, _i64, _i32, _i64, _i64, _p, _p]),
+    "gatres_model_desc_bytes": (_sz, []),
     "gatres_param_count": (_i64, [_i32, _i32]),
     "gatres_saved_floats": (_i64, [C.POINTER(ModelDesc)]),
     "gatres_scratch_floats": (_i64, [C.POINTER(ModelDesc), _i32]),
@@ -105,6 +106,9 @@ def load() -> C.CDLL:
     got = lib.gatres_abi_version()
     if got != ABI_VERSION:
         raise ImportError(f"libgatres_b200.so ABI {got} != expected {ABI_VERSION}; rebuild")
+    if lib.gatres_model_desc_bytes() != C.sizeof(ModelDesc):
+        raise ImportError(f"struct gatres_model_desc is {lib.gatres_model_desc_bytes()} bytes in the library but "
+                          f"{C.sizeof(ModelDesc)} in the binding; rebuild")
     _lib = lib
     return lib
 

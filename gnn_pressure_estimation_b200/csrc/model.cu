@@ -51,6 +51,8 @@ using namespace gatres;
     if (rc_) return rc_;     \
   } while (0)
 
+extern "C" size_t gatres_model_desc_bytes(void) { return sizeof(gatres_model_desc); }
+
 extern "C" int64_t gatres_param_count(int32_t num_blocks, int32_t nc) { return ParamLayout(num_blocks, nc).count(); }
 
 extern "C" int64_t gatres_saved_floats(const gatres_model_desc* d) {

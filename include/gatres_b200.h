@@ -281,6 +281,8 @@ typedef struct gatres_model_desc {
   int32_t p_ecap[4];
 } gatres_model_desc;
 
+/* sizeof(gatres_model_desc) as this library was built (a binding checks its own struct against it). */
+size_t gatres_model_desc_bytes(void);
 int64_t gatres_param_count(int32_t num_blocks, int32_t nc);
 /* floats of activation storage forward(training) hands to backward */
 int64_t gatres_saved_floats(const gatres_model_desc* d);

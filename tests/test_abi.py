@@ -34,6 +34,17 @@ def test_abi_version_and_param_count():
     assert lib.gatres_param_count(25, 128) == 1667585       # gatres_large
 
 
+def test_model_desc_layout_matches_the_library():
+    lib = _lib.load()
+    assert lib.gatres_model_desc_bytes() == ctypes.sizeof(_lib.ModelDesc)
+    names = [f[0] for f in _lib.ModelDesc._fields_]
+    header = open(os.path.join(ROOT, "include", "gatres_b200.h")).read()
+    body = header[header.index("typedef struct gatres_model_desc {"):header.index("} gatres_model_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[\d+\])?\s*;", body)
+    assert declared == names                                   # same fields, same order
+
+
 def test_argument_validation_reports_errors():
     lib = _lib.load()
     rc = lib.gatres_gat_agg_fwd(None, None, None, None, None, None, None, None, None, 1, 4, 8, 3, 32, 0, None)

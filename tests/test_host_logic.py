@@ -112,3 +112,29 @@ def test_default_init_statistics():
     assert float(b.conv1.lin_src.weight.abs().max()) <= (6 / (64 + 32)) ** 0.5
     assert float(b.conv1.att_src.abs().max()) <= (6 / (2 + 32)) ** 0.5
     assert float(m.lin0.weight.abs().max()) <= 1.0 and float(m.lin1.weight.abs().max()) <= 32 ** -0.5
+
+
+def test_locality_order_and_permuted_csr():
+    """host-side locality plan of the resident kernels (graph.locality_order / permute_csr): a permutation, the same
+    rows with the same entry order, and neighbours mostly inside one of eight equal row slices"""
+    import numpy as np
+    from gnn_pressure_estimation_b200 import graph as Gr, topology as T
+    from oracle import topology_oracle as TO
+    for wn in (T.tiny_network(), T.ctown_shaped()):
+        ei, names = T.reference_edge_index(wn)
+        N = len(names)
+        perm = Gr.locality_order(ei, N)
+        assert sorted(perm.tolist()) == list(range(N))
+        assert np.array_equal(perm, Gr.locality_order(ei, N))              # deterministic
+        rp, col = TO.csr_by_target(ei, N)
+        rpp, colp = Gr.permute_csr(rp.astype(np.int64), col.astype(np.int64), perm)
+        assert rpp[-1] == rp[-1] and rpp.dtype == np.int32
+        for r in range(N):
+            i = perm[r]
+            assert np.array_equal(perm[colp[rpp[r]:rpp[r + 1]]], col[rp[i]:rp[i + 1]])
+    inv = np.empty(N, dtype=np.int64)
+    inv[perm] = np.arange(N)
+    R = -(-N // 8)
+    before = float((ei[0] // R == ei[1] // R).mean())
+    after = float((inv[ei[0]] // R == inv[ei[1]] // R).mean())
+    assert before < 0.2 and after > 0.9, (before, after)               # random ids -> 96 % of the neighbours local
