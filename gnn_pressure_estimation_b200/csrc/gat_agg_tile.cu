@@ -271,10 +271,11 @@ int gat_agg_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float
 // =============================================================================
 // Fused backward (pass 1 + pass 2 of gat_agg.cu) for one snapshot per CTA.
 // Both feature slabs of the snapshot (h and g = dL/d(out)) and its per-node scalars
-// are staged by TMA; pass 1 leaves D and ds_dst in shared memory, so the `rec`
-// round trip through HBM and one kernel launch disappear, and h / g are read from
-// DRAM once instead of twice (12*S + 28*H algorithmic bytes per node instead of
-// 20*S + 52*H).
+// are staged by TMA; pass 1 leaves ds_dst in shared memory and scatters every edge's
+// ds_src term to its source with a shared-memory atomic, so the `rec` round trip
+// through HBM and one kernel launch disappear, h / g are read from DRAM once instead
+// of twice (12*S + 28*H algorithmic bytes per node instead of 20*S + 52*H), and pass 2
+// is a pure alpha-weighted gather of g rows (no second evaluation of <g_i, h_j>).
 // =============================================================================
 namespace gatres {
 
@@ -368,6 +369,10 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     ad[v] = ldg4(att_dst + 4 * RM::chunk(lig, v));
     accs[v] = accd[v] = bacc[v] = f4zero();
   }
+  // DD accumulates ds_src[j] = sum over the out-edges of j of dz_e: pass 1 (which owns dalpha_e and D_i of every edge)
+  // adds each edge's term with a shared-memory atomic, pass 2 reads the sum and clears it for the next snapshot —
+  // so pass 2 needs neither the per-edge dot products <g_i, h_j> again nor D of the edges' targets
+  for (unsigned k = tid; k < N * H; k += THREADS) DD[k] = 0.f;
   __syncthreads();
   pdl_wait();
   if (tid == 0 && blockIdx.x < B) issue(blockIdx.x, 0);
@@ -409,10 +414,10 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
         il[v] = 1.f / (LL[i * H + hd] + kSoftmaxEps);
         S1[v] = S2[v] = S3[v] = 0.f;
       }
-      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
+      // one chunk of up to LPH in-edges: lane `slot` owns edge e0 + slot (alpha, LeakyReLU slope, dalpha = <g_i, h_j>)
+      auto chunk = [&](int e0, int& j, float (&alpha)[V], float (&sl)[V], float (&da)[V]) {
         const bool valid = e0 + slot < deg;
-        const int j = valid ? (int)ci[beg + e0 + slot] : 0;
-        float alpha[V], sl[V], da[V];
+        j = valid ? (int)ci[beg + e0 + slot] : 0;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const float z = SS[j * H + RM::head(lig, v)] + sd[v];
@@ -430,6 +435,11 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
             da[v] = slot == t ? d : da[v];
           }
         }
+      };
+      int j;
+      float alpha[V], sl[V], da[V];
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
+        chunk(e0, j, alpha, sl, da);
 #pragma unroll
         for (int v = 0; v < V; ++v) {             // idle slots have alpha = 0
           S1[v] = fmaf(alpha[v], da[v], S1[v]);
@@ -437,13 +447,20 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
           S3[v] = fmaf(alpha[v], sl[v], S3[v]);
         }
       }
+      float Dv[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float D = group_sum<LPH>(S1[v], gmask);
+        Dv[v] = group_sum<LPH>(S1[v], gmask);
         const float T2 = group_sum<LPH>(S2[v], gmask), T3 = group_sum<LPH>(S3[v], gmask);
-        if (slot == 0 && row_ok) {
-          DD[i * H + RM::head(lig, v)] = D;
-          DSD[i * H + RM::head(lig, v)] = T2 - D * T3;
+        if (slot == 0 && row_ok) DSD[i * H + RM::head(lig, v)] = T2 - Dv[v] * T3;
+      }
+      // ds_src contribution of every in-edge of this row: dz_e = alpha_e (dalpha_e - D_i) slope_e, added to its SOURCE
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
+        if (deg_max > LPH) chunk(e0, j, alpha, sl, da);        // rows with more in-edges than lanes: recompute the chunk
+        if (row_ok && e0 + slot < deg) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)                          // every (edge, head) is held by exactly one lane
+            atomicAdd(DD + j * H + RM::head(lig, v), alpha[v] * sl[v] * (da[v] - Dv[v]));
         }
       }
     }
@@ -456,26 +473,22 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
       const int beg = rpo[jn], deg = rpo[jn + 1] - beg;
       const int deg_max = __reduce_max_sync(gmask, deg);
       float4 hv[V], dacc[V];
-      float ss[V], dsrc[V];
+      float ss[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         hv[v] = *reinterpret_cast<const float4*>(HS + jn * F + 4 * RM::chunk(lig, v));
         ss[v] = SS[jn * H + RM::head(lig, v)];
         dacc[v] = f4zero();
-        dsrc[v] = 0.f;
       }
       for (int e0 = 0; e0 < deg_max; e0 += LPH) {
         const bool valid = e0 + slot < deg;
         const int i = valid ? (int)co[beg + e0 + slot] : 0;
-        float alpha[V], k2[V], Dt[V], da[V];
+        float alpha[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const int o = i * H + RM::head(lig, v);
           const float z = ss[v] + SD[o];
           alpha[v] = valid ? __fdividef(__expf(lrelu(z) - MM[o]), LL[o] + kSoftmaxEps) : 0.f;
-          k2[v] = alpha[v] * lrelu_slope(z);
-          Dt[v] = DD[o];
-          da[v] = 0.f;
         }
         const int cnt_max = min(LPH, deg_max - e0);
         for (int t = 0; t < cnt_max; ++t) {
@@ -483,17 +496,20 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
 #pragma unroll
           for (int v = 0; v < V; ++v) {
             const float4 gx = *reinterpret_cast<const float4*>(GS + itg * F + 4 * RM::chunk(lig, v));
-            const float d = group_sum<LPH>(dot4(gx, hv[v]), gmask);
-            da[v] = slot == t ? d : da[v];
             fma4(dacc[v], __shfl_sync(gmask, alpha[v], t, LPH), gx);
           }
         }
-#pragma unroll
-        for (int v = 0; v < V; ++v) dsrc[v] = fmaf(k2[v], da[v] - Dt[v], dsrc[v]);
       }
+      float dsv[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) dsv[v] = DD[jn * H + RM::head(lig, v)];      // ds_src[j], accumulated by pass 1
+      __syncwarp();
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (slot == 0 && row_ok) DD[jn * H + RM::head(lig, v)] = 0.f;          // cleared for the next snapshot
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float ds = group_sum<LPH>(dsrc[v], gmask);
+        const float ds = dsv[v];
         const float dd = DSD[jn * H + RM::head(lig, v)];
         fma4(dacc[v], ds, as[v]);
         fma4(dacc[v], dd, ad[v]);
