@@ -161,3 +161,4 @@ def test_dsm_backward_in_block_ranges_equals_one_call(dev, knobs):
         _lib.call("gatres_backward_range", d, p(ts.flat), p(ts.xm), p(ts.saved), p(ts.d_out), None, p(ts.grads), p(ts.scratch), hi, lo, s())
     assert lib.gatres_launch_count() - n0 == 3
     assert float((ts.grads - whole).abs().max()) <= 1e-5 * float(whole.abs().max())
+
