@@ -44,6 +44,7 @@ _PROTOTYPES = {
     "gatres_set_resident_profile": (None, [_p, _i32]),
     "gatres_set_tensor_core": (C.c_int, [C.c_int]),
     "gatres_set_resident_dsm": (C.c_int, [C.c_int]),
+    "gatres_set_resident_tc": (C.c_int, [C.c_int]),
     "gatres_set_resident_barrier": (C.c_int, [C.c_int]),
     "gatres_csr_scratch_bytes": (_sz, [_i64, _i32]),
     "gatres_csr_build": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),

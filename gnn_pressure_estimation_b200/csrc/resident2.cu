@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "layout.cuh"
+#include "umma.cuh"
 
 namespace gatres {
 namespace res2 {
@@ -328,10 +329,18 @@ __device__ __forceinline__ void load_scores(unsigned ss_base, int packed, float 
   } else s[0] = ldsc1(a);
 }
 
-template <int H>
+// float offset of the 16-byte chunk q (0..7) of row r in a [rows x 32] SWIZZLE_128B operand tile (rows of 128 B, chunk
+// index XOR row % 8: the canonical K-major UMMA layout, and — read with rows as K — the MN-major one)
+__device__ __forceinline__ int sw_chunk(int r, int q) { return r * 32 + ((q ^ (r & 7)) << 2); }
+__device__ __forceinline__ float4 lo4(float4 x) { return make_float4(lo_tf32(x.x), lo_tf32(x.y), lo_tf32(x.z), lo_tf32(x.w)); }
+
+// SW = false: out_s is a padded row-major tile (row stride ld_out floats).  SW = true: out_s is a tensor-core operand,
+// one [rows x 32] SWIZZLE_128B tile per head (tile stride ld_out floats), and out_lo receives the 3xTF32 low parts.
+template <int H, bool SW = false>
 __device__ __forceinline__ void agg_fwd(const int* rp_s, const int* col_s, unsigned h_base, int ldh, unsigned ss_base,
                                         const float* sd_s, const float* bias_s, float* out_s, int ld_out,
-                                        float* m_dst, float* l_dst, int n, int self_owner, bool relu) {
+                                        float* m_dst, float* l_dst, int n, int self_owner, bool relu,
+                                        float* out_lo = nullptr) {
   constexpr int RPW = 8, PRE = H == 1 ? 4 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 2, slot = lane & 3;
@@ -425,7 +434,11 @@ __device__ __forceinline__ void agg_fwd(const int* rp_s, const int* col_s, unsig
         float4 o = make_float4(fmaf(acc[v][c].x, inv, bv[v][c].x), fmaf(acc[v][c].y, inv, bv[v][c].y),
                                fmaf(acc[v][c].z, inv, bv[v][c].z), fmaf(acc[v][c].w, inv, bv[v][c].w));
         if (relu) o = relu4(o);
-        st4(out_s + il * ld_out + 32 * v + 16 * c + 4 * slot, o);
+        if (SW) {
+          const int off = v * ld_out + sw_chunk(il, 4 * c + slot);
+          st4(out_s + off, o);
+          st4(out_lo + off, lo4(o));
+        } else st4(out_s + il * ld_out + 32 * v + 16 * c + 4 * slot, o);
       }
       if (m_dst != nullptr && slot == 0) { m_dst[il * H + v] = mrun[v]; l_dst[il * H + v] = lrun[v]; }
     }
@@ -596,6 +609,312 @@ fwd_kernel(const Args a) {
     }
   }
   cluster_wait();
+}
+
+// =============================================================================== forward, tcgen05 projections
+// Same stack as fwd_kernel, with the two projections of a block on the 5th-generation tensor cores: the mma.sync
+// 3xTF32 contractions were the largest single item of a block (3.0 of 9.7 us: ~15 cycles per MMA per scheduler).
+//   * the block input x and the conv1 output y1 — the A operands — live in shared memory as SWIZZLE_128B K-major
+//     tiles (rows of 128 B, one tile per 32 columns) together with their 3xTF32 low parts, both written by the phase
+//     that produces them (encoder / mean / conv1 aggregation);
+//   * W1 / W2 are staged by cp.async straight into K-major SWIZZLE_128B tiles (single-buffered: the next block's
+//     copy of a matrix is requested as soon as its MMAs have completed) and every thread derives the low parts of
+//     the chunks it copied;
+//   * one thread issues the 3 x K/8 tcgen05.mma (M = 128: the CTA's <= 64 rows are the first rows of the tile, the rest
+//     of the datapath reads whatever follows in shared memory and its accumulator rows are never read), commits to
+//     an mbarrier, and warps 0/1 (+ 4/5 for the second column half) drain the accumulator with tcgen05.ld — thread
+//     = row, so the attention scores are in-thread dot products — into the padded tiles the neighbours gather from.
+// Saved activations keep the layout of fwd_kernel (the stores un-swizzle), so bwd_kernel is unchanged.
+constexpr int TC_COLS = 64;                  // TMEM columns per CTA (conv1: N = 64, conv2: N = 32)
+
+struct FwdTcSmem {
+  int xa, xl, ya, yl, w1h, w1l, w2h, w2l, h1s, h2s, ss1, sd1, ss2, sd2, ml1, ml2, vec, rp, col, bar, total, RP;
+  __host__ __device__ FwdTcSmem(int R, int ecap) {
+    RP = (R + 7) & ~7;
+    int o = 0;
+    auto take = [&](int nfl) { const int at = o; o += (int)a4(nfl); return at; };
+    xa = take(RP * 32); xl = take(RP * 32); ya = take(2 * RP * 32); yl = take(2 * RP * 32);       // 1024-byte multiples
+    w1h = take(2 * NC * NC); w1l = take(2 * NC * NC); w2h = take(2 * NC * NC); w2l = take(2 * NC * NC);
+    h1s = take(R * LDY); h2s = take(R * LDX);
+    ss1 = take(2 * R); sd1 = take(2 * R); ss2 = take(R); sd2 = take(R); ml1 = take(4 * R); ml2 = take(2 * R);
+    vec = take(2 * VECF); rp = take(R + 1); col = take(ecap); bar = take(4);
+    total = o;
+  }
+};
+
+// one block's W1 -> [64 x 32] K-major SWIZZLE_128B tile; W2 -> two [32 x 32] tiles (one per 32 input columns)
+__device__ __forceinline__ void stage_w1_tc(const float* blk, float* W1H) {
+  for (int c = threadIdx.x; c < 2 * NC * NC / 4; c += T) cp16(W1H + sw_chunk(c >> 3, c & 7), blk + 4 * c);
+}
+__device__ __forceinline__ void stage_w2_tc(const float* blk, float* W2H) {
+  const float* w2 = blk + 2 * NC * NC + 6 * NC;
+  for (int c = threadIdx.x; c < 2 * NC * NC / 4; c += T)
+    cp16(W2H + ((c >> 3) & 1) * (NC * 32) + sw_chunk(c >> 4, c & 7), w2 + 4 * c);
+}
+__device__ __forceinline__ void stage_vec_tc(const float* blk, float* vec) {
+  for (int c = threadIdx.x; c < 9 * NC / 4; c += T)
+    cp16(vec + 4 * c, blk + (c < 6 * NC / 4 ? 2 * NC * NC + 4 * c : 4 * NC * NC + 4 * c));
+}
+// 3xTF32 low parts of the weight chunks THIS thread copied (same chunk -> thread map as the staging loops)
+__device__ __forceinline__ void lo_own_weights(const float* W1H, float* W1L, const float* W2H, float* W2L) {
+  for (int c = threadIdx.x; c < 2 * NC * NC / 4; c += T) {
+    const int o1 = sw_chunk(c >> 3, c & 7), o2 = ((c >> 3) & 1) * (NC * 32) + sw_chunk(c >> 4, c & 7);
+    st4(W1L + o1, lo4(lds4(W1H + o1)));
+    st4(W2L + o2, lo4(lds4(W2H + o2)));
+  }
+}
+// D[128 x NOUT] (TMEM) = A[128 x K] B[NOUT x K]^T, 3xTF32; A / B: SWIZZLE_128B K-major tiles, one per 32 columns of K
+template <int K, int NOUT>
+__device__ __forceinline__ void issue_proj_tc(uint32_t tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_tile_bytes,
+                                              uint32_t b_hi, uint32_t b_lo, uint32_t b_tile_bytes) {
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#pragma unroll
+  for (int s = 0; s < K / 8; ++s) {
+    const uint32_t ka = (uint32_t)(s >> 2) * a_tile_bytes + (uint32_t)(s & 3) * 32u;
+    const uint32_t kb = (uint32_t)(s >> 2) * b_tile_bytes + (uint32_t)(s & 3) * 32u;
+    umma_tf32(tmem, umma_desc_k128(a_hi + ka), umma_desc_k128(b_hi + kb), IDESC, s > 0);
+    umma_tf32(tmem, umma_desc_k128(a_lo + ka), umma_desc_k128(b_hi + kb), IDESC, 1);
+    umma_tf32(tmem, umma_desc_k128(a_hi + ka), umma_desc_k128(b_lo + kb), IDESC, 1);
+  }
+}
+// accumulator row (thread = row) -> padded shared tile + the two attention scores of the row's 32 columns
+__device__ __forceinline__ void drain_row_tc(uint32_t taddr, const float* att_s, const float* att_d, float* h_row,
+                                             float* ss_dst, float* sd_dst, bool ok) {
+  float v[32];
+  tmem_ld32(taddr, v);
+  if (!ok) return;
+  float ps = 0.f, pd = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 s4 = lds4(att_s + 4 * q), d4 = lds4(att_d + 4 * q);
+    ps = fmaf(v[4 * q], s4.x, fmaf(v[4 * q + 1], s4.y, fmaf(v[4 * q + 2], s4.z, fmaf(v[4 * q + 3], s4.w, ps))));
+    pd = fmaf(v[4 * q], d4.x, fmaf(v[4 * q + 1], d4.y, fmaf(v[4 * q + 2], d4.z, fmaf(v[4 * q + 3], d4.w, pd))));
+    st4(h_row + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+  }
+  *ss_dst = ps;
+  *sd_dst = pd;
+}
+// own rows of a SWIZZLE_128B operand (TILES tiles of 32 columns) -> row-major global tensor (streaming stores)
+template <int TILES>
+__device__ __forceinline__ void store_rows_sw(const float* s, int tile_floats, float* g, int n) {
+  for (int c = threadIdx.x; c < n * TILES * 8; c += T) {
+    const int row = c / (TILES * 8), qq = c % (TILES * 8);
+    st4_stream(g + 4 * c, lds4(s + (qq >> 3) * tile_floats + sw_chunk(row, qq & 7)));
+  }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(T, 2)
+fwd_tc_kernel(const Args a) {
+  extern __shared__ __align__(1024) float smem_tc[];
+  float* const smem = smem_tc;
+  const int R = a.R, N = a.N;
+  const FwdTcSmem L(R, a.ecap);
+  const int TF = L.RP * 32;                  // floats per operand tile
+  float* XA = smem + L.xa;
+  float* XL = smem + L.xl;
+  float* YA = smem + L.ya;
+  float* YL = smem + L.yl;
+  float* zs = YL;                            // conv2 output z [R][LDX] over the dead low part of y1
+  float* W1H = smem + L.w1h;
+  float* W1L = smem + L.w1l;
+  float* W2H = smem + L.w2h;
+  float* W2L = smem + L.w2l;
+  float* h1s = smem + L.h1s;
+  float* h2s = smem + L.h2s;
+  float* ss1 = smem + L.ss1;
+  float* sd1 = smem + L.sd1;
+  float* ss2 = smem + L.ss2;
+  float* sd2 = smem + L.sd2;
+  float* ml1 = smem + L.ml1;
+  float* ml2 = smem + L.ml2;
+  float* vec = smem + L.vec;
+  int* rp_s = reinterpret_cast<int*>(smem + L.rp);
+  int* col_s = reinterpret_cast<int*>(smem + L.col);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar + 2);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();            // SWIZZLE_128B atoms are 1024-byte aligned
+  const int rank = (int)cluster_ctarank();
+  const ClusterBarrier cb = {a.barrier};
+  const long long b = cluster_id_x();
+  const int lo = rank * R, n = max(0, min(R, N - lo));
+  const long long M = a.M, rb = b * N, ro = rb + lo;
+  const ParamLayout pl(a.nb, NC);
+  const SavedLayout sl(M, NC);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (warp == 0) tmem_alloc(tmem_slot, TC_COLS);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (n > 0) stage_csr_slice(a.rowptr, a.col, lo, n, R, rp_s, col_s, a.ecap);
+  pdl_wait();
+  Stamper stamp(a);
+  stamp();
+  if (a.nb > 0) {
+    const float* blk = a.params + pl.block(0);
+    stage_w1_tc(blk, W1H);
+    stage_w2_tc(blk, W2H);
+    stage_vec_tc(blk, vec);
+  }
+  cp_commit();
+
+  // encoder Linear(1, nc)  (GraphModels.py:487) -> operand tile + low part
+  {
+    const int lig = lane & 7, sub = lane >> 3;
+    const float4 wv = ldg4(a.params + pl.lin0_w() + 4 * lig), bv = ldg4(a.params + pl.lin0_b() + 4 * lig);
+    for (int il = warp * 4 + sub; il < n; il += T / 8) {
+      const float xv = __ldg(a.x + rb + __ldg(a.perm + lo + il));
+      const float4 o = make_float4(fmaf(xv, wv.x, bv.x), fmaf(xv, wv.y, bv.y), fmaf(xv, wv.z, bv.z), fmaf(xv, wv.w, bv.w));
+      const int off = sw_chunk(il, lig);
+      st4(XA + off, o);
+      st4(XL + off, lo4(o));
+    }
+  }
+  cp_wait_all();
+  if (a.nb > 0) lo_own_weights(W1H, W1L, W2H, W2L);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const unsigned h1_base = smem_u32(h1s), h2_base = smem_u32(h2s), z_base = smem_u32(zs);
+  const unsigned ss1_base = smem_u32(ss1), ss2_base = smem_u32(ss2);
+  const uint32_t xa_u = smem_u32(XA), xl_u = smem_u32(XL), ya_u = smem_u32(YA), yl_u = smem_u32(YL);
+  const uint32_t w1h_u = smem_u32(W1H), w1l_u = smem_u32(W1L), w2h_u = smem_u32(W2H), w2l_u = smem_u32(W2L);
+  uint32_t phase = 0;
+
+  for (int k = 0; k < a.nb; ++k) {
+    const int buf = k & 1;
+    const float* vc = vec + buf * VECF;
+    fence_proxy_async();                     // x / low parts / weights written through the generic proxy -> tensor core
+    __syncthreads();
+
+    // conv1 projection + scores  (GraphModels.py:464)
+    stamp();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      issue_proj_tc<NC, 2 * NC>(tmem, xa_u, xl_u, 0u, w1h_u, w1l_u, 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);                   // every thread: W1 / x are free for whoever writes them next
+    phase ^= 1u;
+    if ((warp & 3) < 2) {
+      tc_fence_after();
+      const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+      drain_row_tc(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 32u * half, vc + 32 * half, vc + 2 * NC + 32 * half,
+                   h1s + row * LDY + 32 * half, ss1 + row * 2 + half, sd1 + row * 2 + half, row < n);
+      tc_fence_before();
+    }
+    stamp();
+    cb.arrive();
+    if (k + 1 < a.nb) stage_w1_tc(a.params + pl.block(k + 1), W1H);
+    cp_commit();
+    if (TRAIN) store_rows_sw<1>(XA, TF, a.saved + (k > 0 ? sl.xout(k - 1) : sl.x_enc()) + ro * NC, n);
+    cluster_wait();
+    stamp();
+    // conv1 aggregation + bias + ReLU -> y1 operand tiles (one per head) + low parts
+    agg_fwd<2, true>(rp_s, col_s, h1_base, LDY * 4, ss1_base, sd1, vc + 4 * NC, YA, TF, TRAIN ? ml1 : nullptr,
+                     TRAIN ? ml1 + 2 * R : nullptr, n, rank, true, YL);
+    fence_proxy_async();
+    __syncthreads();
+    stamp();
+    // conv2 projection + scores  (:465)
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      issue_proj_tc<2 * NC, NC>(tmem, ya_u, yl_u, (uint32_t)TF * 4u, w2h_u, w2l_u, NC * 32 * 4u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    if (warp < 2) {
+      tc_fence_after();
+      const int row = 32 * warp + lane;
+      drain_row_tc(tmem + ((uint32_t)(32 * warp) << 16), vc + 6 * NC, vc + 7 * NC, h2s + row * LDX, ss2 + row, sd2 + row,
+                   row < n);
+      tc_fence_before();
+    }
+    stamp();
+    cb.arrive();
+    if (k + 1 < a.nb) {
+      stage_w2_tc(a.params + pl.block(k + 1), W2H);
+      stage_vec_tc(a.params + pl.block(k + 1), vec + (buf ^ 1) * VECF);
+    }
+    cp_commit();
+    if (TRAIN) {
+      store_rows<2 * NC, LDY>(h1s, a.saved + sl.h1(k) + ro * 2 * NC, n);
+      store_rows_sw<2>(YA, TF, a.saved + sl.y1(k) + ro * 2 * NC, n);
+      store_scalars(ss1, a.saved + sl.ss1(k) + ro * 2, 2 * n);
+      store_scalars(sd1, a.saved + sl.sd1(k) + ro * 2, 2 * n);
+      store_scalars(ml1, a.saved + sl.m1(k) + ro * 2, 2 * n);
+      store_scalars(ml1 + 2 * R, a.saved + sl.l1(k) + ro * 2, 2 * n);
+    }
+    cluster_wait();
+    stamp();
+    // conv2 aggregation + bias -> z (neighbours read it in the mean)
+    agg_fwd<1>(rp_s, col_s, h2_base, LDX * 4, ss2_base, sd2, vc + 8 * NC, zs, LDX, TRAIN ? ml2 : nullptr,
+               TRAIN ? ml2 + R : nullptr, n, rank, false);
+    stamp();
+    cb.arrive();
+    if (TRAIN) {
+      store_rows<NC, LDX>(h2s, a.saved + sl.h2(k) + ro * NC, n);
+      store_scalars(ss2, a.saved + sl.ss2(k) + ro, n);
+      store_scalars(sd2, a.saved + sl.sd2(k) + ro, n);
+      __syncthreads();                       // (m, l) of conv2 were written by other warps just before the arrival
+      store_scalars(ml2, a.saved + sl.m2(k) + ro, n);
+      store_scalars(ml2 + R, a.saved + sl.l2(k) + ro, n);
+    }
+    cp_wait_all();                           // the next block's W1 / W2 / vectors have landed
+    if (k + 1 < a.nb) lo_own_weights(W1H, W1L, W2H, W2L);
+    cluster_wait();
+    stamp();
+    // SimpleConv(mean) + residual + ReLU  (:466-467) -> next block's x operand + low part
+    {
+      const int slot = lane & 3, sub = lane >> 2;
+      for (int il = warp * 8 + sub; il < n; il += T / 4) {
+        const int beg = rp_s[il], end = rp_s[il + 1] - 1;
+        float4 acc0 = f4zero(), acc1 = f4zero();
+#pragma unroll 4
+        for (int e = beg; e < end; ++e) {
+          const unsigned ar = row_addr(z_base, col_s[e], LDX * 4) + 16u * slot;
+          add4(acc0, ldsc4(ar));
+          add4(acc1, ldsc4(ar + 64u));
+        }
+        const int deg = end - beg;
+        const float inv = 1.f / (float)(deg > 1 ? deg : 1);
+        const int o0 = sw_chunk(il, slot), o1 = sw_chunk(il, slot + 4);
+        const float4 r0 = lds4(XA + o0), r1 = lds4(XA + o1);
+        const float4 n0 = relu4(make_float4(fmaf(acc0.x, inv, r0.x), fmaf(acc0.y, inv, r0.y), fmaf(acc0.z, inv, r0.z), fmaf(acc0.w, inv, r0.w)));
+        const float4 n1 = relu4(make_float4(fmaf(acc1.x, inv, r1.x), fmaf(acc1.y, inv, r1.y), fmaf(acc1.z, inv, r1.z), fmaf(acc1.w, inv, r1.w)));
+        st4(XA + o0, n0);
+        st4(XA + o1, n1);
+        st4(XL + o0, lo4(n0));
+        st4(XL + o1, lo4(n1));
+      }
+    }
+  }
+  cp_wait_all();
+  __syncthreads();
+  // no CTA may leave while a neighbour still reads its shared memory
+  cb.arrive();
+  if (TRAIN) store_rows_sw<1>(XA, TF, a.saved + (a.nb > 0 ? sl.xout(a.nb - 1) : sl.x_enc()) + ro * NC, n);
+  // decoder Linear(nc, 1)  (:492)
+  {
+    const int lig = lane & 7, sub = lane >> 3;
+    const float4 wv = ldg4(a.params + pl.lin1_w() + 4 * lig);
+    const float bias = __ldg(a.params + pl.lin1_b());
+    const bool bad = a.poison != nullptr && __ldg(a.poison) != 0;
+    for (int i0 = 0; i0 < n; i0 += T / 8) {
+      const int il = i0 + warp * 4 + sub;
+      float p = il < n ? dot4(lds4(XA + sw_chunk(il, lig)), wv) : 0.f;
+      p = group_sum<8>(p, FULL);
+      if (il < n && lig == 0) a.out[rb + __ldg(a.perm + lo + il)] = bad ? __int_as_float(0x7fc00000) : p + bias;
+    }
+  }
+  cluster_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TC_COLS);
 }
 
 // =============================================================================== backward
@@ -1355,6 +1674,15 @@ static int barrier_flavour() {
   return g_barrier;
 }
 
+static int g_tc = -1;
+static bool tc_enabled() {                  // tcgen05 projections in the forward stack (GATRES_RES2_TC=0: mma.sync form)
+  if (g_tc < 0) {
+    const char* e = getenv("GATRES_RES2_TC");
+    g_tc = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return g_tc == 1;
+}
+static size_t fwd_tc_smem(int R, int ecap) { return sizeof(float) * (size_t)FwdTcSmem(R, ecap).total; }
 static size_t fwd_smem(int R, int ecap) { return sizeof(float) * (size_t)FwdSmem(R, ecap).total; }
 static size_t bwd_smem(int R, int ecap) { return sizeof(float) * (size_t)BwdSmem(R, ecap).total; }
 
@@ -1430,6 +1758,12 @@ int resident2_forward(const gatres_model_desc* d, const float* params, const flo
   const int cs = res2_cluster(d->B);
   a.R = (d->N + cs - 1) / cs;
   a.ecap = res2_ecap(d, cs);
+  // tensor-core projections when the operand tiles fit next to a second CTA (M = 128 datapath: at most 64 rows per CTA
+  // are drained) — otherwise the mma.sync form
+  const size_t tc_smem = res2::fwd_tc_smem(a.R, a.ecap);
+  if (res2::tc_enabled() && a.R <= 64 && tc_smem <= res2::kMaxSmem)
+    return saved != nullptr ? res2::launch_cluster<res2::fwd_tc_kernel<true>>("resident2_forward_tc(train)", cs, d->B, tc_smem, st, a)
+                            : res2::launch_cluster<res2::fwd_tc_kernel<false>>("resident2_forward_tc", cs, d->B, tc_smem, st, a);
   const size_t smem = res2::fwd_smem(a.R, a.ecap);
   return saved != nullptr ? res2::launch_cluster<res2::fwd_kernel<true>>("resident2_forward(train)", cs, d->B, smem, st, a)
                           : res2::launch_cluster<res2::fwd_kernel<false>>("resident2_forward", cs, d->B, smem, st, a);
@@ -1456,6 +1790,12 @@ int resident2_backward(const gatres_model_desc* d, const float* params, const fl
 extern "C" int gatres_set_resident_barrier(int flavour) {
   const int prev = gatres::res2::barrier_flavour();
   if (flavour >= 0 && flavour <= 2) gatres::res2::g_barrier = flavour;
+  return prev;
+}
+
+extern "C" int gatres_set_resident_tc(int on) {
+  const int prev = gatres::res2::tc_enabled() ? 1 : 0;
+  if (on == 0 || on == 1) gatres::res2::g_tc = on;
   return prev;
 }
 

@@ -24,6 +24,7 @@ used for a batch whose CONTENT was checked against it.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from dataclasses import dataclass
 from math import gcd
@@ -120,6 +121,20 @@ def locality_order(edge_index: np.ndarray, num_nodes: int, leaf: int = 6, slices
     return np.asarray(order, dtype=np.int64)
 
 
+def degree_sort_slices(perm: np.ndarray, degree: np.ndarray, slices: int = 8) -> np.ndarray:
+    """Reorder `perm` INSIDE each of the `slices` row slices by the row's degree (stable: ties keep the locality order).
+    The resident kernels give a warp four or eight CONSECUTIVE rows of a slice and run its edge loops to the largest
+    degree among them (warp-uniform control flow); with equal-degree neighbours in the order no lane idles on padding
+    edges.  Rows never leave their slice, so the share of CTA-local neighbours is unchanged."""
+    N = len(perm)
+    R = -(-N // slices)
+    out = perm.copy()
+    for lo in range(0, N, R):
+        seg = perm[lo:lo + R]
+        out[lo:lo + R] = seg[np.argsort(degree[seg], kind="stable")]
+    return out
+
+
 def permute_csr(rowptr: np.ndarray, col: np.ndarray, perm: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """the same CSR in locality numbering: row r = node perm[r]; its entries are the locality ids of that node's
     neighbours IN THE SAME ORDER (the reference's summation order: ascending original source id, self-loop last)"""
@@ -152,6 +167,9 @@ class LocalityPlan:
         dev = topo.rowptr.device
         ei = topo.edge_index.cpu().numpy()
         perm = locality_order(ei, N)
+        if os.environ.get("GATRES_DEGREE_SORT", "1") != "0":
+            rp0 = topo.rowptr.cpu().numpy().astype(np.int64)
+            perm = degree_sort_slices(perm, rp0[1:] - rp0[:-1])
         rp, col = permute_csr(topo.rowptr.cpu().numpy().astype(np.int64), topo.col.cpu().numpy().astype(np.int64), perm)
         rpt, colt = permute_csr(topo.rowptr_t.cpu().numpy().astype(np.int64), topo.col_t.cpu().numpy().astype(np.int64), perm)
         ecap = []

@@ -141,6 +141,10 @@ void gatres_set_resident_profile(int64_t* device_buf, int32_t slots_per_cta);
  * of gatres_model_desc): 1 = use it when applicable (default; GATRES_RESIDENT_DSM presets it), 0 = never.  Other
  * values only query.  Returns the previous setting. */
 int gatres_set_resident_dsm(int on);
+/* Projections of the second-generation forward stack on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
+ * 3xTF32, accumulator in TMEM; operands in SWIZZLE_128B shared tiles): 1 = when the tiles fit (default;
+ * GATRES_RES2_TC presets it), 0 = the mma.sync form.  Other values only query.  Returns the previous setting. */
+int gatres_set_resident_tc(int on);
 /* Cluster-barrier flavour of those kernels: 0 = every thread arrives with .release (gpu-scope fence per barrier),
  * 1 = one releasing warp, 2 = CTA-scope fence + CTA barrier + relaxed arrival (default: the exchange is shared memory
  * only; rationale and measurements in csrc/resident2.cu).  GATRES_RES2_BARRIER presets it.  Other values only query.

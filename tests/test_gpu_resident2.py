@@ -49,8 +49,9 @@ def knobs():
     from gnn_pressure_estimation_b200 import _lib
     lib = _lib.load()
     prev = (lib.gatres_set_resident_dsm(-1), lib.gatres_set_resident_cluster(-1), lib.gatres_set_resident_max_batch(-1),
-            lib.gatres_set_resident_barrier(-1))
+            lib.gatres_set_resident_barrier(-1), lib.gatres_set_resident_tc(-1))
     yield lib
+    lib.gatres_set_resident_tc(prev[4])
     lib.gatres_set_resident_dsm(prev[0])
     lib.gatres_set_resident_cluster(prev[1])
     lib.gatres_set_resident_max_batch(prev[2])
@@ -80,15 +81,17 @@ def test_locality_plan_is_a_relabelled_copy_of_the_csr(dev):
     assert float((inv[ei[0].numpy()] // R == inv[ei[1].numpy()] // R).mean()) > 0.9
 
 
+@pytest.mark.parametrize("tc", [1, 0])          # projections on tcgen05 (default where the tiles fit) / mma.sync
 @pytest.mark.parametrize("cluster", [0, 1, 2, 4, 8])
 @pytest.mark.parametrize("kind,B,blocks", [("tiny", 5, 2), ("directed", 3, 3), ("ctown", 4, 4), ("ctown", 32, 15), ("ctown", 40, 2)])
-def test_dsm_inference_forward(kind, B, blocks, cluster, dev, knobs):
+def test_dsm_inference_forward(kind, B, blocks, cluster, tc, dev, knobs):
     from gnn_pressure_estimation_b200 import _lib
     ei, N, ref, model, topo, ts, (x, y, mask) = _setup(kind, B, blocks, dev)
     d, p, s = C.byref(ts.desc), _lib.ptr, _lib.stream
     lib = knobs
     lib.gatres_set_resident_max_batch(1 << 30)
     lib.gatres_set_resident_cluster(cluster)
+    lib.gatres_set_resident_tc(tc)
     scratch = torch.empty(int(lib.gatres_scratch_floats(d, 0)), device=dev)
     _lib.call("gatres_apply_mask", p(ts.x), p(ts.mask), p(ts.xm), ts.M, s())
     outs = {}
@@ -104,10 +107,11 @@ def test_dsm_inference_forward(kind, B, blocks, cluster, dev, knobs):
     assert rel_err(outs[1], outs[0]) < 2e-5, "dsm vs first-generation resident kernel"
 
 
+@pytest.mark.parametrize("tc", [1, 0])
 @pytest.mark.parametrize("barrier", [2, 0, 1])
 @pytest.mark.parametrize("cluster", [0, 4, 8])
 @pytest.mark.parametrize("kind,B,blocks", [("tiny", 5, 2), ("directed", 3, 3), ("ctown", 4, 4), ("ctown", 32, 15)])
-def test_dsm_training_pair_matches_first_generation_and_oracle(kind, B, blocks, cluster, barrier, dev, knobs):
+def test_dsm_training_pair_matches_first_generation_and_oracle(kind, B, blocks, cluster, barrier, tc, dev, knobs):
     """forward(training) + backward through the C ABI with the DSMEM kernels, against the first-generation resident
     kernels (same inputs) and against the CPU oracle (forward 1e-4, gradients 1e-3)"""
     from gnn_pressure_estimation_b200 import _lib
@@ -117,6 +121,7 @@ def test_dsm_training_pair_matches_first_generation_and_oracle(kind, B, blocks, 
     lib.gatres_set_resident_max_batch(1 << 30)
     lib.gatres_set_resident_cluster(cluster)
     lib.gatres_set_resident_barrier(barrier)
+    lib.gatres_set_resident_tc(tc)
     res = {}
     for dsm in (1, 0):
         lib.gatres_set_resident_dsm(dsm)

@@ -138,3 +138,34 @@ def test_locality_order_and_permuted_csr():
     before = float((ei[0] // R == ei[1] // R).mean())
     after = float((inv[ei[0]] // R == inv[ei[1]] // R).mean())
     assert before < 0.2 and after > 0.9, (before, after)               # random ids -> 96 % of the neighbours local
+
+
+def test_degree_sorted_slices_keep_locality_and_remove_padding():
+    """graph.degree_sort_slices: rows stay inside their slice (locality share unchanged), the order inside a slice is
+    stable by degree, and the warp-level padding (largest degree of 4 / 8 consecutive rows over the mean) shrinks"""
+    import numpy as np
+    from gnn_pressure_estimation_b200 import graph as Gr, topology as T
+    from oracle import topology_oracle as TO
+    ei, names = T.reference_edge_index(T.ctown_shaped())
+    N = len(names)
+    rp, _ = TO.csr_by_target(ei, N)
+    deg = (rp[1:] - rp[:-1]).astype(np.int64)
+    perm = Gr.locality_order(ei, N)
+    sorted_perm = Gr.degree_sort_slices(perm, deg)
+    R = -(-N // 8)
+    assert sorted(sorted_perm.tolist()) == list(range(N))
+    for lo in range(0, N, R):
+        assert sorted(sorted_perm[lo:lo + R].tolist()) == sorted(perm[lo:lo + R].tolist())
+        assert np.all(np.diff(deg[sorted_perm[lo:lo + R]]) >= 0)
+
+    def padded_work(p, rows_per_warp):
+        total = 0
+        for lo in range(0, N, R):
+            d = deg[p[lo:lo + R]]
+            for w in range(0, len(d), rows_per_warp):
+                total += int(d[w:w + rows_per_warp].max()) * len(d[w:w + rows_per_warp])
+        return total / float(deg.sum())
+
+    for rpw in (4, 8):
+        before, after = padded_work(perm, rpw), padded_work(sorted_perm, rpw)
+        assert after < before and after < 1.1, (rpw, before, after)
