@@ -56,6 +56,8 @@ struct Args {
   int N, nb, R, ecap;    // ecap: shared-memory capacity (ints) of one CTA's slice of a CSR (max over the cluster)
   int k_hi, k_lo, head, tail;
   int barrier;           // ClusterBarrier flavour
+  int cs;                // CTAs per snapshot (cluster size)
+  int images;            // saved activations in the CTA-image layout (ImageLayout) instead of SavedLayout
   long long* prof;       // optional phase-timestamp buffer [CTA][prof_slots] (tools/resident_probe.py), else NULL
   int prof_slots;
 };
@@ -611,6 +613,45 @@ fwd_kernel(const Args a) {
   cluster_wait();
 }
 
+// =============================================================================== saved activations as CTA images
+// The tensor-core forward / backward pair keeps its saved activations as straight IMAGES of the forward's shared-memory
+// arrays, one record per (block, snapshot, CTA): every array is contiguous in shared memory AND in the record, so the
+// forward writes a block's activations with seven bulk copies (cp.async.bulk shared -> global, issued by one thread,
+// carried out by the TMA engine) instead of ~3000 LDS + STG per CTA and block — those stores cost the training forward
+// 2.3 us per block in the shadow of its barrier waits (153 us against 120 us for the same stack without them), and one
+// bulk copy per ROW was worse still (per-request overhead: 205 us).  Record (floats, R rows per CTA):
+//   x   [R][32]      block input, SWIZZLE_128B operand rows (16-byte chunk index XOR row % 8)
+//   h1  [R][LDY]     conv1 projection, padded rows as the neighbours gather them
+//   y1  2 x [R][32]  conv1 output, one SWIZZLE_128B operand tile per head
+//   s1  4 x a4(2R)   s_src, s_dst, m, l of conv1 ([row][head])
+//   h2  [R][LDX]     conv2 projection, padded rows
+//   s2  4 x a4(R)    s_src, s_dst, m, l of conv2
+// followed, after the last block, by one x image per CTA (the stack's output = the decoder's input).  ~5 % larger than
+// SavedLayout (padding); gatres_saved_floats covers both.  Private to this file: the backward's loaders undo the
+// swizzle / padding while they copy.
+struct ImageLayout {
+  long long B;
+  int R, cs, off_h1, off_y, off_s1, off_h2, off_s2, rec;
+  __host__ __device__ ImageLayout(int R_, long long B_, int cs_) : B(B_), R(R_), cs(cs_) {
+    off_h1 = R * 32;
+    off_y = off_h1 + R * LDY;
+    off_s1 = off_y + 2 * R * 32;
+    off_h2 = off_s1 + 4 * (int)a4(2 * R);
+    off_s2 = off_h2 + R * LDX;
+    rec = off_s2 + 4 * (int)a4(R);
+  }
+  __host__ __device__ long long record(int k, long long b, int rank) const { return ((k * B + b) * cs + rank) * (long long)rec; }
+  __host__ __device__ long long tail(int nb, long long b, int rank) const { return nb * B * cs * (long long)rec + (b * cs + rank) * (long long)(R * 32); }
+  __host__ __device__ long long total(int nb) const { return nb * B * cs * (long long)rec + B * cs * (long long)(R * 32); }
+};
+__device__ __forceinline__ void bulk_s2g(float* gdst, const float* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // =============================================================================== forward, tcgen05 projections
 // Same stack as fwd_kernel, with the two projections of a block on the 5th-generation tensor cores: the mma.sync
 // 3xTF32 contractions were the largest single item of a block (3.0 of 9.7 us: ~15 cycles per MMA per scheduler).
@@ -624,11 +665,11 @@ fwd_kernel(const Args a) {
 //     of the datapath reads whatever follows in shared memory and its accumulator rows are never read), commits to
 //     an mbarrier, and warps 0/1 (+ 4/5 for the second column half) drain the accumulator with tcgen05.ld — thread
 //     = row, so the attention scores are in-thread dot products — into the padded tiles the neighbours gather from.
-// Saved activations keep the layout of fwd_kernel (the stores un-swizzle), so bwd_kernel is unchanged.
+// Saved activations go to HBM as images of the shared-memory arrays (ImageLayout above): seven bulk copies per block.
 constexpr int TC_COLS = 64;                  // TMEM columns per CTA (conv1: N = 64, conv2: N = 32)
 
 struct FwdTcSmem {
-  int xa, xl, ya, yl, w1h, w1l, w2h, w2l, h1s, h2s, ss1, sd1, ss2, sd2, ml1, ml2, vec, rp, col, bar, total, RP;
+  int xa, xl, ya, yl, w1h, w1l, w2h, w2l, h1s, h2s, s1, s2, vec, rp, col, bar, total, RP;
   __host__ __device__ FwdTcSmem(int R, int ecap) {
     RP = (R + 7) & ~7;
     int o = 0;
@@ -636,7 +677,7 @@ struct FwdTcSmem {
     xa = take(RP * 32); xl = take(RP * 32); ya = take(2 * RP * 32); yl = take(2 * RP * 32);       // 1024-byte multiples
     w1h = take(2 * NC * NC); w1l = take(2 * NC * NC); w2h = take(2 * NC * NC); w2l = take(2 * NC * NC);
     h1s = take(R * LDY); h2s = take(R * LDX);
-    ss1 = take(2 * R); sd1 = take(2 * R); ss2 = take(R); sd2 = take(R); ml1 = take(4 * R); ml2 = take(2 * R);
+    s1 = take(4 * (int)a4(2 * R)); s2 = take(4 * (int)a4(R));        // (s_src, s_dst, m, l) blocks: images of the saved records
     vec = take(2 * VECF); rp = take(R + 1); col = take(ecap); bar = take(4);
     total = o;
   }
@@ -694,15 +735,6 @@ __device__ __forceinline__ void drain_row_tc(uint32_t taddr, const float* att_s,
   *ss_dst = ps;
   *sd_dst = pd;
 }
-// own rows of a SWIZZLE_128B operand (TILES tiles of 32 columns) -> row-major global tensor (streaming stores)
-template <int TILES>
-__device__ __forceinline__ void store_rows_sw(const float* s, int tile_floats, float* g, int n) {
-  for (int c = threadIdx.x; c < n * TILES * 8; c += T) {
-    const int row = c / (TILES * 8), qq = c % (TILES * 8);
-    st4_stream(g + 4 * c, lds4(s + (qq >> 3) * tile_floats + sw_chunk(row, qq & 7)));
-  }
-}
-
 template <bool TRAIN>
 __global__ void __launch_bounds__(T, 2)
 fwd_tc_kernel(const Args a) {
@@ -722,12 +754,14 @@ fwd_tc_kernel(const Args a) {
   float* W2L = smem + L.w2l;
   float* h1s = smem + L.h1s;
   float* h2s = smem + L.h2s;
-  float* ss1 = smem + L.ss1;
-  float* sd1 = smem + L.sd1;
-  float* ss2 = smem + L.ss2;
-  float* sd2 = smem + L.sd2;
-  float* ml1 = smem + L.ml1;
-  float* ml2 = smem + L.ml2;
+  float* ss1 = smem + L.s1;
+  float* sd1 = ss1 + a4(2 * R);
+  float* m1 = sd1 + a4(2 * R);
+  float* l1 = m1 + a4(2 * R);
+  float* ss2 = smem + L.s2;
+  float* sd2 = ss2 + a4(R);
+  float* m2 = sd2 + a4(R);
+  float* l2 = m2 + a4(R);
   float* vec = smem + L.vec;
   int* rp_s = reinterpret_cast<int*>(smem + L.rp);
   int* col_s = reinterpret_cast<int*>(smem + L.col);
@@ -738,10 +772,16 @@ fwd_tc_kernel(const Args a) {
   const ClusterBarrier cb = {a.barrier};
   const long long b = cluster_id_x();
   const int lo = rank * R, n = max(0, min(R, N - lo));
-  const long long M = a.M, rb = b * N, ro = rb + lo;
+  const long long M = a.M, rb = b * N;
   const ParamLayout pl(a.nb, NC);
-  const SavedLayout sl(M, NC);
+  const ImageLayout im(R, M / N, a.cs);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // saved activations: thread 32 issues the bulk copies of a group after the barrier arrival that follows the last
+  // write of its arrays (every writer has fenced them towards the async proxy before arriving)
+  const bool storer = TRAIN && threadIdx.x == 32;
+  auto after_arrival = [&]() {
+    if (TRAIN && cb.flavour == 0) __syncthreads();          // flavour 0 arrives without a CTA barrier
+  };
 
   if (warp == 0) tmem_alloc(tmem_slot, TC_COLS);
   if (threadIdx.x == 0) {
@@ -787,12 +827,13 @@ fwd_tc_kernel(const Args a) {
   for (int k = 0; k < a.nb; ++k) {
     const int buf = k & 1;
     const float* vc = vec + buf * VECF;
+    if (storer) bulk_wait_read<0>();         // the previous block's h1 / y1 / h2 / score images have left shared memory
     fence_proxy_async();                     // x / low parts / weights written through the generic proxy -> tensor core
     __syncthreads();
 
     // conv1 projection + scores  (GraphModels.py:464)
     stamp();
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_proj_tc<NC, 2 * NC>(tmem, xa_u, xl_u, 0u, w1h_u, w1l_u, 0u);
       umma_commit(bar);
@@ -810,17 +851,21 @@ fwd_tc_kernel(const Args a) {
     cb.arrive();
     if (k + 1 < a.nb) stage_w1_tc(a.params + pl.block(k + 1), W1H);
     cp_commit();
-    if (TRAIN) store_rows_sw<1>(XA, TF, a.saved + (k > 0 ? sl.xout(k - 1) : sl.x_enc()) + ro * NC, n);
+    after_arrival();
+    if (storer) {                            // the block input
+      bulk_s2g(a.saved + im.record(k, b, rank), XA, (unsigned)R * 32u * 4u);
+      bulk_commit();
+    }
     cluster_wait();
     stamp();
     // conv1 aggregation + bias + ReLU -> y1 operand tiles (one per head) + low parts
-    agg_fwd<2, true>(rp_s, col_s, h1_base, LDY * 4, ss1_base, sd1, vc + 4 * NC, YA, TF, TRAIN ? ml1 : nullptr,
-                     TRAIN ? ml1 + 2 * R : nullptr, n, rank, true, YL);
+    agg_fwd<2, true>(rp_s, col_s, h1_base, LDY * 4, ss1_base, sd1, vc + 4 * NC, YA, TF, TRAIN ? m1 : nullptr,
+                     TRAIN ? l1 : nullptr, n, rank, true, YL);
     fence_proxy_async();
     __syncthreads();
     stamp();
     // conv2 projection + scores  (:465)
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_proj_tc<2 * NC, NC>(tmem, ya_u, yl_u, (uint32_t)TF * 4u, w2h_u, w2l_u, NC * 32 * 4u);
       umma_commit(bar);
@@ -835,34 +880,37 @@ fwd_tc_kernel(const Args a) {
       tc_fence_before();
     }
     stamp();
+    if (TRAIN) fence_proxy_async();          // h1 / scores / (m, l) of conv1 -> async proxy (the bulk copies below)
     cb.arrive();
     if (k + 1 < a.nb) {
       stage_w2_tc(a.params + pl.block(k + 1), W2H);
       stage_vec_tc(a.params + pl.block(k + 1), vec + (buf ^ 1) * VECF);
     }
     cp_commit();
-    if (TRAIN) {
-      store_rows<2 * NC, LDY>(h1s, a.saved + sl.h1(k) + ro * 2 * NC, n);
-      store_rows_sw<2>(YA, TF, a.saved + sl.y1(k) + ro * 2 * NC, n);
-      store_scalars(ss1, a.saved + sl.ss1(k) + ro * 2, 2 * n);
-      store_scalars(sd1, a.saved + sl.sd1(k) + ro * 2, 2 * n);
-      store_scalars(ml1, a.saved + sl.m1(k) + ro * 2, 2 * n);
-      store_scalars(ml1 + 2 * R, a.saved + sl.l1(k) + ro * 2, 2 * n);
+    after_arrival();
+    if (storer) {                            // conv1's tensors: all final, none rewritten before the next block
+      float* rec = a.saved + im.record(k, b, rank);
+      bulk_s2g(rec + im.off_h1, h1s, (unsigned)R * LDY * 4u);
+      bulk_s2g(rec + im.off_y, YA, (unsigned)R * 32u * 4u);
+      bulk_s2g(rec + im.off_y + R * 32, YA + TF, (unsigned)R * 32u * 4u);
+      bulk_s2g(rec + im.off_s1, ss1, 4u * (unsigned)a4(2 * R) * 4u);
+      bulk_commit();
     }
     cluster_wait();
     stamp();
     // conv2 aggregation + bias -> z (neighbours read it in the mean)
-    agg_fwd<1>(rp_s, col_s, h2_base, LDX * 4, ss2_base, sd2, vc + 8 * NC, zs, LDX, TRAIN ? ml2 : nullptr,
-               TRAIN ? ml2 + R : nullptr, n, rank, false);
+    agg_fwd<1>(rp_s, col_s, h2_base, LDX * 4, ss2_base, sd2, vc + 8 * NC, zs, LDX, TRAIN ? m2 : nullptr,
+               TRAIN ? l2 : nullptr, n, rank, false);
     stamp();
+    if (storer) bulk_wait_read<1>();         // the block input has left the x tile (the mean below rewrites it)
+    if (TRAIN) fence_proxy_async();          // h2 / scores / (m, l) of conv2 -> async proxy
     cb.arrive();
-    if (TRAIN) {
-      store_rows<NC, LDX>(h2s, a.saved + sl.h2(k) + ro * NC, n);
-      store_scalars(ss2, a.saved + sl.ss2(k) + ro, n);
-      store_scalars(sd2, a.saved + sl.sd2(k) + ro, n);
-      __syncthreads();                       // (m, l) of conv2 were written by other warps just before the arrival
-      store_scalars(ml2, a.saved + sl.m2(k) + ro, n);
-      store_scalars(ml2 + R, a.saved + sl.l2(k) + ro, n);
+    after_arrival();
+    if (storer) {
+      float* rec = a.saved + im.record(k, b, rank);
+      bulk_s2g(rec + im.off_h2, h2s, (unsigned)R * LDX * 4u);
+      bulk_s2g(rec + im.off_s2, ss2, 4u * (unsigned)a4(R) * 4u);
+      bulk_commit();
     }
     cp_wait_all();                           // the next block's W1 / W2 / vectors have landed
     if (k + 1 < a.nb) lo_own_weights(W1H, W1L, W2H, W2L);
@@ -894,10 +942,14 @@ fwd_tc_kernel(const Args a) {
     }
   }
   cp_wait_all();
+  if (TRAIN) fence_proxy_async();
   __syncthreads();
   // no CTA may leave while a neighbour still reads its shared memory
   cb.arrive();
-  if (TRAIN) store_rows_sw<1>(XA, TF, a.saved + (a.nb > 0 ? sl.xout(a.nb - 1) : sl.x_enc()) + ro * NC, n);
+  if (storer) {                              // the stack's output (decoder input)
+    bulk_s2g(a.saved + im.tail(a.nb, b, rank), XA, (unsigned)R * 32u * 4u);
+    bulk_commit();
+  }
   // decoder Linear(nc, 1)  (:492)
   {
     const int lig = lane & 7, sub = lane >> 3;
@@ -911,6 +963,7 @@ fwd_tc_kernel(const Args a) {
       if (il < n && lig == 0) a.out[rb + __ldg(a.perm + lo + il)] = bad ? __int_as_float(0x7fc00000) : p + bias;
     }
   }
+  if (storer) bulk_wait_all();
   cluster_wait();
   tc_fence_before();
   __syncthreads();
@@ -1465,6 +1518,7 @@ bwd_kernel(const Args a) {
   const long long M = a.M, rb = b * N, ro = rb + lo;
   const ParamLayout pl(nb, NC);
   const SavedLayout sl(M, NC);
+  const ImageLayout im(R, M / N, a.cs);    // a.images: the tensor-core forward's records (loaders undo swizzle / padding)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* sv = a.saved;
 
@@ -1491,6 +1545,12 @@ bwd_kernel(const Args a) {
   //   [A: h2 / s2 scalars of k-1, after phase 2] [B: h1 / s1 scalars of k-1, after phase 5] [C: parameters of k-1, after
   //   phase 6] | cluster barrier | [D: y1 / x0 of k-1]
   auto load_conv2_side = [&](int k) {
+    if (a.images) {                          // padded h2 rows and the (s_src, s_dst, m, l) block: straight copies
+      const float* rec = sv + im.record(k, b, rank);
+      for (int c = threadIdx.x; c < n * (LDX / 4); c += T) cp16(h2s + 4 * c, rec + im.off_h2 + 4 * c);
+      for (int c = threadIdx.x; c < (int)a4(R); c += T) cp16(ss2 + 4 * c, rec + im.off_s2 + 4 * c);
+      return;
+    }
     stage_rows<NC, LDX>(sv + sl.h2(k) + ro * NC, h2s, n);
     // scalar arrays start at ro (not 16-byte aligned in general): 4-byte copies
     for (int c = threadIdx.x; c < n; c += T) {
@@ -1501,6 +1561,12 @@ bwd_kernel(const Args a) {
     }
   };
   auto load_conv1_side = [&](int k) {
+    if (a.images) {
+      const float* rec = sv + im.record(k, b, rank);
+      for (int c = threadIdx.x; c < n * (LDY / 4); c += T) cp16(h1s + 4 * c, rec + im.off_h1 + 4 * c);
+      for (int c = threadIdx.x; c < (int)a4(2 * R); c += T) cp16(ss1 + 4 * c, rec + im.off_s1 + 4 * c);
+      return;
+    }
     stage_rows<2 * NC, LDY>(sv + sl.h1(k) + ro * 2 * NC, h1s, n);
     for (int c = threadIdx.x; c < 2 * n; c += T) {
       cp4(ss1 + c, sv + sl.ss1(k) + ro * 2 + c);
@@ -1510,6 +1576,15 @@ bwd_kernel(const Args a) {
     }
   };
   auto load_row_local = [&](int k) {
+    if (a.images) {                          // SWIZZLE_128B operand rows -> padded row-major tiles
+      const float* rec = sv + im.record(k, b, rank);
+      for (int c = threadIdx.x; c < n * 16; c += T) {
+        const int row = c >> 4, v = (c >> 3) & 1, q = c & 7;
+        cp16(ys + row * LDY + 32 * v + 4 * q, rec + im.off_y + v * (R * 32) + sw_chunk(row, q));
+      }
+      for (int c = threadIdx.x; c < n * 8; c += T) cp16(xs + (c >> 3) * LDX + 4 * (c & 7), rec + sw_chunk(c >> 3, c & 7));
+      return;
+    }
     stage_rows<2 * NC, LDY>(sv + sl.y1(k) + ro * 2 * NC, ys, n);
     stage_rows<NC, LDX>(sv + (k > 0 ? sl.xout(k - 1) : sl.x_enc()) + ro * NC, xs, n);
   };
@@ -1524,12 +1599,13 @@ bwd_kernel(const Args a) {
     // decoder backward: g[i][c] = d_out[i] w[c] (masked by the last ReLU), dw = sum d_out x, db = sum d_out
     const int lig = lane & 7, sub = lane >> 3;
     const float* xl = sv + (nb > 0 ? sl.xout(nb - 1) : sl.x_enc());
+    const float* xi = sv + im.tail(nb, b, rank);
     const float4 wv = ldg4(a.params + pl.lin1_w() + 4 * lig);
     float4 aw = f4zero();
     float ab = 0.f;
     for (int il = warp * 4 + sub; il < n; il += T / 8) {
       const float gv = __ldg(a.d_out + rb + __ldg(a.perm + lo + il));
-      const float4 xv = ldg4(xl + (ro + il) * NC + 4 * lig);
+      const float4 xv = a.images ? ldg4(xi + sw_chunk(il, lig)) : ldg4(xl + (ro + il) * NC + 4 * lig);
       float4 d = make_float4(gv * wv.x, gv * wv.y, gv * wv.z, gv * wv.w);
       if (nb > 0) d = mask4(d, xv);
       st4(gs + il * LDX + 4 * lig, d);
@@ -1727,6 +1803,11 @@ static int res2_cluster(long long B) {
   return cs;
 }
 
+// the tensor-core forward (and with it the CTA-image layout of the saved activations) applies
+static bool res2_tc_pair(int R, int ecap) {
+  return res2::tc_enabled() && R <= 64 && res2::fwd_tc_smem(R, ecap) <= res2::kMaxSmem;
+}
+
 static int res2_ecap(const gatres_model_desc* d, int cs) { return d->p_ecap[cs == 8 ? 3 : (cs == 4 ? 2 : (cs == 2 ? 1 : 0))]; }
 
 // Applicable when the descriptor carries a locality plan, nc = 32, atomics mode, and the slices fit shared memory.
@@ -1747,6 +1828,20 @@ bool resident2_eligible(const gatres_model_desc* d, bool training, long long max
   return !training || res2::bwd_smem(R, ecap) <= budget;
 }
 
+// floats the saved-activation buffer needs when the pair uses the CTA-image layout (upper bound over the cluster
+// sizes the knobs can select); 0 when the kernels cannot apply
+long long resident2_saved_floats(const gatres_model_desc* d) {
+  if (d->nc != 32) return 0;               // (whether a locality plan is attached may change after the buffer is sized)
+  long long worst = 0;
+  for (int cs = 1; cs <= 8; cs <<= 1) {
+    const int R = (d->N + cs - 1) / cs;
+    if (R > 64) continue;
+    const long long t = res2::ImageLayout(R, d->B, cs).total(d->num_blocks);
+    worst = t > worst ? t : worst;
+  }
+  return worst;
+}
+
 int resident2_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,
                       cudaStream_t st) {
   res2::Args a = {};
@@ -1758,10 +1853,12 @@ int resident2_forward(const gatres_model_desc* d, const float* params, const flo
   const int cs = res2_cluster(d->B);
   a.R = (d->N + cs - 1) / cs;
   a.ecap = res2_ecap(d, cs);
+  a.cs = cs;
   // tensor-core projections when the operand tiles fit next to a second CTA (M = 128 datapath: at most 64 rows per CTA
   // are drained) — otherwise the mma.sync form
   const size_t tc_smem = res2::fwd_tc_smem(a.R, a.ecap);
-  if (res2::tc_enabled() && a.R <= 64 && tc_smem <= res2::kMaxSmem)
+  a.images = res2_tc_pair(a.R, a.ecap) ? 1 : 0;
+  if (a.images)
     return saved != nullptr ? res2::launch_cluster<res2::fwd_tc_kernel<true>>("resident2_forward_tc(train)", cs, d->B, tc_smem, st, a)
                             : res2::launch_cluster<res2::fwd_tc_kernel<false>>("resident2_forward_tc", cs, d->B, tc_smem, st, a);
   const size_t smem = res2::fwd_smem(a.R, a.ecap);
@@ -1782,6 +1879,8 @@ int resident2_backward(const gatres_model_desc* d, const float* params, const fl
   const int cs = res2_cluster(d->B);
   a.R = (d->N + cs - 1) / cs;
   a.ecap = res2_ecap(d, cs);
+  a.cs = cs;
+  a.images = res2_tc_pair(a.R, a.ecap) ? 1 : 0;          // same predicate as the forward: the two agree on the layout
   return res2::launch_cluster<res2::bwd_kernel>("resident2_backward", cs, d->B, res2::bwd_smem(a.R, a.ecap), st, a);
 }
 

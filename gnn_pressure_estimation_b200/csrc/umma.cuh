@@ -34,6 +34,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully active warp (elect.sync).  Issue tcgen05.mma / commit under `if (warp == W) if (elect_one())`:
+// with a warp-uniform outer branch ptxas keeps descriptors in uniform registers and emits the UTCHMMAs back to back;
+// under a divergent `if (threadIdx.x == 0)` every MMA is wrapped in an ELECT / BRA.U.ANY loop with ~10 setup instructions
+// (measured: ~55 cycles per MMA, 0.66 us for the 12 MMAs of one projection).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -1,3 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_resident2.py -x -q > gpurun_out/r3c_pytest.log 2>&1; tail -15 gpurun_out/r3c_pytest.log
-timeout 300 python tools/resident_probe.py --batches 32 --phases --out gpurun_out/r3c_probe.json > gpurun_out/r3c_probe.log 2>&1
-tail -c 1500 gpurun_out/r3c_probe.log
+timeout 900 python -m pytest tests/test_gpu_resident2.py -x -q > gpurun_out/r3i_pytest.log 2>&1; tail -5 gpurun_out/r3i_pytest.log
+timeout 300 python tools/resident_probe.py --batches 32 --phases --out gpurun_out/r3i_probe.json > gpurun_out/r3i_probe.log 2>&1
+tail -c 1800 gpurun_out/r3i_probe.log
