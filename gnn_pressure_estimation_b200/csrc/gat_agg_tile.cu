@@ -24,9 +24,36 @@ __device__ __forceinline__ float tile_group_max(float v, unsigned mask) {
   return v;
 }
 
+// Rows in ascending degree (counting sort in shared memory, degrees capped at 31).  A warp runs the edge loops of its 4-8
+// rows to the LARGEST degree among them (warp-uniform control flow); handing it rows of equal degree removes the padding
+// iterations (C-Town-shaped network: 1.23x the edge visits with 4 rows per warp in node order, 1.03x sorted).  The order
+// inside a degree class is whatever the atomics give: rows are independent, only the row -> warp assignment changes.
+// rp: staged row pointers (visible: call after a CTA barrier).  Ends with a CTA barrier.
+template <int THREADS>
+__device__ __forceinline__ void degree_order(const int* rp, unsigned N, unsigned short* ord, int* hist) {
+  const int tid = threadIdx.x;
+  if (tid < 32) hist[tid] = 0;
+  __syncthreads();
+  for (unsigned k = tid; k < N; k += THREADS) atomicAdd(&hist[min(rp[k + 1] - rp[k], 31)], 1);
+  __syncthreads();
+  if (tid < 32) {                                   // exclusive scan: first slot of every degree class
+    const int c = hist[tid];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += up;
+    }
+    hist[tid] = incl - c;
+  }
+  __syncthreads();
+  for (unsigned k = tid; k < N; k += THREADS) ord[atomicAdd(&hist[min(rp[k + 1] - rp[k], 31)], 1)] = (unsigned short)k;
+  __syncthreads();
+}
+
 // shared-memory plan of the forward tile kernel (host and device agree through these)
 struct FwdTilePlan {
-  uint32_t h_bytes, ss_bytes, tx_bytes, stage_bytes, zs_off, xs_off, rp_off, col_off, bar_off, total;
+  uint32_t h_bytes, ss_bytes, tx_bytes, stage_bytes, zs_off, xs_off, rp_off, col_off, ord_off, hist_off, bar_off, total;
   // fuse_mean: two more slabs, the layer output z of the snapshot (never written to HBM) and the block input x0
   __host__ __device__ FwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1, bool fuse_mean = false) {
     h_bytes = N * F * 4u;
@@ -37,7 +64,9 @@ struct FwdTilePlan {
     xs_off = zs_off + (fuse_mean ? h_bytes : 0u);
     rp_off = xs_off + (fuse_mean ? h_bytes : 0u);
     col_off = rp_off + (((N + 1u) * 4u + 15u) & ~15u);
-    bar_off = col_off + ((E1 * 4u + 15u) & ~15u);
+    ord_off = col_off + ((E1 * 4u + 15u) & ~15u);                  // degree order of the rows (uint16) + its histogram
+    hist_off = ord_off + ((N * 2u + 15u) & ~15u);
+    bar_off = hist_off + 128u;
     total = bar_off + 32u;
   }
 };
@@ -62,6 +91,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   const FwdTilePlan plan(N, F, H, E1, FUSE_MEAN);
   int* rp_s = reinterpret_cast<int*>(smem + plan.rp_off);
   int* col_s = reinterpret_cast<int*>(smem + plan.col_off);
+  unsigned short* ord = reinterpret_cast<unsigned short*>(smem + plan.ord_off);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + plan.bar_off);          // [0], [1]: stages; [2]: x0 slab
   float* ZS = reinterpret_cast<float*>(smem + plan.zs_off);
   const float* XS = reinterpret_cast<const float*>(smem + plan.xs_off);
@@ -87,6 +117,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   for (unsigned k = tid; k <= N; k += kTileThreads) rp_s[k] = __ldg(rowptr + k);
   for (unsigned k = tid; k < E1; k += kTileThreads) col_s[k] = __ldg(col + k);
   __syncthreads();
+  degree_order<THREADS>(rp_s, N, ord, reinterpret_cast<int*>(smem + plan.hist_off));
   pdl_wait();                                     // CSR staging above overlapped the previous kernel's tail
   if (tid == 0) {
     if (blockIdx.x < B) issue(0, blockIdx.x);
@@ -115,7 +146,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
       // rows past the end are clamped (recompute the last row, store nothing): every lane of the warp
       // runs the same instruction stream, so shuffles are plain full-mask SHFLs
       const bool row_ok = i0 + sub < N;
-      const unsigned i = row_ok ? i0 + sub : N - 1;
+      const unsigned i = ord[row_ok ? i0 + sub : N - 1];             // rows in ascending degree
       const size_t r = (size_t)b * N + i;
       const int beg = rp_s[i], deg = rp_s[i + 1] - beg;
       const int deg_max = __reduce_max_sync(gmask, deg);
@@ -184,7 +215,8 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     }
     if (FUSE_MEAN) {
       mbar_wait(&full[2], k & 1);
-      for (unsigned i = warp * RPW + sub; i < N; i += kTileWarps * RPW) {
+      for (unsigned io = warp * RPW + sub; io < N; io += kTileWarps * RPW) {
+        const unsigned i = ord[io];
         const int beg = rp_s[i], end = rp_s[i + 1] - 1;                    // drop the self-loop
         float4 acc = f4zero();
 #pragma unroll 4
@@ -282,7 +314,7 @@ namespace gatres {
 struct BwdTilePlan {
   // [inputs of a snapshot: h slab, g slab, s_src, s_dst, m, l] x nbuf, then D, ds_dst, the two CSRs, barriers
   uint32_t slab, sc, in_bytes, nbuf, hs_off, gs_off, ss_off, sd_off, mm_off, ll_off, dd_off, dsd_off, rpi_off, ci_off,
-      rpo_off, co_off, bar_off, total, tx_bytes;
+      rpo_off, co_off, oi_off, oo_off, hist_off, bar_off, total, tx_bytes;
   __host__ __device__ BwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1, unsigned nbuf_ = 1) {
     slab = N * F * 4u;
     sc = N * H * 4u;
@@ -301,7 +333,10 @@ struct BwdTilePlan {
     ci_off = rpi_off + rp;
     rpo_off = ci_off + cl;
     co_off = rpo_off + rp;
-    bar_off = co_off + cl;
+    oi_off = co_off + cl;                                 // degree orders of the rows: in-degree (pass 1), out-degree (pass 2)
+    oo_off = oi_off + ((N * 2u + 15u) & ~15u);
+    hist_off = oo_off + ((N * 2u + 15u) & ~15u);
+    bar_off = hist_off + 128u;
     total = bar_off + 16u;
     tx_bytes = 2u * slab + 4u * sc;
   }
@@ -335,6 +370,8 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   unsigned short* ci = reinterpret_cast<unsigned short*>(smem + plan.ci_off);
   int* rpo = reinterpret_cast<int*>(smem + plan.rpo_off);
   unsigned short* co = reinterpret_cast<unsigned short*>(smem + plan.co_off);
+  unsigned short* ord_in = reinterpret_cast<unsigned short*>(smem + plan.oi_off);
+  unsigned short* ord_out = reinterpret_cast<unsigned short*>(smem + plan.oo_off);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + plan.bar_off);        // [NBUF]
   float* red = reinterpret_cast<float*>(smem);     // reused for the final CTA reduction (slabs are dead by then)
 
@@ -374,6 +411,8 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   // so pass 2 needs neither the per-edge dot products <g_i, h_j> again nor D of the edges' targets
   for (unsigned k = tid; k < N * H; k += THREADS) DD[k] = 0.f;
   __syncthreads();
+  degree_order<THREADS>(rpi, N, ord_in, reinterpret_cast<int*>(smem + plan.hist_off));
+  degree_order<THREADS>(rpo, N, ord_out, reinterpret_cast<int*>(smem + plan.hist_off));
   pdl_wait();
   if (tid == 0 && blockIdx.x < B) issue(blockIdx.x, 0);
 
@@ -399,7 +438,7 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     // ---------------- pass 1: per target row, D and ds_dst into shared memory
     for (unsigned i0 = warp * RPW; i0 < N; i0 += kWarpsT * RPW) {
       const bool row_ok = i0 + sub < N;
-      const unsigned i = row_ok ? i0 + sub : N - 1;
+      const unsigned i = ord_in[row_ok ? i0 + sub : N - 1];          // rows in ascending in-degree
       const int beg = rpi[i], deg = rpi[i + 1] - beg;
       const int deg_max = __reduce_max_sync(gmask, deg);
       float4 gv[V];
@@ -469,7 +508,7 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     // ---------------- pass 2: per source row, dh and the attention-vector gradients
     for (unsigned j0 = warp * RPW; j0 < N; j0 += kWarpsT * RPW) {
       const bool row_ok = j0 + sub < N;
-      const unsigned jn = row_ok ? j0 + sub : N - 1;
+      const unsigned jn = ord_out[row_ok ? j0 + sub : N - 1];        // rows in ascending out-degree
       const int beg = rpo[jn], deg = rpo[jn + 1] - beg;
       const int deg_max = __reduce_max_sync(gmask, deg);
       float4 hv[V], dacc[V];
