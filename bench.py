@@ -671,7 +671,7 @@ def roofline_leg(args, line, wl, step_ms, dev):
         rtraffic = tj.get("bytes_per_launch", {}).get("resident_bwd_kernel") if tj.get("resident_batch") == B else None
         ach = bytes_bwd / t_b / 1e9
         line["roofline"] = {
-            "bound": "hbm", "kernel": f"resident_bwd_kernel (whole backward stack, {nb} blocks, one launch)",
+            "bound": "hbm", "kernel": f"res2::bwd_kernel (whole backward stack, {nb} blocks, one launch)",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": rtraffic, "traffic_over_algorithmic": (rtraffic / bytes_bwd) if rtraffic else None,
             "traffic_source": tj_name, "peak_source": which, "share_of_step": t_b * 1e3 / step_ms,
@@ -681,7 +681,7 @@ def roofline_leg(args, line, wl, step_ms, dev):
                       "dependent phases (cluster exchange + barriers), not by HBM; the HBM-regime figures of the aggregation "
                       "kernels are under roofline_hbm_regime",
             "workload": f"bench batch ({B} snapshots): {t_b * 1e6:.0f} us/launch for {per_node_bwd} algorithmic B/node",
-            "forward_stack": {"kernel": "resident_fwd_kernel<train>", "us": t_f * 1e6, "algorithmic_bytes_per_launch": bytes_fwd,
+            "forward_stack": {"kernel": "res2::fwd_tc_kernel<train> (tcgen05 projections, saved activations by bulk copies)", "us": t_f * 1e6, "algorithmic_bytes_per_launch": bytes_fwd,
                               "achieved": bytes_fwd / t_f / 1e9, "frac": bytes_fwd / t_f / 1e9 / peak},
             "secondary_unfused_accounting": {"bytes_per_launch": unf_bwd, "achieved": unf_bwd / t_b / 1e9,
                                              "frac": unf_bwd / t_b / 1e9 / peak,
