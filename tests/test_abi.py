@@ -58,7 +58,15 @@ def test_workspace_sizes():
     one = ctypes.c_void_p(16)
     d = _lib.ModelDesc(15, 32, 388, 97, 1246, 0, 32, one, one, one, one, None)
     M = 32 * 388
-    assert lib.gatres_saved_floats(ctypes.byref(d)) == M * 32 + 15 * (6 * M * 32 + 12 * M)
+    layer = M * 32 + 15 * (6 * M * 32 + 12 * M)                 # compact tensors of the layer kernels (SavedLayout)
+    # CTA images of the snapshot-resident tensor-core pair (csrc/resident2.cu ImageLayout; 8 CTAs x 49 rows per snapshot):
+    # x [R][32], h1 [R][68], y1 2 x [R][32], 4 x a4(2R) scores, h2 [R][36], 4 x a4(R) scores; one x image more at the end
+    R, a4 = 49, lambda n: (n + 3) & ~3
+    rec = R * 32 + R * 68 + 2 * R * 32 + 4 * a4(2 * R) + R * 36 + 4 * a4(R)
+    images = 15 * 32 * 8 * rec + 32 * 8 * R * 32
+    assert lib.gatres_saved_floats(ctypes.byref(d)) == max(layer, images) == images
+    d128 = _lib.ModelDesc(15, 128, 388, 97, 1246, 0, 32, one, one, one, one, None)
+    assert lib.gatres_saved_floats(ctypes.byref(d128)) == M * 128 + 15 * (6 * M * 128 + 12 * M)     # no resident pair at nc = 128
     assert lib.gatres_scratch_floats(ctypes.byref(d), 0) == 8 * M * 32 + 4 * M
     assert lib.gatres_scratch_floats(ctypes.byref(d), 1) == 8 * M * 32 + 10 * M
 
