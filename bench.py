@@ -321,8 +321,8 @@ def kernel_table(B, N, topo, nc, hbm_regime, dev):
         call("gatres_mean_res_fwd", ptr(topo.rowptr), ptr(topo.col), ptr(z[k]), ptr(x0[k]), ptr(o[k]), B, N, nc, stream())
 
     def meanb(k):
-        call("gatres_mean_res_bwd", ptr(topo.rowptr), ptr(topo.rowptr_t), ptr(topo.col_t), ptr(z[k]), None, ptr(o[k]),
-             None, B, N, nc, stream())
+        call("gatres_mean_res_bwd_e1", ptr(topo.rowptr), ptr(topo.rowptr_t), ptr(topo.col_t), topo.E1, ptr(z[k]), ptr(o[k]),
+             B, N, nc, stream())
 
     for name, fn, bpn in ((f"mean_res_fwd C={nc}", mean, 12 * nc), (f"mean_res_bwd C={nc}", meanb, 8 * nc)):
         t = time_launches(fn, reps, n_sets)

@@ -55,6 +55,7 @@ _PROTOTYPES = {
     "gatres_gat_agg_bwd": (C.c_int, [_p] * 16 + [_i64, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _p]),
     "gatres_mean_res_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "gatres_mean_res_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
+    "gatres_mean_res_bwd_e1": (C.c_int, [_p, _p, _p, _i32, _p, _p, _i64, _i32, _i32, _p]),
     "gatres_linear_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i64, _i64, _i32, _i32, _i32, _p]),
     "gatres_encoder_fwd": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p]),
     "gatres_encoder_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i64, _i64, _i64, _i32, _p]),

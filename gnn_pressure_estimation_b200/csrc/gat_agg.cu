@@ -477,6 +477,39 @@ int gat_agg_mean_res_fwd(const int* rowptr, const int* col, unsigned E1, const f
 
 using namespace gatres;
 
+namespace gatres {
+// SimpleConv(mean) backward of the model's layer path (ReLU mask already applied): snapshot-tile kernel for large
+// batches of graphs whose slab fits shared memory, else the gather kernel.  1 = done, 0 = not applicable, < 0 = error.
+bool mean_bwd_tile_eligible(unsigned N, unsigned C, unsigned E1);
+int mean_res_bwd_tile(const int* rowptr, const int* rowptr_t, const int* col_t, unsigned E1, const float* g, float* dz,
+                      unsigned B, unsigned N, int C, cudaStream_t st);
+int mean_res_bwd_model(const int* rowptr, const int* rowptr_t, const int* col_t, unsigned E1, const float* g, float* dz,
+                       long long B, int N, int C, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("GATRES_MEAN_BWD_TILE");
+    enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  if (!enabled || E1 == 0 || B < tile_min_batch() || B * (long long)N >= (1ll << 31) ||
+      !mean_bwd_tile_eligible((unsigned)N, (unsigned)C, E1))
+    return 0;
+  const int rc = mean_res_bwd_tile(rowptr, rowptr_t, col_t, E1, g, dz, (unsigned)B, (unsigned)N, C, st);
+  return rc == GATRES_OK ? 1 : rc;
+}
+}  // namespace gatres
+
+extern "C" int gatres_mean_res_bwd(const int32_t* rowptr, const int32_t* rowptr_t, const int32_t* col_t,
+                                   const float* g_out, const float* out, float* dz, float* dres,
+                                   int64_t B, int32_t N, int32_t C, void* stream);
+extern "C" int gatres_mean_res_bwd_e1(const int32_t* rowptr, const int32_t* rowptr_t, const int32_t* col_t, int32_t E1,
+                                      const float* g_masked, float* dz, int64_t B, int32_t N, int32_t C, void* stream) {
+  GATRES_REQUIRE(B >= 0 && N > 0 && E1 >= 0, "mean_res_bwd_e1: bad B=%lld N=%d E1=%d", (long long)B, N, E1);
+  if (B == 0) return GATRES_OK;
+  const int tiled = mean_res_bwd_model(rowptr, rowptr_t, col_t, (unsigned)E1, g_masked, dz, B, N, C, as_stream(stream));
+  if (tiled != 0) return tiled < 0 ? tiled : GATRES_OK;
+  return gatres_mean_res_bwd(rowptr, rowptr_t, col_t, g_masked, nullptr, dz, nullptr, B, N, C, stream);
+}
+
 extern "C" int64_t gatres_set_tile_min_batch(int64_t min_batch) {
   const long long prev = tile_min_batch();
   if (min_batch >= 0) g_tile_min_batch = min_batch;

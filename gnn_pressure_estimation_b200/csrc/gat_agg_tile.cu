@@ -670,3 +670,131 @@ int gat_agg_bwd_tile(const int* rowptr, const int* col, const int* rowptr_t, con
 }
 
 }  // namespace gatres
+
+// =============================================================================
+// SimpleConv(mean) backward for one snapshot per CTA iteration: dz[j] = sum over the out-edges j -> i (self-loop
+// excluded) of g[i] / max(indeg(i), 1)  (mean_res.cu: mean_res_bwd_kernel with the ReLU mask already applied, the form
+// the model's backward uses).  The gather version walks col_t -> rowptr -> g through L1 / L2 per edge (44 % of the
+// copy bandwidth); here the snapshot's gradient slab is staged by TMA (double-buffered), the out-edge CSR and the
+// per-edge weights 1 / max(indeg, 1) sit in shared memory, rows are handed out in ascending out-degree.
+// =============================================================================
+namespace gatres {
+
+struct MeanBwdPlan {
+  uint32_t slab, stage, rp_off, co_off, wt_off, ord_off, hist_off, bar_off, total;
+  __host__ __device__ MeanBwdPlan(unsigned N, unsigned C, unsigned E1) {
+    slab = N * C * 4u;
+    stage = (slab + 127u) & ~127u;
+    rp_off = 2u * stage;
+    co_off = rp_off + (((N + 1u) * 4u + 15u) & ~15u);
+    wt_off = co_off + ((E1 * 2u + 15u) & ~15u);
+    ord_off = wt_off + ((E1 * 4u + 15u) & ~15u);
+    hist_off = ord_off + ((N * 2u + 15u) & ~15u);
+    bar_off = hist_off + 128u;
+    total = bar_off + 16u;
+  }
+};
+
+template <int C, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
+mean_res_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ rowptr_t, const int* __restrict__ col_t,
+                         unsigned E1, const float* __restrict__ g, float* __restrict__ dz, unsigned B, unsigned N) {
+  constexpr int LPR = C / 4, RPW = 32 / LPR, kWarpsT = THREADS / 32;
+  static_assert(LPR <= 32, "row wider than one warp pass");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const MeanBwdPlan plan(N, C, E1);
+  int* rpo = reinterpret_cast<int*>(smem + plan.rp_off);
+  unsigned short* co = reinterpret_cast<unsigned short*>(smem + plan.co_off);
+  float* wt = reinterpret_cast<float*>(smem + plan.wt_off);
+  unsigned short* ord = reinterpret_cast<unsigned short*>(smem + plan.ord_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + plan.bar_off);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPR, lig = lane % LPR;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  for (unsigned k = tid; k <= N; k += THREADS) rpo[k] = __ldg(rowptr_t + k);
+  for (unsigned k = tid; k < E1; k += THREADS) {
+    const int t = __ldg(col_t + k);
+    co[k] = (unsigned short)t;
+    const int dg = __ldg(rowptr + t + 1) - __ldg(rowptr + t) - 1;        // in-degree of the target without its self-loop
+    wt[k] = 1.f / (float)(dg > 1 ? dg : 1);
+  }
+  __syncthreads();
+  degree_order<THREADS>(rpo, N, ord, reinterpret_cast<int*>(smem + plan.hist_off));
+  pdl_wait();
+  auto issue = [&](int stage, unsigned bb) {
+    mbar_arrive_expect_tx(&full[stage], plan.slab);
+    bulk_g2s(smem + (size_t)stage * plan.stage, g + (size_t)bb * N * C, plan.slab, &full[stage]);
+  };
+  if (tid == 0) {
+    if (blockIdx.x < B) issue(0, blockIdx.x);
+    if (blockIdx.x + gridDim.x < B) issue(1, blockIdx.x + gridDim.x);
+  }
+  unsigned k = 0;
+  if (gridDim.x >= B) pdl_launch_dependents();
+  for (unsigned b = blockIdx.x; b < B; b += gridDim.x, ++k) {
+    const int stage = k & 1;
+    const float* gs = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage) + 4 * lig;
+    mbar_wait(&full[stage], (k >> 1) & 1);
+    for (unsigned j0 = warp * RPW + sub; j0 < N; j0 += kWarpsT * RPW) {
+      const unsigned j = ord[j0];
+      const int beg = rpo[j], end = rpo[j + 1] - 1;                      // the self-loop is the last out-edge of a row
+      float4 acc = f4zero();
+#pragma unroll 4
+      for (int e = beg; e < end; ++e) fma4(acc, wt[e], *reinterpret_cast<const float4*>(gs + co[e] * C));
+      st4(dz + ((size_t)b * N + j) * C + 4 * lig, acc);
+    }
+    __syncthreads();                               // every warp is done with this stage
+    if (tid == 0) {
+      const unsigned nb = b + 2u * gridDim.x;
+      if (nb < B) {
+        fence_proxy_async();
+        issue(stage, nb);
+      }
+    }
+  }
+}
+
+bool mean_bwd_tile_eligible(unsigned N, unsigned C, unsigned E1) {
+  const MeanBwdPlan plan(N, C, E1);
+  return (N * C) % 4u == 0 && N < 65536u && plan.total <= 227u * 1024u && (C == 32 || C == 64 || C == 128);
+}
+
+template <int C>
+static int launch_mean_bwd_tile(const int* rowptr, const int* rowptr_t, const int* col_t, unsigned E1, const float* g,
+                                float* dz, unsigned B, unsigned N, cudaStream_t st) {
+  const MeanBwdPlan plan(N, C, E1);
+  unsigned per_sm = (unsigned)((227u * 1024u) / (plan.total + 1024u));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  unsigned grid = (unsigned)sm_count() * per_sm;
+  if (grid > B) grid = B;
+#define LAUNCH(THR)                                                                                                \
+  do {                                                                                                             \
+    auto kern = mean_res_bwd_tile_kernel<C, THR>;                                                                  \
+    static uint32_t configured = 0;                                                                                \
+    if (configured < plan.total) {                                                                                 \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
+        return check_launch("mean_res_bwd_tile: smem attribute");                                                  \
+      configured = plan.total;                                                                                     \
+    }                                                                                                              \
+    launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, rowptr_t, col_t, E1, g, dz, B, N);          \
+  } while (0)
+  if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);
+#undef LAUNCH
+  return check_launch("mean_res_bwd_tile");
+}
+
+int mean_res_bwd_tile(const int* rowptr, const int* rowptr_t, const int* col_t, unsigned E1, const float* g, float* dz,
+                      unsigned B, unsigned N, int C, cudaStream_t st) {
+  if (C == 32) return launch_mean_bwd_tile<32>(rowptr, rowptr_t, col_t, E1, g, dz, B, N, st);
+  if (C == 64) return launch_mean_bwd_tile<64>(rowptr, rowptr_t, col_t, E1, g, dz, B, N, st);
+  if (C == 128) return launch_mean_bwd_tile<128>(rowptr, rowptr_t, col_t, E1, g, dz, B, N, st);
+  set_error("mean_res_bwd_tile: unsupported channels %d", C);
+  return GATRES_ERR_ARG;
+}
+
+}  // namespace gatres

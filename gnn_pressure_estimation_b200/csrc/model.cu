@@ -176,7 +176,7 @@ extern "C" int gatres_backward_range(const gatres_model_desc* d, const float* pa
     float* gB = gbuf[(nb - k) & 1];
     const float* x0 = k > 0 ? saved + sl.xout(k - 1) : saved + sl.x_enc();
     // SimpleConv(mean) + residual: gA already carries the ReLU mask of this block's output
-    TRY(gatres_mean_res_bwd(d->rowptr, d->rowptr_t, d->col_t, gA, nullptr, dz, nullptr, d->B, N, C, stream));
+    TRY(gatres_mean_res_bwd_e1(d->rowptr, d->rowptr_t, d->col_t, d->E1, gA, dz, d->B, N, C, stream));
     // conv2 (heads=1, mean over one head)
     TRY(gatres_gat_agg_bwd(d->rowptr, d->col, d->rowptr_t, d->col_t, dz, saved + sl.h2(k), saved + sl.ss2(k),
                            saved + sl.sd2(k), saved + sl.m2(k), saved + sl.l2(k), params + pl.c2_as(k),

@@ -36,7 +36,7 @@ constexpr int W1F = 2 * NC * LDX;  // conv1 weight [64][32] padded
 constexpr int W2F = NC * LDY;      // conv2 weight [32][64] padded
 constexpr int VECF = 9 * NC;       // as1 ad1 b1 (64 each) as2 ad2 b2 (32 each)
 constexpr unsigned FULL = 0xffffffffu;
-constexpr size_t kMaxSmem = 110 * 1024;     // two CTAs per SM
+constexpr size_t kMaxSmem = 113 * 1024;     // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
 
 struct Args {
   const int* rowptr;     // in-edge CSR in LOCALITY numbering (self-loop last in every row)

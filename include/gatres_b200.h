@@ -226,6 +226,15 @@ int gatres_mean_res_fwd(const int32_t* rowptr, const int32_t* col,
 int gatres_mean_res_bwd(const int32_t* rowptr, const int32_t* rowptr_t, const int32_t* col_t,
                         const float* g_out, const float* out, float* dz, float* dres,
                         int64_t B, int32_t N, int32_t C, void* stream);
+/*
+ * The form the model's backward uses (ReLU mask already applied, no residual output: out = dres = NULL above) with
+ * the E1 hint of the aggregation kernels: for batches >= the tile threshold of graphs whose gradient slab [N, C] fits
+ * shared memory twice, the snapshot's slab is staged by TMA (double-buffered), the out-edge CSR and the per-edge
+ * weights 1 / max(indeg, 1) sit in shared memory and rows are handed out in ascending out-degree; otherwise (or with
+ * E1 = 0) the gather kernel of gatres_mean_res_bwd runs.  Same results.
+ */
+int gatres_mean_res_bwd_e1(const int32_t* rowptr, const int32_t* rowptr_t, const int32_t* col_t, int32_t E1,
+                           const float* g_masked, float* dz, int64_t B, int32_t N, int32_t C, void* stream);
 
 /*
  * Backward of the projection: dx = dh W (+ add, if non-NULL) (* (relu_ref > 0), if non-NULL),
