@@ -590,6 +590,313 @@ gat_agg_bwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   }
 }
 
+// -----------------------------------------------------------------------------
+// Pipelined form of the fused backward for shapes whose two slabs fill shared memory (two heads x 32 channels, one head
+// x 64 channels on the C-Town-sized graphs): with one input set per CTA the kernel above loads a snapshot (213 KB, ~7 us
+// at one SM's share of HBM) and only then runs its two passes (~10 us) — the copy engine and the warps take turns.  Here
+// the two halves of the input set travel separately and each flies under the OTHER pass:
+//   stage H = {h slab, s_src}        requested when pass 1 of the previous snapshot is done (pass 2 no longer reads the
+//                                    h slab: the row's own h — needed only at the end of its iteration, for the
+//                                    attention-vector gradients — is a global load issued at the top of the iteration
+//                                    and served by L2, where the TMA copy put the slab microseconds earlier; s_src is
+//                                    double-buffered, 3 KB);
+//   stage G = {g slab, s_dst, m, l}  requested when pass 2 of the previous snapshot is done, in row chunks of one
+//                                    warp-iteration each with one mbarrier per chunk: pass 1 walks the chunks in order
+//                                    (degree-sorted inside a chunk) and only waits for the chunk it is about to read.
+// Same arithmetic, same results as the kernel above (the tests run both).
+// -----------------------------------------------------------------------------
+constexpr int kPipeMaxChunks = 8;
+
+struct BwdPipePlan {
+  uint32_t slab, sc, hs_off, gs_off, ss_off, sd_off, mm_off, ll_off, dd_off, dsd_off, rpi_off, ci_off, rpo_off, co_off,
+      oi_off, oo_off, hist_off, bar_off, total;
+  __host__ __device__ BwdPipePlan(unsigned N, unsigned F, unsigned H, unsigned E1) {
+    slab = N * F * 4u;
+    sc = N * H * 4u;
+    hs_off = 0;
+    gs_off = slab;
+    ss_off = 2u * slab;                                   // two s_src buffers
+    sd_off = ss_off + 2u * sc;
+    mm_off = sd_off + sc;
+    ll_off = mm_off + sc;
+    dd_off = (ll_off + sc + 15u) & ~15u;
+    dsd_off = dd_off + sc;
+    rpi_off = dsd_off + sc;
+    const uint32_t rp = ((N + 1u) * 4u + 15u) & ~15u, cl = (E1 * 2u + 15u) & ~15u;
+    ci_off = rpi_off + rp;
+    rpo_off = ci_off + cl;
+    co_off = rpo_off + rp;
+    oi_off = co_off + cl;
+    oo_off = oi_off + ((N * 2u + 15u) & ~15u);
+    hist_off = oo_off + ((N * 2u + 15u) & ~15u);
+    bar_off = hist_off + 128u;
+    total = bar_off + 8u * (1u + kPipeMaxChunks);
+  }
+};
+
+template <int H, int C, int THREADS, bool PACK>
+__global__ void __launch_bounds__(THREADS, 1)
+gat_agg_bwd_tile_pipe_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                             const int* __restrict__ rowptr_t, const int* __restrict__ col_t, unsigned E1,
+                             const float* __restrict__ g, const float* __restrict__ h,
+                             const float* __restrict__ s_src, const float* __restrict__ s_dst,
+                             const float* __restrict__ m, const float* __restrict__ l,
+                             const float* __restrict__ att_src, const float* __restrict__ att_dst,
+                             float* __restrict__ dh, float* __restrict__ grads,
+                             long long off_att_src, long long off_att_dst, long long off_bias,
+                             unsigned B, unsigned N) {
+  using RM = RowMap<H, C, PACK>;
+  constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
+  constexpr int kWarpsT = THREADS / 32;
+  constexpr unsigned RC = kWarpsT * RPW;                  // rows per chunk = rows of one warp-iteration of the CTA
+  constexpr unsigned gmask = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const BwdPipePlan plan(N, F, H, E1);
+  const float* HS = reinterpret_cast<const float*>(smem + plan.hs_off);
+  const float* GS = reinterpret_cast<const float*>(smem + plan.gs_off);
+  const float* SD = reinterpret_cast<const float*>(smem + plan.sd_off);
+  const float* MM = reinterpret_cast<const float*>(smem + plan.mm_off);
+  const float* LL = reinterpret_cast<const float*>(smem + plan.ll_off);
+  float* DD = reinterpret_cast<float*>(smem + plan.dd_off);
+  float* DSD = reinterpret_cast<float*>(smem + plan.dsd_off);
+  int* rpi = reinterpret_cast<int*>(smem + plan.rpi_off);
+  unsigned short* ci = reinterpret_cast<unsigned short*>(smem + plan.ci_off);
+  int* rpo = reinterpret_cast<int*>(smem + plan.rpo_off);
+  unsigned short* co = reinterpret_cast<unsigned short*>(smem + plan.co_off);
+  unsigned short* ord_in = reinterpret_cast<unsigned short*>(smem + plan.oi_off);
+  unsigned short* ord_out = reinterpret_cast<unsigned short*>(smem + plan.oo_off);
+  uint64_t* bar_h = reinterpret_cast<uint64_t*>(smem + plan.bar_off);
+  uint64_t* bar_g = bar_h + 1;                            // [nch]
+  float* red = reinterpret_cast<float*>(smem);            // final CTA reduction (slabs are dead by then)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
+  const unsigned nch = (N + RC - 1) / RC;
+
+  auto issue_h = [&](unsigned bb, unsigned buf) {         // one thread
+    const size_t ro = (size_t)bb * N;
+    mbar_arrive_expect_tx(bar_h, plan.slab + plan.sc);
+    bulk_g2s(smem + plan.hs_off, h + ro * F, plan.slab, bar_h);
+    bulk_g2s(smem + plan.ss_off + buf * plan.sc, s_src + ro * H, plan.sc, bar_h);
+  };
+  auto issue_g = [&](unsigned bb) {                       // one thread; the small arrays ride with the first chunk
+    const size_t ro = (size_t)bb * N;
+    for (unsigned p = 0; p < nch; ++p) {
+      const unsigned r0 = p * RC, rows = min(RC, N - r0), bytes = rows * F * 4u;
+      mbar_arrive_expect_tx(bar_g + p, bytes + (p == 0 ? 3u * plan.sc : 0u));
+      if (p == 0) {
+        bulk_g2s(smem + plan.sd_off, s_dst + ro * H, plan.sc, bar_g);
+        bulk_g2s(smem + plan.mm_off, m + ro * H, plan.sc, bar_g);
+        bulk_g2s(smem + plan.ll_off, l + ro * H, plan.sc, bar_g);
+      }
+      bulk_g2s(smem + plan.gs_off + (size_t)r0 * F * 4u, g + (ro + r0) * F, bytes, bar_g + p);
+    }
+  };
+  constexpr unsigned kBarCount = 1;
+  const bool issuer = tid == 0;
+
+  if (tid == 0) {
+    mbar_init(bar_h, kBarCount);
+    for (unsigned p = 0; p < nch; ++p) mbar_init(bar_g + p, kBarCount);
+    mbar_fence_init();
+  }
+  for (unsigned k = tid; k <= N; k += THREADS) { rpi[k] = __ldg(rowptr + k); rpo[k] = __ldg(rowptr_t + k); }
+  for (unsigned k = tid; k < E1; k += THREADS) {
+    ci[k] = (unsigned short)__ldg(col + k);
+    co[k] = (unsigned short)__ldg(col_t + k);
+  }
+  float4 as[V], ad[V], accs[V], accd[V], bacc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    as[v] = ldg4(att_src + 4 * RM::chunk(lig, v));
+    ad[v] = ldg4(att_dst + 4 * RM::chunk(lig, v));
+    accs[v] = accd[v] = bacc[v] = f4zero();
+  }
+  for (unsigned k = tid; k < N * H; k += THREADS) DD[k] = 0.f;
+  __syncthreads();
+  // pass 1 walks the row chunks in order: ascending in-degree inside every chunk; pass 2: ascending out-degree overall
+  for (unsigned p = 0; p < nch; ++p)
+    degree_order<THREADS>(rpi + p * RC, min(RC, N - p * RC), ord_in + p * RC, reinterpret_cast<int*>(smem + plan.hist_off));
+  degree_order<THREADS>(rpo, N, ord_out, reinterpret_cast<int*>(smem + plan.hist_off));
+  pdl_wait();
+  if (issuer && blockIdx.x < B) {
+    issue_h(blockIdx.x, 0);
+    issue_g(blockIdx.x);
+  }
+
+  unsigned it = 0;
+  if (gridDim.x >= B) pdl_launch_dependents();
+  for (unsigned b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+    const unsigned cur = it & 1u, par = it & 1u;
+    const float* SS = reinterpret_cast<const float*>(smem + plan.ss_off + cur * plan.sc);
+    mbar_wait(bar_h, par);
+
+    // ---------------- pass 1: per target row, D and ds_dst into shared memory, ds_src scattered to the sources
+    for (unsigned p = 0; p < nch; ++p) {
+      mbar_wait(bar_g + p, par);
+      const unsigned kk = p * RC + warp * RPW + sub;
+      const bool row_ok = kk < N;
+      const unsigned i = p * RC + ord_in[row_ok ? kk : p * RC];        // (the order is local to the chunk)
+      const int beg = rpi[i], deg = rpi[i + 1] - beg;
+      const int deg_max = __reduce_max_sync(gmask, deg);
+      float4 gv[V];
+      float sd[V], mi[V], il[V], S1[V], S2[V], S3[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int hd = RM::head(lig, v);
+        gv[v] = *reinterpret_cast<const float4*>(GS + i * F + 4 * RM::chunk(lig, v));
+        if (row_ok) add4(bacc[v], gv[v]);
+        sd[v] = SD[i * H + hd];
+        mi[v] = MM[i * H + hd];
+        il[v] = 1.f / (LL[i * H + hd] + kSoftmaxEps);
+        S1[v] = S2[v] = S3[v] = 0.f;
+      }
+      auto chunk = [&](int e0, int& j, float (&alpha)[V], float (&sl)[V], float (&da)[V]) {
+        const bool valid = e0 + slot < deg;
+        j = valid ? (int)ci[beg + e0 + slot] : 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float z = SS[j * H + RM::head(lig, v)] + sd[v];
+          alpha[v] = valid ? __expf(lrelu(z) - mi[v]) * il[v] : 0.f;
+          sl[v] = lrelu_slope(z);
+          da[v] = 0.f;
+        }
+        const int cnt_max = min(LPH, deg_max - e0);
+        for (int t = 0; t < cnt_max; ++t) {
+          const int jt = __shfl_sync(gmask, j, t, LPH);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float4 x = *reinterpret_cast<const float4*>(HS + jt * F + 4 * RM::chunk(lig, v));
+            const float d = group_sum<LPH>(dot4(gv[v], x), gmask);
+            da[v] = slot == t ? d : da[v];
+          }
+        }
+      };
+      int j;
+      float alpha[V], sl[V], da[V];
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
+        chunk(e0, j, alpha, sl, da);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          S1[v] = fmaf(alpha[v], da[v], S1[v]);
+          S2[v] = fmaf(alpha[v] * sl[v], da[v], S2[v]);
+          S3[v] = fmaf(alpha[v], sl[v], S3[v]);
+        }
+      }
+      float Dv[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        Dv[v] = group_sum<LPH>(S1[v], gmask);
+        const float T2 = group_sum<LPH>(S2[v], gmask), T3 = group_sum<LPH>(S3[v], gmask);
+        if (slot == 0 && row_ok) DSD[i * H + RM::head(lig, v)] = T2 - Dv[v] * T3;
+      }
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
+        if (deg_max > LPH) chunk(e0, j, alpha, sl, da);
+        if (row_ok && e0 + slot < deg) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            atomicAdd(DD + j * H + RM::head(lig, v), alpha[v] * sl[v] * (da[v] - Dv[v]));
+        }
+      }
+    }
+    __syncthreads();                               // the h slab and this s_src buffer's readers of pass 1 are done
+    if (issuer && b + gridDim.x < B) {             // stage H of the next snapshot flies under pass 2
+      fence_proxy_async();
+      issue_h(b + gridDim.x, cur ^ 1u);
+    }
+
+    // ---------------- pass 2: per source row, dh and the attention-vector gradients
+    for (unsigned j0 = warp * RPW; j0 < N; j0 += kWarpsT * RPW) {
+      const bool row_ok = j0 + sub < N;
+      const unsigned jn = ord_out[row_ok ? j0 + sub : N - 1];
+      const int beg = rpo[jn], deg = rpo[jn + 1] - beg;
+      const int deg_max = __reduce_max_sync(gmask, deg);
+      float4 hv[V], dacc[V];
+      float ss[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        // own row of h: needed only at the end of the iteration -> global load (L2), the slab belongs to the next snapshot
+        hv[v] = ldg4(h + ((size_t)b * N + jn) * F + 4 * RM::chunk(lig, v));
+        ss[v] = SS[jn * H + RM::head(lig, v)];
+        dacc[v] = f4zero();
+      }
+      for (int e0 = 0; e0 < deg_max; e0 += LPH) {
+        const bool valid = e0 + slot < deg;
+        const int i = valid ? (int)co[beg + e0 + slot] : 0;
+        float alpha[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int o = i * H + RM::head(lig, v);
+          const float z = ss[v] + SD[o];
+          alpha[v] = valid ? __fdividef(__expf(lrelu(z) - MM[o]), LL[o] + kSoftmaxEps) : 0.f;
+        }
+        const int cnt_max = min(LPH, deg_max - e0);
+        for (int t = 0; t < cnt_max; ++t) {
+          const int itg = __shfl_sync(gmask, i, t, LPH);
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float4 gx = *reinterpret_cast<const float4*>(GS + itg * F + 4 * RM::chunk(lig, v));
+            fma4(dacc[v], __shfl_sync(gmask, alpha[v], t, LPH), gx);
+          }
+        }
+      }
+      float dsv[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) dsv[v] = DD[jn * H + RM::head(lig, v)];
+      __syncwarp();
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (slot == 0 && row_ok) DD[jn * H + RM::head(lig, v)] = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float ds = dsv[v];
+        const float dd = DSD[jn * H + RM::head(lig, v)];
+        fma4(dacc[v], ds, as[v]);
+        fma4(dacc[v], dd, ad[v]);
+        if (row_ok) {
+          st4(dh + ((size_t)b * N + jn) * F + 4 * RM::chunk(lig, v), dacc[v]);
+          fma4(accs[v], ds, hv[v]);
+          fma4(accd[v], dd, hv[v]);
+        }
+      }
+    }
+    __syncthreads();                               // the g slab and s_dst / m / l are free again
+    if (issuer && b + gridDim.x < B) {             // stage G of the next snapshot: its chunks land under pass 1
+      fence_proxy_async();
+      issue_g(b + gridDim.x);
+    }
+  }
+
+  // ---------------- parameter gradients: CTA reduction, then one atomic add per column chunk
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    float4 accv[3] = {accs[v], accd[v], bacc[v]};
+    const long long offs[3] = {off_att_src, off_att_dst, off_bias};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      __syncthreads();
+      st4(red + tid * 4, accv[q]);
+      __syncthreads();
+      if (tid < LPR) {
+        float4 s = f4zero();
+        for (int w = 0; w < kWarpsT; ++w)
+#pragma unroll
+          for (int sb = 0; sb < 32 / LPR; ++sb) add4(s, *reinterpret_cast<float4*>(red + (w * 32 + sb * LPR + tid) * 4));
+        atomicAdd(reinterpret_cast<float4*>(grads + offs[q] + 4 * (tid + v * LPR)), s);
+      }
+    }
+  }
+}
+
+static bool bwd_tile_pipe() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GATRES_BWD_TILE_PIPE");      // 0 = load a snapshot, then run its passes (kernel above)
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 static int bwd_tile_pack() {
   static int v = -1;
   if (v < 0) {
@@ -636,6 +943,29 @@ static int launch_bwd_tile(const int* rowptr, const int* col, const int* rowptr_
     launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, rowptr_t, col_t, E1, g, h, s_src, s_dst, m, l, att_src,      \
                                         att_dst, dh, grads, off_as, off_ad, off_b, B, N);                         \
   } while (0)
+  if (per_sm < 2 && !dbl && bwd_tile_pipe()) {
+    // one input set per SM: the pipelined kernel (halves of the set under the other pass)
+    const BwdPipePlan pp(N, H * C, H, E1);
+    const bool pack = H == 2 && C == 32 && bwd_tile_pack() != 0;
+    const unsigned rc = pack ? (640u / 32u) * 4u : 32u * (32u / (unsigned)(H * C / 4));      // rows per chunk of the variant below
+    if (pp.total <= 227u * 1024u && (N + rc - 1) / rc <= (unsigned)kPipeMaxChunks && (rc * H * C * 4u) % 16u == 0) {
+#define LAUNCH_PIPE(THR, PK)                                                                                         \
+  do {                                                                                                               \
+    auto kern = gat_agg_bwd_tile_pipe_kernel<H, C, THR, PK>;                                                         \
+    static uint32_t configured = 0;                                                                                  \
+    if (configured < pp.total) {                                                                                     \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp.total) != cudaSuccess)     \
+        return check_launch("gat_agg_bwd_tile_pipe: smem attribute");                                                \
+      configured = pp.total;                                                                                         \
+    }                                                                                                                \
+    launch_kernel(kern, dim3(grid), dim3(THR), pp.total, st, rowptr, col, rowptr_t, col_t, E1, g, h, s_src, s_dst, m, l, \
+                  att_src, att_dst, dh, grads, off_as, off_ad, off_b, B, N);                                         \
+  } while (0)
+      if (pack) LAUNCH_PIPE(640, true); else LAUNCH_PIPE(1024, false);
+#undef LAUNCH_PIPE
+      return check_launch("gat_agg_bwd_tile_pipe");
+    }
+  }
   if (per_sm >= 2) LAUNCH(512, false, 1);
   else if (dbl) LAUNCH(1024, false, 2);
   else if (H == 2 && C == 32 && bwd_tile_pack() == 2) LAUNCH(640, true, 1);

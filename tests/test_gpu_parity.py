@@ -201,6 +201,48 @@ def test_tensor_core_projection_many_tiles(H, C, fin, dev):
         assert_close(ss.view(M, H), s64.float(), 1e-5, f"{name} s_src")
         assert_close(sd.view(M, H), d64.float(), 1e-5, f"{name} s_dst")
 
+@pytest.mark.parametrize("H,C,fin,concat", [(2, 32, 32, True), (1, 32, 64, False), (1, 64, 128, False)])
+def test_tile_kernels_many_snapshots_per_cta(H, C, fin, concat, dev):
+    """333 snapshots = more than two per persistent CTA (148 SMs): the software pipelines of the snapshot-tile kernels
+    (double-buffered stages, the two-stage backward that loads one half of a snapshot under the other pass, the
+    SimpleConv(mean) backward tile kernel) run several iterations per CTA.  Checked against the gather kernels on the same
+    inputs (those are held to the oracle at small sizes above) and, for the first snapshots, against the oracle."""
+    from gnn_pressure_estimation_b200 import _lib, ops as gops
+    lib = _lib.load()
+    ei_np, names = GRAPHS["ctown"](); n = len(names); ei = torch.from_numpy(ei_np)
+    B = 333
+    M = B * n
+    x, W, a_s, a_d = _layer_inputs(M, fin, H, C, seed=77)
+    bias = torch.randn(H * C if concat else C, generator=torch.Generator().manual_seed(3)) * 0.1
+    go = torch.randn(M, H * C if concat else C, generator=torch.Generator().manual_seed(9))
+    topo = _topology(ei, n, dev)
+    res = {}
+    prev_tile, prev_tc = lib.gatres_set_tile_min_batch(-1), lib.gatres_set_tensor_core(-1)
+    try:
+        for variant, min_batch in (("tile", 1), ("gather", 1 << 40)):
+            lib.gatres_set_tile_min_batch(min_batch)
+            lib.gatres_set_tensor_core(0)
+            cl = [t.detach().clone().to(dev).requires_grad_() for t in (x, W, a_s, a_d, bias)]
+            out = gops.gat_conv(cl[0], cl[1], cl[2], cl[3], cl[4], topo, B, H, concat, relu=True)
+            out.backward(go.to(dev))
+            res[variant] = [out.detach()] + [t.grad for t in cl]
+            if C == 32 and not concat:                      # SimpleConv(mean) backward, model form (mask already applied)
+                gm = go.to(dev).contiguous()
+                dz = torch.full_like(gm, float("nan"))
+                _lib.call("gatres_mean_res_bwd_e1", _lib.ptr(topo.rowptr), _lib.ptr(topo.rowptr_t), _lib.ptr(topo.col_t),
+                          topo.E1, _lib.ptr(gm), _lib.ptr(dz), B, n, C, _lib.stream())
+                res[variant].append(dz)
+    finally:
+        lib.gatres_set_tile_min_batch(prev_tile)
+        lib.gatres_set_tensor_core(prev_tc)
+    for name, a, b in zip(("out", "dx", "dW", "datt_src", "datt_dst", "dbias", "mean_bwd dz"), res["tile"], res["gather"]):
+        assert_close(a, b, 2e-5, f"tile vs gather: {name}")
+    # first two snapshots against the oracle (forward)
+    k = 2 * n
+    ref = O.gat_conv(x[:k], O.collate_edge_index(ei, n, 2), W, a_s, a_d, bias, H, concat).relu()
+    assert_close(res["tile"][0][:k], ref, FWD_TOL, "tile forward vs oracle")
+
+
 
 @pytest.mark.parametrize("graph,B", [("tiny", 4), ("ctown", 2), ("directed", 3)])
 @pytest.mark.parametrize("C", [32, 64, 128])
