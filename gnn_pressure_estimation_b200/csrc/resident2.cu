@@ -1121,7 +1121,7 @@ template <int H, bool MEAN>
 __device__ __forceinline__ void bwd_p1_head(const int v, const int* rp_s, const int* col_s, const int* rpt_s,
                                             const int* colt_s, const float* wt_s, unsigned g_base, float* dz_s,
                                             const float* g_s, int ldg_s, unsigned h_base, int ldh, unsigned ss_base,
-                                            const float* sd_s, const float* m_s, const float* l_s, float* rec_s,
+                                            const float* sd_s, const float* m_s, const float* l_s, float* erec_s,
                                             float* dsd_s, float* vred_bias, int n, int self_owner) {
   static_assert(!MEAN || H == 1, "the mean backward feeds conv2 (one head)");
   constexpr int RPW = 8, PRE = 4;
@@ -1138,6 +1138,7 @@ __device__ __forceinline__ void bwd_p1_head(const int v, const int* rp_s, const 
     const int self = (self_owner << 16) | il;
     const float sd = sd_s[il * H + v], mi = m_s[il * H + v], il_ = 1.f / (l_s[il * H + v] + kSoftmaxEps);
     float S1 = 0.f, S2 = 0.f, S3 = 0.f;
+    float la0 = 0.f, la1 = 0.f, lk0 = 0.f, lk1 = 0.f, ld0 = 0.f, ld1 = 0.f;      // the last chunk's per-edge values
     float4 gv0, gv1;
     if (MEAN) {
       const int tb = rpt_s[il], te = rpt_s[il + 1] - 1;     // out-edges minus the self-loop
@@ -1193,11 +1194,40 @@ __device__ __forceinline__ void bwd_p1_head(const int v, const int* rp_s, const 
       S1 = fmaf(alpha0, da0, fmaf(alpha1, da1, S1));
       S2 = fmaf(alpha0 * sl0, da0, fmaf(alpha1 * sl1, da1, S2));
       S3 = fmaf(alpha0, sl0, fmaf(alpha1, sl1, S3));
+      la0 = alpha0; la1 = alpha1; lk0 = alpha0 * sl0; lk1 = alpha1 * sl1; ld0 = da0; ld1 = da1;
     }
     const float D = group_sum<4>(S1, FULL), T2 = group_sum<4>(S2, FULL), T3 = group_sum<4>(S3, FULL);
-    if (slot == 0 && ok) {
-      st4(rec_s + (il * H + v) * 4, make_float4(sd, mi, il_, D));
-      dsd_s[il * H + v] = T2 - D * T3;
+    if (slot == 0 && ok) dsd_s[il * H + v] = T2 - D * T3;
+    // edge records {alpha_e, dz_e = alpha_e slope_e (dalpha_e - D_i)} at the in-edge's position: pass 2 of the edge's SOURCE
+    // reads them through distributed shared memory and needs neither the softmax record of the target nor <g_i, h_j> again
+    if (deg_max <= 8) {
+      if (ok && slot < deg) *reinterpret_cast<float2*>(erec_s + (beg + slot) * 2 * H + 2 * v) = make_float2(la0, lk0 * (ld0 - D));
+      if (ok && slot + 4 < deg) *reinterpret_cast<float2*>(erec_s + (beg + slot + 4) * 2 * H + 2 * v) = make_float2(la1, lk1 * (ld1 - D));
+    } else {                                   // rows with more than eight in-edges: second sweep (values recomputed)
+      for (int e0 = 0; e0 < deg_max; e0 += 8) {
+        const bool valid0 = e0 + slot < deg, valid1 = e0 + slot + 4 < deg;
+        const int j0 = valid0 ? col_s[beg + e0 + slot] : self;
+        const int j1 = valid1 ? col_s[beg + e0 + slot + 4] : self;
+        const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
+        const float z0 = ldsc1(row_addr(ss_base, j0, 4 * H) + 4u * v) + sd;
+        const float z1 = ldsc1(row_addr(ss_base, j1, 4 * H) + 4u * v) + sd;
+        const float alpha0 = valid0 ? __expf(lrelu(z0) - mi) * il_ : 0.f;
+        const float alpha1 = valid1 ? __expf(lrelu(z1) - mi) * il_ : 0.f;
+        float da0 = 0.f, da1 = 0.f;
+        for (int t = 0; t < cnt_max; ++t) {
+          const int jt = __shfl_sync(FULL, t < 4 ? j0 : j1, t & 3, 4);
+          const unsigned at = row_addr(h_base, jt, ldh) + hoff;
+          const bool on = t < cnt;
+          const float4 xa = on ? ldsc4(at) : f4zero(), xb = on ? ldsc4(at + 64u) : f4zero();
+          const float d = group_sum<4>(dot4(gv0, xa) + dot4(gv1, xb), FULL);
+          if (t < 4) da0 = slot == t ? d : da0;
+          else da1 = slot == (t & 3) ? d : da1;
+        }
+        if (ok && valid0)
+          *reinterpret_cast<float2*>(erec_s + (beg + e0 + slot) * 2 * H + 2 * v) = make_float2(alpha0, alpha0 * lrelu_slope(z0) * (da0 - D));
+        if (ok && valid1)
+          *reinterpret_cast<float2*>(erec_s + (beg + e0 + slot + 4) * 2 * H + 2 * v) = make_float2(alpha1, alpha1 * lrelu_slope(z1) * (da1 - D));
+      }
     }
   }
   warp_chunk_park4(bacc0, vred_bias + 32 * v);
@@ -1213,7 +1243,7 @@ template <int H, bool MEAN>
 __device__ __forceinline__ void bwd_p1_packed(const int* rp_s, const int* col_s, const int* rpt_s, const int* colt_s,
                                        const float* wt_s, unsigned g_base, float* dz_s, const float* g_s, int ldg_s,
                                        unsigned h_base, int ldh, unsigned ss_base, const float* sd_s, const float* m_s,
-                                       const float* l_s, float* rec_s, float* dsd_s, float* vred_bias, int n,
+                                       const float* l_s, float* erec_s, float* dsd_s, float* vred_bias, int n,
                                        int self_owner) {
   static_assert(!MEAN || H == 1, "the mean backward feeds conv2 (one head)");
   constexpr int RPW = 4, PRE = 4;
@@ -1256,6 +1286,9 @@ __device__ __forceinline__ void bwd_p1_packed(const int* rp_s, const int* col_s,
       il_[v] = 1.f / (l_s[il * H + v] + kSoftmaxEps);
       S1[v] = S2[v] = S3[v] = 0.f;
     }
+    float la[H], lk[H], ld[H];                 // the last chunk's per-edge values
+#pragma unroll
+    for (int v = 0; v < H; ++v) la[v] = lk[v] = ld[v] = 0.f;
     float4 gv[H];
     if (MEAN) {
       const int tb = rpt_s[il], te = rpt_s[il + 1] - 1;     // out-edges minus the self-loop
@@ -1327,14 +1360,54 @@ __device__ __forceinline__ void bwd_p1_packed(const int* rp_s, const int* col_s,
         S1[v] = fmaf(alpha[v], da[v], S1[v]);
         S2[v] = fmaf(alpha[v] * sl[v], da[v], S2[v]);
         S3[v] = fmaf(alpha[v], sl[v], S3[v]);
+        la[v] = alpha[v]; lk[v] = alpha[v] * sl[v]; ld[v] = da[v];
       }
     }
+    float Dv[H];
 #pragma unroll
     for (int v = 0; v < H; ++v) {
       const float D = group_sum<8>(S1[v], FULL), T2 = group_sum<8>(S2[v], FULL), T3 = group_sum<8>(S3[v], FULL);
-      if (slot == 0 && ok) {
-        st4(rec_s + (il * H + v) * 4, make_float4(sd[v], mi[v], il_[v], D));
-        dsd_s[il * H + v] = T2 - D * T3;
+      if (slot == 0 && ok) dsd_s[il * H + v] = T2 - D * T3;
+      Dv[v] = D;
+    }
+    // edge records {alpha_e, dz_e} of every head at the in-edge's position (see bwd_p1_head)
+    auto put = [&](int pos, const float (&al)[H], const float (&dz)[H]) {
+      if (H == 2) st4(erec_s + pos * 4, make_float4(al[0], dz[0], al[H - 1], dz[H - 1]));
+      else *reinterpret_cast<float2*>(erec_s + pos * 2) = make_float2(al[0], dz[0]);
+    };
+    if (deg_max <= 8) {
+      if (ok && slot < deg) {
+        float dz[H];
+#pragma unroll
+        for (int v = 0; v < H; ++v) dz[v] = lk[v] * (ld[v] - Dv[v]);
+        put(beg + slot, la, dz);
+      }
+    } else {                                   // rows with more than eight in-edges: second sweep (values recomputed)
+      for (int e0 = 0; e0 < deg_max; e0 += 8) {
+        const bool valid = e0 + slot < deg;
+        const int j = valid ? col_s[beg + e0 + slot] : self;
+        const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
+        float ssv[H], alpha[H], dz[H], da[H];
+        load_scores<H>(ss_base, j, ssv);
+#pragma unroll
+        for (int v = 0; v < H; ++v) da[v] = 0.f;
+        for (int t = 0; t < cnt_max; ++t) {
+          const int jt = __shfl_sync(FULL, j, t, 8);
+          const unsigned at = row_addr(h_base, jt, ldh) + 16u * slot;
+#pragma unroll
+          for (int v = 0; v < H; ++v) {
+            const float4 xa = t < cnt ? ldsc4(at + 128u * v) : f4zero();
+            const float d = group_sum<8>(dot4(gv[v], xa), FULL);
+            da[v] = slot == t ? d : da[v];
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < H; ++v) {
+          const float z = ssv[v] + sd[v];
+          alpha[v] = valid ? __expf(lrelu(z) - mi[v]) * il_[v] : 0.f;
+          dz[v] = alpha[v] * lrelu_slope(z) * (da[v] - Dv[v]);
+        }
+        if (ok && valid) put(beg + e0 + slot, alpha, dz);
       }
     }
   }
@@ -1346,22 +1419,22 @@ template <int H, bool MEAN>
 __device__ __forceinline__ void bwd_p1(const int* rp_s, const int* col_s, const int* rpt_s, const int* colt_s,
                                        const float* wt_s, unsigned g_base, float* dz_s, const float* g_s, int ldg_s,
                                        unsigned h_base, int ldh, unsigned ss_base, const float* sd_s, const float* m_s,
-                                       const float* l_s, float* rec_s, float* dsd_s, float* vred_bias, int n,
+                                       const float* l_s, float* erec_s, float* dsd_s, float* vred_bias, int n,
                                        int self_owner) {
   if (H == 1)
     bwd_p1_head<H, MEAN>(0, rp_s, col_s, rpt_s, colt_s, wt_s, g_base, dz_s, g_s, ldg_s, h_base, ldh, ss_base, sd_s, m_s, l_s,
-                         rec_s, dsd_s, vred_bias, n, self_owner);
+                         erec_s, dsd_s, vred_bias, n, self_owner);
   else
     bwd_p1_packed<H, MEAN>(rp_s, col_s, rpt_s, colt_s, wt_s, g_base, dz_s, g_s, ldg_s, h_base, ldh, ss_base, sd_s, m_s, l_s,
-                           rec_s, dsd_s, vred_bias, n, self_owner);
+                           erec_s, dsd_s, vred_bias, n, self_owner);
 }
 // Backward pass 2 over own source rows: dh[j] (-> own shared tile), ds_src, datt_src / datt_dst partials.  Eight lanes
 // per row with the heads packed per lane (measured faster than the four-lane / one-head form for this pass: its chain
 // is dominated by the dependent dot -> softmax-gradient -> accumulate sequence, not by the number of row passes).  The
 // gradient rows g[i] and the records of the edges' targets come through DSMEM; h, s_src, ds_dst of the row are own.
 template <int H>
-__device__ __forceinline__ void bwd_p2(const int* rpt_s, const int* colt_s, unsigned g_base, int ldg, unsigned rec_base,
-                                       const float* dsd_s, const float* h_s, int ldh_own, const float* ss_s,
+__device__ __forceinline__ void bwd_p2(const int* rpt_s, const int* colt_s, const int* emap_s, unsigned g_base, int ldg,
+                                       unsigned erec_base, const float* dsd_s, const float* h_s, int ldh_own,
                                        const float* att_s, const float* att_d, float* dh_s, int ld_dh, float* vred_as,
                                        float* vred_ad, int n, int self_owner) {
   constexpr int RPW = 4, PRE = H == 1 ? 4 : 2;     // two heads per lane: fewer gathers in flight (registers)
@@ -1383,17 +1456,17 @@ __device__ __forceinline__ void bwd_p2(const int* rpt_s, const int* colt_s, unsi
     const int deg_max = __reduce_max_sync(FULL, deg);
     const int self = (self_owner << 16) | il;
     float4 hv[H], dacc[H];
-    float ss[H], dsrc[H];
+    float dsrc[H];
 #pragma unroll
     for (int v = 0; v < H; ++v) {
       hv[v] = lds4(h_s + il * ldh_own + 32 * v + 4 * slot);
-      ss[v] = ss_s[il * H + v];
       dacc[v] = f4zero();
       dsrc[v] = 0.f;
     }
     for (int e0 = 0; e0 < deg_max; e0 += 8) {
       const bool valid = e0 + slot < deg;
       const int i = valid ? colt_s[beg + e0 + slot] : self;
+      const int em = valid ? emap_s[beg + e0 + slot] : 0;
       const int cnt = min(8, deg - e0), cnt_max = min(8, deg_max - e0);
       float4 gx[PRE][H];
 #pragma unroll
@@ -1403,25 +1476,24 @@ __device__ __forceinline__ void bwd_p2(const int* rpt_s, const int* colt_s, unsi
 #pragma unroll
         for (int v = 0; v < H; ++v) gx[u][v] = u < cnt ? ldsc4(au + 128u * v) : f4zero();
       }
-      float alpha[H], k2[H], Dt[H], da[H];
-      const unsigned ar = row_addr(rec_base, i, 16 * H);
-#pragma unroll
-      for (int v = 0; v < H; ++v) {
-        const float4 t4 = ldsc4(ar + 16u * v);      // {s_dst, m, 1/l, D} of the edge's target
-        const float z = ss[v] + t4.x;
-        alpha[v] = valid ? __expf(lrelu(z) - t4.y) * t4.z : 0.f;
-        k2[v] = alpha[v] * lrelu_slope(z);
-        Dt[v] = t4.w;
-        da[v] = 0.f;
+      // {alpha_e, dz_e} of this lane's out-edge, written by pass 1 of the edge's TARGET at the edge's in-position
+      float alpha[H];
+      {
+        const unsigned ar = row_addr(erec_base, em, 8 * H);
+        if (H == 2) {
+          const float4 t4 = valid ? ldsc4(ar) : f4zero();
+          alpha[0] = t4.x; alpha[H - 1] = t4.z;
+          dsrc[0] += t4.y; dsrc[H - 1] += t4.w;
+        } else {
+          const float2 t2 = valid ? ldsc2(ar) : make_float2(0.f, 0.f);
+          alpha[0] = t2.x;
+          dsrc[0] += t2.y;
+        }
       }
 #pragma unroll
       for (int u = 0; u < PRE; ++u)
 #pragma unroll
-        for (int v = 0; v < H; ++v) {
-          const float d = group_sum<8>(dot4(gx[u][v], hv[v]), FULL);
-          da[v] = slot == u ? d : da[v];
-          fma4(dacc[v], __shfl_sync(FULL, alpha[v], u, 8), gx[u][v]);
-        }
+        for (int v = 0; v < H; ++v) fma4(dacc[v], __shfl_sync(FULL, alpha[v], u, 8), gx[u][v]);
       for (int t = PRE; t < cnt_max; t += 2) {
         const int i0_ = __shfl_sync(FULL, i, t, 8), i1_ = __shfl_sync(FULL, i, t + 1, 8);
         const unsigned a0 = row_addr(g_base, i0_, ldg) + 16u * slot, a1 = row_addr(g_base, i1_, ldg) + 16u * slot;
@@ -1429,15 +1501,11 @@ __device__ __forceinline__ void bwd_p2(const int* rpt_s, const int* colt_s, unsi
         for (int v = 0; v < H; ++v) {
           const float4 g0 = t < cnt ? ldsc4(a0 + 128u * v) : f4zero();
           const float4 g1 = t + 1 < cnt ? ldsc4(a1 + 128u * v) : f4zero();
-          const float d0 = group_sum<8>(dot4(g0, hv[v]), FULL), d1 = group_sum<8>(dot4(g1, hv[v]), FULL);
-          da[v] = slot == t ? d0 : (slot == t + 1 ? d1 : da[v]);
           const float a0v = __shfl_sync(FULL, alpha[v], t, 8), a1v = __shfl_sync(FULL, alpha[v], t + 1, 8);
           fma4(dacc[v], a0v, g0);
           fma4(dacc[v], t + 1 < 8 ? a1v : 0.f, g1);
         }
       }
-#pragma unroll
-      for (int v = 0; v < H; ++v) dsrc[v] = fmaf(k2[v], da[v] - Dt[v], dsrc[v]);
     }
 #pragma unroll
     for (int v = 0; v < H; ++v) {
@@ -1460,16 +1528,16 @@ __device__ __forceinline__ void bwd_p2(const int* rpt_s, const int* colt_s, unsi
 }
 
 // Shared memory (floats): g[R][LDX] h2s[R][LDX] dzd[R][2 LDX] (dz | dh2, later dh1) h1s[R][LDY] ys[R][LDY] xs[R][LDX]
-//   ss2[R] sc2[3R] (sd2 m2 l2) rec2[4R] dsd2[R] ss1[2R] sc1[6R] (sd1 m1 l1) rec1[8R] dsd1[2R]
+//   ss2[R] sc2[3R] (sd2 m2 l2) erec2[2 ecap] dsd2[R] ss1[2R] sc1[6R] (sd1 m1 l1) erec1[4 ecap] dsd1[2R] emap[ecap]
 //   W1s[W1F] W2s[W2F] vec[VECF] vred[8][VECF] wt[ecap] | ints: rp[R+1] col[ecap] rpt[R+1] colt[ecap]
 struct BwdSmem {
-  int g, h2s, dzd, h1s, ys, xs, ss2, sc2, rec2, dsd2, ss1, sc1, rec1, dsd1, W1s, W2s, vec, vred, wt, rp, col, rpt, colt, total;
+  int g, h2s, dzd, h1s, ys, xs, ss2, sc2, erec2, dsd2, ss1, sc1, erec1, dsd1, emap, W1s, W2s, vec, vred, wt, rp, col, rpt, colt, total;
   __host__ __device__ BwdSmem(int R, int ecap) {
     int o = 0;
     auto take = [&](int nfl) { const int at = o; o += (int)a4(nfl); return at; };
     g = take(R * LDX); h2s = take(R * LDX); dzd = take(R * 2 * LDX > T * 4 ? R * 2 * LDX : T * 4); h1s = take(R * LDY); ys = take(R * LDY); xs = take(R * LDX);
-    ss2 = take(R); sc2 = take(3 * (int)a4(R)); rec2 = take(4 * R); dsd2 = take(R);
-    ss1 = take(2 * R); sc1 = take(3 * (int)a4(2 * R)); rec1 = take(8 * R); dsd1 = take(2 * R);
+    ss2 = take(R); sc2 = take(3 * (int)a4(R)); erec2 = take(2 * ecap); dsd2 = take(R);
+    ss1 = take(2 * R); sc1 = take(3 * (int)a4(2 * R)); erec1 = take(4 * ecap); dsd1 = take(2 * R); emap = take(ecap);
     W1s = take(W1F); W2s = take(W2F); vec = take(VECF); vred = take((T / 32) * VECF); wt = take(ecap);
     rp = take(R + 1); col = take(ecap); rpt = take(R + 1); colt = take(ecap);
     total = o;
@@ -1493,13 +1561,14 @@ bwd_kernel(const Args a) {
   float* sd2 = smem + L.sc2;
   float* m2 = sd2 + a4(R);
   float* l2 = m2 + a4(R);
-  float* rec2 = smem + L.rec2;
+  float* erec2 = smem + L.erec2;           // per in-edge {alpha, dz} of conv2 (neighbours' pass 2 reads them)
   float* dsd2 = smem + L.dsd2;
   float* ss1 = smem + L.ss1;
   float* sd1 = smem + L.sc1;
   float* m1 = sd1 + a4(2 * R);
   float* l1 = m1 + a4(2 * R);
-  float* rec1 = smem + L.rec1;
+  float* erec1 = smem + L.erec1;           // per in-edge {alpha, dz} x 2 heads of conv1
+  int* emap_s = reinterpret_cast<int*>(smem + L.emap);      // out-edge slot -> (owner CTA << 16 | in-edge position there)
   float* dsd1 = smem + L.dsd1;
   float* W1 = smem + L.W1s;
   float* W2 = smem + L.W2s;
@@ -1533,6 +1602,26 @@ bwd_kernel(const Args a) {
       colt_s[c] = (owner << 16) | (t - owner * R);
       const int dg = __ldg(a.rowptr + t + 1) - __ldg(a.rowptr + t) - 1;
       wt[c] = 1.f / (float)(dg > 1 ? dg : 1);
+    }
+    // where pass 1 of an out-edge's TARGET leaves the edge's record: the position of this edge inside the target's in-edge
+    // list, relative to the in-edge slice of the CTA that owns the target.  Both CSRs keep parallel edges in edge-list
+    // order, so the m-th occurrence of the target in this row's out-list is the m-th occurrence of this row in its in-list.
+    // (one thread per out-edge; the edge's row by bisection of the global row pointers of this slice)
+    for (int e = threadIdx.x; e < cnt; e += T) {
+      int lo_r = 0, hi_r = n;                  // largest row with rowptr_t[lo + row] - e_lo <= e
+      while (hi_r - lo_r > 1) {
+        const int mid = (lo_r + hi_r) >> 1;
+        if (__ldg(a.rowptr_t + lo + mid) - e_lo <= e) lo_r = mid; else hi_r = mid;
+      }
+      const int jg = lo + lo_r, eb = __ldg(a.rowptr_t + jg) - e_lo;
+      const int t = __ldg(a.col_t + e_lo + e);
+      int m = 0;
+      for (int q = eb; q < e; ++q) m += __ldg(a.col_t + e_lo + q) == t ? 1 : 0;
+      const int tb = __ldg(a.rowptr + t), te = __ldg(a.rowptr + t + 1), owner = t / R;
+      int pos = tb;
+      for (int q = tb; q < te; ++q)
+        if (__ldg(a.col + q) == jg && m-- == 0) { pos = q; break; }
+      emap_s[e] = (owner << 16) | (pos - __ldg(a.rowptr + owner * R));
     }
   }
   pdl_wait();
@@ -1626,7 +1715,7 @@ bwd_kernel(const Args a) {
 
   const unsigned g_base = smem_u32(gs), h2_base = smem_u32(h2s), h1_base = smem_u32(h1s), dz_base = smem_u32(dz);
   const unsigned y_base = smem_u32(ys), ss2_base = smem_u32(ss2), ss1_base = smem_u32(ss1);
-  const unsigned rec2_base = smem_u32(rec2), rec1_base = smem_u32(rec1);
+  const unsigned erec2_base = smem_u32(erec2), erec1_base = smem_u32(erec1);
 
   for (int k = k_first; k >= a.k_lo && k >= 0; --k) {
     const bool more = k - 1 >= a.k_lo && k - 1 >= 0;
@@ -1634,15 +1723,15 @@ bwd_kernel(const Args a) {
     cp_commit();
     stamp();
     // (1) SimpleConv(mean) backward fused with conv2 pass 1 (incoming gradient dz stays in registers)
-    bwd_p1<1, true>(rp_s, col_s, rpt_s, colt_s, wt, g_base, dz, nullptr, 0, h2_base, LDX * 4, ss2_base, sd2, m2, l2, rec2,
+    bwd_p1<1, true>(rp_s, col_s, rpt_s, colt_s, wt, g_base, dz, nullptr, 0, h2_base, LDX * 4, ss2_base, sd2, m2, l2, erec2,
                     dsd2, vred + warp * VECF + 8 * NC, n, rank);
     cp_wait_but_one();                       // this block's parameters have landed (group D may still fly)
     stamp();
     cb.arrive();
-    cluster_wait();                          // dz / rec2 cluster-wide, parameters CTA-wide
+    cluster_wait();                          // dz / edge records of conv2 cluster-wide, parameters CTA-wide
     stamp();
     // (2) conv2 pass 2 -> dh2 (own)
-    bwd_p2<1>(rpt_s, colt_s, dz_base, LDX * 4, rec2_base, dsd2, h2s, LDX, ss2, vc + 6 * NC, vc + 7 * NC, d2s, LDX,
+    bwd_p2<1>(rpt_s, colt_s, emap_s, dz_base, LDX * 4, erec2_base, dsd2, h2s, LDX, vc + 6 * NC, vc + 7 * NC, d2s, LDX,
               vred + warp * VECF + 6 * NC, vred + warp * VECF + 7 * NC, n, rank);
     cp_wait_all();                           // y1 / x0 rows of this block
     __syncthreads();                         // dh2, y1 and x0 are in shared memory; h2 / s2 buffers are free
@@ -1660,14 +1749,14 @@ bwd_kernel(const Args a) {
     __syncthreads();
     stamp();
     // (4) conv1 pass 1 (incoming gradient = dy1 from the own tile)
-    bwd_p1<2, false>(rp_s, col_s, rpt_s, colt_s, wt, 0u, nullptr, ys, LDY, h1_base, LDY * 4, ss1_base, sd1, m1, l1, rec1,
+    bwd_p1<2, false>(rp_s, col_s, rpt_s, colt_s, wt, 0u, nullptr, ys, LDY, h1_base, LDY * 4, ss1_base, sd1, m1, l1, erec1,
                      dsd1, vred + warp * VECF + 4 * NC, n, rank);
     stamp();
     cb.arrive();
-    cluster_wait();                          // dy1 / rec1 cluster-wide
+    cluster_wait();                          // dy1 / edge records of conv1 cluster-wide
     stamp();
     // (5) conv1 pass 2 -> dh1 (own, over dz | dh2: every CTA is past its pass 2 of conv2)
-    bwd_p2<2>(rpt_s, colt_s, y_base, LDY * 4, rec1_base, dsd1, h1s, LDY, ss1, vc, vc + 2 * NC, dh1, LDY,
+    bwd_p2<2>(rpt_s, colt_s, emap_s, y_base, LDY * 4, erec1_base, dsd1, h1s, LDY, vc, vc + 2 * NC, dh1, LDY,
               vred + warp * VECF, vred + warp * VECF + 2 * NC, n, rank);
     __syncthreads();                         // dh1 complete; h1 / s1 buffers are free
     if (more) load_conv1_side(k - 1);        // group B
