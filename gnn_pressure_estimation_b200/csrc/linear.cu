@@ -627,6 +627,8 @@ reduce_partials_kernel(const float* __restrict__ partial, long long P, int slots
 }
 
 // tensor-core (tcgen05 3xTF32) variants, linear_tc.cu
+int linear_bwd_fused_dispatch(int NO, int KI, const float* dh, const float* x, const float* W, const float* add,
+                              const float* relu_ref, float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st);
 int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const float* W, const float* e0,
                      const float* e1, float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st);
 
@@ -679,6 +681,11 @@ extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W
   GATRES_REQUIRE(P % 4 == 0 && off_W % 4 == 0, "linear_bwd: bad P/off_W");
   cudaStream_t st = as_stream(stream);
   const int NO = H * C;
+  if (dx != nullptr && slots <= 0 && tensor_core_enabled(M)) {
+    // atomic accumulation mode, large launch, nc = 32 shapes: dx and dW in one pass over dh (linear_tc.cu)
+    const int rc = linear_bwd_fused_dispatch(NO, K, dh, x, W, add, relu_ref, dx, partial, off_W, (unsigned)M, st);
+    if (rc != 0) return rc < 0 ? rc : GATRES_OK;
+  }
   if (dx != nullptr) {
     int rc = tensor_core_enabled(M)
                  ? gemm_tc_dispatch(1, 1, NO, K, dh, W, add, relu_ref, dx, nullptr, nullptr, (unsigned)M, st)

@@ -229,6 +229,273 @@ static int launch_tc(const float* A, const float* W, const float* e0, const floa
 
 
 // ---------------------------------------------------------------------------------------------------------
+// Fused backward of a projection (conv1 of the nc = 32 model: dh [rows, 64], x [rows, 32]): dx = dh W (+ residual)
+// (* ReLU mask) AND dW += dh^T x in ONE pass over dh.  The two-kernel form reads dh twice (data gradient on tcgen05,
+// weight gradient on mma.sync in a second launch that re-reads dh and x: 305 MB for an 8 KB result).  Here a persistent
+// CTA (256 threads, two per SM) stages a 128-row tile of dh (SWIZZLE_128B K-major, the tcgen05 A operand) and of x
+// once; one elected thread issues the data gradient's 3 x NO/8 tcgen05.mma into TMEM, and WHILE they run all eight
+// warps contract the same shared tiles for the weight gradient with mma.sync 3xTF32 (fragments of dh^T straight from
+// the swizzled tile: row steps are multiples of 8, so the swizzled offsets are loop invariants), accumulating in
+// registers across all tiles of the CTA (atomics at the end).  Then the epilogue of gemm_tc MODE 1 (accumulator rows
+// parked in shared memory, coalesced write-out with the residual / ReLU-reference loads batched).  The phases of a tile
+// are serial inside a CTA, so the tile buffers are single and the SECOND CTA of the SM fills the gaps.
+// Measured at 2048 snapshots (two kernels: 149.6 us for dh [., 64], 145.1 us for dh [., 32]): this form 134.4 / 149.0 us;
+// one double-buffered CTA per SM 137.0 / 141.9; warp-specialised (four loader / data-gradient warps, four weight-gradient
+// warps meeting at mbarriers) 129.6 / 150.6; weight gradient on the FP32 pipe instead (4 x 8 register patches, exact
+// fp32) 150.2 / 196.3.  All forms are held by the weight gradient: 768 mma.sync per tile at ~20 cycles per scheduler on
+// the legacy tensor path, which the tcgen05 MMAs also contend with; a tcgen05 weight gradient needs dh in a second
+// shared layout (MN-major tf32 operands must be SWIZZLE_128B_BASE32B) and does not fit next to the data gradient's.
+// Used for the dh [., 64] shape only.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fb_lo_bits(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  return (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+}
+__device__ __forceinline__ void fb_mma(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int NO, int KI>
+struct FusedBwdPlan {                       // bytes; the epilogue staging [128][KI] lies over the low-part tile / the x tile
+  static constexpr int BM = 128, LDX = KI + 4;
+  static constexpr uint32_t DH = BM * NO * 4, XT = BM * LDX * 4, BW = KI * NO * 4, STG = BM * KI * 4;
+  static constexpr uint32_t dh0 = 0, dhl = DH, x0 = 2 * DH, bh = (x0 + XT + 1023u) & ~1023u, bl = bh + BW, bar = bl + BW,
+                            total = bar + 32;
+  static constexpr uint32_t stg = dhl;      // dead once the MMAs have completed (DH + XT >= STG for both shapes)
+  static_assert(DH + XT >= STG, "staging over the low-part and x tiles");
+};
+
+template <int NO, int KI>
+__global__ void __launch_bounds__(256, 2)
+linear_bwd_fused_kernel(const float* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ W,
+                        const float* __restrict__ add, const float* __restrict__ relu_ref, float* __restrict__ dx,
+                        float* __restrict__ grads, long long off_W, unsigned M) {
+  using P = FusedBwdPlan<NO, KI>;
+  constexpr int BM = P::BM, T = 256, LDX = P::LDX;
+  constexpr int NT = KI / 8, TILES = (NO / 16) * NT, TPW = TILES / 8;
+  static_assert(TILES % 8 == 0 && NT % TPW == 0, "a warp's weight-gradient tiles share one 16-row block of dh^T");
+  static_assert(NO % 32 == 0 && (KI == 32 || KI == 64), "shapes of the nc = 32 model");
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KI >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  extern __shared__ __align__(1024) unsigned char sm[];
+  const uint32_t base = smem_u32(sm);
+  if ((base & 1023u) != 0) __trap();
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + P::bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const unsigned ntiles = (M + BM - 1) / BM;
+
+  // ---- prologue: TMEM, barrier, W as the data gradient's B operand ([KI rows n][NO k], K-major, hi / lo) ----
+  if (warp == 0) tmem_alloc(tmem_slot, KI);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  for (int idx = tid; idx < KI * NO; idx += T) {
+    const int n = idx % KI, k = idx / KI;                      // W[k][n] as stored ([NO][KI]): coalesced reads
+    const float w = __ldg(W + (size_t)k * KI + n);
+    const float hi = to_tf32(w), lo = to_tf32(w - hi);
+    const uint32_t off = swz_off(n, k, KI);
+    *reinterpret_cast<float*>(sm + P::bh + off) = hi;
+    *reinterpret_cast<float*>(sm + P::bl + off) = lo;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  auto issue_load = [&](unsigned tl) {
+#pragma unroll
+    for (int q = 0; q < BM * (NO / 4) / T; ++q) {
+      const int idx = q * T + tid;
+      const uint32_t row = idx / (NO / 4), c = idx % (NO / 4);
+      const unsigned grow = tl * BM + row;
+      const bool ok = grow < M;
+      tc_cp_async16(base + P::dh0 + swz_off(row, 4 * c, BM), dh + (size_t)(ok ? grow : 0) * NO + 4 * c, ok ? 16 : 0);
+    }
+#pragma unroll
+    for (int q = 0; q < BM * (KI / 4) / T; ++q) {
+      const int idx = q * T + tid;
+      const uint32_t row = idx / (KI / 4), c = idx % (KI / 4);
+      const unsigned grow = tl * BM + row;
+      const bool ok = grow < M;
+      tc_cp_async16(base + P::x0 + (row * LDX + 4 * c) * 4u, x + (size_t)(ok ? grow : 0) * KI + 4 * c, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // weight-gradient tiles of this warp: output rows no0 .. no0 + 15 (columns of dh), columns ki0 + 8 q
+  const int tile0 = warp * TPW, no0 = (tile0 / NT) * 16, ki0 = (tile0 % NT) * 8;
+  int aoff[4];                                                 // float offsets of the four dh^T fragment elements, minus 32 * m0
+  {
+    const int c0 = no0 + g, kb = (c0 >> 5) * (BM * 32), ch = (c0 & 31) >> 2, lw = c0 & 3;
+    aoff[0] = kb + t * 32 + ((ch ^ t) << 2) + lw;
+    aoff[1] = kb + t * 32 + (((ch + 2) ^ t) << 2) + lw;
+    aoff[2] = kb + (t + 4) * 32 + ((ch ^ (t + 4)) << 2) + lw;
+    aoff[3] = kb + (t + 4) * 32 + (((ch + 2) ^ (t + 4)) << 2) + lw;
+  }
+  float acc[TPW][4], acl[TPW][4], acm[TPW][4];
+#pragma unroll
+  for (int q = 0; q < TPW; ++q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[q][i] = acl[q][i] = acm[q][i] = 0.f;
+
+  if (gridDim.x >= ntiles) pdl_launch_dependents();
+  uint32_t phase = 0;
+  if (blockIdx.x < ntiles) issue_load(blockIdx.x);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // ---- low parts of the dh chunks this thread copied ----
+#pragma unroll
+    for (int q = 0; q < BM * (NO / 4) / T; ++q) {
+      const int idx = q * T + tid;
+      const uint32_t off = swz_off(idx / (NO / 4), 4 * (idx % (NO / 4)), BM);
+      const float4 v = *reinterpret_cast<const float4*>(sm + P::dh0 + off);
+      *reinterpret_cast<float4*>(sm + P::dhl + off) = make_float4(lo_tf32(v.x), lo_tf32(v.y), lo_tf32(v.z), lo_tf32(v.w));
+    }
+    fence_proxy_async();
+    __syncthreads();                                           // tile visible CTA-wide
+    // ---- data gradient: one thread issues 3 x NO / 8 MMAs ----
+    if (warp == 0 && elect_one()) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < NO / 8; ++s) {
+        const uint32_t ka = (uint32_t)(s >> 2) * BM * 128u + (uint32_t)(s & 3) * 32u;
+        const uint32_t kb = (uint32_t)(s >> 2) * KI * 128u + (uint32_t)(s & 3) * 32u;
+        umma_tf32(tmem, umma_desc_k128(base + P::dh0 + ka), umma_desc_k128(base + P::bh + kb), IDESC, s > 0);
+        umma_tf32(tmem, umma_desc_k128(base + P::dhl + ka), umma_desc_k128(base + P::bh + kb), IDESC, 1);
+        umma_tf32(tmem, umma_desc_k128(base + P::dh0 + ka), umma_desc_k128(base + P::bl + kb), IDESC, 1);
+      }
+      umma_commit(bar);
+    }
+    // ---- weight gradient of the tile on mma.sync while the MMAs above run ----
+    {
+      const float* hs = reinterpret_cast<const float*>(sm + P::dh0);
+      const float* xs = reinterpret_cast<const float*>(sm + P::x0);
+#pragma unroll 2
+      for (int m0 = 0; m0 < BM; m0 += 8) {                     // rows past M were zero-filled
+        const float* hr = hs + m0 * 32;
+        const float av[4] = {hr[aoff[0]], hr[aoff[1]], hr[aoff[2]], hr[aoff[3]]};
+        unsigned a[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = __float_as_uint(av[i]); al[i] = fb_lo_bits(av[i]); }
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+          const float b0 = xs[(m0 + t) * LDX + ki0 + 8 * q + g], b1 = xs[(m0 + t + 4) * LDX + ki0 + 8 * q + g];
+          const unsigned b[2] = {__float_as_uint(b0), __float_as_uint(b1)}, bl[2] = {fb_lo_bits(b0), fb_lo_bits(b1)};
+          fb_mma(acl[q], al, b);
+          fb_mma(acm[q], a, bl);
+          fb_mma(acc[q], a, b);
+        }
+      }
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    __syncthreads();                                           // every warp is done with the tiles: staging may overwrite them
+    // ---- epilogue: thread = (accumulator row, column half) -> shared staging -> coalesced write-out ----
+    constexpr int NCH = KI / 4, HALF = KI / 2;
+    {
+      const int lane_row = tid & 127, half = tid >> 7;
+      float v[HALF];
+      if constexpr (HALF == 16) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * HALF, v);
+      else tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * HALF, v);
+#pragma unroll
+      for (int k = 0; k < HALF; k += 4) {
+        const int c = (half * HALF + k) / 4;
+        *reinterpret_cast<float4*>(sm + P::stg + (size_t)lane_row * (KI * 4) + (((c ^ lane_row) & (NCH - 1)) << 4)) =
+            make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                           // staging complete; TMEM accumulator free
+    const unsigned next = tile + gridDim.x;
+    constexpr int EPB = 4, EPI = BM * NCH / T;
+    static_assert(EPI % EPB == 0, "epilogue batching");
+#pragma unroll 1
+    for (int q0 = 0; q0 < EPI; q0 += EPB) {
+      float4 addv[EPB], refv[EPB];
+      size_t off[EPB];
+      bool okv[EPB];
+#pragma unroll
+      for (int u = 0; u < EPB; ++u) {
+        const int idx = (q0 + u) * T + tid;
+        const int r = idx / NCH, c = idx % NCH;
+        const unsigned grow = tile * BM + r;
+        okv[u] = grow < M;
+        off[u] = (size_t)grow * KI + 4 * c;
+        addv[u] = (okv[u] && add != nullptr) ? ldg4_stream(add + off[u]) : f4zero();
+        refv[u] = (okv[u] && relu_ref != nullptr) ? ldg4_stream(relu_ref + off[u]) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+#pragma unroll
+      for (int u = 0; u < EPB; ++u) {
+        const int idx = (q0 + u) * T + tid;
+        const int r = idx / NCH, c = idx % NCH;
+        if (okv[u]) {
+          float4 o = *reinterpret_cast<const float4*>(sm + P::stg + (size_t)r * (KI * 4) + (((c ^ r) & (NCH - 1)) << 4));
+          add4(o, addv[u]);
+          o.x = refv[u].x > 0.f ? o.x : 0.f; o.y = refv[u].y > 0.f ? o.y : 0.f;
+          o.z = refv[u].z > 0.f ? o.z : 0.f; o.w = refv[u].w > 0.f ? o.w : 0.f;
+          st4(dx + off[u], o);
+        }
+      }
+    }
+    __syncthreads();                                           // staging read: its buffers may be refilled
+    if (next < ntiles) issue_load(next);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  float* out = grads + off_W;
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    const int k = ki0 + 8 * q + 2 * t;
+    atomicAdd(reinterpret_cast<float2*>(out + (size_t)(no0 + g) * KI + k),
+              make_float2(acc[q][0] + acl[q][0] + acm[q][0], acc[q][1] + acl[q][1] + acm[q][1]));
+    atomicAdd(reinterpret_cast<float2*>(out + (size_t)(no0 + g + 8) * KI + k),
+              make_float2(acc[q][2] + acl[q][2] + acm[q][2], acc[q][3] + acl[q][3] + acm[q][3]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, KI);
+}
+
+template <int NO, int KI>
+static int launch_linear_bwd_fused(const float* dh, const float* x, const float* W, const float* add, const float* relu_ref,
+                                   float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st) {
+  using P = FusedBwdPlan<NO, KI>;
+  auto kern = linear_bwd_fused_kernel<NO, KI>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total) != cudaSuccess)
+      return check_launch("linear_bwd_fused: smem attribute");
+    configured = true;
+  }
+  const unsigned ntiles = (M + 127) / 128;
+  unsigned per_sm = (unsigned)((228u * 1024u) / (P::total + 1024u));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  unsigned grid = (unsigned)sm_count() * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  launch_kernel(kern, dim3(grid), dim3(256), (size_t)P::total, st, dh, x, W, add, relu_ref, dx, grads, off_W, M);
+  return check_launch("linear_bwd_fused");
+}
+
+// 1 = done, 0 = shape not covered (caller runs the two-kernel form), < 0 = error
+int linear_bwd_fused_dispatch(int NO, int KI, const float* dh, const float* x, const float* W, const float* add,
+                              const float* relu_ref, float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("GATRES_LINEAR_BWD_FUSED");
+    enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  if (!enabled) return 0;
+  int rc;
+  if (NO == 64 && KI == 32) rc = launch_linear_bwd_fused<64, 32>(dh, x, W, add, relu_ref, dx, grads, off_W, M, st);
+  else return 0;                              // (dh [., 32] / x [., 64]: the two-kernel form measured faster)
+  return rc == GATRES_OK ? 1 : rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Wide shapes (nc = 64 / 128: K up to 256, N up to 256): the operands of a whole tile no longer fit shared
 // memory, so K is walked in 32-column chunks (one SWIZZLE_128B atom column) through a software pipeline:
 //   A chunk [128 x 32] fp32 : cp.async into a 3-deep ring two chunks ahead (the tensor core reads its TF32
