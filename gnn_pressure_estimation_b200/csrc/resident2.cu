@@ -667,6 +667,11 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 //     = row, so the attention scores are in-thread dot products — into the padded tiles the neighbours gather from.
 // Saved activations go to HBM as images of the shared-memory arrays (ImageLayout above): seven bulk copies per block.
 constexpr int TC_COLS = 64;                  // TMEM columns per CTA (conv1: N = 64, conv2: N = 32)
+#ifndef GATRES_TC_M
+#define GATRES_TC_M 64
+#endif
+constexpr int TC_M = GATRES_TC_M;            // UMMA M: 64 (accumulator row r in TMEM lane 32 (r / 16) + r % 16: the CTA's <= 64 rows
+                                             // spread over the four lane quarters, all eight warps drain, half the A reads) or 128
 
 struct FwdTcSmem {
   int xa, xl, ya, yl, w1h, w1l, w2h, w2l, h1s, h2s, s1, s2, vec, rp, col, bar, total, RP;
@@ -708,7 +713,7 @@ __device__ __forceinline__ void lo_own_weights(const float* W1H, float* W1L, con
 template <int K, int NOUT>
 __device__ __forceinline__ void issue_proj_tc(uint32_t tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_tile_bytes,
                                               uint32_t b_hi, uint32_t b_lo, uint32_t b_tile_bytes) {
-  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 #pragma unroll
   for (int s = 0; s < K / 8; ++s) {
     const uint32_t ka = (uint32_t)(s >> 2) * a_tile_bytes + (uint32_t)(s & 3) * 32u;
@@ -840,11 +845,12 @@ fwd_tc_kernel(const Args a) {
     }
     mbar_wait(bar, phase);                   // every thread: W1 / x are free for whoever writes them next
     phase ^= 1u;
-    if ((warp & 3) < 2) {
+    if (TC_M == 64 || (warp & 3) < 2) {
       tc_fence_after();
-      const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+      const int row = TC_M == 64 ? 16 * (warp & 3) + (lane & 15) : 32 * (warp & 3) + lane, half = warp >> 2;
       drain_row_tc(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 32u * half, vc + 32 * half, vc + 2 * NC + 32 * half,
-                   h1s + row * LDY + 32 * half, ss1 + row * 2 + half, sd1 + row * 2 + half, row < n);
+                   h1s + row * LDY + 32 * half, ss1 + row * 2 + half, sd1 + row * 2 + half,
+                   row < n && (TC_M == 128 || lane < 16));
       tc_fence_before();
     }
     stamp();
@@ -872,11 +878,11 @@ fwd_tc_kernel(const Args a) {
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
-    if (warp < 2) {
+    if (warp < (TC_M == 64 ? 4 : 2)) {
       tc_fence_after();
-      const int row = 32 * warp + lane;
+      const int row = TC_M == 64 ? 16 * warp + (lane & 15) : 32 * warp + lane;
       drain_row_tc(tmem + ((uint32_t)(32 * warp) << 16), vc + 6 * NC, vc + 7 * NC, h2s + row * LDX, ss2 + row, sd2 + row,
-                   row < n);
+                   row < n && (TC_M == 128 || lane < 16));
       tc_fence_before();
     }
     stamp();

@@ -1,2 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "gat_conv_forward_backward or many_tiles or many_snapshots or model_matches_golden" > gpurun_out/r4a_pytest.log 2>&1; tail -3 gpurun_out/r4a_pytest.log
-timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --kernels-json gpurun_out/r4a_kernels.json > gpurun_out/r4a_bench.json 2> gpurun_out/r4a_bench.err; tail -c 300 gpurun_out/r4a_bench.err
+timeout 900 python -m pytest tests/test_gpu_resident2.py -x -q > gpurun_out/r4b_pytest.log 2>&1; tail -3 gpurun_out/r4b_pytest.log
+timeout 300 python tools/resident_probe.py --batches 32 --phases --out gpurun_out/r4b_probe.json > gpurun_out/r4b_probe.log 2>&1
+tail -c 1300 gpurun_out/r4b_probe.log | head -c 700
