@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgatres_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p = C.c_void_p
 _i32 = C.c_int32

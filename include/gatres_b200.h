@@ -52,7 +52,7 @@ extern "C" {
 #define GATRES_ERR_ARG (-1)       /* bad argument / unsupported shape */
 #define GATRES_ERR_CUDA (-2)      /* a CUDA runtime call failed        */
 
-#define GATRES_ABI_VERSION 2
+#define GATRES_ABI_VERSION 3
 
 int gatres_abi_version(void);
 const char* gatres_last_error(void);
