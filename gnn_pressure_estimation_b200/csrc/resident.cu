@@ -97,6 +97,9 @@ bool resident_eligible(const gatres_model_desc* d, bool backward) {
 
 int resident_forced_cluster() { return res::forced_cluster(); }
 long long resident_max_batch() { return res::max_batch(); }
+// the knob still holds its built-in value (a caller that restores the value it read keeps the defaults): the second
+// generation then applies its own measured crossovers (resident2.cu)
+bool resident_max_batch_is_default() { return res::max_batch() == (2ll * sm_count()) / 4; }
 void resident_profile(long long** buf, int* slots) { *buf = res::g_prof; *slots = res::g_prof_slots; }
 
 int resident_forward(const gatres_model_desc* d, const float* params, const float* x, float* out, float* saved,

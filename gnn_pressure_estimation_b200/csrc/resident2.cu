@@ -1887,15 +1887,18 @@ static int launch_cluster(const char* what, int cs, long long B, size_t smem, cu
 }  // namespace res2
 
 int resident_forced_cluster();      // resident.cu (gatres_set_resident_cluster)
+bool resident_max_batch_is_default();
 void resident_profile(long long** buf, int* slots);      // resident.cu (gatres_set_resident_profile)
 
-// cluster size: as many CTAs per snapshot as keeps the whole batch co-resident at two CTAs per SM
+// Cluster size: eight CTAs per snapshot, whatever the batch.  Clusters are independent (one snapshot each), so a batch
+// that does not fit the GPU at two CTAs per SM (37 clusters) simply runs in waves; measured (tools/resident_probe.py,
+// training step, us): 48 snapshots 853 against 1279 with 4 CTAs per snapshot in one wave + the layer backward, 64:
+// 911 / 1503, 96: 1343 / 1591 (layer kernels), 128: 1774 / 1839, 192: 2630 / 2789, 256: 3456 / 3066 — the layer kernels
+// take over between 192 and 256 snapshots (inference: between 256 and ~400).
+constexpr long long kRes2MaxTrain = 208, kRes2MaxInfer = 320;
 static int res2_cluster(long long B) {
-  int cs = 8;
-  if (resident_forced_cluster() > 0) cs = resident_forced_cluster();
-  else
-    while (cs > 1 && B * cs > 2ll * sm_count()) cs >>= 1;
-  return cs;
+  (void)B;
+  return resident_forced_cluster() > 0 ? resident_forced_cluster() : 8;
 }
 
 // the tensor-core forward (and with it the CTA-image layout of the saved activations) applies
@@ -1910,11 +1913,9 @@ static int res2_ecap(const gatres_model_desc* d, int cs) { return d->p_ecap[cs =
 bool resident2_eligible(const gatres_model_desc* d, bool training, long long max_batch) {
   if (!res2::enabled() || d->perm == nullptr || d->p_rowptr == nullptr || d->p_col == nullptr) return false;
   if (d->nc != 32 || d->E1 <= 0 || d->slots > 0) return false;
-  if (d->B > max_batch) return false;
+  // the caller's limit when GATRES_RESIDENT_MAX_B / gatres_set_resident_max_batch chose one, else the measured crossovers
+  if (d->B > (resident_max_batch_is_default() ? (training ? kRes2MaxTrain : kRes2MaxInfer) : max_batch)) return false;
   const int cs = res2_cluster(d->B);
-  // the backward stack only pays off with 8 CTAs per snapshot (profiles/r1_resident.md); larger batches keep the
-  // first-generation forward + layer-by-layer backward pair
-  if (training && resident_forced_cluster() == 0 && cs < 8) return false;
   const int R = (d->N + cs - 1) / cs, ecap = res2_ecap(d, cs);
   if (R >= 65536 || ecap <= 0) return false;
   // two CTAs per SM while the batch needs them, one otherwise

@@ -116,11 +116,12 @@ int64_t gatres_set_tile_min_batch(int64_t min_batch);
  * Kernel-selection knob for gatres_forward / gatres_backward[_range]: batches of at most `max_batch`
  * snapshots (nc = 32, gradient mode slots = 0 for the backward, graph slice fits shared memory) run the
  * snapshot-resident cluster kernels — one thread-block cluster per snapshot carries the whole stack, layers
- * separated by cluster barriers instead of kernel launches; larger batches run layer by layer.  Default
- * SM count / 2 (74 on B200: one wave of 4-CTA clusters at two CTAs per SM), or the GATRES_RESIDENT_MAX_B
- * environment variable; 0 disables.  The backward stack additionally needs 8 CTAs per snapshot to be co-resident
- * (B <= SM count / 4 = 37): between 38 and 74 snapshots the forward stack is resident and the backward runs layer by layer.  Negative = query only.  Returns
- * the previous value.
+ * separated by cluster barriers instead of kernel launches; larger batches run layer by layer.  While the knob holds
+ * its built-in value (SM count / 2 = 74 on B200; GATRES_RESIDENT_MAX_B presets it) the second-generation kernels
+ * (locality plan attached) apply their own measured crossovers: 8 CTAs per snapshot whatever the batch — clusters
+ * that do not fit the GPU at once run in waves — up to 208 snapshots for training and 320 for inference; the first
+ * generation (no plan) keeps 74.  Any other value is the limit for both generations; 0 disables.  Negative = query
+ * only.  Returns the previous value.
  */
 int64_t gatres_set_resident_max_batch(int64_t max_batch);
 /* CTAs per snapshot cluster of the resident kernels: 1, 2, 4 or 8; 0 = automatic (as many as keeps the batch

@@ -142,9 +142,14 @@ def test_large_model_layer_path_matches_oracle(B, dev, G):
         assert_close(model(x.to(dev), eib.to(dev)), out_ref, FWD_TOL, "gatres_large inference forward")
 
 
-def test_small_model_large_batch_tile_path_matches_oracle(dev, G):
-    """configs[2] regime: gatres_small at a batch that runs the TMA snapshot-tile aggregation kernels and the tcgen05
-    projections (B >= 64 snapshots, >= 32 768 rows): B = 96"""
+@pytest.mark.parametrize("path", ["layer", "resident-waves"])
+def test_small_model_large_batch_tile_path_matches_oracle(path, dev, G):
+    """configs[2] regime at B = 96 (37 248 rows).  "layer": the TMA snapshot-tile aggregation kernels, the tcgen05
+    projections and the fused projection backward (what batches beyond ~200 snapshots take; forced here).
+    "resident-waves": the default at this size — the snapshot-resident cluster kernels with 8 CTAs per snapshot, 96
+    clusters on 37 cluster slots, i.e. three waves of one launch."""
+    from gnn_pressure_estimation_b200 import _lib
+    lib = _lib.load()
     ei_np, names = T.reference_edge_index(T.ctown_shaped())
     ei, N, B = torch.from_numpy(ei_np), len(names), 96
     model, ref = _pair(G, dev, 15, 32)
@@ -152,7 +157,15 @@ def test_small_model_large_batch_tile_path_matches_oracle(dev, G):
     eib = O.collate_edge_index(ei, N, B)
     out_ref, loss_ref, grads_ref = O.train_step_loss_and_grads(ref, x, y, mask, eib)
     md = mask.to(dev)
-    out = model(x.to(dev), eib.to(dev), None, None)
-    torch.nn.functional.mse_loss(out[md], y.to(dev)[md]).backward()
+    prev = lib.gatres_set_resident_max_batch(0) if path == "layer" else None
+    try:
+        n0 = lib.gatres_launch_count()
+        out = model(x.to(dev), eib.to(dev), None, None)
+        torch.nn.functional.mse_loss(out[md], y.to(dev)[md]).backward()
+        launches = lib.gatres_launch_count() - n0
+    finally:
+        if prev is not None:
+            lib.gatres_set_resident_max_batch(prev)
+    assert (launches > 100) if path == "layer" else (launches < 10), launches
     assert_close(out, out_ref, FWD_TOL, "gatres_small B=96 forward")
     _check_grads([(k, p.grad) for k, p in model.named_parameters()], grads_ref, "gatres_small B=96 gradients")
