@@ -1,1 +1,2 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r4f_bench_8gpu.json 2> gpurun_out/r4f_bench_8gpu.err; tail -c 300 gpurun_out/r4f_bench_8gpu.err; head -c 300 gpurun_out/r4f_bench_8gpu.json
+ncu --set full --clock-control none --import-source on -k regex:'linear_bwd_fused|mean_res_bwd_tile|gat_agg_bwd_tile_pipe' -c 6 -o gpurun_out/prof_r4g_new_kernels -f python bench.py --profile-kernels > gpurun_out/r4g_ncu.log 2>&1
+tail -3 gpurun_out/r4g_ncu.log | cut -c1-200
