@@ -741,6 +741,10 @@ static int launch_tc_wide(const float* A, const float* W, const float* e0, const
   return check_launch("gemm_tc_wide");
 }
 
+// warp-specialised form of the wide projections (linear_tc_wide.cu); 0 = not covered / switched off
+int gemm_tc_wide2_dispatch(int H, int KK, int NN, const float* A, const float* W, const float* e0, const float* e1,
+                           float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st);
+
 // -> 1 if handled, 0 if this shape has no tensor-core path (caller falls back to the FFMA kernel), <0 on error
 int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const float* W, const float* e0,
                      const float* e1, float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st) {
@@ -755,6 +759,10 @@ int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const floa
   TC(32, 64, 1, 1)      // conv2 data gradient (dh2 [M,32] -> dy1 [M,64])
   TC(64, 32, 1, 1)      // conv1 data gradient (dh1 [M,64] -> dx0 [M,32])
 #undef TC
+  if (mode == 0) {
+    rc = gemm_tc_wide2_dispatch(H, KK, NN, A, W, e0, e1, Cout, s0, s1, M, st);
+    if (rc != 0) return rc;
+  }
 #define TCW(KKv, NNv, Hv)                                                                                  \
   if (mode == 0 && KK == KKv && NN == NNv && H == Hv) {                                                    \
     rc = launch_tc_wide<KKv, NNv, Hv>(A, W, e0, e1, Cout, s0, s1, M, st);                                   \

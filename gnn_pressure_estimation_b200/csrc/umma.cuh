@@ -80,6 +80,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
 }
 
+// MN-major descriptor for 32-bit (tf32) operands.  tcgen05 reads an MN-major tf32 operand only in the
+// SWIZZLE_128B_BASE32B layout (cute: Layout_MN_SW128_32B_Atom, "the only available smem layout" for mn-major tf32):
+// the tile is [K rows][32 elements = 128 B along M or N], rows 128 B apart, and the 32-byte chunk index (0..3) of a row is
+// XORed with row % 4 (Swizzle<2,5,2> on byte addresses); atoms are 4 rows = 512 B.  LBO = byte distance between
+// consecutive groups of 32 elements along M / N, SBO = between groups of 4 rows along K (512: dense rows).
+__device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
 // 32 lanes x 16 columns of fp32 accumulator -> 16 registers per thread
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
