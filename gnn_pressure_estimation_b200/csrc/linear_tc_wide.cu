@@ -26,11 +26,26 @@
 //                            tile t + 1.
 //
 // One CTA per SM (224 KB of shared memory), persistent over 128-row tiles.
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
 
 namespace gatres {
+
+// shared -> global 2-D tiled bulk store (TMA): the box described by `map` at element coordinates (x = column, y = row);
+// rows beyond the tensor's extent are clipped by the engine
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
+               "r"(smem_src)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int KK, int NN>
 struct WideShape {
@@ -39,8 +54,9 @@ struct WideShape {
   static constexpr uint32_t B_CH = NN * KC * 4;                 // one W part of a chunk
   static constexpr int SA = 2;                                  // A stages (hi + lo each)
   static constexpr int SB = NN == 256 ? 2 : 4;                  // W stages (hi + lo each): 128 KB either way
+  static constexpr uint32_t EPI_WARP = 2 * 4096;               // two [32 rows x 128 B] transposing buffers per epilogue warp
   static constexpr uint32_t OFF_A = 0, OFF_B = OFF_A + SA * 2 * A_CH, OFF_EPI = OFF_B + SB * 2 * B_CH,
-                            OFF_ATT = OFF_EPI + 4 * 4096, OFF_BAR = OFF_ATT + 2 * NN * 4;
+                            OFF_ATT = OFF_EPI + 4 * EPI_WARP, OFF_BAR = OFF_ATT + 2 * NN * 4;
   static constexpr int NBAR = 2 * SA + 2 * SB + 4;
   static constexpr uint32_t TOTAL = OFF_BAR + NBAR * 8 + 16;
   static_assert(KK % KC == 0 && (NN == 128 || NN == 256), "unsupported wide tensor-core shape");
@@ -68,10 +84,13 @@ __global__ void __launch_bounds__(256) wide_w_image_kernel(const float* __restri
   }
 }
 
-template <int KK, int NN, int H>
+// TS = rows leave through TMA tensor stores (out_map describes Cout as [M][NN] with 32 x 32 boxes, SWIZZLE_128B);
+// otherwise the epilogue warps read their transposing buffer back and store 128-byte lines themselves.
+template <int KK, int NN, int H, bool TS>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_src, const float* __restrict__ att_dst,
-                     float* __restrict__ Cout, float* __restrict__ s0, float* __restrict__ s1, unsigned M) {
+                     float* __restrict__ Cout, float* __restrict__ s0, float* __restrict__ s1, unsigned M,
+                     const __grid_constant__ CUtensorMap out_map) {
   using S = WideShape<KK, NN>;
   constexpr int BM = S::BM, KC = S::KC, NCHUNK = S::NCHUNK, SA = S::SA, SB = S::SB;
   constexpr uint32_t A_CH = S::A_CH, B_CH = S::B_CH;
@@ -155,7 +174,7 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
   } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue: warp w drains TMEM lanes 32 (w % 4) ..
     const int quarter = warp & 3;
-    unsigned char* stg = sm + S::OFF_EPI + quarter * 4096;                       // [32 rows][128 B], 16-byte chunks XOR row % 8
+    unsigned char* stg0 = sm + S::OFF_EPI + quarter * S::EPI_WARP;               // 2 x [32 rows][128 B], 16-byte chunks XOR row % 8
     for (unsigned t = 0; t < my_tiles; ++t) {
       const unsigned tile = blockIdx.x + t * gridDim.x, acc = t & 1u;
       const unsigned row0 = tile * BM + quarter * 32;
@@ -184,18 +203,29 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
         } else {
           ps[0] += a; pd[0] += b;
         }
+        unsigned char* stg = stg0 + (cb & 1) * 4096;
+        if (TS) {                                                                 // the store issued two column blocks ago has read this buffer
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
               make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        __syncwarp();
+        if (TS) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && row0 < M) tma_store_2d(&out_map, smem_u32(stg), col0, (int)row0);
+        } else {
+          __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = j * 4 + (lane >> 3), c = lane & 7;
-          const float4 o = *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
-          if (row0 + r < M) st4(Cout + (size_t)(row0 + r) * NN + col0 + 4 * c, o);
+          for (int j = 0; j < 8; ++j) {
+            const int r = j * 4 + (lane >> 3), c = lane & 7;
+            const float4 o = *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
+            if (row0 + r < M) st4(Cout + (size_t)(row0 + r) * NN + col0 + 4 * c, o);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (row0 + lane < M) {
 #pragma unroll
@@ -205,6 +235,7 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
         }
       }
     }
+    if (TS && lane == 0) tma_store_wait_all();
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
     for (unsigned q = 0; q < total; ++q) {
@@ -247,22 +278,60 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
   if (warp == 0) tmem_dealloc(tmem, 2 * NN);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+// row-major fp32 [rows][cols] described in 32-row x 32-column boxes whose shared-memory image is SWIZZLE_128B
+static bool make_box_map(CUtensorMap* map, const float* ptr, unsigned rows, unsigned cols) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t dims[2] = {cols, rows}, strides[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int KK, int NN, int H>
 static int launch_tc_wide2(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
                            float* s1, unsigned M, cudaStream_t st) {
   using S = WideShape<KK, NN>;
-  auto kern = gemm_tc_wide2_kernel<KK, NN, H>;
-  static bool configured = false;
-  if (!configured) {
+  static int tma_store = -1;
+  if (tma_store < 0) {
+    const char* e = getenv("GATRES_TC_WIDE2_TMA_STORE");
+    tma_store = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  CUtensorMap map;
+  const bool ts = tma_store == 1 && make_box_map(&map, Cout, M, NN);
+  if (!ts) memset(&map, 0, sizeof(map));
+  auto kern = ts ? gemm_tc_wide2_kernel<KK, NN, H, true> : gemm_tc_wide2_kernel<KK, NN, H, false>;
+  static bool configured[2] = {false, false};
+  if (!configured[ts]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL) != cudaSuccess)
       return check_launch("gemm_tc_wide2: smem attribute");
-    configured = true;
+    configured[ts] = true;
   }
   const unsigned ntiles = (M + 127) / 128;
   unsigned grid = (unsigned)sm_count();
   if (grid > ntiles) grid = ntiles;
   launch_kernel(wide_w_image_kernel<KK, NN>, dim3(NN * (KK / 4) / 256), dim3(256), (size_t)0, st, W);
-  launch_kernel(kern, dim3(grid), dim3(320), (size_t)S::TOTAL, st, A, e0, e1, Cout, s0, s1, M);
+  launch_kernel(kern, dim3(grid), dim3(320), (size_t)S::TOTAL, st, A, e0, e1, Cout, s0, s1, M, map);
   return check_launch("gemm_tc_wide2");
 }
 
