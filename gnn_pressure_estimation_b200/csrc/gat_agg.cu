@@ -466,7 +466,7 @@ static int fused_mean_enabled() {
 int gat_agg_mean_res_fwd(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
                          const float* s_dst, const float* bias, float* m, float* l, const float* x0, float* xout,
                          long long B, int N, int C, cudaStream_t st) {
-  if (!fused_mean_enabled() || E1 == 0 || B < tile_min_batch() || (C != 32 && C != 64) ||
+  if (!fused_mean_enabled() || E1 == 0 || B < tile_min_batch() || (C != 32 && C != 64 && C != 128) ||
       !fwd_tile_mean_eligible((unsigned)N, (unsigned)C, E1))
     return 0;
   const int rc = gat_agg_mean_res_fwd_tile(rowptr, col, E1, h, s_src, s_dst, bias, m, l, x0, xout, (unsigned)B, (unsigned)N, C, st);

@@ -8,12 +8,24 @@
 // warps' critical path (round-1 ncu: the gather version is long-scoreboard bound).
 //
 // Same arithmetic and lane mapping as gat_agg.cu (cooperative per-row softmax).
+#include <cuda.h>
 #include <math_constants.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
+#include "tensormap.cuh"
 #include "tma.cuh"
 
 namespace gatres {
+
+// global -> shared 2-D tiled bulk load (TMA): the box of `map` at element coordinates (x = column, y = row) lands densely
+// ([box rows][box columns]) at smem_dst; completion is signalled on `bar` as the box's bytes
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
 
 // CTA size: 1024 threads when only one CTA fits per SM (slab > ~110 KB double-buffered), 512 when two fit.
 
@@ -75,20 +87,33 @@ struct FwdTilePlan {
 // SimpleConv(mean) + residual + ReLU that always follows (GraphModels.py:466-467) runs in the same kernel:
 // xout[i] = relu(mean_{j in N(i)} z[j] + x0[i]).  z is neither written to nor re-read from HBM and one launch
 // disappears: 272 + 384 algorithmic B/node become 400.
-template <int H, int C, int THREADS, bool FUSE_MEAN>
+//
+// SLICED (rows wider than a slab that fits: nc = 128, two heads of nc = 64): the aggregation is independent per channel
+// once the attention coefficients are known, so a work unit is (snapshot, slice of C channels of ONE head) instead of a
+// snapshot: the slab is the [N x C] column block of h[b] (row stride ld floats), fetched by 2-D TMA tensor loads
+// (hmap / xmap: boxes of C columns x box_rows rows, dense in shared memory, i.e. the layout of the contiguous case);
+// every slice of a head recomputes that head's softmax from the (tiny) score vectors, the first slice of a head
+// writes (m, l).  H = 1 in this mode; Hs = heads of the score tensors, sph = slices per head.
+template <int H, int C, int THREADS, bool FUSE_MEAN, bool SLICED>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
 gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, unsigned E1,
                         const float* __restrict__ h, const float* __restrict__ s_src,
                         const float* __restrict__ s_dst, const float* __restrict__ bias,
                         float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ l_out,
                         const float* __restrict__ x0, float* __restrict__ xout,
-                        unsigned B, unsigned N, int relu) {
+                        unsigned B, unsigned N, int relu, unsigned Hs, unsigned sph, unsigned box_rows,
+                        const __grid_constant__ CUtensorMap hmap, const __grid_constant__ CUtensorMap xmap) {
   using RM = RowMap<H, C, true>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
   constexpr int kTileThreads = THREADS, kTileWarps = THREADS / 32;
   static_assert(!FUSE_MEAN || (H == 1 && V == 1), "the fused mean follows the one-head layer");
+  static_assert(!SLICED || H == 1, "a slice belongs to one head");
   extern __shared__ __align__(128) unsigned char smem[];
-  const FwdTilePlan plan(N, F, H, E1, FUSE_MEAN);
+  const unsigned HS = SLICED ? Hs : (unsigned)H;            // heads of the score tensors
+  const unsigned nsl = SLICED ? Hs * sph : 1u;              // slices per row
+  const unsigned ld = nsl * F;                              // row stride of h / out / x0 / xout
+  const unsigned U = B * nsl;                               // work units
+  const FwdTilePlan plan(N, F, HS, E1, FUSE_MEAN);
   int* rp_s = reinterpret_cast<int*>(smem + plan.rp_off);
   int* col_s = reinterpret_cast<int*>(smem + plan.col_off);
   unsigned short* ord = reinterpret_cast<unsigned short*>(smem + plan.ord_off);
@@ -100,12 +125,18 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   const int sub = lane / LPR, lig = lane % LPR, slot = lig % LPH;
   constexpr unsigned gmask = 0xffffffffu;          // control flow below is warp-uniform: full-mask shuffles
 
-  auto issue = [&](int stage, unsigned bb) {       // one elected thread
+  auto issue = [&](int stage, unsigned u) {        // one elected thread; u = work unit (snapshot, or snapshot * nsl + slice)
     unsigned char* dst = smem + (size_t)stage * plan.stage_bytes;
+    const unsigned bb = SLICED ? u / nsl : u, q = SLICED ? u % nsl : 0u;
     mbar_arrive_expect_tx(&full[stage], plan.tx_bytes);
-    bulk_g2s(dst, h + (size_t)bb * N * F, plan.h_bytes, &full[stage]);
-    bulk_g2s(dst + plan.h_bytes, s_src + (size_t)bb * N * H, plan.ss_bytes, &full[stage]);
-    bulk_g2s(dst + plan.h_bytes + plan.ss_bytes, s_dst + (size_t)bb * N * H, plan.ss_bytes, &full[stage]);
+    if (SLICED) {
+      for (unsigned r0 = 0; r0 < N; r0 += box_rows)
+        tma_load_2d(dst + (size_t)r0 * F * 4, &hmap, (int)(q * F), (int)(bb * N + r0), &full[stage]);
+    } else {
+      bulk_g2s(dst, h + (size_t)bb * N * F, plan.h_bytes, &full[stage]);
+    }
+    bulk_g2s(dst + plan.h_bytes, s_src + (size_t)bb * N * HS, plan.ss_bytes, &full[stage]);
+    bulk_g2s(dst + plan.h_bytes + plan.ss_bytes, s_dst + (size_t)bb * N * HS, plan.ss_bytes, &full[stage]);
   };
 
   if (tid == 0) {
@@ -120,25 +151,36 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   degree_order<THREADS>(rp_s, N, ord, reinterpret_cast<int*>(smem + plan.hist_off));
   pdl_wait();                                     // CSR staging above overlapped the previous kernel's tail
   if (tid == 0) {
-    if (blockIdx.x < B) issue(0, blockIdx.x);
-    if (blockIdx.x + gridDim.x < B) issue(1, blockIdx.x + gridDim.x);
+    if (blockIdx.x < U) issue(0, blockIdx.x);
+    if (blockIdx.x + gridDim.x < U) issue(1, blockIdx.x + gridDim.x);
   }
 
   float4 bv[V];
+  if (!SLICED) {
 #pragma unroll
-  for (int v = 0; v < V; ++v) bv[v] = ldg4(bias + 4 * RM::chunk(lig, v));
+    for (int v = 0; v < V; ++v) bv[v] = ldg4(bias + 4 * RM::chunk(lig, v));
+  }
 
   unsigned k = 0;
-  if (gridDim.x >= B) pdl_launch_dependents();
-  for (unsigned b = blockIdx.x; b < B; b += gridDim.x, ++k) {
+  if (gridDim.x >= U) pdl_launch_dependents();
+  for (unsigned u = blockIdx.x; u < U; u += gridDim.x, ++k) {
+    const unsigned b = SLICED ? u / nsl : u, q = SLICED ? u % nsl : 0u;
+    const unsigned hq = SLICED ? q / sph : 0u;     // head of this slice
+    const bool write_ml = !SLICED || q % sph == 0;
     const int stage = k & 1;
     const float* hs = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes) + 4 * lig;
     const float* sss = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes + plan.h_bytes);
-    const float* sds = sss + N * H;
+    const float* sds = sss + N * HS;
+    if (SLICED) bv[0] = ldg4(bias + q * F + 4 * lig);
     if (FUSE_MEAN && tid == 0) {                   // the previous snapshot's mean phase is done with the x0 slab
       fence_proxy_async();
       mbar_arrive_expect_tx(&full[2], plan.h_bytes);
-      bulk_g2s(smem + plan.xs_off, x0 + (size_t)b * N * F, plan.h_bytes, &full[2]);
+      if (SLICED) {
+        for (unsigned r0 = 0; r0 < N; r0 += box_rows)
+          tma_load_2d(smem + plan.xs_off + (size_t)r0 * F * 4, &xmap, (int)(q * F), (int)(b * N + r0), &full[2]);
+      } else {
+        bulk_g2s(smem + plan.xs_off, x0 + (size_t)b * N * F, plan.h_bytes, &full[2]);
+      }
     }
     mbar_wait(&full[stage], (k >> 1) & 1);
 
@@ -154,7 +196,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
       float4 acc[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        sd[v] = sds[i * H + RM::head(lig, v)];
+        sd[v] = sds[i * HS + (SLICED ? hq : (unsigned)RM::head(lig, v))];
         mrun[v] = -CUDART_INF_F;
         lrun[v] = 0.f;
         acc[v] = f4zero();
@@ -165,7 +207,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
         float p[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const float a = valid ? lrelu(sss[j * H + RM::head(lig, v)] + sd[v]) : -CUDART_INF_F;
+          const float a = valid ? lrelu(sss[j * HS + (SLICED ? hq : (unsigned)RM::head(lig, v))] + sd[v]) : -CUDART_INF_F;
           const float nm = fmaxf(mrun[v], tile_group_max<LPH>(a, gmask));
           if (e0 > 0) {
             const float sc = __expf(mrun[v] - nm);
@@ -198,19 +240,19 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
           o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
         }
         if (FUSE_MEAN) st4(ZS + i * F + 4 * RM::chunk(lig, v), o);
-        else st4(out + r * F + 4 * RM::chunk(lig, v), o);
-        if (m_out != nullptr && slot == 0) {
-          m_out[r * H + RM::head(lig, v)] = mrun[v];
-          l_out[r * H + RM::head(lig, v)] = lrun[v];
+        else st4(out + r * ld + q * F + 4 * RM::chunk(lig, v), o);
+        if (m_out != nullptr && slot == 0 && write_ml) {
+          m_out[r * HS + (SLICED ? hq : (unsigned)RM::head(lig, v))] = mrun[v];
+          l_out[r * HS + (SLICED ? hq : (unsigned)RM::head(lig, v))] = lrun[v];
         }
       }
     }
     __syncthreads();                               // every warp is done with this stage (and z is complete)
     if (tid == 0) {
-      const unsigned nb = b + 2u * gridDim.x;
-      if (nb < B) {
+      const unsigned nu = u + 2u * gridDim.x;
+      if (nu < U) {
         fence_proxy_async();
-        issue(stage, nb);
+        issue(stage, nu);
       }
     }
     if (FUSE_MEAN) {
@@ -229,7 +271,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
         o.y = fmaxf(fmaf(acc.y, inv, xr.y), 0.f);
         o.z = fmaxf(fmaf(acc.z, inv, xr.z), 0.f);
         o.w = fmaxf(fmaf(acc.w, inv, xr.w), 0.f);
-        st4(xout + ((size_t)b * N + i) * F + 4 * lig, o);
+        st4(xout + ((size_t)b * N + i) * ld + q * F + 4 * lig, o);
       }
       __syncthreads();                             // z and x0 slabs are free for the next snapshot
     }
@@ -245,55 +287,132 @@ static int launch_fwd_tile(const int* rowptr, const int* col, unsigned E1, const
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
   unsigned grid = (unsigned)sm_count() * per_sm;
   if (grid > B) grid = B;
+  CUtensorMap none;
+  memset(&none, 0, sizeof(none));
 #define LAUNCH(THR)                                                                                               \
   do {                                                                                                            \
-    auto kern = gat_agg_fwd_tile_kernel<H, C, THR, FUSE>;                                                         \
+    auto kern = gat_agg_fwd_tile_kernel<H, C, THR, FUSE, false>;                                                  \
     static uint32_t configured = 0;                                                                               \
     if (configured < plan.total) {                                                                                \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
         return check_launch("gat_agg_fwd_tile: smem attribute");                                                  \
       configured = plan.total;                                                                                    \
     }                                                                                                             \
-    launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, x0, xout, B, N, relu); \
+    launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, x0, xout, B, N, relu, \
+                  (unsigned)H, 1u, 0u, none, none);                                                               \
   } while (0)
   if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);
 #undef LAUNCH
   return check_launch("gat_agg_fwd_tile");
 }
 
+// ---- channel-sliced work units (rows wider than a slab that fits; see the kernel's header) ----
+static bool sliced_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GATRES_TILE_SLICED");
+    v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+// rows per TMA box: the snapshot's N rows in equal boxes of at most 256 rows (0 = no such split)
+static unsigned slice_box_rows(unsigned N) {
+  const unsigned nbox = (N + 255u) / 256u;
+  return N % nbox == 0 ? N / nbox : 0u;
+}
+// slice width (channels) for (H heads x C channels): 64 for the plain aggregation (the [N x 64] slab of the two-head nc = 32
+// kernel), 32 with the fused mean (four slabs); 0 = the sliced form does not apply
+static unsigned slice_width(unsigned N, unsigned H, unsigned C, unsigned E1, bool fuse_mean) {
+  const unsigned CS = fuse_mean ? 32u : 64u;
+  if (!sliced_enabled() || C % CS != 0 || C <= CS || slice_box_rows(N) == 0 || (N * H) % 4u != 0) return 0;
+  if (encode_tiled_fn() == nullptr) return 0;
+  const FwdTilePlan plan(N, CS, H, E1, fuse_mean);
+  return plan.total <= 227u * 1024u ? CS : 0u;
+}
+
+template <int CS, bool FUSE>
+static int launch_fwd_tile_sliced(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
+                                  const float* s_dst, const float* bias, float* out, float* m, float* l, const float* x0,
+                                  float* xout, unsigned B, unsigned N, unsigned H, unsigned C, int relu, cudaStream_t st) {
+  const FwdTilePlan plan(N, CS, H, E1, FUSE);
+  const unsigned sph = C / CS, nsl = H * sph, box_rows = slice_box_rows(N);
+  CUtensorMap hmap, xmap;
+  memset(&xmap, 0, sizeof(xmap));
+  if (!make_map_2d(&hmap, h, (unsigned long long)B * N, H * C, CS, box_rows, false) ||
+      (FUSE && !make_map_2d(&xmap, x0, (unsigned long long)B * N, H * C, CS, box_rows, false))) {
+    set_error("gat_agg_fwd_tile: cuTensorMapEncodeTiled failed");
+    return GATRES_ERR_CUDA;
+  }
+  unsigned per_sm = (unsigned)((227u * 1024u) / (plan.total + 1024u));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  unsigned grid = (unsigned)sm_count() * per_sm;
+  if (grid > B * nsl) grid = B * nsl;
+#define LAUNCH(THR)                                                                                               \
+  do {                                                                                                            \
+    auto kern = gat_agg_fwd_tile_kernel<1, CS, THR, FUSE, true>;                                                  \
+    static uint32_t configured = 0;                                                                               \
+    if (configured < plan.total) {                                                                                \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
+        return check_launch("gat_agg_fwd_tile (sliced): smem attribute");                                         \
+      configured = plan.total;                                                                                    \
+    }                                                                                                             \
+    launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, x0, xout, B, N, relu, \
+                  H, sph, box_rows, hmap, xmap);                                                                  \
+  } while (0)
+  if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);
+#undef LAUNCH
+  return check_launch("gat_agg_fwd_tile (sliced)");
+}
+
 // Eligibility: slab + scores double-buffered + CSR must fit, and the per-snapshot byte
 // counts must be 16 B multiples (bulk-copy granularity).
-// conv2 aggregation + SimpleConv(mean) + residual + ReLU in one launch (nc = 32 / 64, one head)
-bool fwd_tile_mean_eligible(unsigned N, unsigned C, unsigned E1) {
+// conv2 aggregation + SimpleConv(mean) + residual + ReLU in one launch (one head; nc = 32 / 64 whole rows, wider rows in
+// 32-channel slices)
+static bool fwd_tile_mean_plain(unsigned N, unsigned C, unsigned E1) {
   const FwdTilePlan plan(N, C, 1, E1, true);
   return N % 4u == 0 && plan.total <= 227u * 1024u && (C == 32 || C == 64);
+}
+bool fwd_tile_mean_eligible(unsigned N, unsigned C, unsigned E1) {
+  return fwd_tile_mean_plain(N, C, E1) || slice_width(N, 1, C, E1, true) != 0;
 }
 
 int gat_agg_mean_res_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
                               const float* s_dst, const float* bias, float* m, float* l, const float* x0, float* xout,
                               unsigned B, unsigned N, int C, cudaStream_t st) {
-  if (C == 32) return launch_fwd_tile<1, 32, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 0, st);
-  if (C == 64) return launch_fwd_tile<1, 64, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 0, st);
+  if (fwd_tile_mean_plain(N, (unsigned)C, E1)) {
+    if (C == 32) return launch_fwd_tile<1, 32, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 0, st);
+    if (C == 64) return launch_fwd_tile<1, 64, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 0, st);
+  }
+  if (slice_width(N, 1, (unsigned)C, E1, true) == 32)
+    return launch_fwd_tile_sliced<32, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 1u, (unsigned)C, 0, st);
   set_error("gat_agg_mean_res_fwd_tile: unsupported channels %d", C);
   return GATRES_ERR_ARG;
 }
 
-bool fwd_tile_eligible(unsigned N, unsigned H, unsigned C, unsigned E1) {
+static bool fwd_tile_plain(unsigned N, unsigned H, unsigned C, unsigned E1) {
   const FwdTilePlan plan(N, H * C, H, E1);
   return (N * H) % 4u == 0 && plan.total <= 227u * 1024u && (H * C) <= 128;
+}
+bool fwd_tile_eligible(unsigned N, unsigned H, unsigned C, unsigned E1) {
+  return fwd_tile_plain(N, H, C, E1) || slice_width(N, H, C, E1, false) != 0;
 }
 
 int gat_agg_fwd_tile(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
                      const float* s_dst, const float* bias, float* out, float* m, float* l, unsigned B, unsigned N,
                      int H, int C, int relu, cudaStream_t st) {
+  if (fwd_tile_plain(N, (unsigned)H, (unsigned)C, E1)) {
 #define T(HH, CC) \
   if (H == HH && C == CC) return launch_fwd_tile<HH, CC, false>(rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, nullptr, nullptr, B, N, relu, st)
-  T(1, 32);
-  T(2, 32);
-  T(1, 64);
-  T(2, 64);
-  T(1, 128);
+    T(1, 32);
+    T(2, 32);
+    T(1, 64);
+    T(2, 64);
+    T(1, 128);
 #undef T
+  }
+  if (slice_width(N, (unsigned)H, (unsigned)C, E1, false) == 64)
+    return launch_fwd_tile_sliced<64, false>(rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, nullptr, nullptr, B, N,
+                                             (unsigned)H, (unsigned)C, relu, st);
   set_error("gat_agg_fwd_tile: unsupported (H=%d, C=%d)", H, C);
   return GATRES_ERR_ARG;
 }

@@ -30,6 +30,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tensormap.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
 
@@ -278,36 +279,6 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
   if (warp == 0) tmem_dealloc(tmem, 2 * NN);
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    else
-      cudaGetLastError();
-  }
-  return fn;
-}
-// row-major fp32 [rows][cols] described in 32-row x 32-column boxes whose shared-memory image is SWIZZLE_128B
-static bool make_box_map(CUtensorMap* map, const float* ptr, unsigned rows, unsigned cols) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (fn == nullptr) return false;
-  const cuuint64_t dims[2] = {cols, rows}, strides[1] = {(cuuint64_t)cols * 4};
-  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int KK, int NN, int H>
 static int launch_tc_wide2(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
                            float* s1, unsigned M, cudaStream_t st) {
@@ -318,7 +289,7 @@ static int launch_tc_wide2(const float* A, const float* W, const float* e0, cons
     tma_store = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
   CUtensorMap map;
-  const bool ts = tma_store == 1 && make_box_map(&map, Cout, M, NN);
+  const bool ts = tma_store == 1 && make_map_2d(&map, Cout, M, NN, 32, 32, true);
   if (!ts) memset(&map, 0, sizeof(map));
   auto kern = ts ? gemm_tc_wide2_kernel<KK, NN, H, true> : gemm_tc_wide2_kernel<KK, NN, H, false>;
   static bool configured[2] = {false, false};
