@@ -107,7 +107,9 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
   constexpr int kTileThreads = THREADS, kTileWarps = THREADS / 32;
   static_assert(!FUSE_MEAN || (H == 1 && V == 1), "the fused mean follows the one-head layer");
-  static_assert(!SLICED || H == 1, "a slice belongs to one head");
+  // SLICED: every chunk of a lane belongs to the slice's head (H = 2 only selects the packed lane map: 8 lanes x 2 chunks
+  // per row, 4 rows per warp, as in the two-head nc = 32 kernel whose slab has the same shape)
+  static_assert(!SLICED || !FUSE_MEAN || H == 1, "the fused mean follows the one-head layer");
   extern __shared__ __align__(128) unsigned char smem[];
   const unsigned HS = SLICED ? Hs : (unsigned)H;            // heads of the score tensors
   const unsigned nsl = SLICED ? Hs * sph : 1u;              // slices per row
@@ -171,7 +173,10 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     const float* hs = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes) + 4 * lig;
     const float* sss = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes + plan.h_bytes);
     const float* sds = sss + N * HS;
-    if (SLICED) bv[0] = ldg4(bias + q * F + 4 * lig);
+    if (SLICED) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) bv[v] = ldg4(bias + q * F + 4 * RM::chunk(lig, v));
+    }
     if (FUSE_MEAN && tid == 0) {                   // the previous snapshot's mean phase is done with the x0 slab
       fence_proxy_async();
       mbar_arrive_expect_tx(&full[2], plan.h_bytes);
@@ -207,6 +212,14 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
         float p[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
+          if (SLICED && v > 0) {                     // same head as chunk 0: same softmax
+            if (e0 > 0) {
+              const float sc = __expf(mrun[v] - mrun[0]);
+              acc[v].x *= sc; acc[v].y *= sc; acc[v].z *= sc; acc[v].w *= sc;
+            }
+            p[v] = p[0]; lrun[v] = lrun[0]; mrun[v] = mrun[0];
+            continue;
+          }
           const float a = valid ? lrelu(sss[j * HS + (SLICED ? hq : (unsigned)RM::head(lig, v))] + sd[v]) : -CUDART_INF_F;
           const float nm = fmaxf(mrun[v], tile_group_max<LPH>(a, gmask));
           if (e0 > 0) {
@@ -241,7 +254,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
         }
         if (FUSE_MEAN) st4(ZS + i * F + 4 * RM::chunk(lig, v), o);
         else st4(out + r * ld + q * F + 4 * RM::chunk(lig, v), o);
-        if (m_out != nullptr && slot == 0 && write_ml) {
+        if (m_out != nullptr && slot == 0 && write_ml && (!SLICED || v == 0)) {
           m_out[r * HS + (SLICED ? hq : (unsigned)RM::head(lig, v))] = mrun[v];
           l_out[r * HS + (SLICED ? hq : (unsigned)RM::head(lig, v))] = lrun[v];
         }
@@ -349,7 +362,7 @@ static int launch_fwd_tile_sliced(const int* rowptr, const int* col, unsigned E1
   if (grid > B * nsl) grid = B * nsl;
 #define LAUNCH(THR)                                                                                               \
   do {                                                                                                            \
-    auto kern = gat_agg_fwd_tile_kernel<1, CS, THR, FUSE, true>;                                                  \
+    auto kern = gat_agg_fwd_tile_kernel<(FUSE ? 1 : 2), (FUSE ? CS : CS / 2), THR, FUSE, true>;                                                  \
     static uint32_t configured = 0;                                                                               \
     if (configured < plan.total) {                                                                                \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
