@@ -48,6 +48,26 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ask the L2 for a contiguous block ahead of its use (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+// The A tile of a persistent CTA's NEXT tile (128 rows x K floats, contiguous) is prefetched into L2 as one sequential
+// block when the current tile starts: the chunk loads read a 128-byte slice of each of 128 rows (row stride K floats), and
+// issued straight at DRAM they open a page per 128 bytes (K = 256: 56 % of the copy bandwidth whatever the pipeline
+// around them looked like — single CTA, CTA pair, four or eight producer warps).
+__device__ __forceinline__ void prefetch_a_tile(const float* A, unsigned tile, unsigned M, unsigned KK) {
+  const unsigned row0 = tile * 128u;
+  if (row0 >= M) return;
+  const unsigned rows = M - row0 < 128u ? M - row0 : 128u;
+  l2_prefetch_bulk(A + (size_t)row0 * KK, rows * KK * 4u);
+}
+
+#ifndef GATRES_WIDE_L2PF
+#define GATRES_WIDE_L2PF 1
+#endif
+constexpr bool L2PF = GATRES_WIDE_L2PF != 0;
+
 template <int KK, int NN>
 struct WideShape {
   static constexpr int BM = 128, KC = 32, NCHUNK = KK / KC;
@@ -138,6 +158,7 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
     float4 r0[8], r1[8];
     auto request = [&](unsigned q, float4 (&r)[8]) {
       const unsigned tile = blockIdx.x + (q / NCHUNK) * gridDim.x, ch = q % NCHUNK;
+      if (L2PF && ch == 0 && tid == 0) prefetch_a_tile(A, tile + gridDim.x, M, KK);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int idx = it * 128 + tid;
@@ -279,6 +300,403 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
   if (warp == 0) tmem_dealloc(tmem, 2 * NN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair form (tcgen05 cta_group::2): two CTAs of a cluster (one TPC) share every MMA.  CTA r owns the 128-row tile
+// 2 p + r of pair p and HALF of the weight chunk (rows r N/2 .. of W); one instruction M = 256 x N x 8 issued by CTA 0 reads
+// A from both CTAs' shared memory and each half of B once per pair: 8 KB of operand reads per CTA and MMA instead of 12
+// (N = 256) and half the bulk-copy writes of W per CTA — the single-CTA form is bound by exactly that traffic (ncu: LSU +
+// tensor-core + TMA wavefronts of the shared-memory data array ~ 90 % of the tile time, tensor pipe 54 %).
+//   * barriers live at the same offsets in both CTAs; "full" barriers that the issuing CTA waits on count the arrivals of
+//     both CTAs (the peer's producer / epilogue threads arrive remotely through mapa), the peer's bulk copies complete on
+//     its own barrier and one relay lane forwards that completion; tcgen05.commit multicasts "stage free" / "accumulator
+//     full" to both CTAs.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned wide_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned wide_cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned wide_nclusters() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void wide_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, unsigned rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread arrive on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int KK, int NN>
+struct PairShape {
+  static constexpr int BM = 128, KC = 32, NCHUNK = KK / KC, NH = NN / 2;
+  static constexpr uint32_t A_CH = BM * KC * 4;                 // one A part (hi or lo) of a chunk
+  static constexpr uint32_t B_CH = NH * KC * 4;                 // one part of this CTA's half of a W chunk
+  static constexpr int SA = NN == 256 ? 3 : 4;
+  static constexpr int SB = NN == 256 ? 3 : 4;
+  static constexpr uint32_t EPI_WARP = 2 * 4096;
+  static constexpr uint32_t OFF_A = 0, OFF_B = OFF_A + SA * 2 * A_CH, OFF_EPI = OFF_B + SB * 2 * B_CH,
+                            OFF_ATT = OFF_EPI + 4 * EPI_WARP, OFF_BAR = OFF_ATT + 2 * NN * 4;
+  static constexpr int NBAR = 3 * SA + 3 * SB + 6;
+  static constexpr uint32_t TOTAL = OFF_BAR + NBAR * 8 + 16;
+  static_assert(KK % KC == 0 && (NN == 128 || NN == 256), "unsupported wide tensor-core shape");
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+// image[ch][rank][part][swz(n - rank N/2, k % 32)]: every (chunk, rank) block = the hi and lo tiles of one CTA's half
+template <int KK, int NN>
+__device__ __align__(1024) float g_pair_image[2 * KK * NN];
+
+template <int KK, int NN>
+__global__ void __launch_bounds__(256) pair_w_image_kernel(const float* __restrict__ W) {
+  using S = PairShape<KK, NN>;
+  pdl_wait();
+  unsigned char* img = reinterpret_cast<unsigned char*>(g_pair_image<KK, NN>);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NN * (KK / 4); idx += gridDim.x * blockDim.x) {
+    const int n = idx / (KK / 4), k = 4 * (idx % (KK / 4));
+    const float4 w = ldg4(W + (size_t)n * KK + k);
+    float4 lo;
+    lo.x = lo_tf32(w.x); lo.y = lo_tf32(w.y); lo.z = lo_tf32(w.z); lo.w = lo_tf32(w.w);
+    const uint32_t off = ((uint32_t)(k / S::KC) * 2u + (uint32_t)(n / S::NH)) * 2u * S::B_CH +
+                         swz_off((uint32_t)(n % S::NH), (uint32_t)(k % S::KC), S::NH);
+    *reinterpret_cast<float4*>(img + off) = w;
+    *reinterpret_cast<float4*>(img + off + S::B_CH) = lo;
+  }
+}
+
+#ifndef GATRES_WIDE_L2PF
+#define GATRES_WIDE_L2PF 1
+#endif
+constexpr int PAIR_PRODUCER_WARPS = 8;                      // + 4 epilogue warps, MMA issuer / W relay, W loader, A relay
+constexpr int PAIR_THREADS = (PAIR_PRODUCER_WARPS + 7) * 32;
+
+template <int KK, int NN, int H>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+gemm_tc_pair_kernel(const float* __restrict__ A, const float* __restrict__ att_src, const float* __restrict__ att_dst,
+                    float* __restrict__ s0, float* __restrict__ s1, unsigned M, const __grid_constant__ CUtensorMap out_map) {
+  using S = PairShape<KK, NN>;
+  constexpr int BM = S::BM, KC = S::KC, NCHUNK = S::NCHUNK, SA = S::SA, SB = S::SB;
+  constexpr uint32_t A_CH = S::A_CH, B_CH = S::B_CH;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+  static_assert(H == 1 || H == 2, "heads");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();
+  unsigned char* sm = smem_raw;
+  float* att = reinterpret_cast<float*>(sm + S::OFF_ATT);                       // [2][NN]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);              // [SA] own producer warps
+  uint64_t* a_empty = a_full + SA;                                              // [SA] tcgen05.commit (multicast)
+  uint64_t* w_full = a_empty + SA;                                              // [SB] own bulk copies
+  uint64_t* w_peer = w_full + SB;                                               // [SB] CTA 0: the peer's half has landed (relay)
+  uint64_t* w_empty = w_peer + SB;                                              // [SB] tcgen05.commit (multicast)
+  uint64_t* acc_full = w_empty + SB;                                            // [2]  tcgen05.commit (multicast)
+  uint64_t* acc_empty = acc_full + 2;                                           // [2]  own epilogue warps
+  uint64_t* a_peer = acc_empty + 2;                                             // [SA] CTA 0: the peer's A stage is published (relay)
+  uint64_t* acc_peer = a_peer + SA;                                             // [2]  CTA 0: the peer's accumulator is drained (relay)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_peer + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned rank = wide_cluster_rank();
+  const unsigned ntiles = (M + BM - 1) / BM, npairs = (ntiles + 1) / 2;
+  const unsigned cid = wide_cluster_id(), ncl = wide_nclusters();
+  const unsigned my_pairs = cid < npairs ? (npairs - cid + ncl - 1) / ncl : 0;
+  const unsigned total = my_pairs * NCHUNK;                                     // flattened (pair, chunk) sequence
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * NN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full + i, PAIR_PRODUCER_WARPS); mbar_init(a_empty + i, 1); mbar_init(a_peer + i, 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(w_full + i, 1); mbar_init(w_peer + i, 1); mbar_init(w_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); mbar_init(acc_peer + i, 1); }
+    mbar_fence_init();
+  }
+  for (int idx = tid; idx < NN; idx += blockDim.x) {
+    att[idx] = __ldg(att_src + idx);
+    att[NN + idx] = __ldg(att_dst + idx);
+  }
+  tc_fence_before();
+  __syncthreads();
+  wide_cluster_sync();                                                          // both CTAs' barriers exist before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp < PAIR_PRODUCER_WARPS) {
+    // ------------------------------------------------------------------ A producers (as in the single-CTA form, eight warps)
+    constexpr int PT = PAIR_PRODUCER_WARPS * 32, PI = 1024 / PT;          // producer threads, float4 per thread and chunk
+    float4 r0[PI], r1[PI];
+    auto request = [&](unsigned q, float4 (&r)[PI]) {
+      const unsigned tile = 2 * (cid + (q / NCHUNK) * ncl) + rank, ch = q % NCHUNK;
+      if (L2PF && ch == 0 && tid == 0) prefetch_a_tile(A, tile + 2 * ncl, M, KK);
+#pragma unroll
+      for (int it = 0; it < PI; ++it) {
+        const int idx = it * PT + tid;
+        const unsigned grow = tile * BM + (unsigned)(idx >> 3);
+        r[it] = grow < M ? ldg4_stream(A + (size_t)grow * KK + ch * KC + 4 * (idx & 7)) : f4zero();
+      }
+    };
+#ifdef GATRES_TC_PROF
+    long long qt[3] = {0, 0, 0}, ql = clock64();
+#define QQ(i) do { const long long now_ = clock64(); qt[i] += now_ - ql; ql = now_; } while (0)
+#else
+#define QQ(i)
+#endif
+    auto publish = [&](unsigned q, const float4 (&r)[PI]) {
+      const unsigned s = q % SA, n = q / SA;
+      QQ(2);
+      if (n > 0) mbar_wait(a_empty + s, (n - 1) & 1u);
+      QQ(0);
+      unsigned char* hi = sm + S::OFF_A + s * 2 * A_CH;
+#pragma unroll
+      for (int it = 0; it < PI; ++it) {
+        const int idx = it * PT + tid;
+        const uint32_t off = swz_off((uint32_t)(idx >> 3), 4u * (uint32_t)(idx & 7), BM);
+        const float4 x = r[it];
+        float4 lo;
+        lo.x = lo_tf32(x.x); lo.y = lo_tf32(x.y); lo.z = lo_tf32(x.z); lo.w = lo_tf32(x.w);
+        *reinterpret_cast<float4*>(hi + off) = x;
+        *reinterpret_cast<float4*>(hi + A_CH + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + s);                                   // one (local) arrival per producer warp
+      QQ(1);
+    };
+    if (total > 0) request(0, r0);
+    if (total > 1) request(1, r1);
+    for (unsigned q = 0; q < total; q += 2) {
+      publish(q, r0);
+      if (q + 2 < total) request(q + 2, r0);
+      if (q + 1 < total) {
+        publish(q + 1, r1);
+        if (q + 3 < total) request(q + 3, r1);
+      }
+    }
+#ifdef GATRES_TC_PROF
+    if (cid == 0 && tid == 0)
+      printf("tc_pair<%d,%d> rank %u producer: wait_empty %lld publish %lld request %lld (cycles per chunk)\n", KK, NN, rank,
+             qt[0] / total, qt[1] / total, qt[2] / total);
+#endif
+  } else if (warp < PAIR_PRODUCER_WARPS + 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;
+    unsigned char* stg0 = sm + S::OFF_EPI + quarter * S::EPI_WARP;
+    for (unsigned t = 0; t < my_pairs; ++t) {
+      const unsigned tile = 2 * (cid + t * ncl) + rank, acc = t & 1u;
+      const unsigned row0 = tile * BM + quarter * 32;
+      mbar_wait(acc_full + acc, (t >> 1) & 1u);
+      tc_fence_after();
+      float ps[H], pd[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) ps[h] = pd[h] = 0.f;
+#pragma unroll
+      for (int cb = 0; cb < NN / 32; ++cb) {
+        const int col0 = cb * 32, h = (H == 2 && cb >= NN / 64) ? 1 : 0;
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + acc * NN + col0, v);
+        if (cb == NN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + acc);                          // one (local) arrival per epilogue warp
+        }
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          a = fmaf(v[k], att[col0 + k], a);
+          b = fmaf(v[k], att[NN + col0 + k], b);
+        }
+        if (H == 2) {
+          if (h == 0) { ps[0] += a; pd[0] += b; } else { ps[H - 1] += a; pd[H - 1] += b; }
+        } else {
+          ps[0] += a; pd[0] += b;
+        }
+        unsigned char* stg = stg0 + (cb & 1) * 4096;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < M) tma_store_2d(&out_map, smem_u32(stg), col0, (int)row0);
+      }
+      if (row0 + lane < M) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          s0[(size_t)(row0 + lane) * H + h] = ps[h];
+          s1[(size_t)(row0 + lane) * H + h] = pd[h];
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  } else if (warp == PAIR_PRODUCER_WARPS + 4) {
+    if (rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (CTA 0 of the pair)
+#ifdef GATRES_TC_PROF
+      long long pt[5] = {0, 0, 0, 0, 0}, pl = clock64();
+#define PP(i) do { const long long now_ = clock64(); pt[i] += now_ - pl; pl = now_; } while (0)
+#else
+#define PP(i)
+#endif
+      for (unsigned q = 0; q < total; ++q) {
+        const unsigned t = q / NCHUNK, ch = q % NCHUNK, acc = t & 1u;
+        const unsigned sa = q % SA, sb = q % SB;
+        if (ch == 0 && t >= 2) {
+          mbar_wait(acc_empty + acc, ((t >> 1) - 1) & 1u);
+          mbar_wait_cluster(acc_peer + acc, ((t >> 1) - 1) & 1u);
+        }
+        PP(0);
+        mbar_wait(w_full + sb, (q / SB) & 1u);
+        PP(1);
+        mbar_wait_cluster(w_peer + sb, (q / SB) & 1u);
+        PP(2);
+        mbar_wait(a_full + sa, (q / SA) & 1u);
+        mbar_wait_cluster(a_peer + sa, (q / SA) & 1u);
+        PP(3);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = base + S::OFF_A + sa * 2 * A_CH, a_lo = a_hi + A_CH;
+          const uint32_t b_hi = base + S::OFF_B + sb * 2 * B_CH, b_lo = b_hi + B_CH;
+          const uint32_t d = tmem + acc * NN;
+#pragma unroll
+          for (int ks = 0; ks < KC / 8; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 32u;
+            umma_tf32_2cta(d, umma_desc_k128(a_hi + ko), umma_desc_k128(b_hi + ko), IDESC, (ch > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32_2cta(d, umma_desc_k128(a_lo + ko), umma_desc_k128(b_hi + ko), IDESC, 1);
+            umma_tf32_2cta(d, umma_desc_k128(a_hi + ko), umma_desc_k128(b_lo + ko), IDESC, 1);
+          }
+          umma_commit_2cta(a_empty + sa);
+          umma_commit_2cta(w_empty + sb);
+          if (ch == NCHUNK - 1) umma_commit_2cta(acc_full + acc);
+        }
+        __syncwarp();
+        PP(4);
+      }
+#ifdef GATRES_TC_PROF
+      if (cid == 0 && lane == 0)
+        printf("tc_pair<%d,%d> chunks %u: acc_empty %lld w_full %lld w_peer %lld a_full %lld issue %lld (cycles per chunk)\n", KK, NN,
+               total, pt[0] / total, pt[1] / total, pt[2] / total, pt[3] / total, pt[4] / total);
+#endif
+    } else if (lane == 0) {
+      // ---------------------------------------------------------------- relay (CTA 1): own half of W landed -> tell CTA 0
+      for (unsigned q = 0; q < total; ++q) {
+        const unsigned sb = q % SB;
+        mbar_wait(w_full + sb, (q / SB) & 1u);
+        mbar_arrive_cluster(w_peer + sb, 0);
+      }
+    }
+  } else if (warp == PAIR_PRODUCER_WARPS + 6) {
+    // ------------------------------------------------------------------ relay (CTA 1): published A stages and drained
+    // accumulators are forwarded to CTA 0 by a lane that has no memory operations of its own in flight: the cluster-scope
+    // release of a remote arrival waits for the issuing thread's outstanding loads, which stalled the producers on their
+    // own prefetches when they arrived remotely themselves (2.0 k of 2.8 k cycles per chunk)
+    if (rank == 1 && lane == 0) {
+      for (unsigned q = 0; q < total; ++q) {
+        const unsigned t = q / NCHUNK, ch = q % NCHUNK, acc = t & 1u, sa = q % SA;
+        if (ch == 0 && t >= 2) {
+          mbar_wait(acc_empty + acc, ((t >> 1) - 1) & 1u);
+          mbar_arrive_cluster(acc_peer + acc, 0);
+        }
+        mbar_wait(a_full + sa, (q / SA) & 1u);
+        mbar_arrive_cluster(a_peer + sa, 0);
+      }
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ W loader: this CTA's half of every chunk
+    const unsigned char* img = reinterpret_cast<const unsigned char*>(g_pair_image<KK, NN>);
+    for (unsigned q = 0; q < total; ++q) {
+      const unsigned sb = q % SB, n = q / SB, ch = q % NCHUNK;
+      if (n > 0) mbar_wait(w_empty + sb, (n - 1) & 1u);
+      mbar_arrive_expect_tx(w_full + sb, 2 * B_CH);
+      bulk_g2s(sm + S::OFF_B + sb * 2 * B_CH, img + ((size_t)ch * 2 + rank) * 2 * B_CH, 2 * B_CH, w_full + sb);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  wide_cluster_sync();                                                          // the peer's MMAs / remote arrivals are done with this CTA
+  tc_fence_after();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * NN) : "memory");
+}
+
+template <int KK, int NN, int H>
+static int launch_tc_pair(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
+                          float* s1, unsigned M, cudaStream_t st) {
+  using S = PairShape<KK, NN>;
+  CUtensorMap map;
+  if (!make_map_2d(&map, Cout, M, NN, 32, 32, true)) return 0;                  // no driver entry point: single-CTA form
+  auto kern = gemm_tc_pair_kernel<KK, NN, H>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL) != cudaSuccess)
+      return check_launch("gemm_tc_pair: smem attribute");
+    configured = true;
+  }
+  const unsigned npairs = ((M + 127) / 128 + 1) / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(PAIR_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static int resident_pairs = -1;                 // CTA pairs the device runs at once (the work split is static)
+  if (resident_pairs < 0) {
+    cfg.gridDim = dim3((unsigned)sm_count());
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = sm_count() / 2;
+    }
+    resident_pairs = n;
+  }
+  unsigned ncl = (unsigned)resident_pairs;
+  if (ncl > npairs) ncl = npairs;
+  cfg.gridDim = dim3(2 * ncl);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  launch_kernel(pair_w_image_kernel<KK, NN>, dim3(NN * (KK / 4) / 256), dim3(256), (size_t)0, st, W);
+  count_launch();
+  cudaLaunchKernelEx(&cfg, kern, A, e0, e1, s0, s1, M, map);
+  const int rc = check_launch("gemm_tc_pair");
+  return rc == GATRES_OK ? 1 : rc;
+}
+
 template <int KK, int NN, int H>
 static int launch_tc_wide2(const float* A, const float* W, const float* e0, const float* e1, float* Cout, float* s0,
                            float* s1, unsigned M, cudaStream_t st) {
@@ -315,7 +733,19 @@ int gemm_tc_wide2_dispatch(int H, int KK, int NN, const float* A, const float* W
     enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
   if (!enabled) return 0;
+  static int pair = -1;
+  if (pair < 0) {
+    const char* e = getenv("GATRES_TC_PAIR");             // opt-in: measured equal to the single-CTA form (see the header)
+    pair = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
   int rc;
+  if (pair) {
+    rc = 0;
+    if (KK == 128 && NN == 256 && H == 2) rc = launch_tc_pair<128, 256, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
+    else if (KK == 256 && NN == 128 && H == 1) rc = launch_tc_pair<256, 128, 1>(A, W, e0, e1, Cout, s0, s1, M, st);
+    else if (KK == 64 && NN == 128 && H == 2) rc = launch_tc_pair<64, 128, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
+    if (rc != 0) return rc;
+  }
   if (KK == 128 && NN == 256 && H == 2) rc = launch_tc_wide2<128, 256, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
   else if (KK == 256 && NN == 128 && H == 1) rc = launch_tc_wide2<256, 128, 1>(A, W, e0, e1, Cout, s0, s1, M, st);
   else if (KK == 64 && NN == 128 && H == 2) rc = launch_tc_wide2<64, 128, 2>(A, W, e0, e1, Cout, s0, s1, M, st);

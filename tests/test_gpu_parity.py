@@ -201,7 +201,9 @@ def test_tensor_core_projection_many_tiles(H, C, fin, dev):
         assert_close(ss.view(M, H), s64.float(), 1e-5, f"{name} s_src")
         assert_close(sd.view(M, H), d64.float(), 1e-5, f"{name} s_dst")
 
-@pytest.mark.parametrize("H,C,fin,concat", [(2, 32, 32, True), (1, 32, 64, False), (1, 64, 128, False)])
+@pytest.mark.parametrize("H,C,fin,concat", [(2, 32, 32, True), (1, 32, 64, False), (1, 64, 128, False),
+                                            # rows wider than a slab: channel-sliced work units (2-D TMA tensor loads)
+                                            (2, 64, 64, True), (2, 128, 128, True), (1, 128, 256, False)])
 def test_tile_kernels_many_snapshots_per_cta(H, C, fin, concat, dev):
     """333 snapshots = more than two per persistent CTA (148 SMs): the software pipelines of the snapshot-tile kernels
     (double-buffered stages, the two-stage backward that loads one half of a snapshot under the other pass, the
@@ -242,6 +244,22 @@ def test_tile_kernels_many_snapshots_per_cta(H, C, fin, concat, dev):
     ref = O.gat_conv(x[:k], O.collate_edge_index(ei, n, 2), W, a_s, a_d, bias, H, concat).relu()
     assert_close(res["tile"][0][:k], ref, FWD_TOL, "tile forward vs oracle")
 
+
+
+def test_cta_pair_projection_in_a_subprocess(dev):
+    """The cta_group::2 form of the wide projections is opt-in (GATRES_TC_PAIR=1, read once per process): run the probe
+    of tools/wide_probe.py under that switch and hold its fp64 comparison to the tolerance of the in-process test."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GATRES_TC_PAIR="1")
+    rows = 128 * 148 * 2 + 128 * 5 + 77                      # odd number of tiles: the last pair is half empty and ragged
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "wide_probe.py"), "--rows", str(rows), "--iters", "2"],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    recs = [json.loads(line) for line in out.stdout.splitlines() if line.startswith("{")]
+    assert len(recs) == 3
+    for r in recs:
+        assert r["err_h"] < 5e-6 and r["err_s_src"] < 1e-5 and r["err_s_dst"] < 1e-5, r
 
 
 @pytest.mark.parametrize("graph,B", [("tiny", 4), ("ctown", 2), ("directed", 3)])

@@ -29,7 +29,7 @@ def main():
         peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    out = {"rows": args.rows, "wide2": os.environ.get("GATRES_TC_WIDE2", "1"), "kernels": []}
+    out = {"rows": args.rows, "wide2": os.environ.get("GATRES_TC_WIDE2", "1"), "pair": os.environ.get("GATRES_TC_PAIR", "0"), "kernels": []}
     lib.gatres_set_tensor_core(2)
     for H, C, fin in [(2, 128, 128), (1, 128, 256), (2, 64, 64)]:
         M = args.rows
