@@ -21,11 +21,18 @@
 //                            chunk (4 K-steps x {hi hi, lo hi, hi lo}) and commits them to the "stage free" barriers; the
 //                            last chunk of a tile also commits to "accumulator full".
 //   warps 4-7  epilogue    : TWO accumulators in TMEM (2 x N columns: all 512 for N = 256), so the drain of tile t
-//                            (tcgen05.ld, thread = row: the attention scores are in-thread dot products, rows leave
-//                            through a 4 KB per-warp transposing buffer as full 128-byte lines) runs under the MMAs of
-//                            tile t + 1.
+//                            (tcgen05.ld, thread = row: the attention scores are in-thread dot products) runs under the
+//                            MMAs of tile t + 1; rows leave as 32 x 32 boxes through TMA tensor stores
+//                            (cp.async.bulk.tensor.2d from a SWIZZLE_128B staging buffer, two buffers per warp) — the
+//                            register-store epilogue (read the buffer back, st.global) stays as the fallback when the
+//                            driver entry point for cuTensorMapEncodeTiled is missing.
 //
-// One CTA per SM (224 KB of shared memory), persistent over 128-row tiles.
+// One CTA per SM (226 KB of shared memory), persistent over 128-row tiles; the next tile's A block (contiguous) is
+// prefetched into L2 with one cp.async.bulk.prefetch.  Measured (B200, 794 624 rows, profiles/r2_wide_and_sliced.md):
+// K = 128 -> N = 256: 473 -> 280 us (40 -> 67 % of the copy bandwidth, tensor pipe 27 -> 70 %), K = 256 -> N = 128: 480 -> 316 us,
+// K = 64 -> N = 128: 177 -> 111 us (86 %).  Bound by the traffic of the shared-memory data array (SS-mode operand reads + W
+// bulk copies + staging) and, in sustained runs, by the board power cap.  A CTA-pair form (cta_group::2, half the W bytes
+// and 8 instead of 12 KB of operand reads per CTA and instruction) is kept opt-in below: parity-green, same speed.
 #include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
