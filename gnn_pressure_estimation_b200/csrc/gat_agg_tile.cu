@@ -67,14 +67,16 @@ __device__ __forceinline__ void degree_order(const int* rp, unsigned N, unsigned
 struct FwdTilePlan {
   uint32_t h_bytes, ss_bytes, tx_bytes, stage_bytes, zs_off, xs_off, rp_off, col_off, ord_off, hist_off, bar_off, total;
   // fuse_mean: two more slabs, the layer output z of the snapshot (never written to HBM) and the block input x0
-  __host__ __device__ FwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1, bool fuse_mean = false) {
+  // lean (fused mean in 64-channel slices): ONE stage and no x0 slab — the next unit's slab is requested when the aggregation
+  // phase is done with the stage and lands under the mean phase, x0 rows are read from global memory
+  __host__ __device__ FwdTilePlan(unsigned N, unsigned F, unsigned H, unsigned E1, bool fuse_mean = false, bool lean = false) {
     h_bytes = N * F * 4u;
     ss_bytes = N * H * 4u;
     tx_bytes = h_bytes + 2u * ss_bytes;                       // slab + source scores + target scores (what the TMA delivers)
     stage_bytes = (tx_bytes + 127u) & ~127u;                  // stride between the two stages
-    zs_off = 2u * stage_bytes;
+    zs_off = (lean ? 1u : 2u) * stage_bytes;
     xs_off = zs_off + (fuse_mean ? h_bytes : 0u);
-    rp_off = xs_off + (fuse_mean ? h_bytes : 0u);
+    rp_off = xs_off + ((fuse_mean && !lean) ? h_bytes : 0u);
     col_off = rp_off + (((N + 1u) * 4u + 15u) & ~15u);
     ord_off = col_off + ((E1 * 4u + 15u) & ~15u);                  // degree order of the rows (uint16) + its histogram
     hist_off = ord_off + ((N * 2u + 15u) & ~15u);
@@ -101,21 +103,20 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
                         const float* __restrict__ s_dst, const float* __restrict__ bias,
                         float* __restrict__ out, float* __restrict__ m_out, float* __restrict__ l_out,
                         const float* __restrict__ x0, float* __restrict__ xout,
-                        unsigned B, unsigned N, int relu, unsigned Hs, unsigned sph, unsigned box_rows,
+                        unsigned B, unsigned N, int relu, unsigned Hs, unsigned sph, unsigned box_rows, int lean,
                         const __grid_constant__ CUtensorMap hmap, const __grid_constant__ CUtensorMap xmap) {
   using RM = RowMap<H, C, true>;
   constexpr int F = RM::F, V = RM::V, LPR = RM::LPR, RPW = RM::RPW, LPH = RM::LPH;
   constexpr int kTileThreads = THREADS, kTileWarps = THREADS / 32;
-  static_assert(!FUSE_MEAN || (H == 1 && V == 1), "the fused mean follows the one-head layer");
+  static_assert(!FUSE_MEAN || SLICED || (H == 1 && V == 1), "the fused mean follows the one-head layer");
   // SLICED: every chunk of a lane belongs to the slice's head (H = 2 only selects the packed lane map: 8 lanes x 2 chunks
   // per row, 4 rows per warp, as in the two-head nc = 32 kernel whose slab has the same shape)
-  static_assert(!SLICED || !FUSE_MEAN || H == 1, "the fused mean follows the one-head layer");
   extern __shared__ __align__(128) unsigned char smem[];
   const unsigned HS = SLICED ? Hs : (unsigned)H;            // heads of the score tensors
   const unsigned nsl = SLICED ? Hs * sph : 1u;              // slices per row
   const unsigned ld = nsl * F;                              // row stride of h / out / x0 / xout
   const unsigned U = B * nsl;                               // work units
-  const FwdTilePlan plan(N, F, HS, E1, FUSE_MEAN);
+  const FwdTilePlan plan(N, F, HS, E1, FUSE_MEAN, FUSE_MEAN && lean);
   int* rp_s = reinterpret_cast<int*>(smem + plan.rp_off);
   int* col_s = reinterpret_cast<int*>(smem + plan.col_off);
   unsigned short* ord = reinterpret_cast<unsigned short*>(smem + plan.ord_off);
@@ -154,7 +155,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
   pdl_wait();                                     // CSR staging above overlapped the previous kernel's tail
   if (tid == 0) {
     if (blockIdx.x < U) issue(0, blockIdx.x);
-    if (blockIdx.x + gridDim.x < U) issue(1, blockIdx.x + gridDim.x);
+    if (!lean && blockIdx.x + gridDim.x < U) issue(1, blockIdx.x + gridDim.x);
   }
 
   float4 bv[V];
@@ -169,7 +170,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     const unsigned b = SLICED ? u / nsl : u, q = SLICED ? u % nsl : 0u;
     const unsigned hq = SLICED ? q / sph : 0u;     // head of this slice
     const bool write_ml = !SLICED || q % sph == 0;
-    const int stage = k & 1;
+    const int stage = lean ? 0 : (int)(k & 1);
     const float* hs = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes) + 4 * lig;
     const float* sss = reinterpret_cast<const float*>(smem + (size_t)stage * plan.stage_bytes + plan.h_bytes);
     const float* sds = sss + N * HS;
@@ -177,7 +178,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
 #pragma unroll
       for (int v = 0; v < V; ++v) bv[v] = ldg4(bias + q * F + 4 * RM::chunk(lig, v));
     }
-    if (FUSE_MEAN && tid == 0) {                   // the previous snapshot's mean phase is done with the x0 slab
+    if (FUSE_MEAN && !lean && tid == 0) {          // the previous snapshot's mean phase is done with the x0 slab
       fence_proxy_async();
       mbar_arrive_expect_tx(&full[2], plan.h_bytes);
       if (SLICED) {
@@ -187,7 +188,7 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
         bulk_g2s(smem + plan.xs_off, x0 + (size_t)b * N * F, plan.h_bytes, &full[2]);
       }
     }
-    mbar_wait(&full[stage], (k >> 1) & 1);
+    mbar_wait(&full[stage], lean ? (k & 1) : ((k >> 1) & 1));
 
     for (unsigned i0 = warp * RPW; i0 < N; i0 += kTileWarps * RPW) {
       // rows past the end are clamped (recompute the last row, store nothing): every lane of the warp
@@ -262,29 +263,41 @@ gat_agg_fwd_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
     }
     __syncthreads();                               // every warp is done with this stage (and z is complete)
     if (tid == 0) {
-      const unsigned nu = u + 2u * gridDim.x;
+      const unsigned nu = u + (lean ? 1u : 2u) * gridDim.x;
       if (nu < U) {
         fence_proxy_async();
         issue(stage, nu);
       }
     }
     if (FUSE_MEAN) {
-      mbar_wait(&full[2], k & 1);
+      if (!lean) mbar_wait(&full[2], k & 1);
       for (unsigned io = warp * RPW + sub; io < N; io += kTileWarps * RPW) {
         const unsigned i = ord[io];
         const int beg = rp_s[i], end = rp_s[i + 1] - 1;                    // drop the self-loop
-        float4 acc = f4zero();
+        float4 xg[V], acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc[v] = f4zero();
+          xg[v] = lean ? ldg4_stream(x0 + ((size_t)b * N + i) * ld + q * F + 4 * RM::chunk(lig, v))   // flies under the neighbour sum
+                       : *reinterpret_cast<const float4*>(XS + i * F + 4 * RM::chunk(lig, v));
+        }
 #pragma unroll 4
-        for (int e = beg; e < end; ++e) add4(acc, *reinterpret_cast<const float4*>(ZS + col_s[e] * F + 4 * lig));
+        for (int e = beg; e < end; ++e) {
+          const int j = col_s[e];
+#pragma unroll
+          for (int v = 0; v < V; ++v) add4(acc[v], *reinterpret_cast<const float4*>(ZS + j * F + 4 * RM::chunk(lig, v)));
+        }
         const int deg = end - beg;
         const float inv = 1.f / (float)(deg > 1 ? deg : 1);
-        const float4 xr = *reinterpret_cast<const float4*>(XS + i * F + 4 * lig);
-        float4 o;
-        o.x = fmaxf(fmaf(acc.x, inv, xr.x), 0.f);
-        o.y = fmaxf(fmaf(acc.y, inv, xr.y), 0.f);
-        o.z = fmaxf(fmaf(acc.z, inv, xr.z), 0.f);
-        o.w = fmaxf(fmaf(acc.w, inv, xr.w), 0.f);
-        st4(xout + ((size_t)b * N + i) * ld + q * F + 4 * lig, o);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float4 o;
+          o.x = fmaxf(fmaf(acc[v].x, inv, xg[v].x), 0.f);
+          o.y = fmaxf(fmaf(acc[v].y, inv, xg[v].y), 0.f);
+          o.z = fmaxf(fmaf(acc[v].z, inv, xg[v].z), 0.f);
+          o.w = fmaxf(fmaf(acc[v].w, inv, xg[v].w), 0.f);
+          st4(xout + ((size_t)b * N + i) * ld + q * F + 4 * RM::chunk(lig, v), o);
+        }
       }
       __syncthreads();                             // z and x0 slabs are free for the next snapshot
     }
@@ -312,7 +325,7 @@ static int launch_fwd_tile(const int* rowptr, const int* col, unsigned E1, const
       configured = plan.total;                                                                                    \
     }                                                                                                             \
     launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, x0, xout, B, N, relu, \
-                  (unsigned)H, 1u, 0u, none, none);                                                               \
+                  (unsigned)H, 1u, 0u, 0, none, none);                                                            \
   } while (0)
   if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);
 #undef LAUNCH
@@ -343,11 +356,11 @@ static unsigned slice_width(unsigned N, unsigned H, unsigned C, unsigned E1, boo
   return plan.total <= 227u * 1024u ? CS : 0u;
 }
 
-template <int CS, bool FUSE>
+template <int CS, bool FUSE, bool LEAN = false>
 static int launch_fwd_tile_sliced(const int* rowptr, const int* col, unsigned E1, const float* h, const float* s_src,
                                   const float* s_dst, const float* bias, float* out, float* m, float* l, const float* x0,
                                   float* xout, unsigned B, unsigned N, unsigned H, unsigned C, int relu, cudaStream_t st) {
-  const FwdTilePlan plan(N, CS, H, E1, FUSE);
+  const FwdTilePlan plan(N, CS, H, E1, FUSE, LEAN);
   const unsigned sph = C / CS, nsl = H * sph, box_rows = slice_box_rows(N);
   CUtensorMap hmap, xmap;
   memset(&xmap, 0, sizeof(xmap));
@@ -362,7 +375,7 @@ static int launch_fwd_tile_sliced(const int* rowptr, const int* col, unsigned E1
   if (grid > B * nsl) grid = B * nsl;
 #define LAUNCH(THR)                                                                                               \
   do {                                                                                                            \
-    auto kern = gat_agg_fwd_tile_kernel<(FUSE ? 1 : 2), (FUSE ? CS : CS / 2), THR, FUSE, true>;                                                  \
+    auto kern = gat_agg_fwd_tile_kernel<(CS == 64 ? 2 : 1), (CS == 64 ? 32 : CS), THR, FUSE, true>;                                                  \
     static uint32_t configured = 0;                                                                               \
     if (configured < plan.total) {                                                                                \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) \
@@ -370,7 +383,7 @@ static int launch_fwd_tile_sliced(const int* rowptr, const int* col, unsigned E1
       configured = plan.total;                                                                                    \
     }                                                                                                             \
     launch_kernel(kern, dim3(grid), dim3(THR), plan.total, st, rowptr, col, E1, h, s_src, s_dst, bias, out, m, l, x0, xout, B, N, relu, \
-                  H, sph, box_rows, hmap, xmap);                                                                  \
+                  H, sph, box_rows, (int)LEAN, hmap, xmap);                                                       \
   } while (0)
   if (per_sm >= 2) LAUNCH(512); else LAUNCH(1024);
 #undef LAUNCH
@@ -396,6 +409,14 @@ int gat_agg_mean_res_fwd_tile(const int* rowptr, const int* col, unsigned E1, co
     if (C == 32) return launch_fwd_tile<1, 32, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 0, st);
     if (C == 64) return launch_fwd_tile<1, 64, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 0, st);
   }
+  static int lean = -1;
+  if (lean < 0) {
+    const char* e = getenv("GATRES_TILE_LEAN");
+    lean = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  if (lean && slice_width(N, 1, (unsigned)C, E1, true) != 0 && C % 64 == 0 && C > 64 &&
+      FwdTilePlan(N, 64, 1, E1, true, true).total <= 227u * 1024u)
+    return launch_fwd_tile_sliced<64, true, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 1u, (unsigned)C, 0, st);
   if (slice_width(N, 1, (unsigned)C, E1, true) == 32)
     return launch_fwd_tile_sliced<32, true>(rowptr, col, E1, h, s_src, s_dst, bias, nullptr, m, l, x0, xout, B, N, 1u, (unsigned)C, 0, st);
   set_error("gat_agg_mean_res_fwd_tile: unsupported channels %d", C);
