@@ -749,6 +749,10 @@ int gemm_tc_wide2_dispatch(int H, int KK, int NN, const float* A, const float* W
 int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const float* W, const float* e0,
                      const float* e1, float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st) {
   int rc = 1;
+  if (mode == 0) {                              // warp-specialised form (linear_tc_wide.cu): wide shapes and, by default, nc = 32
+    rc = gemm_tc_wide2_dispatch(H, KK, NN, A, W, e0, e1, Cout, s0, s1, M, st);
+    if (rc != 0) return rc;
+  }
 #define TC(KKv, NNv, MODEv, Hv)                                                                           \
   if (mode == MODEv && KK == KKv && NN == NNv && (MODEv == 1 || H == Hv)) {                               \
     rc = launch_tc<KKv, NNv, MODEv, Hv>(A, W, e0, e1, Cout, s0, s1, M, st, "gemm_tc");                    \
@@ -759,10 +763,6 @@ int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const floa
   TC(32, 64, 1, 1)      // conv2 data gradient (dh2 [M,32] -> dy1 [M,64])
   TC(64, 32, 1, 1)      // conv1 data gradient (dh1 [M,64] -> dx0 [M,32])
 #undef TC
-  if (mode == 0) {
-    rc = gemm_tc_wide2_dispatch(H, KK, NN, A, W, e0, e1, Cout, s0, s1, M, st);
-    if (rc != 0) return rc;
-  }
 #define TCW(KKv, NNv, Hv)                                                                                  \
   if (mode == 0 && KK == KKv && NN == NNv && H == Hv) {                                                    \
     rc = launch_tc_wide<KKv, NNv, Hv>(A, W, e0, e1, Cout, s0, s1, M, st);                                   \

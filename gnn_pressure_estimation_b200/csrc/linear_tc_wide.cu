@@ -80,14 +80,20 @@ struct WideShape {
   static constexpr int BM = 128, KC = 32, NCHUNK = KK / KC;
   static constexpr uint32_t A_CH = BM * KC * 4;                 // one A part (hi or lo) of a chunk
   static constexpr uint32_t B_CH = NN * KC * 4;                 // one W part of a chunk
-  static constexpr int SA = 2;                                  // A stages (hi + lo each)
-  static constexpr int SB = NN == 256 ? 2 : 4;                  // W stages (hi + lo each): 128 KB either way
+  // RESIDENT (nc = 32 shapes: hi + lo of the whole W <= 32 KB): every chunk of W is loaded once per CTA and stays; the
+  // shared memory that the W ring would take goes to A stages, and eight producer warps keep up with tiles whose MMAs
+  // take ~400 cycles
+  static constexpr bool RESIDENT = 2 * KK * NN * 4 <= 32768;
+  static constexpr int PW = RESIDENT ? 8 : 4;                   // producer warps; + 4 epilogue warps + MMA issuer + W loader
+  static constexpr int THREADS = (PW + 6) * 32;
+  static constexpr int SA = RESIDENT ? 5 : 2;                   // A stages (hi + lo each)
+  static constexpr int SB = RESIDENT ? NCHUNK : (NN == 256 ? 2 : 4);   // W stages (hi + lo each): 128 KB in the streamed form
   static constexpr uint32_t EPI_WARP = 2 * 4096;               // two [32 rows x 128 B] transposing buffers per epilogue warp
   static constexpr uint32_t OFF_A = 0, OFF_B = OFF_A + SA * 2 * A_CH, OFF_EPI = OFF_B + SB * 2 * B_CH,
                             OFF_ATT = OFF_EPI + 4 * EPI_WARP, OFF_BAR = OFF_ATT + 2 * NN * 4;
   static constexpr int NBAR = 2 * SA + 2 * SB + 4;
   static constexpr uint32_t TOTAL = OFF_BAR + NBAR * 8 + 16;
-  static_assert(KK % KC == 0 && (NN == 128 || NN == 256), "unsupported wide tensor-core shape");
+  static_assert(KK % KC == 0 && (NN == 32 || NN == 64 || NN == 128 || NN == 256), "unsupported tensor-core shape");
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
@@ -115,12 +121,14 @@ __global__ void __launch_bounds__(256) wide_w_image_kernel(const float* __restri
 // TS = rows leave through TMA tensor stores (out_map describes Cout as [M][NN] with 32 x 32 boxes, SWIZZLE_128B);
 // otherwise the epilogue warps read their transposing buffer back and store 128-byte lines themselves.
 template <int KK, int NN, int H, bool TS>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__((WideShape<KK, NN>::THREADS), 1)
 gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_src, const float* __restrict__ att_dst,
                      float* __restrict__ Cout, float* __restrict__ s0, float* __restrict__ s1, unsigned M,
                      const __grid_constant__ CUtensorMap out_map) {
   using S = WideShape<KK, NN>;
-  constexpr int BM = S::BM, KC = S::KC, NCHUNK = S::NCHUNK, SA = S::SA, SB = S::SB;
+  constexpr int BM = S::BM, KC = S::KC, NCHUNK = S::NCHUNK, SA = S::SA, SB = S::SB, PW = S::PW;
+  constexpr bool RESIDENT = S::RESIDENT;
+  constexpr int PT = PW * 32, PI = 1024 / PT;                                   // producer threads, float4 per thread and chunk
   constexpr uint32_t A_CH = S::A_CH, B_CH = S::B_CH;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   static_assert(H == 1 || H == 2, "heads");
@@ -129,7 +137,7 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
   if ((base & 1023u) != 0) __trap();
   unsigned char* sm = smem_raw;
   float* att = reinterpret_cast<float*>(sm + S::OFF_ATT);                       // [2][NN]
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);              // [SA] 128 producer arrivals
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);              // [SA] producer-thread arrivals
   uint64_t* a_empty = a_full + SA;                                              // [SA] tcgen05.commit
   uint64_t* w_full = a_empty + SA;                                              // [SB] bulk-copy transaction bytes
   uint64_t* w_empty = w_full + SB;                                              // [SB] tcgen05.commit
@@ -144,7 +152,7 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
 
   if (warp == 0) tmem_alloc(tmem_slot, 2 * NN);
   if (tid == 32) {
-    for (int i = 0; i < SA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full + i, PT); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
     mbar_fence_init();
@@ -159,27 +167,27 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
 
-  if (warp < 4) {
+  if (warp < PW) {
     // ------------------------------------------------------------------ A producers
-    // element idx = it * 128 + tid of a chunk: row idx / 8, 16-byte column idx % 8 (8 lanes cover one 128-byte row segment)
-    float4 r0[8], r1[8];
-    auto request = [&](unsigned q, float4 (&r)[8]) {
+    // element idx = it * PT + tid of a chunk: row idx / 8, 16-byte column idx % 8 (8 lanes cover one 128-byte row segment)
+    float4 r0[PI], r1[PI];
+    auto request = [&](unsigned q, float4 (&r)[PI]) {
       const unsigned tile = blockIdx.x + (q / NCHUNK) * gridDim.x, ch = q % NCHUNK;
       if (L2PF && ch == 0 && tid == 0) prefetch_a_tile(A, tile + gridDim.x, M, KK);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 128 + tid;
+      for (int it = 0; it < PI; ++it) {
+        const int idx = it * PT + tid;
         const unsigned grow = tile * BM + (unsigned)(idx >> 3);
         r[it] = grow < M ? ldg4_stream(A + (size_t)grow * KK + ch * KC + 4 * (idx & 7)) : f4zero();
       }
     };
-    auto publish = [&](unsigned q, const float4 (&r)[8]) {
+    auto publish = [&](unsigned q, const float4 (&r)[PI]) {
       const unsigned s = q % SA, n = q / SA;
       if (n > 0) mbar_wait(a_empty + s, (n - 1) & 1u);                          // MMAs of step q - SA have read the stage
       unsigned char* hi = sm + S::OFF_A + s * 2 * A_CH;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 128 + tid;
+      for (int it = 0; it < PI; ++it) {
+        const int idx = it * PT + tid;
         const uint32_t off = swz_off((uint32_t)(idx >> 3), 4u * (uint32_t)(idx & 7), BM);
         const float4 x = r[it];
         float4 lo;
@@ -200,10 +208,11 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
         if (q + 3 < total) request(q + 3, r1);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < PW + 4) {
     // ------------------------------------------------------------------ epilogue: warp w drains TMEM lanes 32 (w % 4) ..
     const int quarter = warp & 3;
     unsigned char* stg0 = sm + S::OFF_EPI + quarter * S::EPI_WARP;               // 2 x [32 rows][128 B], 16-byte chunks XOR row % 8
+    unsigned nstage = 0;
     for (unsigned t = 0; t < my_tiles; ++t) {
       const unsigned tile = blockIdx.x + t * gridDim.x, acc = t & 1u;
       const unsigned row0 = tile * BM + quarter * 32;
@@ -232,7 +241,7 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
         } else {
           ps[0] += a; pd[0] += b;
         }
-        unsigned char* stg = stg0 + (cb & 1) * 4096;
+        unsigned char* stg = stg0 + (nstage++ & 1u) * 4096;          // alternate per store (N = 32: one store per tile)
         if (TS) {                                                                 // the store issued two column blocks ago has read this buffer
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
@@ -265,13 +274,13 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
       }
     }
     if (TS && lane == 0) tma_store_wait_all();
-  } else if (warp == 8) {
+  } else if (warp == PW + 4) {
     // ------------------------------------------------------------------ MMA issuer
     for (unsigned q = 0; q < total; ++q) {
       const unsigned t = q / NCHUNK, ch = q % NCHUNK, acc = t & 1u;
-      const unsigned sa = q % SA, sb = q % SB;
+      const unsigned sa = q % SA, sb = RESIDENT ? ch : q % SB;
       if (ch == 0 && t >= 2) mbar_wait(acc_empty + acc, ((t >> 1) - 1) & 1u);    // epilogue of tile t - 2 has drained it
-      mbar_wait(w_full + sb, (q / SB) & 1u);
+      mbar_wait(w_full + sb, RESIDENT ? 0u : ((q / SB) & 1u));                   // resident chunks complete once
       mbar_wait(a_full + sa, (q / SA) & 1u);
       tc_fence_after();
       if (elect_one()) {
@@ -286,15 +295,15 @@ gemm_tc_wide2_kernel(const float* __restrict__ A, const float* __restrict__ att_
           umma_tf32(d, umma_desc_k128(a_hi + ko), umma_desc_k128(b_lo + ko), IDESC, 1);
         }
         umma_commit(a_empty + sa);
-        umma_commit(w_empty + sb);
+        if (!RESIDENT) umma_commit(w_empty + sb);
         if (ch == NCHUNK - 1) umma_commit(acc_full + acc);
       }
       __syncwarp();
     }
   } else if (lane == 0) {
-    // ------------------------------------------------------------------ W loader (one lane of warp 9)
+    // ------------------------------------------------------------------ W loader (one lane of the last warp)
     const unsigned char* img = reinterpret_cast<const unsigned char*>(g_wide_image<KK, NN>);
-    for (unsigned q = 0; q < total; ++q) {
+    for (unsigned q = 0; q < (RESIDENT ? (total > 0 ? (unsigned)NCHUNK : 0u) : total); ++q) {
       const unsigned sb = q % SB, n = q / SB, ch = q % NCHUNK;
       if (n > 0) mbar_wait(w_empty + sb, (n - 1) & 1u);
       mbar_arrive_expect_tx(w_full + sb, 2 * B_CH);
@@ -518,6 +527,7 @@ gemm_tc_pair_kernel(const float* __restrict__ A, const float* __restrict__ att_s
     // ------------------------------------------------------------------ epilogue
     const int quarter = warp & 3;
     unsigned char* stg0 = sm + S::OFF_EPI + quarter * S::EPI_WARP;
+    unsigned nstage = 0;
     for (unsigned t = 0; t < my_pairs; ++t) {
       const unsigned tile = 2 * (cid + t * ncl) + rank, acc = t & 1u;
       const unsigned row0 = tile * BM + quarter * 32;
@@ -547,7 +557,7 @@ gemm_tc_pair_kernel(const float* __restrict__ A, const float* __restrict__ att_s
         } else {
           ps[0] += a; pd[0] += b;
         }
-        unsigned char* stg = stg0 + (cb & 1) * 4096;
+        unsigned char* stg = stg0 + (nstage++ & 1u) * 4096;          // alternate per store (N = 32: one store per tile)
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
 #pragma unroll
@@ -726,8 +736,8 @@ static int launch_tc_wide2(const float* A, const float* W, const float* e0, cons
   const unsigned ntiles = (M + 127) / 128;
   unsigned grid = (unsigned)sm_count();
   if (grid > ntiles) grid = ntiles;
-  launch_kernel(wide_w_image_kernel<KK, NN>, dim3(NN * (KK / 4) / 256), dim3(256), (size_t)0, st, W);
-  launch_kernel(kern, dim3(grid), dim3(320), (size_t)S::TOTAL, st, A, e0, e1, Cout, s0, s1, M, map);
+  launch_kernel(wide_w_image_kernel<KK, NN>, dim3((NN * (KK / 4) + 255) / 256), dim3(256), (size_t)0, st, W);
+  launch_kernel(kern, dim3(grid), dim3(S::THREADS), (size_t)S::TOTAL, st, A, e0, e1, Cout, s0, s1, M, map);
   return check_launch("gemm_tc_wide2");
 }
 
@@ -753,7 +763,18 @@ int gemm_tc_wide2_dispatch(int H, int KK, int NN, const float* A, const float* W
     else if (KK == 64 && NN == 128 && H == 2) rc = launch_tc_pair<64, 128, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
     if (rc != 0) return rc;
   }
-  if (KK == 128 && NN == 256 && H == 2) rc = launch_tc_wide2<128, 256, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
+  static int narrow = -1;
+  if (narrow < 0) {
+    const char* e = getenv("GATRES_TC_NARROW2");
+    narrow = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  if (KK == 32 && NN == 64 && H == 2) {
+    if (!narrow) return 0;
+    rc = launch_tc_wide2<32, 64, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
+  } else if (KK == 64 && NN == 32 && H == 1) {
+    if (!narrow) return 0;
+    rc = launch_tc_wide2<64, 32, 1>(A, W, e0, e1, Cout, s0, s1, M, st);
+  } else if (KK == 128 && NN == 256 && H == 2) rc = launch_tc_wide2<128, 256, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
   else if (KK == 256 && NN == 128 && H == 1) rc = launch_tc_wide2<256, 128, 1>(A, W, e0, e1, Cout, s0, s1, M, st);
   else if (KK == 64 && NN == 128 && H == 2) rc = launch_tc_wide2<64, 128, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
   else return 0;

@@ -182,7 +182,7 @@ def test_tensor_core_projection_many_tiles(H, C, fin, dev):
     fp32 FFMA kernel and an fp64 reference, with several 128-row tiles per CTA and a ragged last tile."""
     from gnn_pressure_estimation_b200 import _lib, ops as gops  # noqa: F401
     lib = _lib.load()
-    M = 128 * 148 * 2 + 128 * 37 + 5
+    M = 128 * 148 * 5 + 128 * 37 + 5                         # several tiles per persistent CTA (staging-buffer reuse), ragged end
     x, W, a_s, a_d = _layer_inputs(M, fin, H, C, seed=17)
     res = []
     prev = lib.gatres_set_tensor_core(-1)

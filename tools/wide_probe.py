@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--rows", type=int, default=2048 * 388)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--narrow", action="store_true", help="also time the nc = 32 projections")
     args = ap.parse_args()
     from gnn_pressure_estimation_b200 import _lib, ops  # noqa: F401
     lib = _lib.load()
@@ -31,7 +32,8 @@ def main():
         pass
     out = {"rows": args.rows, "wide2": os.environ.get("GATRES_TC_WIDE2", "1"), "pair": os.environ.get("GATRES_TC_PAIR", "0"), "kernels": []}
     lib.gatres_set_tensor_core(2)
-    for H, C, fin in [(2, 128, 128), (1, 128, 256), (2, 64, 64)]:
+    shapes = [(2, 128, 128), (1, 128, 256), (2, 64, 64)] + ([(2, 32, 32), (1, 32, 64)] if args.narrow else [])
+    for H, C, fin in shapes:
         M = args.rows
         g = torch.Generator().manual_seed(5)
         x = torch.randn(M, fin, generator=g).to(dev)
