@@ -777,6 +777,7 @@ int gemm_tc_wide2_dispatch(int H, int KK, int NN, const float* A, const float* W
   } else if (KK == 128 && NN == 256 && H == 2) rc = launch_tc_wide2<128, 256, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
   else if (KK == 256 && NN == 128 && H == 1) rc = launch_tc_wide2<256, 128, 1>(A, W, e0, e1, Cout, s0, s1, M, st);
   else if (KK == 64 && NN == 128 && H == 2) rc = launch_tc_wide2<64, 128, 2>(A, W, e0, e1, Cout, s0, s1, M, st);
+  else if (KK == 128 && NN == 64 && H == 1) rc = launch_tc_wide2<128, 64, 1>(A, W, e0, e1, Cout, s0, s1, M, st);   // conv2, nc = 64
   else return 0;
   return rc == GATRES_OK ? 1 : rc;
 }

@@ -32,7 +32,7 @@ def main():
         pass
     out = {"rows": args.rows, "wide2": os.environ.get("GATRES_TC_WIDE2", "1"), "pair": os.environ.get("GATRES_TC_PAIR", "0"), "kernels": []}
     lib.gatres_set_tensor_core(2)
-    shapes = [(2, 128, 128), (1, 128, 256), (2, 64, 64)] + ([(2, 32, 32), (1, 32, 64)] if args.narrow else [])
+    shapes = [(2, 128, 128), (1, 128, 256), (2, 64, 64), (1, 64, 128)] + ([(2, 32, 32), (1, 32, 64)] if args.narrow else [])
     for H, C, fin in shapes:
         M = args.rows
         g = torch.Generator().manual_seed(5)
