@@ -246,18 +246,21 @@ def test_tile_kernels_many_snapshots_per_cta(H, C, fin, concat, dev):
 
 
 
-def test_cta_pair_projection_in_a_subprocess(dev):
-    """The cta_group::2 form of the wide projections is opt-in (GATRES_TC_PAIR=1, read once per process): run the probe
-    of tools/wide_probe.py under that switch and hold its fp64 comparison to the tolerance of the in-process test."""
+@pytest.mark.parametrize("switch", ["GATRES_TC_PAIR=1", "GATRES_TC_WIDE2_TMA_STORE=0", "GATRES_TC_WIDE2=0"])
+def test_projection_kernel_variants_in_a_subprocess(switch, dev):
+    """Kernel-selection switches of the projections are read once per process: the cta_group::2 form (opt-in), the
+    register-store epilogue (the fallback when no tensor map can be encoded) and the first-generation kernels run the probe
+    of tools/wide_probe.py in a subprocess; its fp64 comparison is held to the tolerance of the in-process test."""
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, GATRES_TC_PAIR="1")
-    rows = 128 * 148 * 2 + 128 * 5 + 77                      # odd number of tiles: the last pair is half empty and ragged
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "wide_probe.py"), "--rows", str(rows), "--iters", "2"],
-                         env=env, capture_output=True, text=True, timeout=300)
+    key, val = switch.split("=")
+    env = dict(os.environ, **{key: val})
+    rows = 128 * 148 * 4 + 128 * 5 + 77                      # odd number of tiles: the last pair is half empty and ragged
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "wide_probe.py"), "--rows", str(rows), "--iters", "2",
+                          "--narrow"], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     recs = [json.loads(line) for line in out.stdout.splitlines() if line.startswith("{")]
-    assert len(recs) == 4
+    assert len(recs) == 6
     for r in recs:
         assert r["err_h"] < 5e-6 and r["err_s_src"] < 1e-5 and r["err_s_dst"] < 1e-5, r
 
