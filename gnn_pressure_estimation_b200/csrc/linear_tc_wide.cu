@@ -99,6 +99,9 @@ struct WideShape {
 
 // Weight image of one projection: image[ch][part][swz(n, k % 32)] with part 0 = W (its TF32 truncation is the hi part)
 // and part 1 = rna(w - trunc w); every (chunk, part) block is a ready-to-read K-major SWIZZLE_128B B tile.
+// One image per shape and process, rewritten before every launch in stream order (the writer waits for the kernels
+// ahead of it in the stream): projections of ONE shape must not run concurrently on two streams of one process — the
+// library's callers (model stack, TrainStep, evaluation) enqueue them on a single stream.
 template <int KK, int NN>
 __device__ __align__(1024) float g_wide_image[2 * KK * NN];
 
