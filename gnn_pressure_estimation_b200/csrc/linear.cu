@@ -631,6 +631,7 @@ int linear_bwd_fused_dispatch(int NO, int KI, const float* dh, const float* x, c
                               const float* relu_ref, float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st);
 int gemm_tc_dispatch(int mode, int H, int KK, int NN, const float* A, const float* W, const float* e0,
                      const float* e1, float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st);
+int wgrad_tc_dispatch(int NO, int KI, const float* dh, const float* x, float* grads, long long off_W, unsigned M, cudaStream_t st);
 
 // 0 = never, 1 = auto (launches of at least kTcMinRows rows: below that the 128-row UMMA tiles leave
 // most SMs idle and the FFMA kernel with 64-row tiles is faster), 2 = always
@@ -695,6 +696,8 @@ extern "C" int gatres_linear_bwd(const float* dh, const float* x, const float* W
     if (rc) return rc;
   }
   if (slots <= 0 && tensor_core_enabled(M)) {          // atomic accumulation mode, large launch: tensor-core form
+    const int tc = wgrad_tc_dispatch(NO, K, dh, x, partial, off_W, (unsigned)M, st);      // tcgen05 (linear_tc_wide.cu)
+    if (tc != 0) return tc < 0 ? tc : GATRES_OK;
     if (NO == 64 && K == 32) return launch_wgrad_mma<64, 32>(dh, x, partial, off_W, (unsigned)M, st);
     if (NO == 32 && K == 64) return launch_wgrad_mma<32, 64>(dh, x, partial, off_W, (unsigned)M, st);
   }

@@ -744,6 +744,210 @@ static int launch_tc_wide2(const float* A, const float* W, const float* e0, cons
   return check_launch("gemm_tc_wide2");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient dW = dh^T x of the nc = 32 layers on tcgen05 (atomic accumulation mode, large launches).
+//
+// The reduction runs over ROWS, the dimension both operands are strided in, so both are MN-major for the tensor core:
+// a tile is stored as the rows come from memory — [128 rows][32 floats = 128 B] per 32-column group, the 32-byte chunk of a
+// row XORed with row % 4 (descriptor layout SWIZZLE_128B_BASE32B, the only layout tcgen05 reads an MN-major tf32 operand
+// from; LBO = distance between 32-column groups, SBO = 512 B = 4 rows) — and no transpose is needed.  P = the 64-column
+// operand is A (M = 64), Q = the 32-column operand is B (N = 32): D[64][32] = P^T Q accumulates in 32 TMEM columns over ALL
+// row tiles of a persistent CTA (3xTF32: hi hi + lo hi + hi lo, 48 MMAs per 128 rows).  The tensor core's fp32 accumulation
+// truncates: one accumulator carried through the ~2000 MMAs of a CTA ended 3.4e-5 off the fp64 product (mma.sync with register
+// accumulators: 2.3e-6), so the accumulator is drained every two tiles (96 MMAs, the chain length of the K = 256 forward
+// projection) by four epilogue warps that keep the running sum in registers (round-to-nearest adds); two accumulators
+// alternate so that the drain runs under the next group's MMAs.  One flush with atomics at the end.
+//   conv1 (dh1 [M, 64], x [M, 32]):  P = dh, Q = x,  D = dW1 [64][32]
+//   conv2 (dh2 [M, 32], y1 [M, 64]): P = y1, Q = dh, D = dW2^T
+// Eight producer warps (register prefetch two chunks ahead, hi = raw words, lo = rna(x - trunc x)), four epilogue warps, one MMA-issuer warp; the
+// legacy form (wgrad_mma_kernel, mma.sync m16n8k8) issues 768 instructions per 128 rows at ~20 cycles per scheduler.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mn32_off(uint32_t row, uint32_t j) {        // byte offset of 16-byte chunk j (0..7) of a row
+  return row * 128u + ((((j >> 1) ^ (row & 3u))) << 5) + ((j & 1u) << 4);
+}
+
+struct WgradShape {
+  static constexpr int BM = 128, ST = 2, PW = 8, THREADS = (PW + 5) * 32, GROUP = 2;   // GROUP: tiles per accumulator drain
+  static constexpr uint32_t G = BM * 128;                       // one 32-column group of a tile (hi or lo)
+  static constexpr uint32_t STAGE = 6 * G;                      // P hi (2 groups), P lo (2), Q hi, Q lo
+  static constexpr uint32_t OFF_BAR = ST * STAGE, TOTAL = OFF_BAR + (2 * ST + 4) * 8 + 16;
+};
+
+template <bool P_IS_DH>
+__global__ void __launch_bounds__(WgradShape::THREADS, 1)
+wgrad_tc_kernel(const float* __restrict__ dh, const float* __restrict__ x, float* __restrict__ grads, long long off_W, unsigned M) {
+  using S = WgradShape;
+  constexpr int BM = S::BM, ST = S::ST, PT = S::PW * 32;
+  constexpr uint32_t G = S::G;
+  // M = 64, N = 32, both operands MN-major (bits 15, 16), tf32 inputs, fp32 accumulation
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) |
+                             ((uint32_t)(64 >> 4) << 24);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();
+  unsigned char* sm = smem_raw;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);                // [ST] producer arrivals
+  uint64_t* empty = full + ST;                                                  // [ST] tcgen05.commit
+  uint64_t* acc_full = empty + ST;                                              // [2] tcgen05.commit at the end of a group
+  uint64_t* acc_empty = acc_full + 2;                                           // [2] 128 epilogue arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const float* Pm = P_IS_DH ? dh : x;                                           // [M][64]
+  const float* Qm = P_IS_DH ? x : dh;                                           // [M][32]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned ntiles = (M + BM - 1) / BM;
+  const unsigned total = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  constexpr unsigned GROUP = S::GROUP;
+  const unsigned ngroups = (total + GROUP - 1) / GROUP;
+  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  if (tid == 32) {
+    for (int i = 0; i < ST; ++i) { mbar_init(full + i, PT); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp < S::PW) {
+    // P: 128 rows x 16 chunks (8 per thread), Q: 128 rows x 8 chunks (4 per thread); 16 / 8 lanes cover one row
+    float4 p0[8], q0[4], p1[8], q1[4];
+    auto request = [&](unsigned t, float4 (&pr)[8], float4 (&qr)[4]) {
+      const unsigned row0 = (blockIdx.x + t * gridDim.x) * BM;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * PT + tid;
+        const unsigned r = row0 + (unsigned)(idx >> 4);
+        pr[it] = r < M ? ldg4_stream(Pm + (size_t)r * 64 + 4 * (idx & 15)) : f4zero();
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = it * PT + tid;
+        const unsigned r = row0 + (unsigned)(idx >> 3);
+        qr[it] = r < M ? ldg4_stream(Qm + (size_t)r * 32 + 4 * (idx & 7)) : f4zero();
+      }
+    };
+    auto publish = [&](unsigned t, const float4 (&pr)[8], const float4 (&qr)[4]) {
+      const unsigned s = t % ST, n = t / ST;
+      if (n > 0) mbar_wait(empty + s, (n - 1) & 1u);
+      unsigned char* st = sm + s * S::STAGE;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * PT + tid;
+        const uint32_t j = (uint32_t)(idx & 15), off = (j >> 3) * G + mn32_off((uint32_t)(idx >> 4), j & 7u);
+        const float4 v = pr[it];
+        float4 lo;
+        lo.x = lo_tf32(v.x); lo.y = lo_tf32(v.y); lo.z = lo_tf32(v.z); lo.w = lo_tf32(v.w);
+        *reinterpret_cast<float4*>(st + off) = v;
+        *reinterpret_cast<float4*>(st + 2 * G + off) = lo;
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = it * PT + tid;
+        const uint32_t off = mn32_off((uint32_t)(idx >> 3), (uint32_t)(idx & 7));
+        const float4 v = qr[it];
+        float4 lo;
+        lo.x = lo_tf32(v.x); lo.y = lo_tf32(v.y); lo.z = lo_tf32(v.z); lo.w = lo_tf32(v.w);
+        *reinterpret_cast<float4*>(st + 4 * G + off) = v;
+        *reinterpret_cast<float4*>(st + 5 * G + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(full + s);
+    };
+    if (total > 0) request(0, p0, q0);
+    if (total > 1) request(1, p1, q1);
+    for (unsigned t = 0; t < total; t += 2) {
+      publish(t, p0, q0);
+      if (t + 2 < total) request(t + 2, p0, q0);
+      if (t + 1 < total) {
+        publish(t + 1, p1, q1);
+        if (t + 3 < total) request(t + 3, p1, q1);
+      }
+    }
+  } else if (warp < S::PW + 4) {
+    // ------------------------------------------------------------------ epilogue: running sum in registers
+    // accumulator row r (of 64) sits in TMEM lane 32 (r / 16) + r % 16; warp w owns lane quarter w % 4
+    const int quarter = warp & 3;
+    float sum[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) sum[c] = 0.f;
+    for (unsigned g = 0; g < ngroups; ++g) {
+      const unsigned acc = g & 1u;
+      mbar_wait(acc_full + acc, (g >> 1) & 1u);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + acc * 32, v);
+      tc_fence_before();
+      mbar_arrive(acc_empty + acc);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) sum[c] += v[c];
+    }
+    if (lane < 16 && total > 0) {
+      const int r = quarter * 16 + lane;                                        // P column
+      float* out = grads + off_W;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {                                            // Q column
+        if (P_IS_DH) atomicAdd(out + (size_t)r * 32 + c, sum[c]);               // dW [64][32]: row = dh column, col = x column
+        else atomicAdd(out + (size_t)c * 64 + r, sum[c]);                       // dW [32][64]: row = dh column (Q), col = y1 column (P)
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    for (unsigned t = 0; t < total; ++t) {
+      const unsigned s = t % ST, g = t / GROUP, acc = g & 1u;
+      const bool first = t % GROUP == 0, last = (t % GROUP == GROUP - 1) || t == total - 1;
+      if (first && g >= 2) mbar_wait(acc_empty + acc, ((g >> 1) - 1) & 1u);     // the drain of group g - 2 is done
+      mbar_wait(full + s, (t / ST) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t p_hi = base + s * S::STAGE, p_lo = p_hi + 2 * G, q_hi = p_hi + 4 * G, q_lo = p_hi + 5 * G;
+        const uint32_t d = tmem + acc * 32;
+#pragma unroll
+        for (int ks = 0; ks < BM / 8; ++ks) {                                   // 8 rows = 1024 B per K step
+          const uint32_t ko = (uint32_t)ks * 1024u;
+          umma_tf32(d, umma_desc_mn32(p_hi + ko, G), umma_desc_mn32(q_hi + ko, G), IDESC, (!first || ks > 0) ? 1u : 0u);
+          umma_tf32(d, umma_desc_mn32(p_lo + ko, G), umma_desc_mn32(q_hi + ko, G), IDESC, 1);
+          umma_tf32(d, umma_desc_mn32(p_hi + ko, G), umma_desc_mn32(q_lo + ko, G), IDESC, 1);
+        }
+        umma_commit(empty + s);
+        if (last) umma_commit(acc_full + acc);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+// 1 = done, 0 = shape not covered / switched off (GATRES_WGRAD_TC=0), < 0 = error
+int wgrad_tc_dispatch(int NO, int KI, const float* dh, const float* x, float* grads, long long off_W, unsigned M, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("GATRES_WGRAD_TC");
+    enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  if (!enabled || !((NO == 64 && KI == 32) || (NO == 32 && KI == 64))) return 0;
+  using S = WgradShape;
+  const bool p_is_dh = NO == 64;
+  auto kern = p_is_dh ? wgrad_tc_kernel<true> : wgrad_tc_kernel<false>;
+  static bool configured[2] = {false, false};
+  if (!configured[p_is_dh]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL) != cudaSuccess)
+      return check_launch("wgrad_tc: smem attribute");
+    configured[p_is_dh] = true;
+  }
+  const unsigned ntiles = (M + 127) / 128;
+  unsigned grid = (unsigned)sm_count();
+  if (grid > ntiles) grid = ntiles;
+  launch_kernel(kern, dim3(grid), dim3(S::THREADS), (size_t)S::TOTAL, st, dh, x, grads, off_W, M);
+  const int rc = check_launch("wgrad_tc");
+  return rc == GATRES_OK ? 1 : rc;
+}
+
 // -> 1 if handled, 0 if the shape is not covered or the kernel is switched off (GATRES_TC_WIDE2=0), < 0 on error
 int gemm_tc_wide2_dispatch(int H, int KK, int NN, const float* A, const float* W, const float* e0, const float* e1,
                            float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st) {
