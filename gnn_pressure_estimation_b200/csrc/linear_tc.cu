@@ -480,6 +480,9 @@ static int launch_linear_bwd_fused(const float* dh, const float* x, const float*
   return check_launch("linear_bwd_fused");
 }
 
+int linear_bwd_fused2_dispatch(int NO, int KI, const float* dh, const float* x, const float* W, const float* add,
+                               const float* relu_ref, float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st);
+
 // 1 = done, 0 = shape not covered (caller runs the two-kernel form), < 0 = error
 int linear_bwd_fused_dispatch(int NO, int KI, const float* dh, const float* x, const float* W, const float* add,
                               const float* relu_ref, float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st) {
@@ -489,7 +492,8 @@ int linear_bwd_fused_dispatch(int NO, int KI, const float* dh, const float* x, c
     enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
   if (!enabled) return 0;
-  int rc;
+  int rc = linear_bwd_fused2_dispatch(NO, KI, dh, x, W, add, relu_ref, dx, grads, off_W, M, st);   // all-tcgen05 form (linear_tc_wide.cu)
+  if (rc != 0) return rc;
   if (NO == 64 && KI == 32) rc = launch_linear_bwd_fused<64, 32>(dh, x, W, add, relu_ref, dx, grads, off_W, M, st);
   else return 0;                              // (dh [., 32] / x [., 64]: the two-kernel form measured faster)
   return rc == GATRES_OK ? 1 : rc;

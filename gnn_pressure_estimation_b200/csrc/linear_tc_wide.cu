@@ -948,6 +948,251 @@ int wgrad_tc_dispatch(int NO, int KI, const float* dh, const float* x, float* gr
   return rc == GATRES_OK ? 1 : rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of the conv1 projection of the nc = 32 layers in ONE pass over dh, everything on tcgen05:
+//   dx = dh W (+ residual gradient) (* ReLU mask)      dh [M, 64] K-major SWIZZLE_128B tile  x  W as B[n = ki][k = no]
+//   dW += dh^T x                                        dh and x as MN-major BASE32B tiles (as in wgrad_tc_kernel)
+// The first fused form (linear_tc.cu::linear_bwd_fused_kernel) computed dW with mma.sync from the same tiles and was held
+// by the legacy tensor path (768 instructions per 128 rows).  Here the producers write dh twice — the two layouts differ
+// only in the swizzle inside the 128-byte line — which costs 160 KB per 128-row stage, so there is ONE stage: producers
+// and MMAs of a tile alternate (~2 k cycles each) under the ~4.4 k cycles the tile's 96 KB take at the SM's share of the
+// HBM bandwidth, while the epilogue of the previous tile runs on its own accumulator: four epilogue warps request the
+// residual / ReLU-reference rows BEFORE they wait for the accumulator, park the rows in a swizzled staging buffer and
+// store 128-byte lines; the same warps drain the weight-gradient accumulator every two tiles into registers.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Fused2Shape {
+  static constexpr int BM = 128, PW = 8, THREADS = (PW + 5) * 32, GROUP = 2;
+  static constexpr uint32_t G = BM * 128;                       // [128 rows][128 B]
+  static constexpr uint32_t OFF_DHK = 0;                        // dh K-major: hi atoms 0,1 | lo atoms 0,1
+  static constexpr uint32_t OFF_DHM = 4 * G;                    // dh MN-major: hi groups 0,1 | lo groups 0,1
+  static constexpr uint32_t OFF_XM = 8 * G;                     // x MN-major: hi | lo
+  static constexpr uint32_t OFF_W = 10 * G;                     // W^T K-major [32 rows x 64]: hi (2 atoms of 4 KB) | lo
+  static constexpr uint32_t OFF_EPI = OFF_W + 4 * 4096;         // 4 warps x 4 KB
+  static constexpr uint32_t OFF_BAR = OFF_EPI + 4 * 4096;
+  static constexpr uint32_t TOTAL = OFF_BAR + 10 * 8 + 16;
+};
+
+__global__ void __launch_bounds__(Fused2Shape::THREADS, 1)
+linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ W,
+                         const float* __restrict__ add, const float* __restrict__ relu_ref, float* __restrict__ dx,
+                         float* __restrict__ grads, long long off_W, unsigned M) {
+  using S = Fused2Shape;
+  constexpr int BM = S::BM, PT = S::PW * 32, NO = 64, KI = 32;
+  constexpr unsigned GROUP = S::GROUP;
+  constexpr uint32_t G = S::G;
+  constexpr uint32_t IDESC_D = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KI >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr uint32_t IDESC_W = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(KI >> 3) << 17) |
+                               ((uint32_t)(NO >> 4) << 24);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0) __trap();
+  unsigned char* sm = smem_raw;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);                // producers -> MMA
+  uint64_t* empty = full + 1;                                                   // tcgen05.commit: the stage may be rewritten
+  uint64_t* dacc_full = empty + 1;                                              // [2]
+  uint64_t* dacc_empty = dacc_full + 2;                                         // [2] 128 epilogue arrivals
+  uint64_t* wacc_full = dacc_empty + 2;                                         // [2]
+  uint64_t* wacc_empty = wacc_full + 2;                                         // [2] 128 epilogue arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wacc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned ntiles = (M + BM - 1) / BM;
+  const unsigned total = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 128);                                    // dx accumulators: columns 0 / 32, dW: 64 / 96
+  if (tid == 32) {
+    mbar_init(full, PT);
+    mbar_init(empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(dacc_full + i, 1); mbar_init(dacc_empty + i, 128);
+      mbar_init(wacc_full + i, 1); mbar_init(wacc_empty + i, 128);
+    }
+    mbar_fence_init();
+  }
+  for (int idx = tid; idx < NO * KI; idx += blockDim.x) {                       // B[n = ki][k = no] = W[no][ki], K-major, hi / lo
+    const int n = idx % KI, k = idx / KI;
+    const float w = __ldg(W + (size_t)k * KI + n);
+    const uint32_t off = swz_off((uint32_t)n, (uint32_t)k, KI);
+    *reinterpret_cast<float*>(sm + S::OFF_W + off) = w;
+    *reinterpret_cast<float*>(sm + S::OFF_W + 2 * 4096 + off) = lo_tf32(w);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp < S::PW) {
+    // ------------------------------------------------------------------ producers: one tile ahead in registers
+    float4 pr[8], qr[4];
+    auto request = [&](unsigned t) {
+      const unsigned row0 = (blockIdx.x + t * gridDim.x) * BM;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * PT + tid;
+        const unsigned r = row0 + (unsigned)(idx >> 4);
+        pr[it] = r < M ? ldg4_stream(dh + (size_t)r * NO + 4 * (idx & 15)) : f4zero();
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = it * PT + tid;
+        const unsigned r = row0 + (unsigned)(idx >> 3);
+        qr[it] = r < M ? ldg4_stream(x + (size_t)r * KI + 4 * (idx & 7)) : f4zero();
+      }
+    };
+    if (total > 0) request(0);
+    for (unsigned t = 0; t < total; ++t) {
+      if (t > 0) mbar_wait(empty, (t - 1) & 1u);                                // the MMAs of tile t - 1 have read the stage
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * PT + tid;
+        const uint32_t row = (uint32_t)(idx >> 4), j = (uint32_t)(idx & 15);
+        const uint32_t ok = swz_off(row, 4u * j, BM);                          // K-major (dx)
+        const uint32_t om = (j >> 3) * G + mn32_off(row, j & 7u);               // MN-major (dW)
+        const float4 v = pr[it];
+        float4 lo;
+        lo.x = lo_tf32(v.x); lo.y = lo_tf32(v.y); lo.z = lo_tf32(v.z); lo.w = lo_tf32(v.w);
+        *reinterpret_cast<float4*>(sm + S::OFF_DHK + ok) = v;
+        *reinterpret_cast<float4*>(sm + S::OFF_DHK + 2 * G + ok) = lo;
+        *reinterpret_cast<float4*>(sm + S::OFF_DHM + om) = v;
+        *reinterpret_cast<float4*>(sm + S::OFF_DHM + 2 * G + om) = lo;
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = it * PT + tid;
+        const uint32_t off = mn32_off((uint32_t)(idx >> 3), (uint32_t)(idx & 7));
+        const float4 v = qr[it];
+        float4 lo;
+        lo.x = lo_tf32(v.x); lo.y = lo_tf32(v.y); lo.z = lo_tf32(v.z); lo.w = lo_tf32(v.w);
+        *reinterpret_cast<float4*>(sm + S::OFF_XM + off) = v;
+        *reinterpret_cast<float4*>(sm + S::OFF_XM + G + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(full);
+      if (t + 1 < total) request(t + 1);
+    }
+  } else if (warp < S::PW + 4) {
+    // ------------------------------------------------------------------ epilogue: dx rows + running dW sum
+    const int quarter = warp & 3;
+    unsigned char* stg = sm + S::OFF_EPI + quarter * 4096;
+    float sum[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) sum[c] = 0.f;
+    for (unsigned t = 0; t < total; ++t) {
+      const unsigned acc = t & 1u, row0 = (blockIdx.x + t * gridDim.x) * BM + quarter * 32;
+      float4 addv[8], refv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                                             // requested before the wait for the accumulator
+        const int r = j * 4 + (lane >> 3), c = lane & 7;
+        const size_t off = (size_t)(row0 + r) * KI + 4 * c;
+        const bool ok = row0 + r < M;
+        addv[j] = (ok && add != nullptr) ? ldg4_stream(add + off) : f4zero();
+        refv[j] = (ok && relu_ref != nullptr) ? ldg4_stream(relu_ref + off) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+      mbar_wait(dacc_full + acc, (t >> 1) & 1u);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + acc * 32, v);
+      tc_fence_before();
+      mbar_arrive(dacc_empty + acc);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = j * 4 + (lane >> 3), c = lane & 7;
+        float4 o = *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
+        add4(o, addv[j]);
+        o.x = refv[j].x > 0.f ? o.x : 0.f; o.y = refv[j].y > 0.f ? o.y : 0.f;
+        o.z = refv[j].z > 0.f ? o.z : 0.f; o.w = refv[j].w > 0.f ? o.w : 0.f;
+        if (row0 + r < M) st4(dx + (size_t)(row0 + r) * KI + 4 * c, o);
+      }
+      __syncwarp();
+      if (t % GROUP == GROUP - 1 || t == total - 1) {                            // the group's weight-gradient accumulator is complete
+        const unsigned g = t / GROUP, wa = g & 1u;
+        mbar_wait(wacc_full + wa, (g >> 1) & 1u);
+        tc_fence_after();
+        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + 64 + wa * 32, v);
+        tc_fence_before();
+        mbar_arrive(wacc_empty + wa);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sum[c] += v[c];
+      }
+    }
+    if (lane < 16 && total > 0) {                                               // accumulator row r of 64 = TMEM lane 32 (r / 16) + r % 16
+      float* out = grads + off_W + (size_t)(quarter * 16 + lane) * KI;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) atomicAdd(out + c, sum[c]);
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    for (unsigned t = 0; t < total; ++t) {
+      const unsigned acc = t & 1u, g = t / GROUP, wa = g & 1u;
+      const bool first = t % GROUP == 0, last = (t % GROUP == GROUP - 1) || t == total - 1;
+      if (t >= 2) mbar_wait(dacc_empty + acc, ((t >> 1) - 1) & 1u);
+      if (first && g >= 2) mbar_wait(wacc_empty + wa, ((g >> 1) - 1) & 1u);
+      mbar_wait(full, t & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ak_hi = base + S::OFF_DHK, ak_lo = ak_hi + 2 * G;
+        const uint32_t w_hi = base + S::OFF_W, w_lo = w_hi + 2 * 4096;
+        const uint32_t pm_hi = base + S::OFF_DHM, pm_lo = pm_hi + 2 * G, qm_hi = base + S::OFF_XM, qm_lo = qm_hi + G;
+        const uint32_t dd = tmem + acc * 32, dw = tmem + 64 + wa * 32;
+#pragma unroll
+        for (int ks = 0; ks < NO / 8; ++ks) {                                   // dx: K = 64 dh columns
+          const uint32_t ka = (uint32_t)(ks >> 2) * G + (uint32_t)(ks & 3) * 32u;
+          const uint32_t kb = (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u;
+          umma_tf32(dd, umma_desc_k128(ak_hi + ka), umma_desc_k128(w_hi + kb), IDESC_D, ks > 0 ? 1u : 0u);
+          umma_tf32(dd, umma_desc_k128(ak_lo + ka), umma_desc_k128(w_hi + kb), IDESC_D, 1);
+          umma_tf32(dd, umma_desc_k128(ak_hi + ka), umma_desc_k128(w_lo + kb), IDESC_D, 1);
+        }
+        umma_commit(dacc_full + acc);
+#pragma unroll
+        for (int ks = 0; ks < BM / 8; ++ks) {                                   // dW: K = 128 rows
+          const uint32_t ko = (uint32_t)ks * 1024u;
+          umma_tf32(dw, umma_desc_mn32(pm_hi + ko, G), umma_desc_mn32(qm_hi + ko, G), IDESC_W, (!first || ks > 0) ? 1u : 0u);
+          umma_tf32(dw, umma_desc_mn32(pm_lo + ko, G), umma_desc_mn32(qm_hi + ko, G), IDESC_W, 1);
+          umma_tf32(dw, umma_desc_mn32(pm_hi + ko, G), umma_desc_mn32(qm_lo + ko, G), IDESC_W, 1);
+        }
+        umma_commit(empty);
+        if (last) umma_commit(wacc_full + wa);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// 1 = done, 0 = not covered / switched off (GATRES_LINEAR_BWD_FUSED2=0), < 0 = error
+int linear_bwd_fused2_dispatch(int NO, int KI, const float* dh, const float* x, const float* W, const float* add,
+                               const float* relu_ref, float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("GATRES_LINEAR_BWD_FUSED2");
+    enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  if (!enabled || NO != 64 || KI != 32) return 0;
+  using S = Fused2Shape;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(linear_bwd_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL) != cudaSuccess)
+      return check_launch("linear_bwd_fused2: smem attribute");
+    configured = true;
+  }
+  const unsigned ntiles = (M + 127) / 128;
+  unsigned grid = (unsigned)sm_count();
+  if (grid > ntiles) grid = ntiles;
+  launch_kernel(linear_bwd_fused2_kernel, dim3(grid), dim3(S::THREADS), (size_t)S::TOTAL, st, dh, x, W, add, relu_ref, dx, grads,
+                off_W, M);
+  const int rc = check_launch("linear_bwd_fused2");
+  return rc == GATRES_OK ? 1 : rc;
+}
+
 // -> 1 if handled, 0 if the shape is not covered or the kernel is switched off (GATRES_TC_WIDE2=0), < 0 on error
 int gemm_tc_wide2_dispatch(int H, int KK, int NN, const float* A, const float* W, const float* e0, const float* e1,
                            float* Cout, float* s0, float* s1, unsigned M, cudaStream_t st) {
