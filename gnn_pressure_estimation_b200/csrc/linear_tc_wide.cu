@@ -960,29 +960,37 @@ int wgrad_tc_dispatch(int NO, int KI, const float* dh, const float* x, float* gr
 // residual / ReLU-reference rows BEFORE they wait for the accumulator, park the rows in a swizzled staging buffer and
 // store 128-byte lines; the same warps drain the weight-gradient accumulator every two tiles into registers.
 // ---------------------------------------------------------------------------------------------------------------------
+template <int NO, int KI>
 struct Fused2Shape {
+  static_assert((NO == 64 && KI == 32) || (NO == 32 && KI == 64), "nc = 32 layers");
   static constexpr int BM = 128, PW = 8, THREADS = (PW + 5) * 32, GROUP = 2;
+  static constexpr int GD = NO / 32, GX = KI / 32;              // 32-column groups (= K-major atoms) of dh and x
   static constexpr uint32_t G = BM * 128;                       // [128 rows][128 B]
-  static constexpr uint32_t OFF_DHK = 0;                        // dh K-major: hi atoms 0,1 | lo atoms 0,1
-  static constexpr uint32_t OFF_DHM = 4 * G;                    // dh MN-major: hi groups 0,1 | lo groups 0,1
-  static constexpr uint32_t OFF_XM = 8 * G;                     // x MN-major: hi | lo
-  static constexpr uint32_t OFF_W = 10 * G;                     // W^T K-major [32 rows x 64]: hi (2 atoms of 4 KB) | lo
-  static constexpr uint32_t OFF_EPI = OFF_W + 4 * 4096;         // 4 warps x 4 KB
+  static constexpr uint32_t OFF_DHK = 0;                        // dh K-major: hi atoms | lo atoms
+  static constexpr uint32_t OFF_DHM = 2 * GD * G;               // dh MN-major: hi groups | lo groups
+  static constexpr uint32_t OFF_XM = 4 * GD * G;                // x MN-major: hi groups | lo groups
+  static constexpr uint32_t W_PART = NO * KI * 4;               // W^T K-major [KI rows x NO]: hi | lo
+  static constexpr uint32_t OFF_W = OFF_XM + 2 * GX * G;
+  static constexpr uint32_t OFF_EPI = OFF_W + 2 * W_PART;       // 4 warps x 4 KB
   static constexpr uint32_t OFF_BAR = OFF_EPI + 4 * 4096;
   static constexpr uint32_t TOTAL = OFF_BAR + 10 * 8 + 16;
+  static constexpr uint32_t TMEM_COLS = KI == 32 ? 128 : 256;   // dx accumulators: columns 0 / KI, dW: 2 KI / 2 KI + 32
+  static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-__global__ void __launch_bounds__(Fused2Shape::THREADS, 1)
+template <int NO, int KI>
+__global__ void __launch_bounds__((Fused2Shape<NO, KI>::THREADS), 1)
 linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ W,
                          const float* __restrict__ add, const float* __restrict__ relu_ref, float* __restrict__ dx,
                          float* __restrict__ grads, long long off_W, unsigned M) {
-  using S = Fused2Shape;
-  constexpr int BM = S::BM, PT = S::PW * 32, NO = 64, KI = 32;
+  using S = Fused2Shape<NO, KI>;
+  constexpr int BM = S::BM, PT = S::PW * 32, GD = S::GD, GX = S::GX;
+  constexpr bool P_IS_DH = NO == 64;                            // the 64-column operand is A (M = 64) of the weight gradient
   constexpr unsigned GROUP = S::GROUP;
   constexpr uint32_t G = S::G;
   constexpr uint32_t IDESC_D = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KI >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  constexpr uint32_t IDESC_W = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(KI >> 3) << 17) |
-                               ((uint32_t)(NO >> 4) << 24);
+  constexpr uint32_t IDESC_W = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) |
+                               ((uint32_t)(64 >> 4) << 24);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0) __trap();
@@ -999,7 +1007,7 @@ linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__
   const unsigned ntiles = (M + BM - 1) / BM;
   const unsigned total = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == 0) tmem_alloc(tmem_slot, 128);                                    // dx accumulators: columns 0 / 32, dW: 64 / 96
+  if (warp == 0) tmem_alloc(tmem_slot, S::TMEM_COLS);
   if (tid == 32) {
     mbar_init(full, PT);
     mbar_init(empty, 1);
@@ -1014,7 +1022,7 @@ linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__
     const float w = __ldg(W + (size_t)k * KI + n);
     const uint32_t off = swz_off((uint32_t)n, (uint32_t)k, KI);
     *reinterpret_cast<float*>(sm + S::OFF_W + off) = w;
-    *reinterpret_cast<float*>(sm + S::OFF_W + 2 * 4096 + off) = lo_tf32(w);
+    *reinterpret_cast<float*>(sm + S::OFF_W + S::W_PART + off) = lo_tf32(w);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -1025,48 +1033,50 @@ linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__
 
   if (warp < S::PW) {
     // ------------------------------------------------------------------ producers: one tile ahead in registers
-    float4 pr[8], qr[4];
+    constexpr int ND = BM * (NO / 4) / PT, NX = BM * (KI / 4) / PT;             // float4 per thread and tile
+    float4 pr[ND], qr[NX];
     auto request = [&](unsigned t) {
       const unsigned row0 = (blockIdx.x + t * gridDim.x) * BM;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+      for (int it = 0; it < ND; ++it) {
         const int idx = it * PT + tid;
-        const unsigned r = row0 + (unsigned)(idx >> 4);
-        pr[it] = r < M ? ldg4_stream(dh + (size_t)r * NO + 4 * (idx & 15)) : f4zero();
+        const unsigned r = row0 + (unsigned)(idx / (NO / 4));
+        pr[it] = r < M ? ldg4_stream(dh + (size_t)r * NO + 4 * (idx % (NO / 4))) : f4zero();
       }
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < NX; ++it) {
         const int idx = it * PT + tid;
-        const unsigned r = row0 + (unsigned)(idx >> 3);
-        qr[it] = r < M ? ldg4_stream(x + (size_t)r * KI + 4 * (idx & 7)) : f4zero();
+        const unsigned r = row0 + (unsigned)(idx / (KI / 4));
+        qr[it] = r < M ? ldg4_stream(x + (size_t)r * KI + 4 * (idx % (KI / 4))) : f4zero();
       }
     };
     if (total > 0) request(0);
     for (unsigned t = 0; t < total; ++t) {
       if (t > 0) mbar_wait(empty, (t - 1) & 1u);                                // the MMAs of tile t - 1 have read the stage
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+      for (int it = 0; it < ND; ++it) {
         const int idx = it * PT + tid;
-        const uint32_t row = (uint32_t)(idx >> 4), j = (uint32_t)(idx & 15);
+        const uint32_t row = (uint32_t)(idx / (NO / 4)), j = (uint32_t)(idx % (NO / 4));
         const uint32_t ok = swz_off(row, 4u * j, BM);                          // K-major (dx)
         const uint32_t om = (j >> 3) * G + mn32_off(row, j & 7u);               // MN-major (dW)
         const float4 v = pr[it];
         float4 lo;
         lo.x = lo_tf32(v.x); lo.y = lo_tf32(v.y); lo.z = lo_tf32(v.z); lo.w = lo_tf32(v.w);
         *reinterpret_cast<float4*>(sm + S::OFF_DHK + ok) = v;
-        *reinterpret_cast<float4*>(sm + S::OFF_DHK + 2 * G + ok) = lo;
+        *reinterpret_cast<float4*>(sm + S::OFF_DHK + GD * G + ok) = lo;
         *reinterpret_cast<float4*>(sm + S::OFF_DHM + om) = v;
-        *reinterpret_cast<float4*>(sm + S::OFF_DHM + 2 * G + om) = lo;
+        *reinterpret_cast<float4*>(sm + S::OFF_DHM + GD * G + om) = lo;
       }
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < NX; ++it) {
         const int idx = it * PT + tid;
-        const uint32_t off = mn32_off((uint32_t)(idx >> 3), (uint32_t)(idx & 7));
+        const uint32_t row = (uint32_t)(idx / (KI / 4)), j = (uint32_t)(idx % (KI / 4));
+        const uint32_t off = (j >> 3) * G + mn32_off(row, j & 7u);
         const float4 v = qr[it];
         float4 lo;
         lo.x = lo_tf32(v.x); lo.y = lo_tf32(v.y); lo.z = lo_tf32(v.z); lo.w = lo_tf32(v.w);
         *reinterpret_cast<float4*>(sm + S::OFF_XM + off) = v;
-        *reinterpret_cast<float4*>(sm + S::OFF_XM + G + off) = lo;
+        *reinterpret_cast<float4*>(sm + S::OFF_XM + GX * G + off) = lo;
       }
       fence_proxy_async();
       mbar_arrive(full);
@@ -1081,41 +1091,48 @@ linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__
     for (int c = 0; c < 32; ++c) sum[c] = 0.f;
     for (unsigned t = 0; t < total; ++t) {
       const unsigned acc = t & 1u, row0 = (blockIdx.x + t * gridDim.x) * BM + quarter * 32;
-      float4 addv[8], refv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {                                             // requested before the wait for the accumulator
-        const int r = j * 4 + (lane >> 3), c = lane & 7;
-        const size_t off = (size_t)(row0 + r) * KI + 4 * c;
-        const bool ok = row0 + r < M;
-        addv[j] = (ok && add != nullptr) ? ldg4_stream(add + off) : f4zero();
-        refv[j] = (ok && relu_ref != nullptr) ? ldg4_stream(relu_ref + off) : make_float4(1.f, 1.f, 1.f, 1.f);
-      }
-      mbar_wait(dacc_full + acc, (t >> 1) & 1u);
-      tc_fence_after();
       float v[32];
-      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + acc * 32, v);
-      tc_fence_before();
-      mbar_arrive(dacc_empty + acc);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
-            make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-      __syncwarp();
+      for (int cb = 0; cb < KI / 32; ++cb) {
+        float4 addv[8], refv[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = j * 4 + (lane >> 3), c = lane & 7;
-        float4 o = *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
-        add4(o, addv[j]);
-        o.x = refv[j].x > 0.f ? o.x : 0.f; o.y = refv[j].y > 0.f ? o.y : 0.f;
-        o.z = refv[j].z > 0.f ? o.z : 0.f; o.w = refv[j].w > 0.f ? o.w : 0.f;
-        if (row0 + r < M) st4(dx + (size_t)(row0 + r) * KI + 4 * c, o);
+        for (int j = 0; j < 8; ++j) {                                           // requested before the wait for the accumulator
+          const int r = j * 4 + (lane >> 3), c = lane & 7;
+          const size_t off = (size_t)(row0 + r) * KI + cb * 32 + 4 * c;
+          const bool ok = row0 + r < M;
+          addv[j] = (ok && add != nullptr) ? ldg4_stream(add + off) : f4zero();
+          refv[j] = (ok && relu_ref != nullptr) ? ldg4_stream(relu_ref + off) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        if (cb == 0) {
+          mbar_wait(dacc_full + acc, (t >> 1) & 1u);
+          tc_fence_after();
+        }
+        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + acc * KI + cb * 32, v);
+        if (cb == KI / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(dacc_empty + acc);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = j * 4 + (lane >> 3), c = lane & 7;
+          float4 o = *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
+          add4(o, addv[j]);
+          o.x = refv[j].x > 0.f ? o.x : 0.f; o.y = refv[j].y > 0.f ? o.y : 0.f;
+          o.z = refv[j].z > 0.f ? o.z : 0.f; o.w = refv[j].w > 0.f ? o.w : 0.f;
+          if (row0 + r < M) st4(dx + (size_t)(row0 + r) * KI + cb * 32 + 4 * c, o);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       if (t % GROUP == GROUP - 1 || t == total - 1) {                            // the group's weight-gradient accumulator is complete
         const unsigned g = t / GROUP, wa = g & 1u;
         mbar_wait(wacc_full + wa, (g >> 1) & 1u);
         tc_fence_after();
-        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + 64 + wa * 32, v);
+        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + 2 * KI + wa * 32, v);
         tc_fence_before();
         mbar_arrive(wacc_empty + wa);
 #pragma unroll
@@ -1123,9 +1140,13 @@ linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__
       }
     }
     if (lane < 16 && total > 0) {                                               // accumulator row r of 64 = TMEM lane 32 (r / 16) + r % 16
-      float* out = grads + off_W + (size_t)(quarter * 16 + lane) * KI;
+      const int r = quarter * 16 + lane;                                        // column of the 64-column operand
+      float* out = grads + off_W;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) atomicAdd(out + c, sum[c]);
+      for (int c = 0; c < 32; ++c) {
+        if (P_IS_DH) atomicAdd(out + (size_t)r * 32 + c, sum[c]);               // dW [64][32]: row = dh column, col = x column
+        else atomicAdd(out + (size_t)c * 64 + r, sum[c]);                       // dW [32][64]: row = dh column, col = x column
+      }
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
@@ -1137,14 +1158,16 @@ linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__
       mbar_wait(full, t & 1u);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t ak_hi = base + S::OFF_DHK, ak_lo = ak_hi + 2 * G;
-        const uint32_t w_hi = base + S::OFF_W, w_lo = w_hi + 2 * 4096;
-        const uint32_t pm_hi = base + S::OFF_DHM, pm_lo = pm_hi + 2 * G, qm_hi = base + S::OFF_XM, qm_lo = qm_hi + G;
-        const uint32_t dd = tmem + acc * 32, dw = tmem + 64 + wa * 32;
+        const uint32_t ak_hi = base + S::OFF_DHK, ak_lo = ak_hi + GD * G;
+        const uint32_t w_hi = base + S::OFF_W, w_lo = w_hi + S::W_PART;
+        const uint32_t dm_hi = base + S::OFF_DHM, dm_lo = dm_hi + GD * G, xm_hi = base + S::OFF_XM, xm_lo = xm_hi + GX * G;
+        const uint32_t pm_hi = P_IS_DH ? dm_hi : xm_hi, pm_lo = P_IS_DH ? dm_lo : xm_lo;
+        const uint32_t qm_hi = P_IS_DH ? xm_hi : dm_hi, qm_lo = P_IS_DH ? xm_lo : dm_lo;
+        const uint32_t dd = tmem + acc * KI, dw = tmem + 2 * KI + wa * 32;
 #pragma unroll
-        for (int ks = 0; ks < NO / 8; ++ks) {                                   // dx: K = 64 dh columns
+        for (int ks = 0; ks < NO / 8; ++ks) {                                   // dx: K = the dh columns
           const uint32_t ka = (uint32_t)(ks >> 2) * G + (uint32_t)(ks & 3) * 32u;
-          const uint32_t kb = (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u;
+          const uint32_t kb = (uint32_t)(ks >> 2) * (KI * 128u) + (uint32_t)(ks & 3) * 32u;
           umma_tf32(dd, umma_desc_k128(ak_hi + ka), umma_desc_k128(w_hi + kb), IDESC_D, ks > 0 ? 1u : 0u);
           umma_tf32(dd, umma_desc_k128(ak_lo + ka), umma_desc_k128(w_hi + kb), IDESC_D, 1);
           umma_tf32(dd, umma_desc_k128(ak_hi + ka), umma_desc_k128(w_lo + kb), IDESC_D, 1);
@@ -1165,31 +1188,39 @@ linear_bwd_fused2_kernel(const float* __restrict__ dh, const float* __restrict__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, S::TMEM_COLS);
 }
 
-// 1 = done, 0 = not covered / switched off (GATRES_LINEAR_BWD_FUSED2=0), < 0 = error
-int linear_bwd_fused2_dispatch(int NO, int KI, const float* dh, const float* x, const float* W, const float* add,
-                               const float* relu_ref, float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("GATRES_LINEAR_BWD_FUSED2");
-    enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-  }
-  if (!enabled || NO != 64 || KI != 32) return 0;
-  using S = Fused2Shape;
+template <int NO, int KI>
+static int launch_fused2(const float* dh, const float* x, const float* W, const float* add, const float* relu_ref, float* dx,
+                         float* grads, long long off_W, unsigned M, cudaStream_t st) {
+  using S = Fused2Shape<NO, KI>;
+  auto kern = linear_bwd_fused2_kernel<NO, KI>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(linear_bwd_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL) != cudaSuccess)
       return check_launch("linear_bwd_fused2: smem attribute");
     configured = true;
   }
   const unsigned ntiles = (M + 127) / 128;
   unsigned grid = (unsigned)sm_count();
   if (grid > ntiles) grid = ntiles;
-  launch_kernel(linear_bwd_fused2_kernel, dim3(grid), dim3(S::THREADS), (size_t)S::TOTAL, st, dh, x, W, add, relu_ref, dx, grads,
-                off_W, M);
-  const int rc = check_launch("linear_bwd_fused2");
+  launch_kernel(kern, dim3(grid), dim3(S::THREADS), (size_t)S::TOTAL, st, dh, x, W, add, relu_ref, dx, grads, off_W, M);
+  return check_launch("linear_bwd_fused2");
+}
+
+// 1 = done, 0 = not covered / switched off (GATRES_LINEAR_BWD_FUSED2=0; =1: conv1 only, default 2: conv1 and conv2), < 0 = error
+int linear_bwd_fused2_dispatch(int NO, int KI, const float* dh, const float* x, const float* W, const float* add,
+                               const float* relu_ref, float* dx, float* grads, long long off_W, unsigned M, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("GATRES_LINEAR_BWD_FUSED2");
+    enabled = e == nullptr ? 2 : atoi(e);
+  }
+  int rc;
+  if (enabled >= 1 && NO == 64 && KI == 32) rc = launch_fused2<64, 32>(dh, x, W, add, relu_ref, dx, grads, off_W, M, st);
+  else if (enabled >= 2 && NO == 32 && KI == 64) rc = launch_fused2<32, 64>(dh, x, W, add, relu_ref, dx, grads, off_W, M, st);
+  else return 0;
   return rc == GATRES_OK ? 1 : rc;
 }
 

@@ -64,7 +64,12 @@ def fused(args):
     lib = _lib.load()
     lib.gatres_set_tensor_core(2)
     dev = torch.device("cuda:0")
-    M, NO, KI = args.rows, 64, 32
+    for NO, KI in [(64, 32), (32, 64)]:
+        fused_shape(args, NO, KI, dev, call, ptr, stream)
+
+
+def fused_shape(args, NO, KI, dev, call, ptr, stream):
+    M = args.rows
     g = torch.Generator().manual_seed(11)
     dh = torch.randn(M, NO, generator=g).to(dev)
     x = torch.randn(M, KI, generator=g).to(dev)
@@ -75,7 +80,7 @@ def fused(args):
     grads = torch.zeros(NO * KI, device=dev)
 
     def run():
-        call("gatres_linear_bwd", ptr(dh), ptr(x), ptr(W), ptr(add), ptr(ref), ptr(dx), ptr(grads), NO * KI, 0, 0, M, KI, 2, 32, stream())
+        call("gatres_linear_bwd", ptr(dh), ptr(x), ptr(W), ptr(add), ptr(ref), ptr(dx), ptr(grads), NO * KI, 0, 0, M, KI, NO // 32, 32, stream())
 
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
@@ -99,7 +104,7 @@ def fused(args):
         st.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / args.iters
     bytes_row = 4 * (NO + KI + KI + KI + KI)
-    print(json.dumps({"kernel": "linear_bwd conv1 (dx + dW)", "fused2": os.environ.get("GATRES_LINEAR_BWD_FUSED2", "1"), "us": us,
+    print(json.dumps({"kernel": f"linear_bwd dh[.,{NO}] x[.,{KI}] (dx + dW)", "fused2": os.environ.get("GATRES_LINEAR_BWD_FUSED2", "1"), "us": us,
                       "GBps": M * bytes_row / us / 1e3, "frac": M * bytes_row / us / 1e3 / 6540.5, "err_dx": e_dx, "err_dW": e_dw}), flush=True)
 
 
