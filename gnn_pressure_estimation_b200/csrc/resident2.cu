@@ -1894,8 +1894,11 @@ void resident_profile(long long** buf, int* slots);      // resident.cu (gatres_
 // that does not fit the GPU at two CTAs per SM (37 clusters) simply runs in waves; measured (tools/resident_probe.py,
 // training step, us): 48 snapshots 853 against 1279 with 4 CTAs per snapshot in one wave + the layer backward, 64:
 // 911 / 1503, 96: 1343 / 1591 (layer kernels), 128: 1774 / 1839, 192: 2630 / 2789, 256: 3456 / 3066 — the layer kernels
-// take over between 192 and 256 snapshots (inference: between 256 and ~400).
-constexpr long long kRes2MaxTrain = 208, kRes2MaxInfer = 320;
+// take over between 192 and 256 snapshots (inference: between 256 and ~400).  Third session of round 2 (warp-specialised
+// projections, all-tcgen05 projection backward in the layer path; bench.py --batch B, snapshots/s resident pair / layer
+// kernels): 96: 70.9 k / 57.4 k, 128: 71.6 k / 71.1 k, 192: 72.6 k / 74.8 k, 256: - / 89.8 k — the training crossover moved to
+// between 128 and 192 snapshots.
+constexpr long long kRes2MaxTrain = 160, kRes2MaxInfer = 320;
 static int res2_cluster(long long B) {
   (void)B;
   return resident_forced_cluster() > 0 ? resident_forced_cluster() : 8;
