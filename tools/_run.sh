@@ -1,3 +1,5 @@
-cd _old
-for i in 1 2 3; do timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_resident2.py -m gpu -x -q -k "dsm_training_pair and ctown-4-4-8-2" > ../gpurun_out/r4o_racecheck_old_$i.log 2>&1; tail -1 ../gpurun_out/r4o_racecheck_old_$i.log | cut -c1-200; done
-GATRES_DEGREE_SORT=1 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_resident2.py -m gpu -x -q -k "dsm_training_pair and ctown-32-15-8-2" > ../gpurun_out/r4o_racecheck_old_big.log 2>&1; tail -1 ../gpurun_out/r4o_racecheck_old_big.log | cut -c1-200
+#!/bin/bash
+# Scratch command file for long gpurun invocations: `gpurun -- bash tools/_run.sh`.
+# Default: the GPU parity suite and one short bench line.
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 20 --warmup 5 --skip-config-legs 2>/dev/null | tail -1 | cut -c1-400
