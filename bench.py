@@ -645,6 +645,10 @@ def roofline_leg(args, line, wl, step_ms, dev):
     line["roofline_hbm_regime"]["aggregation_kernels"] = [
         {"kernel": r["kernel"], "us": r["us"], "bytes_per_node": r["bytes_per_node"], "GBps": r["GBps"], "frac": r["GBps"] / peak,
          "accounting": r.get("accounting", "per-kernel algorithmic bytes")} for r in aggs]
+    # the dense contractions of the same layers (tcgen05 3xTF32 projections and their backward) and the mean kernels, same regime
+    line["roofline_hbm_regime"]["other_kernels"] = [
+        {"kernel": r["kernel"], "us": r["us"], "bytes_per_node": r["bytes_per_node"], "GBps": r["GBps"], "frac": r["GBps"] / peak,
+         "accounting": "per-kernel algorithmic bytes"} for r in hbm if not r["kernel"].startswith("gat_agg")]
     if args.mode == "train" and ts is not None and ts.kernels_per_step < 20:
         # the timed step ran the snapshot-resident cluster kernels: its dominant launch is the whole-stack backward
         # (one kernel).  FUSED accounting: what that one launch must move through HBM — the saved activations of every
