@@ -1,4 +1,4 @@
-// Wide projections (nc = 64 / 128: K up to 256, N up to 256) on tcgen05, warp-specialised.
+// Projections on tcgen05, warp-specialised: wide shapes (nc = 64 / 128: K up to 256, N up to 256) and, for large launches, nc = 32.
 //
 //   h = x W^T + attention-score epilogue     (GATConv.forward step 1 of the large GATRes,
 //   /root/reference/gnn_pressure_estimation/GraphModels.py:464-465 with ConfigModels.py:33-42: 25 blocks x 128 channels)
@@ -26,6 +26,10 @@
 //                            (cp.async.bulk.tensor.2d from a SWIZZLE_128B staging buffer, two buffers per warp) — the
 //                            register-store epilogue (read the buffer back, st.global) stays as the fallback when the
 //                            driver entry point for cuTensorMapEncodeTiled is missing.
+//
+// For the nc = 32 shapes (hi + lo of the whole W = 16 KB) W is loaded once per CTA and stays resident, the ring's shared memory
+// goes to five A stages and there are eight producer warps (the other roles move up by four warps); the same file holds the
+// weight gradient and the fused projection backward of those layers on tcgen05 (MN-major operands, below).
 //
 // One CTA per SM (226 KB of shared memory), persistent over 128-row tiles; the next tile's A block (contiguous) is
 // prefetched into L2 with one cp.async.bulk.prefetch.  Measured (B200, 794 624 rows, profiles/r2_wide_and_sliced.md):
